@@ -1,0 +1,197 @@
+/*
+ * syzgy_b200.h -- C ABI of the B200-native search hot path of SyzgyDB.
+ *
+ * The reference (github.com/smhanov/syzgydb, pure Go) has no FFI/plugin interface for
+ * this path: the scan sits behind the Go method (*Collection).Search
+ * (collection.go:569-711).  This header is the boundary a cgo shim inside package
+ * syzgydb binds (INTEGRATION.md shows that shim).  Each entry point cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative SZG_E* code on failure, and never
+ *    throws / aborts across the ABI; szg_last_error() gives the message (thread-local).
+ *  - plain pointers and sizes only.  Host pointers unless the name ends in _dev.
+ *  - cgo rule: the library never retains a caller pointer after returning; inputs are
+ *    copied, outputs are caller-allocated (only radius results are library-owned).
+ *  - vector bytes are EXACTLY stream 1 of a span (encodeDocument, collection.go:713-744):
+ *    4-bit high-nibble-first, 16/32/64-bit big-endian.  rowbytes = getVectorSize
+ *    (collection.go:796-811).
+ *  - threading: concurrent searches on one handle are safe (Search holds only the RLock,
+ *    collection.go:570); mutations (upsert/remove/mask/reserve/fill/destroy) must not
+ *    overlap anything else on the same handle (they run under the write lock,
+ *    collection.go:428, 491, 512).  Different handles are independent.
+ *  - there is no CPU fallback: without a CUDA device every call fails with SZG_ECUDA.
+ */
+#ifndef SYZGY_B200_H
+#define SYZGY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SZG_OK 0
+#define SZG_EINVAL (-1)   /* bad argument (dimension mismatch, unsupported quantization, k too large) */
+#define SZG_ECUDA (-2)    /* CUDA runtime failure or no device */
+#define SZG_ENOMEM (-3)   /* host or device allocation failed */
+#define SZG_ENOTFOUND (-4)
+#define SZG_EINTERNAL (-5)
+
+/* DistanceMethod, collection.go:186-189 */
+#define SZG_EUCLIDEAN 0
+#define SZG_COSINE 1 /* angularDistance: acos(cos)/pi, collection.go:821-832 */
+
+/* search flags */
+#define SZG_F_DEFAULT 0u
+/* return the fp32/integer surrogate distance converted to the reference's unit instead of
+ * the fp64 re-score of the candidate set (faster by a few microseconds; order may then
+ * differ from the reference among near-ties).  Default is fp64 verify ON. */
+#define SZG_F_NO_FP64_VERIFY 1u
+
+/* sentinel distance szg_rescore() writes for an id that is not in the mirror, so that the
+ * shim can return StopSearch like getDocument's error path (collection.go:584-587). */
+#define SZG_MISSING_DISTANCE (-1.0)
+
+#define SZG_MAX_K 224u  /* largest K of one top-k call (candidate set is K rounded up + slack) */
+#define SZG_MAX_DIM 16384
+
+typedef struct szg_index szg_index;   /* GPU mirror of one collection (or one row shard of it) */
+typedef struct szg_result szg_result; /* library-owned radius result */
+
+/* message of the last failure on this thread ("" if none) */
+const char *szg_last_error(void);
+
+/*
+ * Creates an empty GPU mirror on CUDA device `device`.
+ * Replaces: the per-collection state NewCollection sets up for searching
+ * (collection.go:224-314: DimensionCount, Quantization (0 => 64, 254-256), DistanceMethod).
+ */
+int szg_create(int dim, int quantization, int metric, int device, szg_index **out);
+
+/* Replaces: Collection.Close for the mirror (collection.go:408-421). */
+int szg_destroy(szg_index *h);
+
+/* pre-sizes device storage for nrows records (optional) */
+int szg_reserve(szg_index *h, uint64_t nrows);
+
+/*
+ * Inserts or replaces n records.  codes = n * rowbytes bytes, record i = stream 1 of the span
+ * of ids[i].  Replaces: the vector half of AddDocument (collection.go:427-457, after
+ * WriteRecord 446-453) and of the reload loop in NewCollection (298-311).  An existing id is
+ * overwritten in place (spanfile.go:459-472 replaces the span).
+ */
+int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t n);
+
+/* Replaces: removeDocument (collection.go:511-521).  *n_removed (optional) = ids that existed. */
+int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_removed);
+
+/* number of live records (SpanFile.GetStats numRecords, spanfile.go:562-566) */
+int szg_count(szg_index *h, uint64_t *n);
+
+/*
+ * Registers the outcome of a FilterFn (collection.go:184, applied at 592-594) as a bitmask:
+ * pass[i] != 0 <=> Filter(ids[i], metadata) returned true.  Ids not listed do not pass.
+ * The shim evaluates the Go predicate once per record and caches the mask per filter
+ * string; it must be rebuilt after UpdateDocument/AddDocument/removeDocument.
+ */
+int szg_mask_create(szg_index *h, const uint64_t *ids, const uint8_t *pass, uint64_t n, int *mask_id);
+int szg_mask_destroy(szg_index *h, int mask_id);
+
+/*
+ * Exact top-k for nq queries (each scans the whole mirror on its own: single-query GEMV
+ * semantics, not the batched contraction).  Replaces: Search with Precision=="exact",
+ * Radius==0, K>0 (collection.go:672-684 driving consider 583-629 and the drain 693-697).
+ *   queries  nq*dim float64, never quantized (collection.go:596)
+ *   mask_id  -1 = no filter
+ *   out_ids / out_dist   nq*k, ascending distance per query; out_n[q] = results of query q
+ *   scanned  (optional) records considered per query = live count (filtered rows count,
+ *            collection.go:589 precedes 592) -> PercentSearched
+ * Results: ids and order equal the reference scan in lexicographic-decimal-id order
+ * (spanfile.go:540-560) except among distances closer than 1e-5 relative; NaN distances
+ * (cosine ratio rounding above 1) are never returned.
+ */
+int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id,
+                    uint32_t flags, uint64_t *out_ids, double *out_dist, uint32_t *out_n,
+                    uint64_t *scanned);
+
+/*
+ * Radius search: every record with distance <= radius (inclusive, K ignored), ascending.
+ * Replaces: Search with Radius>0, Precision=="exact" (collection.go:598-605).
+ */
+int szg_search_radius(szg_index *h, const double *query, double radius, int mask_id, uint32_t flags,
+                      szg_result **out, uint64_t *scanned);
+int szg_result_count(const szg_result *r, uint64_t *n);
+int szg_result_fetch(const szg_result *r, uint64_t offset, uint64_t n, uint64_t *out_ids,
+                     double *out_dist);
+void szg_result_free(szg_result *r);
+
+/*
+ * fp64 distances, in the reference's operation order, of the records ids[0..m) to the
+ * query (visit order preserved).  Replaces: decodeVector + c.distance inside consider when
+ * it is driven by lshTree.search (lshtree.go:316-335 -> collection.go:584-596): the host
+ * traversal emits candidate ids, this call scores them, the host replays the
+ * accept/radius/k_counter logic over the returned array.  Missing id =>
+ * SZG_MISSING_DISTANCE.  Filter and tombstones are NOT applied here (the replay does it).
+ */
+int szg_rescore(szg_index *h, const double *query, const uint64_t *ids, uint64_t m, double *out_dist);
+
+/* ---- device-resident variants (inputs/outputs already in HBM on the handle's device) ----
+ * Used by the multi-GPU host and by the benchmark's resident-input leg.  All work is
+ * enqueued on `stream` (a cudaStream_t, NULL = default stream) and its helper streams are
+ * joined back into it before returning; nothing is synchronised with the host.
+ * d_out_ids/d_out_dist are nq*k, d_out_n nq (uint32). */
+int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id,
+                        uint32_t flags, uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
+                        void *stream);
+
+/*
+ * Final merge of row-sharded top-k lists: `lists` holds G blocks, block g =
+ * rank g's {ids nq*k, dist nq*k} as gathered by ncclAllGather; writes the global top-k per
+ * query (ascending distance, ties by lexicographic decimal id).  No reference counterpart:
+ * the reference is single-process.
+ */
+int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const double *d_gathered_dist,
+                       const uint32_t *d_gathered_n, uint32_t nranks, uint32_t nq, uint32_t k,
+                       uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, void *stream);
+
+/* ---- synthetic data + introspection (bench/test helpers, no reference counterpart) ---- */
+
+/* Appends rows [row0, row0+nrows) of the synthetic collection `seed` (generator documented
+ * in oracle/syzgy_oracle.c orc_synth_rows; ids = row index) directly in HBM. */
+int szg_fill_synthetic(szg_index *h, uint64_t seed, uint64_t row0, uint64_t nrows);
+
+/* copies records back in stream-1 byte format (round-trip check of the mirror layout) */
+int szg_fetch_codes(szg_index *h, const uint64_t *ids, uint64_t n, uint8_t *out_codes);
+
+typedef struct szg_stats {
+    uint64_t kernel_launches;   /* kernels this handle launched since creation */
+    uint64_t escalations;       /* top-k calls re-run with a larger candidate set */
+    uint64_t uncertain_results; /* top-k queries whose candidate margin stayed below tolerance */
+    uint64_t device_bytes;      /* HBM held by the mirror */
+    uint64_t live_rows;
+    uint64_t slots;             /* rows of HBM layout in use (live + tombstones) */
+    uint32_t rowbytes;          /* getVectorSize(quant, dim) */
+    uint32_t pitch;             /* bytes per row in the column-blocked layout */
+    uint32_t sm_count;
+    uint32_t scan_grid;         /* CTAs of one scan launch */
+    uint32_t scan_block;        /* threads per CTA */
+    uint32_t reserved;
+} szg_stats;
+int szg_get_stats(szg_index *h, szg_stats *out);
+
+/* tuning / test knobs */
+#define SZG_OPT_STREAMS 1            /* streams a multi-query call is spread over (1..4, default 2) */
+#define SZG_OPT_TIMING 2             /* record CUDA events around every scan launch (default 1) */
+#define SZG_OPT_MIN_CANDIDATE_MODE 3 /* force candidate set >= 32<<v (v in 0..3; -1 = automatic) */
+int szg_set_option(szg_index *h, int option, int64_t value);
+
+/* Time of the most recent scan launches on this handle, measured with CUDA events on the
+ * launching stream: fills up to cap entries (ms), returns how many via *n. */
+int szg_last_scan_times_ms(szg_index *h, float *out_ms, uint32_t cap, uint32_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYZGY_B200_H */

@@ -1,0 +1,253 @@
+"""ctypes binding of include/syzgy_b200.h (libsyzgy_b200.so, built in-tree).
+
+This is the same C ABI the Go cgo shim binds.  There is no fallback of
+any kind: if the shared library is missing or no B200 is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsyzgy_b200.so")
+
+EUCLIDEAN = 0
+COSINE = 1
+F_DEFAULT = 0
+F_NO_FP64_VERIFY = 1
+MISSING_DISTANCE = -1.0
+MAX_K = 224
+MAX_DIM = 16384
+OPT_STREAMS = 1
+OPT_TIMING = 2
+OPT_MIN_CANDIDATE_MODE = 3
+
+# every symbol include/syzgy_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "szg_last_error", "szg_create", "szg_destroy", "szg_reserve", "szg_upsert", "szg_remove", "szg_count",
+    "szg_mask_create", "szg_mask_destroy", "szg_search_topk", "szg_search_radius", "szg_result_count",
+    "szg_result_fetch", "szg_result_free", "szg_rescore", "szg_search_topk_dev", "szg_merge_topk_dev",
+    "szg_fill_synthetic", "szg_fetch_codes", "szg_get_stats", "szg_set_option", "szg_last_scan_times_ms",
+]
+
+
+class SzgError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"syzgy_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64), ("escalations", C.c_uint64), ("uncertain_results", C.c_uint64),
+        ("device_bytes", C.c_uint64), ("live_rows", C.c_uint64), ("slots", C.c_uint64),
+        ("rowbytes", C.c_uint32), ("pitch", C.c_uint32), ("sm_count", C.c_uint32), ("scan_grid", C.c_uint32),
+        ("scan_block", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Loads the CUDA library.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C syzgydb_b200/csrc` (or __graft_entry__.build()). "
+            "syzgydb_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, u32p, u64p, f64p, f32p = (C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_float))
+    L.szg_last_error.restype = C.c_char_p
+    L.szg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.szg_destroy.argtypes = [vp]
+    L.szg_reserve.argtypes = [vp, C.c_uint64]
+    L.szg_upsert.argtypes = [vp, u64p, u8p, C.c_uint64]
+    L.szg_remove.argtypes = [vp, u64p, C.c_uint64, u64p]
+    L.szg_count.argtypes = [vp, u64p]
+    L.szg_mask_create.argtypes = [vp, u64p, u8p, C.c_uint64, C.POINTER(C.c_int)]
+    L.szg_mask_destroy.argtypes = [vp, C.c_int]
+    L.szg_search_topk.argtypes = [vp, f64p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u64p, f64p, u32p, u64p]
+    L.szg_search_radius.argtypes = [vp, f64p, C.c_double, C.c_int, C.c_uint32, C.POINTER(vp), u64p]
+    L.szg_result_count.argtypes = [vp, u64p]
+    L.szg_result_fetch.argtypes = [vp, C.c_uint64, C.c_uint64, u64p, f64p]
+    L.szg_result_free.argtypes = [vp]
+    L.szg_result_free.restype = None
+    L.szg_rescore.argtypes = [vp, f64p, u64p, C.c_uint64, f64p]
+    L.szg_search_topk_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, vp, vp, vp, vp]
+    L.szg_merge_topk_dev.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.szg_fill_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.szg_fetch_codes.argtypes = [vp, u64p, C.c_uint64, u8p]
+    L.szg_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.szg_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    L.szg_last_scan_times_ms.argtypes = [vp, f32p, C.c_uint32, u32p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise SzgError(rc, load().szg_last_error().decode("utf-8", "replace"))
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def vector_size(quant: int, dims: int) -> int:
+    """getVectorSize, collection.go:796-811"""
+    if quant == 4:
+        return (dims + 1) // 2
+    if quant in (8, 16, 32, 64):
+        return dims * (quant // 8)
+    raise ValueError("Unsupported quantization level")
+
+
+class Index:
+    """GPU mirror of one collection (or of one row shard).  Thin, 1:1 over the C ABI."""
+
+    def __init__(self, dim: int, quant: int, metric: int, device: int = 0):
+        self._L = load()
+        self._h = C.c_void_p()
+        _check(self._L.szg_create(dim, quant, metric, device, C.byref(self._h)))
+        self.dim, self.quant, self.metric, self.device = dim, (quant or 64), metric, device
+        self.rowbytes = vector_size(self.quant, dim)
+
+    # -- lifecycle
+    def close(self):
+        if self._h:
+            self._L.szg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- mutation
+    def reserve(self, nrows: int):
+        _check(self._L.szg_reserve(self._h, nrows))
+
+    def upsert(self, ids, codes):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if codes.size != ids.size * self.rowbytes:
+            raise ValueError(f"codes must hold {ids.size} x {self.rowbytes} bytes")
+        _check(self._L.szg_upsert(self._h, _p(ids, C.c_uint64), _p(codes, C.c_uint8), ids.size))
+
+    def remove(self, ids) -> int:
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        n = C.c_uint64(0)
+        _check(self._L.szg_remove(self._h, _p(ids, C.c_uint64), ids.size, C.byref(n)))
+        return n.value
+
+    def count(self) -> int:
+        n = C.c_uint64(0)
+        _check(self._L.szg_count(self._h, C.byref(n)))
+        return n.value
+
+    def fill_synthetic(self, seed: int, row0: int, nrows: int):
+        _check(self._L.szg_fill_synthetic(self._h, seed, row0, nrows))
+
+    def fetch_codes(self, ids) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = np.zeros((ids.size, self.rowbytes), dtype=np.uint8)
+        _check(self._L.szg_fetch_codes(self._h, _p(ids, C.c_uint64), ids.size, _p(out, C.c_uint8)))
+        return out
+
+    def mask_create(self, ids, passed) -> int:
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        passed = np.ascontiguousarray(passed, dtype=np.uint8)
+        if ids.size != passed.size:
+            raise ValueError("ids and pass must have the same length")
+        mid = C.c_int(0)
+        _check(self._L.szg_mask_create(self._h, _p(ids, C.c_uint64), _p(passed, C.c_uint8), ids.size, C.byref(mid)))
+        return mid.value
+
+    def mask_destroy(self, mask_id: int):
+        _check(self._L.szg_mask_destroy(self._h, mask_id))
+
+    # -- search (host buffers)
+    def search_topk(self, queries, k: int, mask_id: int = -1, flags: int = 0):
+        """Returns (ids [nq,k] uint64, dist [nq,k] float64, n [nq] uint32, scanned)."""
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            raise ValueError(f"query has {q.shape[1]} dimensions, collection has {self.dim}")  # appendix B-12
+        nq = q.shape[0]
+        kk = max(int(k), 1)
+        ids = np.zeros((nq, kk), dtype=np.uint64)
+        dist = np.zeros((nq, kk), dtype=np.float64)
+        n = np.zeros(nq, dtype=np.uint32)
+        scanned = C.c_uint64(0)
+        _check(self._L.szg_search_topk(self._h, _p(q, C.c_double), nq, int(k), mask_id, flags, _p(ids, C.c_uint64),
+                                       _p(dist, C.c_double), _p(n, C.c_uint32), C.byref(scanned)))
+        return ids, dist, n, scanned.value
+
+    def search_radius(self, query, radius: float, mask_id: int = -1, flags: int = 0):
+        """Returns (ids, dist, scanned), ascending distance."""
+        q = np.ascontiguousarray(query, dtype=np.float64).reshape(-1)
+        if q.size != self.dim:
+            raise ValueError(f"query has {q.size} dimensions, collection has {self.dim}")
+        res = C.c_void_p()
+        scanned = C.c_uint64(0)
+        _check(self._L.szg_search_radius(self._h, _p(q, C.c_double), float(radius), mask_id, flags, C.byref(res),
+                                         C.byref(scanned)))
+        try:
+            n = C.c_uint64(0)
+            _check(self._L.szg_result_count(res, C.byref(n)))
+            ids = np.zeros(n.value, dtype=np.uint64)
+            dist = np.zeros(n.value, dtype=np.float64)
+            if n.value:
+                _check(self._L.szg_result_fetch(res, 0, n.value, _p(ids, C.c_uint64), _p(dist, C.c_double)))
+        finally:
+            self._L.szg_result_free(res)
+        return ids, dist, scanned.value
+
+    def rescore(self, query, ids) -> np.ndarray:
+        q = np.ascontiguousarray(query, dtype=np.float64).reshape(-1)
+        if q.size != self.dim:
+            raise ValueError(f"query has {q.size} dimensions, collection has {self.dim}")
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = np.zeros(ids.size, dtype=np.float64)
+        _check(self._L.szg_rescore(self._h, _p(q, C.c_double), _p(ids, C.c_uint64), ids.size, _p(out, C.c_double)))
+        return out
+
+    # -- search (device-resident; pointers are raw device addresses, e.g. torch tensor.data_ptr())
+    def search_topk_dev(self, d_queries: int, nq: int, k: int, d_out_ids: int, d_out_dist: int, d_out_n: int,
+                        stream: int = 0, mask_id: int = -1, flags: int = 0):
+        _check(self._L.szg_search_topk_dev(self._h, d_queries, nq, k, mask_id, flags, d_out_ids, d_out_dist,
+                                           d_out_n, stream))
+
+    def merge_topk_dev(self, d_g_ids: int, d_g_dist: int, d_g_n: int, nranks: int, nq: int, k: int, d_out_ids: int,
+                       d_out_dist: int, d_out_n: int, stream: int = 0):
+        _check(self._L.szg_merge_topk_dev(self._h, d_g_ids, d_g_dist, d_g_n, nranks, nq, k, d_out_ids, d_out_dist,
+                                          d_out_n, stream))
+
+    # -- introspection
+    def stats(self) -> dict:
+        s = Stats()
+        _check(self._L.szg_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in Stats._fields_ if f != "reserved"}
+
+    def set_option(self, opt: int, value: int):
+        _check(self._L.szg_set_option(self._h, opt, value))
+
+    def last_scan_times_ms(self, cap: int = 4096) -> np.ndarray:
+        out = np.zeros(cap, dtype=np.float32)
+        n = C.c_uint32(0)
+        _check(self._L.szg_last_scan_times_ms(self._h, _p(out, C.c_float), cap, C.byref(n)))
+        return out[:n.value].copy()

@@ -1,0 +1,184 @@
+// common.cuh -- layout constants and device helpers shared by every kernel of the
+// SyzgyDB search hot path (sm_100a only).
+//
+// HBM layout of the mirror ("column-blocked"):
+//   rows are grouped in blocks of 32 (one warp lane per row); a row is cut in 16-byte
+//   chunks; block b stores chunk c of its 32 rows contiguously:
+//       codes[((b * C + c) * 32 + lane)]   (uint4 units, C = chunks per row)
+//   so a warp-wide LDG.128 of "chunk c of my row" reads one contiguous 512-byte span,
+//   and 8 rows x 16 B is exactly one UMMA K-major core matrix (used by the batched
+//   tensor-core path).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace szg {
+
+constexpr int kRowsPerBlock = 32;
+constexpr int kChunkBytes = 16;
+constexpr int ND = 3;              // signed base-128 digits of the fixed-point query
+constexpr int kDigitBits = 7 * ND; // |W| < 2^21
+
+enum QuantType : int { Q4 = 0, Q8 = 1, Q16 = 2, F32 = 3, F64 = 4 };
+enum Metric : int { EUCLID = 0, COSINE = 1 };
+
+__host__ __device__ inline int quant_bits(int qt) { return qt == Q4 ? 4 : qt == Q8 ? 8 : qt == Q16 ? 16 : qt == F32 ? 32 : 64; }
+// elements per 16-byte chunk
+__host__ __device__ inline int elems_per_chunk(int qt) { return 128 / quant_bits(qt); }
+// bytes of prepared-query payload per chunk (digits or converted query values)
+__host__ __device__ inline int pq_bytes_per_chunk(int qt) {
+    return qt == Q4 ? 2 * ND * 16 : qt == Q8 ? ND * 16 : qt == Q16 ? ND * 8 : 16;
+}
+
+// Header of one prepared query (device memory, followed by the per-chunk payload).
+struct __align__(16) PQHeader {
+    double sumW;       // sum of fixed-point coefficients W_i (exact integer)
+    double sumW2;      // sum W_i^2
+    double numc;       // cosine: num = 2*I + numc          (numc = cW * sumW)
+    double c_key;      // scale from integer domain to key unit
+    double base;       // euclid: E = aux*pow2F2 - pow2F1*I + base   (base = sumW2)
+    double pow2F1;     // 2^(F+1)
+    double pow2F2;     // 2^(2F)
+    double qnorm;      // ||q|| (parallel reduction; surrogate only)
+    double radius_key; // radius mode: surrogate threshold (key <= radius_key is a candidate)
+    double radius;     // radius mode: exact threshold
+    int F;
+    int zero_query;    // ||q|| == 0
+    int pad[2];
+};
+static_assert(sizeof(PQHeader) % 16 == 0, "payload must stay 16-byte aligned");
+
+// ---- loads -------------------------------------------------------------------------
+// streaming 128-bit load: read-only path, do not allocate in L1 (each byte is used once)
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// coherent load that bypasses L1 (data written by other CTAs of the same launch)
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) {
+    unsigned long long r;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+
+// ---- integer dot products ------------------------------------------------------------
+// u8 x s8 -> s32   (SASS IDP.4A.U8.S8)
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// s16x2 (a) x s8 bytes {0,1} / {2,3} of b   (SASS IDP.2A.LO/HI.S16.S8)
+__device__ __forceinline__ int dp2a_lo_ss(int a, int b, int c) {
+    int d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_ss(int a, int b, int c) {
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// ---- selection keys ------------------------------------------------------------------
+// Monotone map float -> uint32 (smaller float => smaller uint); NaN => worst.
+__device__ __forceinline__ uint32_t ordered_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+    return (f != f) ? 0xFFFFFFFEu : u;
+}
+__device__ __forceinline__ float key_to_float(uint32_t u) {
+    u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+    return __uint_as_float(u);
+}
+constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
+__device__ __forceinline__ unsigned long long make_key64(float key, uint32_t slot) {
+    return ((unsigned long long)ordered_key(key) << 32) | slot;
+}
+
+// ---- lexicographic order of decimal ids (sort.Strings, spanfile.go:540-560) -----------
+__host__ __device__ inline int dec_digits(unsigned long long v) {
+    int n = 1;
+    while (v >= 10) { v /= 10; ++n; }
+    return n;
+}
+// a * 10^k <= b without overflow surprises (k <= 19)
+__host__ __device__ inline bool scaled_le(unsigned long long a, int k, unsigned long long b) {
+    unsigned long long p = 1;
+    for (int i = 0; i < k; ++i) p *= 10;
+    unsigned long long hi;
+#ifdef __CUDA_ARCH__
+    hi = __umul64hi(a, p);
+#else
+    hi = (unsigned long long)(((unsigned __int128)a * p) >> 64);
+#endif
+    if (hi) return false; // a * 10^k >= 2^64 > b
+    return a * p <= b;
+}
+__host__ __device__ inline bool lex_less_u64(unsigned long long a, unsigned long long b) {
+    if (a == b) return false;
+    const int da = dec_digits(a), db = dec_digits(b);
+    if (da == db) return a < b;
+    // pad the shorter one with zeros; a proper prefix sorts first
+    if (da < db) return scaled_le(a, db - da, b);
+    return !scaled_le(b, da - db, a);
+}
+
+// ---- synthetic data generator (same as oracle/syzgy_oracle.c orc_rand_u64) ------------
+__host__ __device__ inline unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ inline unsigned long long rand_u64(unsigned long long seed, unsigned long long ctr) {
+    return mix64(seed + 0x9E3779B97F4A7C15ull * (ctr + 1));
+}
+
+// ---- storage transform of one 16-byte chunk --------------------------------------------
+// on-disk bytes (stream 1: 16/32/64-bit big-endian) -> HBM representation:
+//   Q4/Q8: verbatim; Q16: little-endian int16 of (u - 32768); F32/F64: little-endian IEEE.
+__host__ __device__ inline void chunk_to_device(int qt, unsigned char *b /*16 bytes, in place*/) {
+    if (qt == Q16) {
+        for (int e = 0; e < 8; ++e) {
+            unsigned u = ((unsigned)b[2 * e] << 8) | b[2 * e + 1];
+            u ^= 0x8000u;
+            b[2 * e] = (unsigned char)(u & 0xFF);
+            b[2 * e + 1] = (unsigned char)(u >> 8);
+        }
+    } else if (qt == F32) {
+        for (int e = 0; e < 4; ++e) {
+            unsigned char t0 = b[4 * e], t1 = b[4 * e + 1];
+            b[4 * e] = b[4 * e + 3]; b[4 * e + 1] = b[4 * e + 2];
+            b[4 * e + 2] = t1; b[4 * e + 3] = t0;
+        }
+    } else if (qt == F64) {
+        for (int e = 0; e < 2; ++e)
+            for (int i = 0; i < 4; ++i) {
+                unsigned char t = b[8 * e + i];
+                b[8 * e + i] = b[8 * e + 7 - i];
+                b[8 * e + 7 - i] = t;
+            }
+    }
+}
+// the transform is an involution for every type (swap / swap+xor), so it also maps back
+__host__ __device__ inline void chunk_to_disk(int qt, unsigned char *b) {
+    if (qt == Q16) {
+        for (int e = 0; e < 8; ++e) {
+            unsigned u = ((unsigned)b[2 * e + 1] << 8) | b[2 * e];
+            u ^= 0x8000u;
+            b[2 * e] = (unsigned char)(u >> 8);
+            b[2 * e + 1] = (unsigned char)(u & 0xFF);
+        }
+    } else {
+        chunk_to_device(qt, b);
+    }
+}
+
+__device__ __forceinline__ size_t chunk_index(uint32_t slot, uint32_t C, uint32_t c) {
+    return ((size_t)(slot >> 5) * C + c) * 32 + (slot & 31);
+}
+
+} // namespace szg

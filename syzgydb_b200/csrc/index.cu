@@ -1,0 +1,937 @@
+// index.cu -- the GPU mirror of one collection (or one row shard) and the C ABI of
+// include/syzgy_b200.h.  Host logic only: slot allocation, id -> slot map, workspaces,
+// streams, launches.  There is deliberately no CPU implementation of any search step.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/syzgy_b200.h"
+#include "kernels.h"
+
+using namespace szg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? SZG_ENOMEM : SZG_ECUDA, "%s failed: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+    } while (0)
+
+constexpr int kMaxStreams = 4;
+constexpr size_t kStageBytes = 64u << 20;
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t want, bool keep = false, cudaStream_t st = 0) {
+        if (want <= n) return SZG_OK;
+        T *np = nullptr;
+        CK(cudaMalloc(&np, want * sizeof(T)));
+        if (keep && p && n) {
+            cudaError_t e = cudaMemcpyAsync(np, p, n * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(np); return fail(SZG_ECUDA, "device copy failed: %s", cudaGetErrorString(e)); }
+        }
+        if (p) cudaFree(p);
+        p = np;
+        n = want;
+        return SZG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t want) {
+        if (want <= n) return SZG_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        CK(cudaMallocHost(&p, want * sizeof(T)));
+        n = want;
+        return SZG_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
+};
+
+struct Workspace {
+    cudaStream_t main = nullptr; // owned for host calls; the caller's stream for *_dev calls
+    bool owns_main = false;
+    cudaStream_t helper[kMaxStreams] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
+    DevBuf<double> d_q;
+    DevBuf<unsigned char> d_pq;
+    DevBuf<unsigned long long> d_cand[kMaxStreams];
+    DevBuf<unsigned int> d_ticket; // kMaxStreams tickets + radius count
+    DevBuf<unsigned long long> d_out_ids;
+    DevBuf<double> d_out_dist;
+    DevBuf<uint32_t> d_out_n, d_out_flags;
+    DevBuf<uint32_t> d_slots;
+    PinBuf<double> h_q;
+    PinBuf<unsigned long long> h_out_ids;
+    PinBuf<double> h_out_dist;
+    PinBuf<uint32_t> h_out_n, h_out_flags, h_slots;
+    std::vector<cudaEvent_t> t0, t1; // per-scan timing events
+    uint32_t timed = 0;
+
+    int init(bool own) {
+        owns_main = own;
+        if (own) CK(cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking));
+        for (int i = 1; i < kMaxStreams; ++i) CK(cudaStreamCreateWithFlags(&helper[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int i = 1; i < kMaxStreams; ++i) CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+        int rc = d_ticket.ensure(kMaxStreams + 4);
+        if (rc) return rc;
+        CK(cudaMemset(d_ticket.p, 0, (kMaxStreams + 4) * sizeof(unsigned int)));
+        return SZG_OK;
+    }
+    void destroy() {
+        d_q.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
+        d_out_n.release(); d_out_flags.release(); d_slots.release();
+        for (auto &c : d_cand) c.release();
+        h_q.release(); h_out_ids.release(); h_out_dist.release(); h_out_n.release(); h_out_flags.release();
+        h_slots.release();
+        for (auto e : t0) cudaEventDestroy(e);
+        for (auto e : t1) cudaEventDestroy(e);
+        for (int i = 1; i < kMaxStreams; ++i) {
+            if (helper[i]) cudaStreamDestroy(helper[i]);
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (owns_main && main) cudaStreamDestroy(main);
+    }
+};
+
+struct IdRange {
+    uint64_t id0;
+    uint32_t slot0, n;
+};
+
+} // namespace
+
+struct szg_result {
+    std::vector<uint64_t> ids;
+    std::vector<double> dist;
+};
+
+struct szg_index {
+    int dim = 0, quant = 0, metric = 0, device = 0, qt = 0;
+    uint32_t rowbytes = 0, C = 0, maxint = 0;
+    int sm_count = 0;
+    // storage
+    DevBuf<uint4> codes;
+    DevBuf<unsigned long long> ids;
+    DevBuf<unsigned long long> aux; // 8 bytes per slot reserved; typed per (quant, metric)
+    DevBuf<uint32_t> live;
+    DevBuf<double> lut;
+    uint32_t capacity = 0; // slots allocated (multiple of 64)
+    uint32_t nslots = 0;   // high-water mark
+    uint64_t live_rows = 0;
+    std::unordered_map<uint64_t, uint32_t> map;
+    std::vector<IdRange> ranges;
+    std::unordered_set<uint64_t> range_dead;
+    std::vector<uint32_t> free_slots;
+    std::map<int, uint32_t *> masks;
+    int next_mask = 1;
+    // staging for mutations
+    PinBuf<unsigned char> h_stage;
+    DevBuf<unsigned char> d_stage;
+    PinBuf<uint32_t> h_slots;
+    DevBuf<uint32_t> d_slots;
+    PinBuf<unsigned long long> h_ids;
+    DevBuf<unsigned long long> d_ids_in;
+    cudaStream_t mut_stream = nullptr;
+    // workspaces
+    std::mutex mu;
+    std::vector<Workspace *> free_ws;
+    std::map<void *, Workspace *> dev_ws;
+    // options / stats
+    int nstreams = 2;
+    int timing = 1;
+    int force_mode = -1;
+    uint64_t launches = 0, escalations = 0, uncertain = 0;
+    std::vector<float> last_times;
+    Workspace *last_timed_ws = nullptr;
+    int grid_cache[5] = {0, 0, 0, 0, 0};
+
+    bool lookup(uint64_t id, uint32_t *slot) const {
+        auto it = map.find(id);
+        if (it != map.end()) { *slot = it->second; return true; }
+        for (const auto &r : ranges)
+            if (id >= r.id0 && id - r.id0 < r.n) {
+                if (!range_dead.empty() && range_dead.count(id)) return false;
+                *slot = r.slot0 + (uint32_t)(id - r.id0);
+                return true;
+            }
+        return false;
+    }
+    RowsArgs rows_args() {
+        RowsArgs a;
+        a.codes = codes.p; a.aux = aux.p; a.live = live.p; a.ids = ids.p;
+        a.C = C; a.dims = (uint32_t)dim; a.metric = (uint32_t)metric; a.maxint = maxint; a.rowbytes = rowbytes;
+        a.qt = qt;
+        return a;
+    }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GUARD(h)                                                                 \
+    if (!(h)) return fail(SZG_EINVAL, "null handle");                            \
+    DeviceGuard guard_((h)->device);                                             \
+    if (!guard_.ok) return fail(SZG_ECUDA, "cannot select CUDA device %d", (h)->device)
+
+int grow(szg_index *h, uint64_t want_slots) {
+    if (want_slots <= h->capacity) return SZG_OK;
+    if (want_slots > 0xFFFFFF00ull) return fail(SZG_EINVAL, "more than 2^32 rows per mirror are not supported");
+    uint64_t cap = std::max<uint64_t>(want_slots, (uint64_t)h->capacity * 2);
+    cap = std::max<uint64_t>(cap, 1024);
+    cap = (cap + 63) / 64 * 64;
+    if (cap > 0xFFFFFF00ull) cap = 0xFFFFFF00ull / 64 * 64;
+    cudaStream_t st = h->mut_stream;
+    int rc;
+    if ((rc = h->codes.ensure((size_t)cap * h->C, true, st))) return rc;
+    if ((rc = h->ids.ensure(cap, true, st))) return rc;
+    if ((rc = h->aux.ensure(cap, true, st))) return rc;
+    size_t old_words = h->live.n, words = cap / 32;
+    if ((rc = h->live.ensure(words, true, st))) return rc;
+    CK(cudaMemsetAsync(h->live.p + old_words, 0, (words - old_words) * 4, st));
+    for (auto &m : h->masks) {
+        uint32_t *np = nullptr;
+        CK(cudaMalloc(&np, words * 4));
+        CK(cudaMemsetAsync(np, 0, words * 4, st));
+        if (old_words) CK(cudaMemcpyAsync(np, m.second, old_words * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        cudaFree(m.second);
+        m.second = np;
+    }
+    CK(cudaStreamSynchronize(st));
+    h->capacity = (uint32_t)cap;
+    return SZG_OK;
+}
+
+int acquire_ws(szg_index *h, Workspace **out) {
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (!h->free_ws.empty()) {
+            *out = h->free_ws.back();
+            h->free_ws.pop_back();
+            return SZG_OK;
+        }
+    }
+    Workspace *ws = new Workspace();
+    int rc = ws->init(true);
+    if (rc) { ws->destroy(); delete ws; return rc; }
+    *out = ws;
+    return SZG_OK;
+}
+void release_ws(szg_index *h, Workspace *ws) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->free_ws.push_back(ws);
+}
+
+int mode_for_k(const szg_index *h, uint32_t k) {
+    int mode = 0;
+    while (mode < 3 && (32u << mode) < k + std::max<uint32_t>(8, k / 8)) ++mode;
+    if (h->force_mode >= 0 && h->force_mode <= 3 && h->force_mode > mode) mode = h->force_mode;
+    return mode;
+}
+
+int scan_grid(szg_index *h, int mode, size_t smem, int *grid) {
+    if (h->grid_cache[mode]) { *grid = h->grid_cache[mode]; return SZG_OK; }
+    int bps = 0;
+    CK(scan_occupancy(h->qt, mode, smem, &bps));
+    if (bps < 1) return fail(SZG_EINTERNAL, "scan kernel does not fit on an SM (smem %zu)", smem);
+    *grid = bps * h->sm_count;
+    h->grid_cache[mode] = *grid;
+    return SZG_OK;
+}
+
+size_t pq_stride(const szg_index *h) {
+    size_t payload = ((size_t)h->C * pq_bytes_per_chunk(h->qt) + 15) / 16 * 16;
+    return sizeof(PQHeader) + payload;
+}
+
+void fill_scan_args(szg_index *h, ScanArgs &a, const uint32_t *mask) {
+    memset(&a, 0, sizeof a);
+    a.codes = h->codes.p;
+    a.aux = h->aux.p;
+    a.live = h->live.p;
+    a.mask = mask;
+    a.ids = h->ids.p;
+    a.lut = h->lut.p;
+    a.C = h->C;
+    a.nblk = (h->nslots + 31) / 32;
+    a.dims = (uint32_t)h->dim;
+    a.metric = (uint32_t)h->metric;
+}
+
+// Enqueues prep + one scan launch per query.  Inputs/outputs are device pointers; `ws`
+// supplies scratch; work is forked over `ns` streams and joined back into ws->main.
+int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32_t k, const uint32_t *mask,
+             uint32_t flags, int mode, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
+             uint32_t *d_out_flags) {
+    const size_t stride = pq_stride(h);
+    int rc;
+    if ((rc = ws->d_pq.ensure(stride * nq))) return rc;
+    const size_t smem = scan_smem_bytes(h->qt, h->C, mode);
+    int grid = 0;
+    if ((rc = scan_grid(h, mode, smem, &grid))) return rc;
+    const int ns = std::max(1, std::min(h->nstreams, kMaxStreams));
+    const size_t Kp = 32u << mode;
+    for (int s = 0; s < ns; ++s)
+        if ((rc = ws->d_cand[s].ensure((size_t)grid * Kp))) return rc;
+
+    cudaStream_t main = ws->main;
+    PrepArgs pa;
+    pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
+    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
+    pa.qt = h->qt; pa.radius_mode = 0; pa.radius = 0.0;
+    CK(launch_prep(nq, main, pa));
+    h->launches++;
+    const int used = (int)std::min<uint32_t>(ns, nq);
+    if (used > 1) {
+        CK(cudaEventRecord(ws->ev_fork, main));
+        for (int s = 1; s < used; ++s) CK(cudaStreamWaitEvent(ws->helper[s], ws->ev_fork, 0));
+    }
+    const bool timing = h->timing != 0;
+    if (timing) {
+        while (ws->t0.size() < nq) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            ws->t0.push_back(a);
+            ws->t1.push_back(b);
+        }
+    }
+    ScanArgs a;
+    fill_scan_args(h, a, mask);
+    a.k = k;
+    a.flags = flags & SZG_F_NO_FP64_VERIFY;
+    for (uint32_t i = 0; i < nq; ++i) {
+        const int s = (int)(i % used);
+        cudaStream_t st = s == 0 ? main : ws->helper[s];
+        a.pq = ws->d_pq.p + stride * i;
+        a.q = d_q + (size_t)i * h->dim;
+        a.cand = ws->d_cand[s].p;
+        a.ticket = ws->d_ticket.p + s;
+        a.out_ids = d_out_ids + (size_t)i * k;
+        a.out_dist = d_out_dist + (size_t)i * k;
+        a.out_n = d_out_n + i;
+        a.out_flags = d_out_flags + i;
+        if (timing) CK(cudaEventRecord(ws->t0[i], st));
+        CK(launch_scan(h->qt, mode, grid, smem, st, a));
+        if (timing) CK(cudaEventRecord(ws->t1[i], st));
+        h->launches++;
+    }
+    if (timing) { ws->timed = nq; h->last_timed_ws = ws; }
+    for (int s = 1; s < used; ++s) {
+        CK(cudaEventRecord(ws->ev_join[s], ws->helper[s]));
+        CK(cudaStreamWaitEvent(main, ws->ev_join[s], 0));
+    }
+    return SZG_OK;
+}
+
+int get_mask(szg_index *h, int mask_id, const uint32_t **out) {
+    *out = nullptr;
+    if (mask_id < 0) return SZG_OK;
+    auto it = h->masks.find(mask_id);
+    if (it == h->masks.end()) return fail(SZG_ENOTFOUND, "unknown mask id %d", mask_id);
+    *out = it->second;
+    return SZG_OK;
+}
+
+int check_search(szg_index *h, const void *q, uint32_t nq) {
+    if (!q && nq) return fail(SZG_EINVAL, "null query");
+    (void)h;
+    return SZG_OK;
+}
+
+} // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *szg_last_error(void) { return g_err.c_str(); }
+
+int szg_create(int dim, int quantization, int metric, int device, szg_index **out) {
+    if (!out) return fail(SZG_EINVAL, "null out pointer");
+    *out = nullptr;
+    if (quantization == 0) quantization = 64; // collection.go:254-256
+    int qt;
+    switch (quantization) {
+    case 4: qt = Q4; break;
+    case 8: qt = Q8; break;
+    case 16: qt = Q16; break;
+    case 32: qt = F32; break;
+    case 64: qt = F64; break;
+    default: return fail(SZG_EINVAL, "unsupported quantization %d (collection.go:796-811 panics)", quantization);
+    }
+    if (metric != SZG_EUCLIDEAN && metric != SZG_COSINE)
+        return fail(SZG_EINVAL, "unsupported distance method %d (collection.go:275-283)", metric);
+    if (dim < 1 || dim > SZG_MAX_DIM) return fail(SZG_EINVAL, "dimension %d outside [1, %d]", dim, SZG_MAX_DIM);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SZG_ECUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SZG_EINVAL, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(SZG_ECUDA, "cannot select CUDA device %d", device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(SZG_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    std::unique_ptr<szg_index> h(new szg_index());
+    h->dim = dim; h->quant = quantization; h->metric = metric; h->device = device; h->qt = qt;
+    h->maxint = quantization <= 16 ? (1u << quantization) - 1u : 0u;
+    h->rowbytes = quantization == 4 ? (uint32_t)(dim + 1) / 2 : (uint32_t)dim * (quantization / 8);
+    h->C = (h->rowbytes + 15) / 16;
+    h->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&h->mut_stream, cudaStreamNonBlocking));
+    CK(scan_configure(qt, 160 * 1024));
+    if (quantization <= 16) {
+        const size_t n = (size_t)1 << quantization;
+        std::vector<double> lut(n);
+        const double maxInt = (double)h->maxint;
+        for (size_t v = 0; v < n; ++v) lut[v] = ((double)v / maxInt) * 2 - 1; // quantization.go:34-35
+        int rc = h->lut.ensure(n);
+        if (rc) return rc;
+        CK(cudaMemcpy(h->lut.p, lut.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    int rc = grow(h.get(), 1024);
+    if (rc) return rc;
+    *out = h.release();
+    return SZG_OK;
+}
+
+int szg_destroy(szg_index *h) {
+    if (!h) return SZG_OK;
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    for (auto ws : h->free_ws) { ws->destroy(); delete ws; }
+    for (auto &kv : h->dev_ws) { kv.second->destroy(); delete kv.second; }
+    for (auto &m : h->masks) cudaFree(m.second);
+    h->codes.release(); h->ids.release(); h->aux.release(); h->live.release(); h->lut.release();
+    h->h_stage.release(); h->d_stage.release(); h->h_slots.release(); h->d_slots.release();
+    h->h_ids.release(); h->d_ids_in.release();
+    if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
+    delete h;
+    return SZG_OK;
+}
+
+int szg_set_option(szg_index *h, int option, int64_t value) {
+    if (!h) return fail(SZG_EINVAL, "null handle");
+    switch (option) {
+    case SZG_OPT_STREAMS:
+        if (value < 1 || value > kMaxStreams) return fail(SZG_EINVAL, "streams must be in [1, %d]", kMaxStreams);
+        h->nstreams = (int)value;
+        return SZG_OK;
+    case SZG_OPT_TIMING: h->timing = value != 0; return SZG_OK;
+    case SZG_OPT_MIN_CANDIDATE_MODE:
+        if (value < -1 || value > 3) return fail(SZG_EINVAL, "candidate mode must be in [-1, 3]");
+        h->force_mode = (int)value;
+        return SZG_OK;
+    }
+    return fail(SZG_EINVAL, "unknown option %d", option);
+}
+
+int szg_reserve(szg_index *h, uint64_t nrows) {
+    GUARD(h);
+    return grow(h, nrows);
+}
+
+int szg_count(szg_index *h, uint64_t *n) {
+    if (!h || !n) return fail(SZG_EINVAL, "null argument");
+    *n = h->live_rows;
+    return SZG_OK;
+}
+
+int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t n) {
+    GUARD(h);
+    if (n && (!ids || !codes)) return fail(SZG_EINVAL, "null ids/codes");
+    const uint64_t per = std::max<uint64_t>(1, kStageBytes / h->rowbytes);
+    int rc;
+    for (uint64_t off = 0; off < n; off += per) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(per, n - off);
+        if ((rc = h->h_slots.ensure(m)) || (rc = h->d_slots.ensure(m)) || (rc = h->h_ids.ensure(m)) ||
+            (rc = h->d_ids_in.ensure(m)) || (rc = h->h_stage.ensure((size_t)m * h->rowbytes)) ||
+            (rc = h->d_stage.ensure((size_t)m * h->rowbytes)))
+            return rc;
+        // slot assignment.  A batch may name an id twice: the last one wins, like two
+        // AddDocument calls in a row; earlier duplicates are skipped (slot 0xFFFFFFFF).
+        if ((rc = grow(h, (uint64_t)h->nslots + m))) return rc;
+        std::unordered_map<uint64_t, uint32_t> last_in_batch;
+        last_in_batch.reserve(m);
+        for (uint32_t i = 0; i < m; ++i) last_in_batch[ids[off + i]] = i;
+        for (uint32_t i = 0; i < m; ++i) {
+            const uint64_t id = ids[off + i];
+            uint32_t slot = 0xFFFFFFFFu;
+            if (last_in_batch[id] == i && !h->lookup(id, &slot)) {
+                if (!h->free_slots.empty()) {
+                    slot = h->free_slots.back();
+                    h->free_slots.pop_back();
+                } else {
+                    slot = h->nslots++;
+                }
+                h->map[id] = slot; // shadows a (dead) synthetic-range entry of the same id
+                h->live_rows++;
+            }
+            h->h_slots.p[i] = slot;
+            h->h_ids.p[i] = id;
+        }
+        memcpy(h->h_stage.p, codes + off * h->rowbytes, (size_t)m * h->rowbytes);
+        cudaStream_t st = h->mut_stream;
+        CK(cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, (size_t)m * h->rowbytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->d_ids_in.p, h->h_ids.p, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        RowsArgs ra = h->rows_args();
+        CK(launch_scatter(ra, h->d_stage.p, h->d_slots.p, h->d_ids_in.p, m, st));
+        CK(launch_aux(ra, h->d_slots.p, 0, m, st));
+        h->launches += 2;
+        CK(cudaStreamSynchronize(st));
+    }
+    return SZG_OK;
+}
+
+int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_removed) {
+    GUARD(h);
+    if (n && !ids) return fail(SZG_EINVAL, "null ids");
+    std::vector<uint32_t> slots;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t slot;
+        if (!h->lookup(ids[i], &slot)) continue;
+        auto it = h->map.find(ids[i]);
+        if (it != h->map.end()) h->map.erase(it);
+        else h->range_dead.insert(ids[i]);
+        h->free_slots.push_back(slot);
+        slots.push_back(slot);
+        h->live_rows--;
+    }
+    if (n_removed) *n_removed = slots.size();
+    if (slots.empty()) return SZG_OK;
+    int rc;
+    if ((rc = h->d_slots.ensure(slots.size()))) return rc;
+    cudaStream_t st = h->mut_stream;
+    CK(cudaMemcpyAsync(h->d_slots.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(launch_kill(h->live.p, h->d_slots.p, (uint32_t)slots.size(), st));
+    h->launches++;
+    CK(cudaStreamSynchronize(st));
+    return SZG_OK;
+}
+
+int szg_fill_synthetic(szg_index *h, uint64_t seed, uint64_t row0, uint64_t nrows) {
+    GUARD(h);
+    if (!nrows) return SZG_OK;
+    if ((uint64_t)h->nslots + nrows > 0xFFFFFF00ull) return fail(SZG_EINVAL, "too many rows");
+    for (const auto &r : h->ranges)
+        if (row0 < r.id0 + r.n && r.id0 < row0 + nrows) return fail(SZG_EINVAL, "synthetic range overlaps an existing one");
+    int rc = grow(h, (uint64_t)h->nslots + nrows);
+    if (rc) return rc;
+    RowsArgs ra = h->rows_args();
+    cudaStream_t st = h->mut_stream;
+    const uint32_t slot0 = h->nslots;
+    const uint64_t step = 1u << 22;
+    for (uint64_t off = 0; off < nrows; off += step) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(step, nrows - off);
+        CK(launch_synth(ra, seed, row0 + off, slot0 + (uint32_t)off, m, st));
+        CK(launch_aux(ra, nullptr, slot0 + (uint32_t)off, m, st));
+        h->launches += 2;
+    }
+    CK(cudaStreamSynchronize(st));
+    h->ranges.push_back(IdRange{row0, slot0, (uint32_t)nrows});
+    h->nslots += (uint32_t)nrows;
+    h->live_rows += nrows;
+    return SZG_OK;
+}
+
+static int map_ids(szg_index *h, const uint64_t *ids, uint64_t n, uint32_t *slots, bool require) {
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t s;
+        if (h->lookup(ids[i], &s)) slots[i] = s;
+        else if (require) return fail(SZG_ENOTFOUND, "id %llu is not in the mirror", (unsigned long long)ids[i]);
+        else slots[i] = 0xFFFFFFFFu;
+    }
+    return SZG_OK;
+}
+
+int szg_fetch_codes(szg_index *h, const uint64_t *ids, uint64_t n, uint8_t *out_codes) {
+    GUARD(h);
+    if (n && (!ids || !out_codes)) return fail(SZG_EINVAL, "null argument");
+    const uint64_t per = std::max<uint64_t>(1, kStageBytes / h->rowbytes);
+    int rc;
+    for (uint64_t off = 0; off < n; off += per) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(per, n - off);
+        if ((rc = h->h_slots.ensure(m)) || (rc = h->d_slots.ensure(m)) ||
+            (rc = h->h_stage.ensure((size_t)m * h->rowbytes)) || (rc = h->d_stage.ensure((size_t)m * h->rowbytes)))
+            return rc;
+        if ((rc = map_ids(h, ids + off, m, h->h_slots.p, true))) return rc;
+        cudaStream_t st = h->mut_stream;
+        CK(cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CK(launch_fetch(h->rows_args(), h->d_slots.p, m, h->d_stage.p, st));
+        h->launches++;
+        CK(cudaMemcpyAsync(h->h_stage.p, h->d_stage.p, (size_t)m * h->rowbytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(out_codes + off * h->rowbytes, h->h_stage.p, (size_t)m * h->rowbytes);
+    }
+    return SZG_OK;
+}
+
+int szg_mask_create(szg_index *h, const uint64_t *ids, const uint8_t *pass, uint64_t n, int *mask_id) {
+    GUARD(h);
+    if (!mask_id || (n && (!ids || !pass))) return fail(SZG_EINVAL, "null argument");
+    if (n > 0xFFFFFFFFull) return fail(SZG_EINVAL, "too many ids");
+    const size_t words = h->capacity / 32;
+    uint32_t *mask = nullptr;
+    CK(cudaMalloc(&mask, words * 4));
+    cudaStream_t st = h->mut_stream;
+    cudaError_t e = cudaMemsetAsync(mask, 0, words * 4, st);
+    int rc = SZG_OK;
+    if (e != cudaSuccess) rc = fail(SZG_ECUDA, "memset failed: %s", cudaGetErrorString(e));
+    if (!rc && n) {
+        std::vector<uint32_t> slots(n);
+        map_ids(h, ids, n, slots.data(), false);
+        DevBuf<unsigned char> d_pass;
+        if (!(rc = h->d_slots.ensure(n)) && !(rc = d_pass.ensure(n))) {
+            e = cudaMemcpyAsync(h->d_slots.p, slots.data(), n * 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_pass.p, pass, n, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = launch_mask_set(mask, h->d_slots.p, d_pass.p, (uint32_t)n, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = fail(SZG_ECUDA, "mask upload failed: %s", cudaGetErrorString(e));
+            h->launches++;
+        }
+        d_pass.release();
+    } else if (!rc) {
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(SZG_ECUDA, "sync failed: %s", cudaGetErrorString(e));
+    }
+    if (rc) { cudaFree(mask); return rc; }
+    *mask_id = h->next_mask++;
+    h->masks[*mask_id] = mask;
+    return SZG_OK;
+}
+
+int szg_mask_destroy(szg_index *h, int mask_id) {
+    GUARD(h);
+    auto it = h->masks.find(mask_id);
+    if (it == h->masks.end()) return fail(SZG_ENOTFOUND, "unknown mask id %d", mask_id);
+    cudaFree(it->second);
+    h->masks.erase(it);
+    return SZG_OK;
+}
+
+int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
+                    uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
+    GUARD(h);
+    int rc;
+    if ((rc = check_search(h, queries, nq))) return rc;
+    if (k < 1 || k > SZG_MAX_K) return fail(SZG_EINVAL, "k=%u outside [1, %u]", k, SZG_MAX_K);
+    if (nq && (!out_ids || !out_dist || !out_n)) return fail(SZG_EINVAL, "null output");
+    if (scanned) *scanned = h->live_rows;
+    if (!nq) return SZG_OK;
+    const uint32_t *mask;
+    if ((rc = get_mask(h, mask_id, &mask))) return rc;
+    if (h->live_rows == 0) { // empty collection: zero results, nothing to launch (collection.go:706-709)
+        for (uint32_t i = 0; i < nq; ++i) out_n[i] = 0;
+        return SZG_OK;
+    }
+    Workspace *ws;
+    if ((rc = acquire_ws(h, &ws))) return rc;
+    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
+    const size_t qn = (size_t)nq * h->dim, on = (size_t)nq * k;
+    if ((rc = ws->h_q.ensure(qn)) || (rc = ws->d_q.ensure(qn)) || (rc = ws->d_out_ids.ensure(on)) ||
+        (rc = ws->d_out_dist.ensure(on)) || (rc = ws->d_out_n.ensure(nq)) || (rc = ws->d_out_flags.ensure(nq)) ||
+        (rc = ws->h_out_ids.ensure(on)) || (rc = ws->h_out_dist.ensure(on)) || (rc = ws->h_out_n.ensure(nq)) ||
+        (rc = ws->h_out_flags.ensure(nq)))
+        return rc;
+    memcpy(ws->h_q.p, queries, qn * sizeof(double));
+    cudaStream_t st = ws->main;
+    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st));
+    int mode = mode_for_k(h, k);
+    if ((rc = run_topk(h, ws, ws->d_q.p, nq, k, mask, flags, mode, ws->d_out_ids.p, ws->d_out_dist.p,
+                       ws->d_out_n.p, ws->d_out_flags.p)))
+        return rc;
+    CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, on * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, on * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out_ids, ws->h_out_ids.p, on * 8);
+    memcpy(out_dist, ws->h_out_dist.p, on * 8);
+    memcpy(out_n, ws->h_out_n.p, nq * 4);
+    // escalate queries whose candidate margin was inside the tolerance band
+    if (!(flags & SZG_F_NO_FP64_VERIFY)) {
+        for (uint32_t i = 0; i < nq; ++i) {
+            int m = mode;
+            while ((ws->h_out_flags.p[i] & 1u) && m < 3) {
+                ++m;
+                h->escalations++;
+                if ((rc = run_topk(h, ws, ws->d_q.p + (size_t)i * h->dim, 1, k, mask, flags, m, ws->d_out_ids.p,
+                                   ws->d_out_dist.p, ws->d_out_n.p, ws->d_out_flags.p)))
+                    return rc;
+                CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ws->h_out_flags.p + i, ws->d_out_flags.p, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                memcpy(out_ids + (size_t)i * k, ws->h_out_ids.p, (size_t)k * 8);
+                memcpy(out_dist + (size_t)i * k, ws->h_out_dist.p, (size_t)k * 8);
+                out_n[i] = ws->h_out_n.p[0];
+            }
+            if (ws->h_out_flags.p[i] & 1u) h->uncertain++;
+        }
+    }
+    return SZG_OK;
+}
+
+int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
+                        uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, void *stream) {
+    GUARD(h);
+    int rc;
+    if ((rc = check_search(h, d_queries, nq))) return rc;
+    if (k < 1 || k > SZG_MAX_K) return fail(SZG_EINVAL, "k=%u outside [1, %u]", k, SZG_MAX_K);
+    if (!nq) return SZG_OK;
+    if (!d_out_ids || !d_out_dist || !d_out_n) return fail(SZG_EINVAL, "null output");
+    const uint32_t *mask;
+    if ((rc = get_mask(h, mask_id, &mask))) return rc;
+    Workspace *ws;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        auto it = h->dev_ws.find(stream);
+        if (it == h->dev_ws.end()) {
+            ws = new Workspace();
+            if ((rc = ws->init(false))) { ws->destroy(); delete ws; return rc; }
+            ws->main = (cudaStream_t)stream;
+            h->dev_ws[stream] = ws;
+        } else ws = it->second;
+    }
+    if ((rc = ws->d_out_flags.ensure(nq))) return rc;
+    if (h->live_rows == 0) {
+        CK(cudaMemsetAsync(d_out_n, 0, nq * 4, ws->main));
+        return SZG_OK;
+    }
+    return run_topk(h, ws, d_queries, nq, k, mask, flags, mode_for_k(h, k), (unsigned long long *)d_out_ids,
+                    d_out_dist, d_out_n, ws->d_out_flags.p);
+}
+
+int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const double *d_gathered_dist,
+                       const uint32_t *d_gathered_n, uint32_t nranks, uint32_t nq, uint32_t k, uint64_t *d_out_ids,
+                       double *d_out_dist, uint32_t *d_out_n, void *stream) {
+    GUARD(h);
+    if (!nq) return SZG_OK;
+    if (!d_gathered_ids || !d_gathered_dist || !d_gathered_n || !d_out_ids || !d_out_dist || !d_out_n)
+        return fail(SZG_EINVAL, "null argument");
+    if (k < 1 || k > SZG_MAX_K || nranks < 1 || (size_t)nranks * k * 16 > 200 * 1024)
+        return fail(SZG_EINVAL, "merge of %u lists of k=%u is not supported", nranks, k);
+    MergeArgs a;
+    a.g_ids = (const unsigned long long *)d_gathered_ids; a.g_dist = d_gathered_dist; a.g_n = d_gathered_n;
+    a.G = nranks; a.nq = nq; a.k = k;
+    a.out_ids = (unsigned long long *)d_out_ids; a.out_dist = d_out_dist; a.out_n = d_out_n;
+    CK(launch_merge(a, (cudaStream_t)stream));
+    h->launches++;
+    return SZG_OK;
+}
+
+int szg_search_radius(szg_index *h, const double *query, double radius, int mask_id, uint32_t flags,
+                      szg_result **out, uint64_t *scanned) {
+    GUARD(h);
+    int rc;
+    if (!out) return fail(SZG_EINVAL, "null out pointer");
+    *out = nullptr;
+    if ((rc = check_search(h, query, 1))) return rc;
+    if (!(radius > 0)) return fail(SZG_EINVAL, "radius must be > 0 (collection.go:598)");
+    if (scanned) *scanned = h->live_rows;
+    const uint32_t *mask;
+    if ((rc = get_mask(h, mask_id, &mask))) return rc;
+    std::unique_ptr<szg_result> res(new szg_result());
+    if (h->live_rows == 0) { *out = res.release(); return SZG_OK; }
+    Workspace *ws;
+    if ((rc = acquire_ws(h, &ws))) return rc;
+    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
+    const size_t stride = pq_stride(h);
+    if ((rc = ws->h_q.ensure(h->dim)) || (rc = ws->d_q.ensure(h->dim)) || (rc = ws->d_pq.ensure(stride)) ||
+        (rc = ws->h_out_n.ensure(1)))
+        return rc;
+    memcpy(ws->h_q.p, query, (size_t)h->dim * sizeof(double));
+    cudaStream_t st = ws->main;
+    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, (size_t)h->dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    PrepArgs pa;
+    pa.queries = ws->d_q.p; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
+    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
+    pa.qt = h->qt; pa.radius_mode = 1; pa.radius = radius;
+    CK(launch_prep(1, st, pa));
+    h->launches++;
+    const size_t smem = scan_smem_bytes(h->qt, h->C, MODE_RADIUS);
+    int grid = 0;
+    if ((rc = scan_grid(h, MODE_RADIUS, smem, &grid))) return rc;
+    unsigned int *d_count = ws->d_ticket.p + kMaxStreams;
+    uint32_t count = 0;
+    size_t cap = std::max<size_t>(4096, h->nslots / 64);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if ((rc = ws->d_slots.ensure(cap))) return rc;
+        CK(cudaMemsetAsync(d_count, 0, 4, st));
+        ScanArgs a;
+        fill_scan_args(h, a, mask);
+        a.pq = ws->d_pq.p; a.q = ws->d_q.p;
+        a.rad_count = d_count; a.rad_slots = ws->d_slots.p; a.rad_cap = (uint32_t)ws->d_slots.n;
+        CK(launch_scan(h->qt, MODE_RADIUS, grid, smem, st, a));
+        h->launches++;
+        CK(cudaMemcpyAsync(ws->h_out_n.p, d_count, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        count = ws->h_out_n.p[0];
+        if (count <= ws->d_slots.n) break;
+        cap = count; // the compaction buffer was too small: size it exactly and rescan
+    }
+    if (count > ws->d_slots.n) return fail(SZG_EINTERNAL, "radius compaction buffer could not be sized");
+    if (count) {
+        if ((rc = ws->d_out_ids.ensure(count)) || (rc = ws->d_out_dist.ensure(count)) ||
+            (rc = ws->h_out_ids.ensure(count)) || (rc = ws->h_out_dist.ensure(count)))
+            return rc;
+        RescoreArgs ra;
+        ra.codes = h->codes.p; ra.ids = h->ids.p; ra.lut = h->lut.p; ra.q = ws->d_q.p; ra.slots = ws->d_slots.p;
+        ra.count_ptr = nullptr; ra.out_dist = ws->d_out_dist.p; ra.out_ids = ws->d_out_ids.p;
+        ra.C = h->C; ra.dims = (uint32_t)h->dim; ra.metric = (uint32_t)h->metric; ra.m = count; ra.qt = h->qt;
+        CK(launch_rescore(ra, st));
+        h->launches++;
+        CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        // exact inclusive test (collection.go:598) on the fp64 distances, then ascending order
+        std::vector<uint32_t> keep;
+        keep.reserve(count);
+        for (uint32_t i = 0; i < count; ++i)
+            if (ws->h_out_dist.p[i] <= radius) keep.push_back(i);
+        const double *hd = ws->h_out_dist.p;
+        const unsigned long long *hi = ws->h_out_ids.p;
+        std::sort(keep.begin(), keep.end(), [&](uint32_t x, uint32_t y) {
+            if (hd[x] != hd[y]) return hd[x] < hd[y];
+            return lex_less_u64(hi[x], hi[y]);
+        });
+        res->ids.resize(keep.size());
+        res->dist.resize(keep.size());
+        for (size_t i = 0; i < keep.size(); ++i) { res->ids[i] = hi[keep[i]]; res->dist[i] = hd[keep[i]]; }
+    }
+    (void)flags;
+    *out = res.release();
+    return SZG_OK;
+}
+
+int szg_result_count(const szg_result *r, uint64_t *n) {
+    if (!r || !n) return fail(SZG_EINVAL, "null argument");
+    *n = r->ids.size();
+    return SZG_OK;
+}
+int szg_result_fetch(const szg_result *r, uint64_t offset, uint64_t n, uint64_t *out_ids, double *out_dist) {
+    if (!r) return fail(SZG_EINVAL, "null result");
+    if (offset > r->ids.size() || n > r->ids.size() - offset) return fail(SZG_EINVAL, "range outside the result");
+    if (out_ids) memcpy(out_ids, r->ids.data() + offset, n * 8);
+    if (out_dist) memcpy(out_dist, r->dist.data() + offset, n * 8);
+    return SZG_OK;
+}
+void szg_result_free(szg_result *r) { delete r; }
+
+int szg_rescore(szg_index *h, const double *query, const uint64_t *ids, uint64_t m, double *out_dist) {
+    GUARD(h);
+    int rc;
+    if ((rc = check_search(h, query, 1))) return rc;
+    if (!m) return SZG_OK;
+    if (!ids || !out_dist) return fail(SZG_EINVAL, "null argument");
+    if (m > 0xFFFFFFF0ull) return fail(SZG_EINVAL, "too many ids");
+    Workspace *ws;
+    if ((rc = acquire_ws(h, &ws))) return rc;
+    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
+    if ((rc = ws->h_q.ensure(h->dim)) || (rc = ws->d_q.ensure(h->dim)) || (rc = ws->h_slots.ensure(m)) ||
+        (rc = ws->d_slots.ensure(m)) || (rc = ws->d_out_dist.ensure(m)) || (rc = ws->h_out_dist.ensure(m)))
+        return rc;
+    memcpy(ws->h_q.p, query, (size_t)h->dim * sizeof(double));
+    map_ids(h, ids, m, ws->h_slots.p, false);
+    cudaStream_t st = ws->main;
+    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, (size_t)h->dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ws->d_slots.p, ws->h_slots.p, m * 4, cudaMemcpyHostToDevice, st));
+    RescoreArgs ra;
+    ra.codes = h->codes.p; ra.ids = h->ids.p; ra.lut = h->lut.p; ra.q = ws->d_q.p; ra.slots = ws->d_slots.p;
+    ra.count_ptr = nullptr; ra.out_dist = ws->d_out_dist.p; ra.out_ids = nullptr;
+    ra.C = h->C; ra.dims = (uint32_t)h->dim; ra.metric = (uint32_t)h->metric; ra.m = (uint32_t)m; ra.qt = h->qt;
+    CK(launch_rescore(ra, st));
+    h->launches++;
+    CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, m * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out_dist, ws->h_out_dist.p, m * 8);
+    return SZG_OK;
+}
+
+int szg_get_stats(szg_index *h, szg_stats *out) {
+    GUARD(h);
+    if (!out) return fail(SZG_EINVAL, "null out");
+    memset(out, 0, sizeof *out);
+    out->kernel_launches = h->launches;
+    out->escalations = h->escalations;
+    out->uncertain_results = h->uncertain;
+    out->device_bytes = h->codes.n * sizeof(uint4) + h->ids.n * 8 + h->aux.n * 8 + h->live.n * 4 +
+                        h->lut.n * 8 + h->masks.size() * (h->capacity / 32) * 4;
+    out->live_rows = h->live_rows;
+    out->slots = h->nslots;
+    out->rowbytes = h->rowbytes;
+    out->pitch = h->C * 16;
+    out->sm_count = (uint32_t)h->sm_count;
+    int grid = 0;
+    int rc = scan_grid(h, 0, scan_smem_bytes(h->qt, h->C, 0), &grid);
+    if (rc) return rc;
+    out->scan_grid = (uint32_t)grid;
+    out->scan_block = kScanThreads;
+    return SZG_OK;
+}
+
+int szg_last_scan_times_ms(szg_index *h, float *out_ms, uint32_t cap, uint32_t *n) {
+    GUARD(h);
+    if (!n) return fail(SZG_EINVAL, "null n");
+    *n = 0;
+    Workspace *ws = h->last_timed_ws;
+    if (!ws || !ws->timed) return SZG_OK;
+    const uint32_t m = std::min(cap, ws->timed);
+    for (uint32_t i = 0; i < m; ++i) {
+        CK(cudaEventSynchronize(ws->t1[i]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ws->t0[i], ws->t1[i]));
+        if (out_ms) out_ms[i] = ms;
+    }
+    *n = m;
+    return SZG_OK;
+}
+
+} // extern "C"

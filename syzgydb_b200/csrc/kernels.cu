@@ -1,0 +1,437 @@
+// kernels.cu -- query preparation, mirror upload / layout transform, synthetic fill,
+// fp64 re-score (K3) and the cross-rank top-k merge (K5).
+#include "kernels.h"
+
+namespace szg {
+
+// ======================================================================= query prep
+// One CTA per query.  Turns the float64 query (never quantized, collection.go:596) into
+// the payload the scan kernel streams against:
+//   4/8/16-bit rows: coefficient w_i (cosine: q_i; euclid: the unrounded code
+//   t_i = M(1+q_i)/2 of quantization.go:19-21, centred for 16-bit) -> W_i = round(w_i 2^F),
+//   |W_i| < 2^21, as three signed base-128 digits laid out per 16-byte chunk;
+//   32/64-bit rows: the query converted to fp32 / kept fp64, padded per chunk.
+__device__ __forceinline__ double coeff(const PrepArgs &a, double qi) {
+    if (a.metric == COSINE) return qi;
+    double t = (double)a.maxint * (1.0 + qi) * 0.5;
+    return a.qt == Q16 ? t - 32768.0 : t;
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
+    __shared__ double s_red[3][8];
+    __shared__ double s_out[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *q = a.queries + (size_t)blockIdx.x * a.dims;
+    unsigned char *out = a.pq + (size_t)blockIdx.x * a.pq_stride;
+    PQHeader *h = reinterpret_cast<PQHeader *>(out);
+    unsigned char *payload = out + sizeof(PQHeader);
+    const bool quantized = a.qt <= Q16;
+
+    const uint32_t n16 = (a.C * (uint32_t)pq_bytes_per_chunk(a.qt) + 15) / 16;
+    for (uint32_t i = tid; i < n16; i += 256) reinterpret_cast<uint4 *>(payload)[i] = make_uint4(0, 0, 0, 0);
+
+    // pass 1: max |w|, max |q|, sum q^2
+    double mw = 0.0, mq = 0.0, sq = 0.0;
+    for (uint32_t i = tid; i < a.dims; i += 256) {
+        double qi = q[i];
+        double w = fabs(coeff(a, qi));
+        if (w == w && w > mw) mw = w;
+        double aq = fabs(qi);
+        if (aq == aq && aq > mq) mq = aq;
+        sq += qi * qi;
+    }
+    for (int o = 16; o; o >>= 1) {
+        mw = fmax(mw, __shfl_xor_sync(0xffffffffu, mw, o));
+        mq = fmax(mq, __shfl_xor_sync(0xffffffffu, mq, o));
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) { s_red[0][warp] = mw; s_red[1][warp] = mq; s_red[2][warp] = sq; }
+    __syncthreads();
+    if (tid == 0) {
+        double a0 = 0, a1 = 0, a2 = 0;
+        for (int w = 0; w < 8; ++w) { a0 = fmax(a0, s_red[0][w]); a1 = fmax(a1, s_red[1][w]); a2 += s_red[2][w]; }
+        s_out[0] = a0; s_out[1] = a1; s_out[2] = a2;
+    }
+    __syncthreads();
+    mw = s_out[0]; mq = s_out[1]; sq = s_out[2];
+    __syncthreads();
+
+    int F = 0;
+    if (quantized && mw > 0.0 && isfinite(mw)) {
+        F = (kDigitBits - 1) - ilogb(mw);
+        F = F > 900 ? 900 : (F < -900 ? -900 : F);
+    }
+
+    // pass 2: payload + sums of W
+    double sW = 0.0, sW2 = 0.0;
+    for (uint32_t i = tid; i < a.dims; i += 256) {
+        double qi = q[i];
+        if (quantized) {
+            double w = coeff(a, qi);
+            long long W = (w == w && isfinite(w)) ? llrint(scalbn(w, F)) : 0;
+            const long long lim = 1ll << kDigitBits;
+            W = W >= lim ? lim - 1 : (W < -lim ? -lim : W);
+            sW += (double)W;
+            sW2 += (double)W * (double)W;
+            signed char dg[ND];
+            long long t = W;
+#pragma unroll
+            for (int j = ND - 1; j >= 1; --j) { dg[j] = (signed char)(t & 127); t >>= 7; }
+            dg[0] = (signed char)t; // most significant, signed
+            if (a.qt == Q8) {
+                uint32_t c = i >> 4, b = i & 15;
+                for (int j = 0; j < ND; ++j) payload[((size_t)c * ND + j) * 16 + b] = (unsigned char)dg[j];
+            } else if (a.qt == Q4) {
+                uint32_t byte = i >> 1, c = byte >> 4, b = byte & 15, arr = i & 1; // even dim = high nibble
+                for (int j = 0; j < ND; ++j) payload[(((size_t)c * 2 + arr) * ND + j) * 16 + b] = (unsigned char)dg[j];
+            } else {
+                uint32_t c = i >> 3, e = i & 7;
+                for (int j = 0; j < ND; ++j) payload[((size_t)c * ND + j) * 8 + e] = (unsigned char)dg[j];
+            }
+        } else if (a.qt == F32) {
+            reinterpret_cast<float *>(payload)[i] = (float)qi;
+        } else {
+            reinterpret_cast<double *>(payload)[i] = qi;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        sW += __shfl_xor_sync(0xffffffffu, sW, o);
+        sW2 += __shfl_xor_sync(0xffffffffu, sW2, o);
+    }
+    if (lane == 0) { s_red[0][warp] = sW; s_red[1][warp] = sW2; }
+    __syncthreads();
+    if (tid == 0) {
+        sW = 0; sW2 = 0;
+        for (int w = 0; w < 8; ++w) { sW += s_red[0][w]; sW2 += s_red[1][w]; }
+        const double M = (double)a.maxint;
+        const double qn = sqrt(sq);
+        PQHeader hh;
+        hh.sumW = sW; hh.sumW2 = sW2;
+        hh.F = F; hh.zero_query = (sq == 0.0); hh.pad[0] = hh.pad[1] = 0;
+        hh.qnorm = qn;
+        hh.pow2F1 = scalbn(1.0, F + 1);
+        hh.pow2F2 = scalbn(1.0, 2 * F);
+        hh.base = sW2;
+        hh.numc = (a.qt == Q16 ? 1.0 : -M) * sW;
+        if (a.metric == COSINE) {
+            hh.c_key = (sq == 0.0) ? 0.0 : (quantized ? scalbn(1.0, -F) / (M * qn) : 1.0 / qn);
+        } else {
+            hh.c_key = quantized ? 4.0 / (M * M) * scalbn(1.0, -2 * F) : 1.0;
+        }
+        hh.radius = a.radius;
+        hh.radius_key = 0.0;
+        if (a.radius_mode) {
+            const double r = a.radius;
+            if (a.metric == COSINE) {
+                hh.radius_key = (r >= 1.0) ? 2.0 : -cos(3.141592653589793 * r) + 1e-5;
+            } else {
+                const double rel = a.qt == F32 ? 1e-3 : (a.qt == F64 ? 1e-6 : 1e-4);
+                const double ab = quantized ? 4e-6 * sqrt((double)a.dims) * fmax(1.0, mq) : 0.0;
+                const double t = r * (1.0 + rel) + ab;
+                hh.radius_key = t * t;
+            }
+        }
+        *h = hh;
+    }
+}
+
+cudaError_t launch_prep(uint32_t nq, cudaStream_t st, const PrepArgs &a) {
+    prep_kernel<<<nq, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// =================================================================== upload / layout
+__device__ __forceinline__ void store_chunk(uint4 *codes, uint32_t slot, uint32_t C, uint32_t c,
+                                            const unsigned char *b) {
+    uint4 v;
+    v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
+    v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+    v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+    v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
+    codes[chunk_index(slot, C, c)] = v;
+}
+__device__ __forceinline__ void load_chunk(const uint4 *codes, uint32_t slot, uint32_t C, uint32_t c,
+                                           unsigned char *b) {
+    uint4 v = codes[chunk_index(slot, C, c)];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < 4; ++i) b[4 * k + i] = (unsigned char)(w[k] >> (8 * i));
+}
+
+// thread per (row, chunk): stream-1 bytes -> column-blocked HBM representation
+__global__ void scatter_kernel(const RowsArgs a, const unsigned char *__restrict__ staged,
+                               const uint32_t *__restrict__ slots, const unsigned long long *__restrict__ ids_in,
+                               uint32_t n) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t row = (uint32_t)(t / a.C), c = (uint32_t)(t % a.C);
+    if (row >= n) return;
+    const uint32_t slot = slots[row];
+    if (slot == 0xFFFFFFFFu) return; // superseded duplicate of the same batch
+    unsigned char b[16];
+    const unsigned char *src = staged + (size_t)row * a.rowbytes + (size_t)c * 16;
+    const uint32_t remain = a.rowbytes - c * 16;
+    for (int i = 0; i < 16; ++i) b[i] = (uint32_t)i < remain ? src[i] : 0;
+    chunk_to_device(a.qt, b);
+    store_chunk(a.codes, slot, a.C, c, b);
+    if (c == 0) {
+        a.ids[slot] = ids_in[row];
+        atomicOr(a.live + (slot >> 5), 1u << (slot & 31));
+    }
+}
+
+cudaError_t launch_scatter(const RowsArgs &a, const unsigned char *staged, const uint32_t *slots,
+                           const unsigned long long *ids_in, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const size_t total = (size_t)n * a.C;
+    scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, staged, slots, ids_in, n);
+    return cudaGetLastError();
+}
+
+// thread per (row, chunk): synthetic rows, generator = oracle/syzgy_oracle.c orc_synth_rows
+__global__ void synth_kernel(const RowsArgs a, unsigned long long seed, unsigned long long row0, uint32_t slot0,
+                             uint32_t n) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = (uint32_t)(t / a.C), c = (uint32_t)(t % a.C);
+    if (r >= n) return;
+    const unsigned long long row = row0 + r;
+    const uint32_t slot = slot0 + r;
+    unsigned char b[16];
+    if (a.qt <= Q16) {
+        const unsigned long long wpr = (a.rowbytes + 7) / 8;
+        for (int half = 0; half < 2; ++half) {
+            const unsigned long long j = (unsigned long long)c * 2 + half;
+            unsigned long long w = (j < wpr) ? rand_u64(seed, row * wpr + j) : 0ull;
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t off = c * 16 + half * 8 + i;
+                b[half * 8 + i] = off < a.rowbytes ? (unsigned char)(w >> (8 * i)) : 0;
+            }
+        }
+        if (a.qt == Q4 && (a.dims & 1)) {
+            const uint32_t last = a.rowbytes - 1;
+            if (last / 16 == c) b[last % 16] &= 0xF0;
+        }
+    } else {
+        const int eb = a.qt == F32 ? 4 : 8, epc = 16 / eb;
+        for (int e = 0; e < epc; ++e) {
+            const uint32_t dim = c * epc + e;
+            unsigned long long bits = 0;
+            if (dim < a.dims) {
+                double v = (double)(rand_u64(seed, row * a.dims + dim) >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+                bits = a.qt == F32 ? (unsigned long long)__float_as_uint((float)v)
+                                   : (unsigned long long)__double_as_longlong(v);
+            }
+            for (int i = 0; i < eb; ++i) b[e * eb + i] = (unsigned char)(bits >> (8 * (eb - 1 - i))); // big-endian
+        }
+    }
+    chunk_to_device(a.qt, b);
+    store_chunk(a.codes, slot, a.C, c, b);
+    if (c == 0) {
+        a.ids[slot] = row;
+        atomicOr(a.live + (slot >> 5), 1u << (slot & 31));
+    }
+}
+
+cudaError_t launch_synth(const RowsArgs &a, unsigned long long seed, unsigned long long row0, uint32_t slot0,
+                         uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const size_t total = (size_t)n * a.C;
+    synth_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, seed, row0, slot0, n);
+    return cudaGetLastError();
+}
+
+// thread per row: per-row auxiliary value the surrogate needs (not streamed as payload):
+//   cosine           float 1/||x||   (0 for a zero-norm row -> distance 1.0, collection.go:828-830)
+//   euclid 4/8-bit   uint32 sum u^2 ; euclid 16-bit: uint64 sum (u-32768)^2 ; float rows: none
+__global__ void aux_kernel(const RowsArgs a, const uint32_t *__restrict__ slots, uint32_t slot0, uint32_t n) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t slot = slots ? slots[r] : slot0 + r;
+    if (slot == 0xFFFFFFFFu) return;
+    if (a.metric == EUCLID && a.qt > Q16) return;
+    unsigned long long S1 = 0, S2 = 0; // quantized (unsigned code sums; Q16: S1 signed below)
+    long long S1s = 0;
+    double fs = 0.0;
+    uint32_t dim = 0;
+    for (uint32_t c = 0; c < a.C && dim < a.dims; ++c) {
+        uint4 v = a.codes[chunk_index(slot, a.C, c)];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int k = 0; k < 4; ++k) {
+            if (a.qt == Q4) {
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t byte = (w[k] >> (8 * i)) & 0xFF;
+                    uint32_t hi = byte >> 4, lo = byte & 15;
+                    if (dim < a.dims) { S1 += hi; S2 += hi * hi; }
+                    ++dim;
+                    if (dim < a.dims) { S1 += lo; S2 += lo * lo; }
+                    ++dim;
+                }
+            } else if (a.qt == Q8) {
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t u = (w[k] >> (8 * i)) & 0xFF;
+                    if (dim < a.dims) { S1 += u; S2 += u * u; }
+                    ++dim;
+                }
+            } else if (a.qt == Q16) {
+                for (int i = 0; i < 2; ++i) {
+                    int s = (int)(short)((w[k] >> (16 * i)) & 0xFFFF);
+                    if (dim < a.dims) { S1s += s; S2 += (unsigned long long)((long long)s * s); }
+                    ++dim;
+                }
+            } else if (a.qt == F32) {
+                double x = (double)__uint_as_float(w[k]);
+                if (dim < a.dims) fs += x * x;
+                ++dim;
+            } else if ((k & 1) == 0) {
+                double x = __hiloint2double((int)w[k + 1], (int)w[k]);
+                if (dim < a.dims) fs += x * x;
+                ++dim;
+            }
+        }
+    }
+    if (a.metric == COSINE) {
+        double nx2;
+        const double M = (double)a.maxint, d = (double)a.dims;
+        if (a.qt == Q16) nx2 = (4.0 * (double)S2 + 4.0 * (double)S1s + d) / (M * M);          // x = (2s+1)/M
+        else if (a.qt <= Q8) nx2 = (4.0 * (double)S2 - 4.0 * M * (double)S1 + M * M * d) / (M * M); // x = (2u-M)/M
+        else nx2 = fs;
+        float rn = (nx2 > 0.0 && isfinite(nx2)) ? (float)(1.0 / sqrt(nx2)) : 0.f;
+        reinterpret_cast<float *>(a.aux)[slot] = rn;
+    } else if (a.qt == Q16) {
+        reinterpret_cast<unsigned long long *>(a.aux)[slot] = S2;
+    } else {
+        reinterpret_cast<uint32_t *>(a.aux)[slot] = (uint32_t)S2;
+    }
+}
+
+cudaError_t launch_aux(const RowsArgs &a, const uint32_t *slots, uint32_t slot0, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    aux_kernel<<<(n + 127) / 128, 128, 0, st>>>(a, slots, slot0, n);
+    return cudaGetLastError();
+}
+
+__global__ void kill_kernel(uint32_t *live, const uint32_t *__restrict__ slots, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAnd(live + (slots[i] >> 5), ~(1u << (slots[i] & 31)));
+}
+cudaError_t launch_kill(uint32_t *live, const uint32_t *slots, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    kill_kernel<<<(n + 255) / 256, 256, 0, st>>>(live, slots, n);
+    return cudaGetLastError();
+}
+
+__global__ void mask_set_kernel(uint32_t *mask, const uint32_t *__restrict__ slots,
+                                const unsigned char *__restrict__ pass, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && pass[i] && slots[i] != 0xFFFFFFFFu) atomicOr(mask + (slots[i] >> 5), 1u << (slots[i] & 31));
+}
+cudaError_t launch_mask_set(uint32_t *mask, const uint32_t *slots, const unsigned char *pass, uint32_t n,
+                            cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    mask_set_kernel<<<(n + 255) / 256, 256, 0, st>>>(mask, slots, pass, n);
+    return cudaGetLastError();
+}
+
+__global__ void fetch_kernel(const RowsArgs a, const uint32_t *__restrict__ slots, uint32_t n,
+                             unsigned char *__restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t row = (uint32_t)(t / a.C), c = (uint32_t)(t % a.C);
+    if (row >= n) return;
+    unsigned char b[16];
+    load_chunk(a.codes, slots[row], a.C, c, b);
+    chunk_to_disk(a.qt, b);
+    const uint32_t remain = a.rowbytes - c * 16;
+    unsigned char *dst = out + (size_t)row * a.rowbytes + (size_t)c * 16;
+    for (int i = 0; i < 16; ++i)
+        if ((uint32_t)i < remain) dst[i] = b[i];
+}
+cudaError_t launch_fetch(const RowsArgs &a, const uint32_t *slots, uint32_t n, unsigned char *out, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const size_t total = (size_t)n * a.C;
+    fetch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, slots, n, out);
+    return cudaGetLastError();
+}
+
+// ============================================================ K3: gather + fp64 re-score
+// thread per candidate, visit order preserved; replaces decodeVector + distance inside
+// `consider` (collection.go:584-596) for the ids an index (lshtree.go:316-335) or the
+// radius compaction produced.
+template <int QT>
+__global__ void __launch_bounds__(128) rescore_kernel(const RescoreArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = a.m;
+    if (a.count_ptr) { uint32_t c = *a.count_ptr; m = c < m ? c : m; }
+    if (i >= m) return;
+    const uint32_t slot = a.slots[i];
+    if (slot == 0xFFFFFFFFu) {
+        a.out_dist[i] = -1.0; // SZG_MISSING_DISTANCE
+        if (a.out_ids) a.out_ids[i] = 0;
+        return;
+    }
+    a.out_dist[i] = exact_distance<QT>(a.codes, a.C, a.dims, (int)a.metric, a.lut, a.q, slot);
+    if (a.out_ids) a.out_ids[i] = a.ids[slot];
+}
+
+cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st) {
+    if (!a.m) return cudaSuccess;
+    const unsigned grid = (a.m + 127) / 128;
+    switch (a.qt) {
+    case Q4: rescore_kernel<Q4><<<grid, 128, 0, st>>>(a); break;
+    case Q8: rescore_kernel<Q8><<<grid, 128, 0, st>>>(a); break;
+    case Q16: rescore_kernel<Q16><<<grid, 128, 0, st>>>(a); break;
+    case F32: rescore_kernel<F32><<<grid, 128, 0, st>>>(a); break;
+    default: rescore_kernel<F64><<<grid, 128, 0, st>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+// ===================================================== K5: merge of row-sharded top-k lists
+// One CTA per query: the G*k gathered (distance, id) pairs are ranked by
+// (distance, lexicographic decimal id) and the first k written out.
+__global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const uint32_t cap = a.G * a.k;
+    double *s_d = reinterpret_cast<double *>(sm);
+    unsigned long long *s_i = reinterpret_cast<unsigned long long *>(s_d + cap);
+    __shared__ uint32_t s_total;
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    for (uint32_t e = tid; e < cap; e += 256) {
+        const uint32_t g = e / a.k, j = e % a.k;
+        const uint32_t n = a.g_n[(size_t)g * a.nq + q];
+        const size_t src = ((size_t)g * a.nq + q) * a.k + j;
+        const bool ok = j < n;
+        s_d[e] = ok ? a.g_dist[src] : __longlong_as_double(0x7ff8000000000000ll);
+        s_i[e] = ok ? a.g_ids[src] : 0ull;
+        if (ok) atomicAdd(&s_total, 1u);
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < cap; e += 256) {
+        const double d = s_d[e];
+        if (!(d == d)) continue;
+        const unsigned long long id = s_i[e];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < cap; ++j) {
+            const double dj = s_d[j];
+            if (j != e && dj == dj && (dj < d || (dj == d && lex_less_u64(s_i[j], id)))) ++rank;
+        }
+        if (rank < a.k) {
+            a.out_ids[(size_t)q * a.k + rank] = id;
+            a.out_dist[(size_t)q * a.k + rank] = d;
+        }
+    }
+    if (tid == 0) a.out_n[q] = s_total < a.k ? s_total : a.k;
+}
+
+cudaError_t launch_merge(const MergeArgs &a, cudaStream_t st) {
+    if (!a.nq) return cudaSuccess;
+    const size_t smem = (size_t)a.G * a.k * 16;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    merge_kernel<<<a.nq, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace szg

@@ -1,0 +1,72 @@
+// kernels.h -- host-callable launchers of every kernel in the library.
+#pragma once
+#include "scan_impl.cuh"
+
+namespace szg {
+
+struct PrepArgs {
+    const double *queries; // nq * dims
+    unsigned char *pq;     // nq * pq_stride
+    size_t pq_stride;
+    uint32_t dims, C, metric, maxint;
+    int qt;
+    int radius_mode;
+    double radius;
+};
+cudaError_t launch_prep(uint32_t nq, cudaStream_t st, const PrepArgs &a);
+
+// scan: one instantiation file per quantization
+cudaError_t launch_scan(int qt, int mode, int grid, size_t smem, cudaStream_t st, const ScanArgs &a);
+cudaError_t scan_configure(int qt, size_t max_smem);
+cudaError_t scan_occupancy(int qt, int mode, size_t smem, int *blocks_per_sm);
+
+struct RowsArgs {
+    uint4 *codes;
+    void *aux;
+    uint32_t *live;
+    unsigned long long *ids;
+    uint32_t C, dims, metric, maxint, rowbytes;
+    int qt;
+};
+// staged: n rows of rowbytes bytes (stream-1 format); slots[n]; ids_in[n]
+cudaError_t launch_scatter(const RowsArgs &a, const unsigned char *staged, const uint32_t *slots,
+                           const unsigned long long *ids_in, uint32_t n, cudaStream_t st);
+// rows [slot0, slot0+n) <- synthetic rows [row0, row0+n) of `seed`; ids = row index
+cudaError_t launch_synth(const RowsArgs &a, unsigned long long seed, unsigned long long row0, uint32_t slot0,
+                         uint32_t n, cudaStream_t st);
+// aux of the given slots (slots == NULL: the range [slot0, slot0+n))
+cudaError_t launch_aux(const RowsArgs &a, const uint32_t *slots, uint32_t slot0, uint32_t n, cudaStream_t st);
+// clears live bits of slots
+cudaError_t launch_kill(uint32_t *live, const uint32_t *slots, uint32_t n, cudaStream_t st);
+// builds a filter bitmask: bit set for slots[i] with pass[i] != 0 (mask pre-zeroed)
+cudaError_t launch_mask_set(uint32_t *mask, const uint32_t *slots, const unsigned char *pass, uint32_t n,
+                            cudaStream_t st);
+// records back to stream-1 bytes
+cudaError_t launch_fetch(const RowsArgs &a, const uint32_t *slots, uint32_t n, unsigned char *out, cudaStream_t st);
+
+struct RescoreArgs {
+    const uint4 *codes;
+    const unsigned long long *ids;
+    const double *lut;
+    const double *q;
+    const uint32_t *slots;      // 0xFFFFFFFF = missing
+    const uint32_t *count_ptr;  // optional device count (min with m)
+    double *out_dist;
+    unsigned long long *out_ids; // optional
+    uint32_t C, dims, metric, m;
+    int qt;
+};
+cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st);
+
+struct MergeArgs {
+    const unsigned long long *g_ids; // [G][nq][k]
+    const double *g_dist;
+    const uint32_t *g_n; // [G][nq]
+    uint32_t G, nq, k;
+    unsigned long long *out_ids; // [nq][k]
+    double *out_dist;
+    uint32_t *out_n;
+};
+cudaError_t launch_merge(const MergeArgs &a, cudaStream_t st);
+
+} // namespace szg

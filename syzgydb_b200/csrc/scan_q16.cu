@@ -1,0 +1,30 @@
+// scan_q16.cu -- instantiates the scan kernel (scan_impl.cuh) for Q16 records.
+#include "kernels.h"
+
+namespace szg {
+
+cudaError_t launch_scan_q16(int mode, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
+    return launch_scan_t<Q16>(mode, grid, smem, st, a);
+}
+
+cudaError_t scan_attr_q16(size_t max_smem) {
+    cudaError_t e;
+#define SZG_ATTR(M)                                                                                            \
+    e = cudaFuncSetAttribute(scan_kernel<Q16, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);  \
+    if (e != cudaSuccess) return e;
+    SZG_ATTR(0) SZG_ATTR(1) SZG_ATTR(2) SZG_ATTR(3) SZG_ATTR(MODE_RADIUS)
+#undef SZG_ATTR
+    return cudaSuccess;
+}
+
+cudaError_t scan_occ_q16(int mode, size_t smem, int *bps) {
+    switch (mode) {
+    case 0: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, scan_kernel<Q16, 0>, kScanThreads, smem);
+    case 1: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, scan_kernel<Q16, 1>, kScanThreads, smem);
+    case 2: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, scan_kernel<Q16, 2>, kScanThreads, smem);
+    case 3: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, scan_kernel<Q16, 3>, kScanThreads, smem);
+    default: return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, scan_kernel<Q16, MODE_RADIUS>, kScanThreads, smem);
+    }
+}
+
+} // namespace szg
