@@ -147,14 +147,18 @@ int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint
                         void *stream);
 
 /*
- * Final merge of row-sharded top-k lists: `lists` holds G blocks, block g =
- * rank g's {ids nq*k, dist nq*k} as gathered by ncclAllGather; writes the global top-k per
- * query (ascending distance, ties by lexicographic decimal id).  No reference counterpart:
- * the reference is single-process.
+ * Final merge of row-sharded top-k lists: rank g's {ids nq*k, dist nq*k, n nq}
+ * as gathered by ncclAllGather; writes the global top-k per query (ascending distance, ties
+ * by lexicographic decimal id).  rank_stride_bytes == 0: the three arrays are separate and
+ * tight ([G][nq][k], [G][nq][k], [G][nq]); otherwise the pointers name rank 0's arrays
+ * inside one packed per-rank record and every rank's record starts rank_stride_bytes after
+ * the previous one (one allgather of one buffer).  No reference counterpart: the reference
+ * is single-process.
  */
 int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const double *d_gathered_dist,
-                       const uint32_t *d_gathered_n, uint32_t nranks, uint32_t nq, uint32_t k,
-                       uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, void *stream);
+                       const uint32_t *d_gathered_n, uint64_t rank_stride_bytes, uint32_t nranks,
+                       uint32_t nq, uint32_t k, uint64_t *d_out_ids, double *d_out_dist,
+                       uint32_t *d_out_n, void *stream);
 
 /* ---- synthetic data + introspection (bench/test helpers, no reference counterpart) ---- */
 
@@ -183,7 +187,8 @@ int szg_get_stats(szg_index *h, szg_stats *out);
 
 /* tuning / test knobs */
 #define SZG_OPT_STREAMS 1            /* streams a multi-query call is spread over (1..4, default 2) */
-#define SZG_OPT_TIMING 2             /* record CUDA events around every scan launch (default 1) */
+#define SZG_OPT_TIMING 2             /* CUDA events around every scan launch: 0 off, 1 keep the last call's
+                                        (default), 2 accumulate over calls until szg_last_scan_times_ms reads them */
 #define SZG_OPT_MIN_CANDIDATE_MODE 3 /* force candidate set >= 32<<v (v in 0..3; -1 = automatic) */
 int szg_set_option(szg_index *h, int option, int64_t value);
 

@@ -80,7 +80,7 @@ def load():
     L.szg_result_free.restype = None
     L.szg_rescore.argtypes = [vp, f64p, u64p, C.c_uint64, f64p]
     L.szg_search_topk_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, vp, vp, vp, vp]
-    L.szg_merge_topk_dev.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.szg_merge_topk_dev.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
     L.szg_fill_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
     L.szg_fetch_codes.argtypes = [vp, u64p, C.c_uint64, u8p]
     L.szg_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -233,9 +233,9 @@ class Index:
                                            d_out_n, stream))
 
     def merge_topk_dev(self, d_g_ids: int, d_g_dist: int, d_g_n: int, nranks: int, nq: int, k: int, d_out_ids: int,
-                       d_out_dist: int, d_out_n: int, stream: int = 0):
-        _check(self._L.szg_merge_topk_dev(self._h, d_g_ids, d_g_dist, d_g_n, nranks, nq, k, d_out_ids, d_out_dist,
-                                          d_out_n, stream))
+                       d_out_dist: int, d_out_n: int, stream: int = 0, rank_stride_bytes: int = 0):
+        _check(self._L.szg_merge_topk_dev(self._h, d_g_ids, d_g_dist, d_g_n, rank_stride_bytes, nranks, nq, k,
+                                          d_out_ids, d_out_dist, d_out_n, stream))
 
     # -- introspection
     def stats(self) -> dict:

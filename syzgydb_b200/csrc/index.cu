@@ -329,8 +329,11 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
         for (int s = 1; s < used; ++s) CK(cudaStreamWaitEvent(ws->helper[s], ws->ev_fork, 0));
     }
     const bool timing = h->timing != 0;
+    // timing == 2 accumulates events over calls (bounded) until szg_last_scan_times_ms drains them
+    uint32_t tbase = 0;
+    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nq <= 65536) tbase = ws->timed;
     if (timing) {
-        while (ws->t0.size() < nq) {
+        while (ws->t0.size() < tbase + nq) {
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a));
             CK(cudaEventCreate(&b));
@@ -353,12 +356,12 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
         a.out_dist = d_out_dist + (size_t)i * k;
         a.out_n = d_out_n + i;
         a.out_flags = d_out_flags + i;
-        if (timing) CK(cudaEventRecord(ws->t0[i], st));
+        if (timing) CK(cudaEventRecord(ws->t0[tbase + i], st));
         CK(launch_scan(h->qt, mode, grid, smem, st, a));
-        if (timing) CK(cudaEventRecord(ws->t1[i], st));
+        if (timing) CK(cudaEventRecord(ws->t1[tbase + i], st));
         h->launches++;
     }
-    if (timing) { ws->timed = nq; h->last_timed_ws = ws; }
+    if (timing) { ws->timed = tbase + nq; h->last_timed_ws = ws; }
     for (int s = 1; s < used; ++s) {
         CK(cudaEventRecord(ws->ev_join[s], ws->helper[s]));
         CK(cudaStreamWaitEvent(main, ws->ev_join[s], 0));
@@ -462,7 +465,10 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
         if (value < 1 || value > kMaxStreams) return fail(SZG_EINVAL, "streams must be in [1, %d]", kMaxStreams);
         h->nstreams = (int)value;
         return SZG_OK;
-    case SZG_OPT_TIMING: h->timing = value != 0; return SZG_OK;
+    case SZG_OPT_TIMING:
+        if (value < 0 || value > 2) return fail(SZG_EINVAL, "timing must be 0, 1 or 2");
+        h->timing = (int)value;
+        return SZG_OK;
     case SZG_OPT_MIN_CANDIDATE_MODE:
         if (value < -1 || value > 3) return fail(SZG_EINVAL, "candidate mode must be in [-1, 3]");
         h->force_mode = (int)value;
@@ -750,8 +756,8 @@ int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint
 }
 
 int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const double *d_gathered_dist,
-                       const uint32_t *d_gathered_n, uint32_t nranks, uint32_t nq, uint32_t k, uint64_t *d_out_ids,
-                       double *d_out_dist, uint32_t *d_out_n, void *stream) {
+                       const uint32_t *d_gathered_n, uint64_t rank_stride_bytes, uint32_t nranks, uint32_t nq,
+                       uint32_t k, uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, void *stream) {
     GUARD(h);
     if (!nq) return SZG_OK;
     if (!d_gathered_ids || !d_gathered_dist || !d_gathered_n || !d_out_ids || !d_out_dist || !d_out_n)
@@ -760,6 +766,7 @@ int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const doubl
         return fail(SZG_EINVAL, "merge of %u lists of k=%u is not supported", nranks, k);
     MergeArgs a;
     a.g_ids = (const unsigned long long *)d_gathered_ids; a.g_dist = d_gathered_dist; a.g_n = d_gathered_n;
+    a.rank_stride = (size_t)rank_stride_bytes;
     a.G = nranks; a.nq = nq; a.k = k;
     a.out_ids = (unsigned long long *)d_out_ids; a.out_dist = d_out_dist; a.out_n = d_out_n;
     CK(launch_merge(a, (cudaStream_t)stream));
@@ -931,6 +938,7 @@ int szg_last_scan_times_ms(szg_index *h, float *out_ms, uint32_t cap, uint32_t *
         if (out_ms) out_ms[i] = ms;
     }
     *n = m;
+    ws->timed = 0; // drained (matters for the accumulating mode)
     return SZG_OK;
 }
 

@@ -398,11 +398,23 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
     __syncthreads();
     for (uint32_t e = tid; e < cap; e += 256) {
         const uint32_t g = e / a.k, j = e % a.k;
-        const uint32_t n = a.g_n[(size_t)g * a.nq + q];
-        const size_t src = ((size_t)g * a.nq + q) * a.k + j;
+        const unsigned long long *ids_g;
+        const double *dist_g;
+        const uint32_t *n_g;
+        if (a.rank_stride) {
+            ids_g = reinterpret_cast<const unsigned long long *>(reinterpret_cast<const char *>(a.g_ids) + g * a.rank_stride);
+            dist_g = reinterpret_cast<const double *>(reinterpret_cast<const char *>(a.g_dist) + g * a.rank_stride);
+            n_g = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(a.g_n) + g * a.rank_stride);
+        } else {
+            ids_g = a.g_ids + (size_t)g * a.nq * a.k;
+            dist_g = a.g_dist + (size_t)g * a.nq * a.k;
+            n_g = a.g_n + (size_t)g * a.nq;
+        }
+        const uint32_t n = n_g[q];
+        const size_t src = (size_t)q * a.k + j;
         const bool ok = j < n;
-        s_d[e] = ok ? a.g_dist[src] : __longlong_as_double(0x7ff8000000000000ll);
-        s_i[e] = ok ? a.g_ids[src] : 0ull;
+        s_d[e] = ok ? dist_g[src] : __longlong_as_double(0x7ff8000000000000ll);
+        s_i[e] = ok ? ids_g[src] : 0ull;
         if (ok) atomicAdd(&s_total, 1u);
     }
     __syncthreads();

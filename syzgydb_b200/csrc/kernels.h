@@ -62,6 +62,7 @@ struct MergeArgs {
     const unsigned long long *g_ids; // [G][nq][k]
     const double *g_dist;
     const uint32_t *g_n; // [G][nq]
+    size_t rank_stride;  // bytes between ranks for all three arrays; 0 = each array tightly packed [G][...]
     uint32_t G, nq, k;
     unsigned long long *out_ids; // [nq][k]
     double *out_dist;
