@@ -181,7 +181,9 @@ typedef struct szg_stats {
     uint32_t sm_count;
     uint32_t scan_grid;         /* CTAs of one scan launch */
     uint32_t scan_block;        /* threads per CTA */
-    uint32_t reserved;
+    uint32_t scan_stages;       /* shared-memory ring stages per warp */
+    uint32_t scan_tile_bytes;   /* bytes of one bulk-copied tile */
+    uint32_t scan_smem_bytes;   /* dynamic shared memory per CTA */
 } szg_stats;
 int szg_get_stats(szg_index *h, szg_stats *out);
 
@@ -190,6 +192,9 @@ int szg_get_stats(szg_index *h, szg_stats *out);
 #define SZG_OPT_TIMING 2             /* CUDA events around every scan launch: 0 off, 1 keep the last call's
                                         (default), 2 accumulate over calls until szg_last_scan_times_ms reads them */
 #define SZG_OPT_MIN_CANDIDATE_MODE 3 /* force candidate set >= 32<<v (v in 0..3; -1 = automatic) */
+#define SZG_OPT_SCAN_WARPS 4         /* warps per scan CTA: 8 or 16 (default 16) */
+#define SZG_OPT_SCAN_STAGES 5        /* ring stages per warp, 2..8 (default 3) */
+#define SZG_OPT_SCAN_TILE_CHUNKS 6   /* upper bound of 16-byte chunks per tile, 1..32 (default 8) */
 int szg_set_option(szg_index *h, int option, int64_t value);
 
 /* Time of the most recent scan launches on this handle, measured with CUDA events on the

@@ -23,6 +23,9 @@ MAX_DIM = 16384
 OPT_STREAMS = 1
 OPT_TIMING = 2
 OPT_MIN_CANDIDATE_MODE = 3
+OPT_SCAN_WARPS = 4
+OPT_SCAN_STAGES = 5
+OPT_SCAN_TILE_CHUNKS = 6
 
 # every symbol include/syzgy_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -44,7 +47,8 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_uint64), ("escalations", C.c_uint64), ("uncertain_results", C.c_uint64),
         ("device_bytes", C.c_uint64), ("live_rows", C.c_uint64), ("slots", C.c_uint64),
         ("rowbytes", C.c_uint32), ("pitch", C.c_uint32), ("sm_count", C.c_uint32), ("scan_grid", C.c_uint32),
-        ("scan_block", C.c_uint32), ("reserved", C.c_uint32),
+        ("scan_block", C.c_uint32), ("scan_stages", C.c_uint32), ("scan_tile_bytes", C.c_uint32),
+        ("scan_smem_bytes", C.c_uint32),
     ]
 
 

@@ -86,8 +86,8 @@ struct Workspace {
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
     DevBuf<double> d_q;
     DevBuf<unsigned char> d_pq;
-    DevBuf<unsigned long long> d_cand[kMaxStreams];
-    DevBuf<unsigned int> d_ticket; // kMaxStreams tickets + radius count
+    DevBuf<unsigned long long> d_cand; // [nq][scan CTAs][32*E] candidate keys, scan -> finalize
+    DevBuf<unsigned int> d_ticket;     // radius hit counter
     DevBuf<unsigned long long> d_out_ids;
     DevBuf<double> d_out_dist;
     DevBuf<uint32_t> d_out_n, d_out_flags;
@@ -113,7 +113,7 @@ struct Workspace {
     void destroy() {
         d_q.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
         d_out_n.release(); d_out_flags.release(); d_slots.release();
-        for (auto &c : d_cand) c.release();
+        d_cand.release();
         h_q.release(); h_out_ids.release(); h_out_dist.release(); h_out_n.release(); h_out_flags.release();
         h_slots.release();
         for (auto e : t0) cudaEventDestroy(e);
@@ -177,7 +177,7 @@ struct szg_index {
     uint64_t launches = 0, escalations = 0, uncertain = 0;
     std::vector<float> last_times;
     Workspace *last_timed_ws = nullptr;
-    int grid_cache[5] = {0, 0, 0, 0, 0};
+    int scan_warps = 16, scan_stages = 3, scan_tile_chunks = 8; // streaming geometry (SZG_OPT_SCAN_*)
 
     bool lookup(uint64_t id, uint32_t *slot) const {
         auto it = map.find(id);
@@ -271,13 +271,20 @@ int mode_for_k(const szg_index *h, uint32_t k) {
     return mode;
 }
 
-int scan_grid(szg_index *h, int mode, size_t smem, int *grid) {
-    if (h->grid_cache[mode]) { *grid = h->grid_cache[mode]; return SZG_OK; }
-    int bps = 0;
-    CK(scan_occupancy(h->qt, mode, smem, &bps));
-    if (bps < 1) return fail(SZG_EINTERNAL, "scan kernel does not fit on an SM (smem %zu)", smem);
-    *grid = bps * h->sm_count;
-    h->grid_cache[mode] = *grid;
+constexpr size_t kScanSmemLimit = 224 * 1024; // dynamic; + ~3 KB static stays under the 227 KB CTA limit
+
+// Persistent launch: one CTA per SM (fewer when the collection has fewer row blocks than warps).
+int plan_scan(szg_index *h, int mode, ScanPlan *p, int *grid) {
+    uint32_t warps = (uint32_t)h->scan_warps, stages = (uint32_t)h->scan_stages;
+    while (!scan_plan(h->qt, h->C, mode, warps, stages, (uint32_t)h->scan_tile_chunks, kScanSmemLimit, p)) {
+        if (stages > 2) --stages;          // very long rows: the query payload crowds the rings out
+        else if (warps > 8) warps = 8;
+        else return fail(SZG_EINVAL, "dimension %d needs more shared memory than one SM has", h->dim);
+    }
+    const uint32_t nblk = (h->nslots + 31) / 32;
+    uint32_t g = (nblk + p->warps - 1) / p->warps;
+    g = std::max<uint32_t>(1, std::min<uint32_t>(g, (uint32_t)h->sm_count));
+    *grid = (int)g;
     return SZG_OK;
 }
 
@@ -308,13 +315,12 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
     const size_t stride = pq_stride(h);
     int rc;
     if ((rc = ws->d_pq.ensure(stride * nq))) return rc;
-    const size_t smem = scan_smem_bytes(h->qt, h->C, mode);
+    ScanPlan plan;
     int grid = 0;
-    if ((rc = scan_grid(h, mode, smem, &grid))) return rc;
+    if ((rc = plan_scan(h, mode, &plan, &grid))) return rc;
     const int ns = std::max(1, std::min(h->nstreams, kMaxStreams));
     const size_t Kp = 32u << mode;
-    for (int s = 0; s < ns; ++s)
-        if ((rc = ws->d_cand[s].ensure((size_t)grid * Kp))) return rc;
+    if ((rc = ws->d_cand.ensure((size_t)nq * grid * Kp))) return rc;
 
     cudaStream_t main = ws->main;
     PrepArgs pa;
@@ -345,19 +351,15 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
     fill_scan_args(h, a, mask);
     a.k = k;
     a.flags = flags & SZG_F_NO_FP64_VERIFY;
+    a.Ct = plan.Ct; a.stages = plan.stages; a.ring_off = plan.ring_off;
     for (uint32_t i = 0; i < nq; ++i) {
         const int s = (int)(i % used);
         cudaStream_t st = s == 0 ? main : ws->helper[s];
         a.pq = ws->d_pq.p + stride * i;
         a.q = d_q + (size_t)i * h->dim;
-        a.cand = ws->d_cand[s].p;
-        a.ticket = ws->d_ticket.p + s;
-        a.out_ids = d_out_ids + (size_t)i * k;
-        a.out_dist = d_out_dist + (size_t)i * k;
-        a.out_n = d_out_n + i;
-        a.out_flags = d_out_flags + i;
+        a.cand = ws->d_cand.p + (size_t)i * grid * Kp;
         if (timing) CK(cudaEventRecord(ws->t0[tbase + i], st));
-        CK(launch_scan(h->qt, mode, grid, smem, st, a));
+        CK(launch_scan(h->qt, mode, grid, (int)plan.warps * 32, plan.smem, st, a));
         if (timing) CK(cudaEventRecord(ws->t1[tbase + i], st));
         h->launches++;
     }
@@ -366,6 +368,14 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
         CK(cudaEventRecord(ws->ev_join[s], ws->helper[s]));
         CK(cudaStreamWaitEvent(main, ws->ev_join[s], 0));
     }
+    // one finalize launch for the whole call: merge of the per-CTA lists, fp64 re-score, ordered output
+    FinalizeArgs f;
+    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.queries = d_q; f.cand = ws->d_cand.p;
+    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
+    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.ncta = (uint32_t)grid;
+    f.out_ids = d_out_ids; f.out_dist = d_out_dist; f.out_n = d_out_n; f.out_flags = d_out_flags;
+    CK(launch_finalize(h->qt, mode, nq, main, f));
+    h->launches++;
     return SZG_OK;
 }
 
@@ -427,7 +437,7 @@ int szg_create(int dim, int quantization, int metric, int device, szg_index **ou
     h->C = (h->rowbytes + 15) / 16;
     h->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&h->mut_stream, cudaStreamNonBlocking));
-    CK(scan_configure(qt, 160 * 1024));
+    CK(scan_configure(qt, kScanSmemLimit));
     if (quantization <= 16) {
         const size_t n = (size_t)1 << quantization;
         std::vector<double> lut(n);
@@ -468,6 +478,18 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
     case SZG_OPT_TIMING:
         if (value < 0 || value > 2) return fail(SZG_EINVAL, "timing must be 0, 1 or 2");
         h->timing = (int)value;
+        return SZG_OK;
+    case SZG_OPT_SCAN_WARPS:
+        if (value != 8 && value != 16) return fail(SZG_EINVAL, "scan warps must be 8 or 16");
+        h->scan_warps = (int)value;
+        return SZG_OK;
+    case SZG_OPT_SCAN_STAGES:
+        if (value < 2 || value > kMaxStages) return fail(SZG_EINVAL, "scan stages must be in [2, %d]", kMaxStages);
+        h->scan_stages = (int)value;
+        return SZG_OK;
+    case SZG_OPT_SCAN_TILE_CHUNKS:
+        if (value < 1 || value > kMaxTileChunks) return fail(SZG_EINVAL, "tile chunks must be in [1, %d]", kMaxTileChunks);
+        h->scan_tile_chunks = (int)value;
         return SZG_OK;
     case SZG_OPT_MIN_CANDIDATE_MODE:
         if (value < -1 || value > 3) return fail(SZG_EINVAL, "candidate mode must be in [-1, 3]");
@@ -803,10 +825,10 @@ int szg_search_radius(szg_index *h, const double *query, double radius, int mask
     pa.qt = h->qt; pa.radius_mode = 1; pa.radius = radius;
     CK(launch_prep(1, st, pa));
     h->launches++;
-    const size_t smem = scan_smem_bytes(h->qt, h->C, MODE_RADIUS);
+    ScanPlan plan;
     int grid = 0;
-    if ((rc = scan_grid(h, MODE_RADIUS, smem, &grid))) return rc;
-    unsigned int *d_count = ws->d_ticket.p + kMaxStreams;
+    if ((rc = plan_scan(h, MODE_RADIUS, &plan, &grid))) return rc;
+    unsigned int *d_count = ws->d_ticket.p;
     uint32_t count = 0;
     size_t cap = std::max<size_t>(4096, h->nslots / 64);
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -816,7 +838,8 @@ int szg_search_radius(szg_index *h, const double *query, double radius, int mask
         fill_scan_args(h, a, mask);
         a.pq = ws->d_pq.p; a.q = ws->d_q.p;
         a.rad_count = d_count; a.rad_slots = ws->d_slots.p; a.rad_cap = (uint32_t)ws->d_slots.n;
-        CK(launch_scan(h->qt, MODE_RADIUS, grid, smem, st, a));
+        a.Ct = plan.Ct; a.stages = plan.stages; a.ring_off = plan.ring_off;
+        CK(launch_scan(h->qt, MODE_RADIUS, grid, (int)plan.warps * 32, plan.smem, st, a));
         h->launches++;
         CK(cudaMemcpyAsync(ws->h_out_n.p, d_count, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -917,10 +940,14 @@ int szg_get_stats(szg_index *h, szg_stats *out) {
     out->pitch = h->C * 16;
     out->sm_count = (uint32_t)h->sm_count;
     int grid = 0;
-    int rc = scan_grid(h, 0, scan_smem_bytes(h->qt, h->C, 0), &grid);
+    ScanPlan plan;
+    int rc = plan_scan(h, 0, &plan, &grid);
     if (rc) return rc;
     out->scan_grid = (uint32_t)grid;
-    out->scan_block = kScanThreads;
+    out->scan_block = plan.warps * 32;
+    out->scan_stages = plan.stages;
+    out->scan_tile_bytes = plan.Ct * 512;
+    out->scan_smem_bytes = (uint32_t)plan.smem;
     return SZG_OK;
 }
 

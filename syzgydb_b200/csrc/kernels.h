@@ -16,9 +16,10 @@ struct PrepArgs {
 cudaError_t launch_prep(uint32_t nq, cudaStream_t st, const PrepArgs &a);
 
 // scan: one instantiation file per quantization
-cudaError_t launch_scan(int qt, int mode, int grid, size_t smem, cudaStream_t st, const ScanArgs &a);
+cudaError_t launch_scan(int qt, int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a);
+// one launch for all nq queries of a call: merges each query's per-CTA lists, fp64 re-score, ordered output
+cudaError_t launch_finalize(int qt, int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a);
 cudaError_t scan_configure(int qt, size_t max_smem);
-cudaError_t scan_occupancy(int qt, int mode, size_t smem, int *blocks_per_sm);
 
 struct RowsArgs {
     uint4 *codes;

@@ -4,19 +4,30 @@
 namespace szg {
 
 #define SZG_DECL(l)                                                                              \
-    cudaError_t launch_scan_##l(int, int, size_t, cudaStream_t, const ScanArgs &);               \
-    cudaError_t scan_attr_##l(size_t);                                                           \
-    cudaError_t scan_occ_##l(int, size_t, int *);
+    cudaError_t launch_scan_##l(int, int, int, size_t, cudaStream_t, const ScanArgs &);          \
+    cudaError_t launch_finalize_##l(int, uint32_t, cudaStream_t, const FinalizeArgs &);           \
+    cudaError_t scan_attr_##l(size_t);
 SZG_DECL(q4) SZG_DECL(q8) SZG_DECL(q16) SZG_DECL(f32) SZG_DECL(f64)
 #undef SZG_DECL
 
-cudaError_t launch_scan(int qt, int mode, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
+cudaError_t launch_scan(int qt, int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
     switch (qt) {
-    case Q4: return launch_scan_q4(mode, grid, smem, st, a);
-    case Q8: return launch_scan_q8(mode, grid, smem, st, a);
-    case Q16: return launch_scan_q16(mode, grid, smem, st, a);
-    case F32: return launch_scan_f32(mode, grid, smem, st, a);
-    case F64: return launch_scan_f64(mode, grid, smem, st, a);
+    case Q4: return launch_scan_q4(mode, grid, threads, smem, st, a);
+    case Q8: return launch_scan_q8(mode, grid, threads, smem, st, a);
+    case Q16: return launch_scan_q16(mode, grid, threads, smem, st, a);
+    case F32: return launch_scan_f32(mode, grid, threads, smem, st, a);
+    case F64: return launch_scan_f64(mode, grid, threads, smem, st, a);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_finalize(int qt, int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a) {
+    switch (qt) {
+    case Q4: return launch_finalize_q4(mode, nq, st, a);
+    case Q8: return launch_finalize_q8(mode, nq, st, a);
+    case Q16: return launch_finalize_q16(mode, nq, st, a);
+    case F32: return launch_finalize_f32(mode, nq, st, a);
+    case F64: return launch_finalize_f64(mode, nq, st, a);
     }
     return cudaErrorInvalidValue;
 }
@@ -28,17 +39,6 @@ cudaError_t scan_configure(int qt, size_t max_smem) {
     case Q16: return scan_attr_q16(max_smem);
     case F32: return scan_attr_f32(max_smem);
     case F64: return scan_attr_f64(max_smem);
-    }
-    return cudaErrorInvalidValue;
-}
-
-cudaError_t scan_occupancy(int qt, int mode, size_t smem, int *bps) {
-    switch (qt) {
-    case Q4: return scan_occ_q4(mode, smem, bps);
-    case Q8: return scan_occ_q8(mode, smem, bps);
-    case Q16: return scan_occ_q16(mode, smem, bps);
-    case F32: return scan_occ_f32(mode, smem, bps);
-    case F64: return scan_occ_f64(mode, smem, bps);
     }
     return cudaErrorInvalidValue;
 }

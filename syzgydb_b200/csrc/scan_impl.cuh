@@ -5,7 +5,15 @@
 //
 // Replaces, per record: getDocument/decodeVector (collection.go:470-484, 768-794), the
 // distance call (596) and the heap logic of `consider` (598-628) -- N calls become one
-// kernel.  HBM-bound: every code byte is read exactly once with coalesced 128-bit loads.
+// kernel.  HBM-bound: every code byte is read exactly once.
+//
+// Data movement: persistent CTAs, one per SM.  A 32-row block of the
+// column-blocked layout is one contiguous span of C*512 bytes, cut into tiles of Ct chunks.
+// Every warp owns a private ring of S shared-memory stages and streams its blocks tile by
+// tile with cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on an mbarrier per
+// stage; one elected lane issues the copies S tiles ahead, all 32 lanes (one row each)
+// consume a stage with conflict-free LDS.128.  Bytes in flight per SM = warps * S * tile,
+// independent of the register file, which is what a latency-bound stream needs.
 //
 // Arithmetic: for 4/8/16-bit codes the row-dependent part of both
 // metrics is I = sum_i u_i * W_i with W_i = round(w_i * 2^F) a 21-bit fixed-point copy of
@@ -18,8 +26,9 @@
 
 namespace szg {
 
-constexpr int kScanThreads = 256;
-constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kMaxScanWarps = 16;       // warps per CTA is a launch parameter (8 or 16)
+constexpr int kMaxStages = 8;           // ring stages per warp (launch parameter, 2..8)
+constexpr int kMaxTileChunks = 32;      // chunks per tile (Q16 flushes int32 partials per tile)
 constexpr int kMaxListE = 8;            // candidates per lane; candidate set = 32 * E
 constexpr int MODE_RADIUS = 4;          // MODE 0..3: top-k with E = 1 << MODE
 
@@ -34,18 +43,59 @@ struct ScanArgs {
     const double *q;            // raw float64 query (re-score)
     uint32_t C, nblk, dims, metric;
     uint32_t k, flags;
-    // top-k workspace / outputs
+    // streaming geometry (host-chosen, see scan_plan)
+    uint32_t Ct;                // chunks per tile
+    uint32_t stages;            // ring stages per warp
+    uint32_t ring_off;          // byte offset of the rings in dynamic shared memory
+    // top-k output: this query's per-CTA candidate lists, consumed by finalize_kernel
     unsigned long long *cand;   // [gridDim.x][32*E]
-    unsigned int *ticket;
-    unsigned long long *out_ids;
-    double *out_dist;
-    uint32_t *out_n;
-    uint32_t *out_flags;        // bit0: candidate margin below tolerance ("uncertain")
     // radius outputs
     uint32_t *rad_count;
     uint32_t *rad_slots;
     uint32_t rad_cap;
 };
+
+// One finalize launch serves every query of a call: CTA q merges the per-CTA candidate lists of
+// query q's scan, re-scores the survivors in fp64 and writes the ordered result.
+struct FinalizeArgs {
+    const uint4 *codes;
+    const unsigned long long *ids;
+    const double *lut;
+    const double *queries;            // [nq][dims] raw float64 queries
+    const unsigned long long *cand;   // [nq][ncta][32*E]
+    uint32_t C, dims, metric, k, flags, ncta;
+    unsigned long long *out_ids;      // [nq][k]
+    double *out_dist;                 // [nq][k]
+    uint32_t *out_n;                  // [nq]
+    uint32_t *out_flags;              // [nq] bit0: candidate margin below tolerance ("uncertain")
+};
+
+// ------------------------------------------------------------------ mbarrier / bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, non-tensor form), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // ------------------------------------------------------------------ per-warp sorted list
 template <int E>
@@ -78,9 +128,36 @@ struct WarpList {
         else if (lane == p && cnt == 0) v[0] = nk;
         thr = __shfl_sync(0xffffffffu, v[E - 1], 31);
     }
+    // E == 1 only: merge a batch of 32 keys (one per lane) with two bitonic networks
+    // (sort the batch, then merge with the sorted list): bounded cost when many keys pass.
+    __device__ __forceinline__ void merge_batch(unsigned long long ck, int lane) {
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long o = __shfl_xor_sync(0xffffffffu, ck, j);
+                bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+                ck = keep_min ? (ck < o ? ck : o) : (ck > o ? ck : o);
+            }
+        }
+        unsigned long long rev = __shfl_sync(0xffffffffu, ck, 31 - lane); // descending batch
+        unsigned long long m = v[0] < rev ? v[0] : rev;                   // bitonic: the 32 smallest of the union
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, m, j);
+            bool keep_min = (lane & j) == 0;
+            m = keep_min ? (m < o ? m : o) : (m > o ? m : o);
+        }
+        v[0] = m;
+        thr = __shfl_sync(0xffffffffu, m, 31);
+    }
     // every lane offers one key (kNoKey = nothing)
     __device__ __forceinline__ void offer(unsigned long long ck, int lane) {
         unsigned m = __ballot_sync(0xffffffffu, ck < thr);
+        if (E == 1 && __popc(m) > 5) {
+            merge_batch(ck, lane);
+            return;
+        }
         while (m) {
             int src = __ffs(m) - 1;
             m &= m - 1;
@@ -91,10 +168,10 @@ struct WarpList {
 };
 
 // ascending bitonic sort of n (power of two) keys in shared memory by the whole CTA
-__device__ __forceinline__ void block_bitonic_sort(unsigned long long *s, int n, int tid) {
+__device__ __forceinline__ void block_bitonic_sort(unsigned long long *s, int n, int tid, int nthreads) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n; i += kScanThreads) {
+            for (int i = tid; i < n; i += nthreads) {
                 int ixj = i ^ j;
                 if (ixj > i) {
                     unsigned long long a = s[i], b = s[ixj];
@@ -109,11 +186,11 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long *s, int n,
 
 template <int E>
 __device__ __forceinline__ void block_merge(const WarpList<E> &L, unsigned long long *pool, int tid, int lane,
-                                            int warp) {
+                                            int warp, int nwarps) {
 #pragma unroll
     for (int e = 0; e < E; ++e) pool[(warp * 32 + lane) * E + e] = L.v[e];
     __syncthreads();
-    block_bitonic_sort(pool, kScanWarps * 32 * E, tid);
+    block_bitonic_sort(pool, nwarps * 32 * E, tid, nwarps * 32);
 }
 
 // ------------------------------------------------------------------------- row scoring
@@ -124,26 +201,45 @@ __device__ __forceinline__ double digits_total(const int (&a)[ND]) {
     return t;
 }
 
+// aux value of one row, fetched when its block starts so that the latency hides behind the tiles
+struct RowAux {
+    float rn;      // cosine: 1/||x||
+    double s2;     // euclid, quantized: sum of squared (centred) codes
+};
 template <int QT>
-__device__ __forceinline__ float finish_quant(const ScanArgs &a, const PQHeader &h, double I, uint32_t slot) {
+__device__ __forceinline__ RowAux load_aux(const ScanArgs &a, uint32_t slot) {
+    RowAux r;
+    r.rn = 0.f;
+    r.s2 = 0.0;
+    if (a.metric == COSINE) r.rn = reinterpret_cast<const float *>(a.aux)[slot];
+    else if (QT == Q16) r.s2 = (double)reinterpret_cast<const unsigned long long *>(a.aux)[slot];
+    else if (QT <= Q8) r.s2 = (double)reinterpret_cast<const uint32_t *>(a.aux)[slot];
+    return r;
+}
+
+__device__ __forceinline__ float finish_quant(const ScanArgs &a, const PQHeader &h, double I, const RowAux &x) {
     if (a.metric == COSINE) {
-        float rn = reinterpret_cast<const float *>(a.aux)[slot];
         double num = 2.0 * I + h.numc;
-        float c = (float)(num * h.c_key) * rn;
-        return (h.zero_query || rn == 0.f) ? 1.0f : -c;
+        float c = (float)(num * h.c_key) * x.rn;
+        return (h.zero_query || x.rn == 0.f) ? 1.0f : -c;
     }
-    double s2 = (QT == Q16) ? (double)reinterpret_cast<const unsigned long long *>(a.aux)[slot]
-                            : (double)reinterpret_cast<const uint32_t *>(a.aux)[slot];
-    double Ev = fma(-h.pow2F1, I, fma(s2, h.pow2F2, h.base));
+    double Ev = fma(-h.pow2F1, I, fma(x.s2, h.pow2F2, h.base));
     return (float)(Ev * h.c_key);
 }
 
+// A Scorer accumulates one row (one lane) over the tiles of its block:
+//   reset(acc); tile(acc, stage + lane, n, spq + c0 * bytes_per_chunk, metric) per tile; finish(...) -> key
 template <int QT>
 struct Scorer;
 
 // 8-bit codes: 16 dims per chunk, payload = ND uint4 of digits per chunk
 template <>
 struct Scorer<Q8> {
+    struct Acc { int a[ND]; };
+    static __device__ __forceinline__ void reset(Acc &s) {
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s.a[j] = 0;
+    }
     static __device__ __forceinline__ void step(const uint4 &v, const uint4 *dg, int (&acc)[ND]) {
 #pragma unroll
         for (int j = 0; j < ND; ++j) {
@@ -154,36 +250,25 @@ struct Scorer<Q8> {
             acc[j] = dp4a_us(v.w, (int)d.w, acc[j]);
         }
     }
-    static __device__ __forceinline__ void run(const ScanArgs &a, const unsigned char *spq, const PQHeader &h,
-                                               const uint4 *p0, const uint4 *p1, uint32_t slot0, uint32_t slot1,
-                                               float (&key)[2]) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int) {
         const uint4 *dg = reinterpret_cast<const uint4 *>(spq);
-        const uint32_t C = a.C;
-        int acc0[ND], acc1[ND];
+        int b[ND]; // second accumulator set: shortens the dependent IDP chains
 #pragma unroll
-        for (int j = 0; j < ND; ++j) acc0[j] = acc1[j] = 0;
-        constexpr int U = 4;
+        for (int j = 0; j < ND; ++j) b[j] = 0;
         uint32_t c = 0;
-        for (; c + U <= C; c += U) {
-            uint4 v0[U], v1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                v0[u] = ldg_stream(p0 + (size_t)(c + u) * 32);
-                v1[u] = ldg_stream(p1 + (size_t)(c + u) * 32);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                step(v0[u], dg + (c + u) * ND, acc0);
-                step(v1[u], dg + (c + u) * ND, acc1);
-            }
+        for (; c + 4 <= n; c += 4) {
+            uint4 v0 = sd[(c + 0) * 32], v1 = sd[(c + 1) * 32], v2 = sd[(c + 2) * 32], v3 = sd[(c + 3) * 32];
+            step(v0, dg + (c + 0) * ND, s.a);
+            step(v1, dg + (c + 1) * ND, b);
+            step(v2, dg + (c + 2) * ND, s.a);
+            step(v3, dg + (c + 3) * ND, b);
         }
-        for (; c < C; ++c) {
-            uint4 v0 = ldg_stream(p0 + (size_t)c * 32), v1 = ldg_stream(p1 + (size_t)c * 32);
-            step(v0, dg + c * ND, acc0);
-            step(v1, dg + c * ND, acc1);
-        }
-        key[0] = finish_quant<Q8>(a, h, digits_total(acc0), slot0);
-        key[1] = finish_quant<Q8>(a, h, digits_total(acc1), slot1);
+        for (; c < n; ++c) step(sd[c * 32], dg + c * ND, s.a);
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s.a[j] += b[j];
+    }
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+        return finish_quant(a, h, digits_total(s.a), x);
     }
 };
 
@@ -191,6 +276,11 @@ struct Scorer<Q8> {
 // ND uint4 for the even dims (applied to w & 0xF0F0F0F0, i.e. 16*u) + ND uint4 for the odd.
 template <>
 struct Scorer<Q4> {
+    struct Acc { int hi[ND], lo[ND]; };
+    static __device__ __forceinline__ void reset(Acc &s) {
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s.hi[j] = s.lo[j] = 0;
+    }
     static __device__ __forceinline__ void step(const uint4 &v, const uint4 *dg, int (&hi)[ND], int (&lo)[ND]) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -204,47 +294,29 @@ struct Scorer<Q4> {
             }
         }
     }
-    static __device__ __forceinline__ void run(const ScanArgs &a, const unsigned char *spq, const PQHeader &h,
-                                               const uint4 *p0, const uint4 *p1, uint32_t slot0, uint32_t slot1,
-                                               float (&key)[2]) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int) {
         const uint4 *dg = reinterpret_cast<const uint4 *>(spq);
-        const uint32_t C = a.C;
-        int hi0[ND], lo0[ND], hi1[ND], lo1[ND];
-#pragma unroll
-        for (int j = 0; j < ND; ++j) hi0[j] = lo0[j] = hi1[j] = lo1[j] = 0;
-        constexpr int U = 4;
         uint32_t c = 0;
-        for (; c + U <= C; c += U) {
-            uint4 v0[U], v1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                v0[u] = ldg_stream(p0 + (size_t)(c + u) * 32);
-                v1[u] = ldg_stream(p1 + (size_t)(c + u) * 32);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                step(v0[u], dg + (c + u) * 2 * ND, hi0, lo0);
-                step(v1[u], dg + (c + u) * 2 * ND, hi1, lo1);
-            }
+        for (; c + 2 <= n; c += 2) {
+            uint4 v0 = sd[(c + 0) * 32], v1 = sd[(c + 1) * 32];
+            step(v0, dg + (c + 0) * 2 * ND, s.hi, s.lo);
+            step(v1, dg + (c + 1) * 2 * ND, s.hi, s.lo);
         }
-        for (; c < C; ++c) {
-            uint4 v0 = ldg_stream(p0 + (size_t)c * 32), v1 = ldg_stream(p1 + (size_t)c * 32);
-            step(v0, dg + c * 2 * ND, hi0, lo0);
-            step(v1, dg + c * 2 * ND, hi1, lo1);
-        }
+        for (; c < n; ++c) step(sd[c * 32], dg + c * 2 * ND, s.hi, s.lo);
+    }
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
         // hi accumulates 16 * u_even * W: I = hi/16 + lo (exact in double)
-        double I0 = digits_total(hi0) * 0.0625 + digits_total(lo0);
-        double I1 = digits_total(hi1) * 0.0625 + digits_total(lo1);
-        key[0] = finish_quant<Q4>(a, h, I0, slot0);
-        key[1] = finish_quant<Q4>(a, h, I1, slot1);
+        return finish_quant(a, h, digits_total(s.hi) * 0.0625 + digits_total(s.lo), x);
     }
 };
 
 // 16-bit codes, stored as little-endian int16 of (u - 32768): 8 dims per chunk, payload =
 // ND uint2 of digits per chunk.  |s16 * s8| <= 2^22, so int32 partials are flushed to
-// double every 32 chunks (256 dims).
+// double at the end of every tile (<= 32 chunks = 256 dims).
 template <>
 struct Scorer<Q16> {
+    struct Acc { double I; };
+    static __device__ __forceinline__ void reset(Acc &s) { s.I = 0.0; }
     static __device__ __forceinline__ void step(const uint4 &v, const uint2 *dg, int (&acc)[ND]) {
 #pragma unroll
         for (int j = 0; j < ND; ++j) {
@@ -255,49 +327,32 @@ struct Scorer<Q16> {
             acc[j] = dp2a_hi_ss((int)v.w, (int)d.y, acc[j]);
         }
     }
-    static __device__ __forceinline__ void run(const ScanArgs &a, const unsigned char *spq, const PQHeader &h,
-                                               const uint4 *p0, const uint4 *p1, uint32_t slot0, uint32_t slot1,
-                                               float (&key)[2]) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int) {
         const uint2 *dg = reinterpret_cast<const uint2 *>(spq);
-        const uint32_t C = a.C;
-        double I0 = 0.0, I1 = 0.0;
-        constexpr uint32_t W = 32;
-        for (uint32_t cw = 0; cw < C; cw += W) {
-            const uint32_t cend = min(C, cw + W);
-            int acc0[ND], acc1[ND];
+        int acc[ND];
 #pragma unroll
-            for (int j = 0; j < ND; ++j) acc0[j] = acc1[j] = 0;
-            constexpr int U = 4;
-            uint32_t c = cw;
-            for (; c + U <= cend; c += U) {
-                uint4 v0[U], v1[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    v0[u] = ldg_stream(p0 + (size_t)(c + u) * 32);
-                    v1[u] = ldg_stream(p1 + (size_t)(c + u) * 32);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    step(v0[u], dg + (c + u) * ND, acc0);
-                    step(v1[u], dg + (c + u) * ND, acc1);
-                }
-            }
-            for (; c < cend; ++c) {
-                uint4 v0 = ldg_stream(p0 + (size_t)c * 32), v1 = ldg_stream(p1 + (size_t)c * 32);
-                step(v0, dg + c * ND, acc0);
-                step(v1, dg + c * ND, acc1);
-            }
-            I0 += digits_total(acc0);
-            I1 += digits_total(acc1);
+        for (int j = 0; j < ND; ++j) acc[j] = 0;
+        uint32_t c = 0;
+        for (; c + 4 <= n; c += 4) {
+            uint4 v0 = sd[(c + 0) * 32], v1 = sd[(c + 1) * 32], v2 = sd[(c + 2) * 32], v3 = sd[(c + 3) * 32];
+            step(v0, dg + (c + 0) * ND, acc);
+            step(v1, dg + (c + 1) * ND, acc);
+            step(v2, dg + (c + 2) * ND, acc);
+            step(v3, dg + (c + 3) * ND, acc);
         }
-        key[0] = finish_quant<Q16>(a, h, I0, slot0);
-        key[1] = finish_quant<Q16>(a, h, I1, slot1);
+        for (; c < n; ++c) step(sd[c * 32], dg + c * ND, acc);
+        s.I += digits_total(acc);
+    }
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+        return finish_quant(a, h, s.I, x);
     }
 };
 
 // 32-bit float rows: payload = the query as float4 per chunk
 template <>
 struct Scorer<F32> {
+    struct Acc { float a[4]; };
+    static __device__ __forceinline__ void reset(Acc &s) { s.a[0] = s.a[1] = s.a[2] = s.a[3] = 0.f; }
     template <int METRIC>
     static __device__ __forceinline__ void step(const uint4 &v, const float4 &q, float (&acc)[4]) {
         const float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
@@ -309,56 +364,34 @@ struct Scorer<F32> {
         }
     }
     template <int METRIC>
-    static __device__ __forceinline__ void loop(const ScanArgs &a, const float4 *sq, const uint4 *p0, const uint4 *p1,
-                                                float &r0, float &r1) {
-        const uint32_t C = a.C;
-        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-        constexpr int U = 4;
+    static __device__ __forceinline__ void loop(Acc &s, const uint4 *sd, uint32_t n, const float4 *sq) {
         uint32_t c = 0;
-        for (; c + U <= C; c += U) {
-            uint4 v0[U], v1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                v0[u] = ldg_stream(p0 + (size_t)(c + u) * 32);
-                v1[u] = ldg_stream(p1 + (size_t)(c + u) * 32);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float4 q = sq[c + u];
-                step<METRIC>(v0[u], q, acc0);
-                step<METRIC>(v1[u], q, acc1);
-            }
+        for (; c + 4 <= n; c += 4) {
+            uint4 v0 = sd[(c + 0) * 32], v1 = sd[(c + 1) * 32], v2 = sd[(c + 2) * 32], v3 = sd[(c + 3) * 32];
+            step<METRIC>(v0, sq[c + 0], s.a);
+            step<METRIC>(v1, sq[c + 1], s.a);
+            step<METRIC>(v2, sq[c + 2], s.a);
+            step<METRIC>(v3, sq[c + 3], s.a);
         }
-        for (; c < C; ++c) {
-            float4 q = sq[c];
-            step<METRIC>(ldg_stream(p0 + (size_t)c * 32), q, acc0);
-            step<METRIC>(ldg_stream(p1 + (size_t)c * 32), q, acc1);
-        }
-        r0 = (acc0[0] + acc0[1]) + (acc0[2] + acc0[3]);
-        r1 = (acc1[0] + acc1[1]) + (acc1[2] + acc1[3]);
+        for (; c < n; ++c) step<METRIC>(sd[c * 32], sq[c], s.a);
     }
-    static __device__ __forceinline__ void run(const ScanArgs &a, const unsigned char *spq, const PQHeader &h,
-                                               const uint4 *p0, const uint4 *p1, uint32_t slot0, uint32_t slot1,
-                                               float (&key)[2]) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int metric) {
         const float4 *sq = reinterpret_cast<const float4 *>(spq);
-        float r0, r1;
-        if (a.metric == COSINE) {
-            loop<COSINE>(a, sq, p0, p1, r0, r1);
-            const float *rn = reinterpret_cast<const float *>(a.aux);
-            float rn0 = rn[slot0], rn1 = rn[slot1], ck = (float)h.c_key;
-            key[0] = (h.zero_query || rn0 == 0.f) ? 1.0f : -(r0 * ck) * rn0;
-            key[1] = (h.zero_query || rn1 == 0.f) ? 1.0f : -(r1 * ck) * rn1;
-        } else {
-            loop<EUCLID>(a, sq, p0, p1, r0, r1);
-            key[0] = r0;
-            key[1] = r1;
-        }
+        if (metric == COSINE) loop<COSINE>(s, sd, n, sq);
+        else loop<EUCLID>(s, sd, n, sq);
+    }
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+        const float r = (s.a[0] + s.a[1]) + (s.a[2] + s.a[3]);
+        if (a.metric == COSINE) return (h.zero_query || x.rn == 0.f) ? 1.0f : -(r * (float)h.c_key) * x.rn;
+        return r;
     }
 };
 
 // 64-bit float rows: payload = the query as double2 per chunk
 template <>
 struct Scorer<F64> {
+    struct Acc { double a[2]; };
+    static __device__ __forceinline__ void reset(Acc &s) { s.a[0] = s.a[1] = 0.0; }
     template <int METRIC>
     static __device__ __forceinline__ void step(const uint4 &v, const double2 &q, double (&acc)[2]) {
         const double x0 = __hiloint2double((int)v.y, (int)v.x), x1 = __hiloint2double((int)v.w, (int)v.z);
@@ -372,50 +405,26 @@ struct Scorer<F64> {
         }
     }
     template <int METRIC>
-    static __device__ __forceinline__ void loop(const ScanArgs &a, const double2 *sq, const uint4 *p0, const uint4 *p1,
-                                                double &r0, double &r1) {
-        const uint32_t C = a.C;
-        double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
-        constexpr int U = 4;
+    static __device__ __forceinline__ void loop(Acc &s, const uint4 *sd, uint32_t n, const double2 *sq) {
         uint32_t c = 0;
-        for (; c + U <= C; c += U) {
-            uint4 v0[U], v1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                v0[u] = ldg_stream(p0 + (size_t)(c + u) * 32);
-                v1[u] = ldg_stream(p1 + (size_t)(c + u) * 32);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                double2 q = sq[c + u];
-                step<METRIC>(v0[u], q, acc0);
-                step<METRIC>(v1[u], q, acc1);
-            }
+        for (; c + 4 <= n; c += 4) {
+            uint4 v0 = sd[(c + 0) * 32], v1 = sd[(c + 1) * 32], v2 = sd[(c + 2) * 32], v3 = sd[(c + 3) * 32];
+            step<METRIC>(v0, sq[c + 0], s.a);
+            step<METRIC>(v1, sq[c + 1], s.a);
+            step<METRIC>(v2, sq[c + 2], s.a);
+            step<METRIC>(v3, sq[c + 3], s.a);
         }
-        for (; c < C; ++c) {
-            double2 q = sq[c];
-            step<METRIC>(ldg_stream(p0 + (size_t)c * 32), q, acc0);
-            step<METRIC>(ldg_stream(p1 + (size_t)c * 32), q, acc1);
-        }
-        r0 = acc0[0] + acc0[1];
-        r1 = acc1[0] + acc1[1];
+        for (; c < n; ++c) step<METRIC>(sd[c * 32], sq[c], s.a);
     }
-    static __device__ __forceinline__ void run(const ScanArgs &a, const unsigned char *spq, const PQHeader &h,
-                                               const uint4 *p0, const uint4 *p1, uint32_t slot0, uint32_t slot1,
-                                               float (&key)[2]) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int metric) {
         const double2 *sq = reinterpret_cast<const double2 *>(spq);
-        double r0, r1;
-        if (a.metric == COSINE) {
-            loop<COSINE>(a, sq, p0, p1, r0, r1);
-            const float *rn = reinterpret_cast<const float *>(a.aux);
-            float rn0 = rn[slot0], rn1 = rn[slot1];
-            key[0] = (h.zero_query || rn0 == 0.f) ? 1.0f : -((float)(r0 * h.c_key)) * rn0;
-            key[1] = (h.zero_query || rn1 == 0.f) ? 1.0f : -((float)(r1 * h.c_key)) * rn1;
-        } else {
-            loop<EUCLID>(a, sq, p0, p1, r0, r1);
-            key[0] = (float)r0;
-            key[1] = (float)r1;
-        }
+        if (metric == COSINE) loop<COSINE>(s, sd, n, sq);
+        else loop<EUCLID>(s, sd, n, sq);
+    }
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+        const double r = s.a[0] + s.a[1];
+        if (a.metric == COSINE) return (h.zero_query || x.rn == 0.f) ? 1.0f : -((float)(r * h.c_key)) * x.rn;
+        return (float)r;
     }
 };
 
@@ -423,8 +432,9 @@ struct Scorer<F64> {
 // pool[0 .. K') holds the K' best (surrogate, slot) keys, ascending.  Re-scores them in
 // fp64, orders by (distance, lexicographic id) and writes min(k, #) results.
 template <int QT>
-__device__ void finalize_topk(const ScanArgs &a, const unsigned long long *pool, int Kp, double *s_ex,
-                              unsigned long long *s_id, int tid) {
+__device__ void finalize_topk(const FinalizeArgs &a, const double *q, unsigned long long *out_ids, double *out_dist,
+                              uint32_t *out_n, uint32_t *out_flags, const unsigned long long *pool, int Kp,
+                              double *s_ex, unsigned long long *s_id, int tid) {
     __shared__ double s_dk, s_dmax;
     if (tid == 0) { s_dk = 0.0; s_dmax = 0.0; }
     bool valid = false;
@@ -436,7 +446,7 @@ __device__ void finalize_topk(const ScanArgs &a, const unsigned long long *pool,
             uint32_t slot = (uint32_t)key;
             id = a.ids[slot];
             if (a.flags & 1u) d = key_to_distance(a.metric, key_to_float((uint32_t)(key >> 32)));
-            else d = exact_distance<QT>(a.codes, a.C, a.dims, a.metric, a.lut, a.q, slot);
+            else d = exact_distance<QT>(a.codes, a.C, a.dims, a.metric, a.lut, q, slot);
             valid = (d == d); // NaN is never returned
         }
         s_ex[tid] = valid ? d : __longlong_as_double(0x7ff8000000000000ll);
@@ -452,8 +462,8 @@ __device__ void finalize_topk(const ScanArgs &a, const unsigned long long *pool,
             if (j != tid && dj == dj && (dj < d || (dj == d && lex_less_u64(s_id[j], id)))) ++rank;
         }
         if ((uint32_t)rank < a.k) {
-            a.out_ids[rank] = id;
-            a.out_dist[rank] = d;
+            out_ids[rank] = id;
+            out_dist[rank] = d;
         }
         if ((uint32_t)rank + 1 == a.k) s_dk = d;
         if (rank == cnt - 1) s_dmax = d;
@@ -461,57 +471,142 @@ __device__ void finalize_topk(const ScanArgs &a, const unsigned long long *pool,
     __syncthreads();
     if (tid == 0) {
         uint32_t n = (uint32_t)cnt < a.k ? (uint32_t)cnt : a.k;
-        *a.out_n = n;
+        *out_n = n;
         // all non-candidates have a surrogate no better than the worst candidate; the result is
         // certain when that candidate is clearly (1e-4 relative) farther than the k-th result
         bool uncertain = (nfull == Kp) && ((uint32_t)cnt >= a.k ? !(s_dmax > s_dk * (1.0 + 1e-4)) : true);
-        *a.out_flags = uncertain ? 1u : 0u;
+        *out_flags = uncertain ? 1u : 0u;
     }
 }
 
-// ------------------------------------------------------------------------ the scan kernel
+constexpr int kFinalizeThreads = 256;
+
 template <int QT, int MODE>
-__global__ void __launch_bounds__(kScanThreads) scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const FinalizeArgs a) {
+    constexpr int E = 1 << MODE;
+    constexpr int Kp = 32 * E;
+    constexpr int NW = kFinalizeThreads / 32;
+    extern __shared__ __align__(16) unsigned char fsm[];
+    unsigned long long *pool = reinterpret_cast<unsigned long long *>(fsm);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t qi = blockIdx.x;
+    const unsigned long long *cand = a.cand + (size_t)qi * a.ncta * Kp;
+    WarpList<E> list;
+    list.init();
+    const uint32_t total = a.ncta * Kp;
+    for (uint32_t base = warp * 32; base < total; base += kFinalizeThreads) {
+        const uint32_t i = base + lane;
+        list.offer(i < total ? cand[i] : kNoKey, lane);
+    }
+    block_merge<E>(list, pool, tid, lane, warp, NW);
+    double *s_ex = reinterpret_cast<double *>(pool + NW * Kp);
+    unsigned long long *s_id = reinterpret_cast<unsigned long long *>(s_ex + Kp);
+    finalize_topk<QT>(a, a.queries + (size_t)qi * a.dims, a.out_ids + (size_t)qi * a.k, a.out_dist + (size_t)qi * a.k,
+                      a.out_n + qi, a.out_flags + qi, pool, Kp, s_ex, s_id, tid);
+}
+inline size_t finalize_smem_bytes(int mode) {
+    const size_t Kp = 32u << mode;
+    return (size_t)(kFinalizeThreads / 32) * Kp * 8 + Kp * 16;
+}
+
+// ------------------------------------------------------------------------ the scan kernel
+// per-warp streaming state of the tile ring: which (block, tile) each stage holds
+struct RingMeta {
+    uint32_t blk[kMaxStages];   // 0xFFFFFFFF = no more tiles
+    uint32_t tile[kMaxStages];
+    uint32_t live[kMaxStages];  // live & filter word of that block
+};
+
+template <int QT, int MODE>
+__global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanArgs a) {
     constexpr int E = (MODE == MODE_RADIUS) ? 1 : (1 << MODE);
     constexpr int Kp = 32 * E;
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_last;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar[kMaxScanWarps][kMaxStages];
+    __shared__ RingMeta s_meta[kMaxScanWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
+    const uint32_t S = a.stages, Ct = a.Ct, C = a.C;
 
-    const PQHeader h = *reinterpret_cast<const PQHeader *>(a.pq);
+    __shared__ PQHeader s_hdr; // read at block ends only: keep it out of the register file
+    const PQHeader &h = s_hdr;
+    if (tid < (int)(sizeof(PQHeader) / 16))
+        reinterpret_cast<uint4 *>(&s_hdr)[tid] = reinterpret_cast<const uint4 *>(a.pq)[tid];
     {
-        const uint32_t n16 = (a.C * (uint32_t)pq_bytes_per_chunk(QT) + 15) / 16;
+        const uint32_t n16 = (C * (uint32_t)pq_bytes_per_chunk(QT) + 15) / 16;
         const uint4 *src = reinterpret_cast<const uint4 *>(a.pq + sizeof(PQHeader));
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (uint32_t i = tid; i < n16; i += kScanThreads) dst[i] = src[i];
+        for (uint32_t i = tid; i < n16; i += nthreads) dst[i] = src[i];
+    }
+    if (lane == 0) {
+        for (uint32_t s = 0; s < S; ++s) mbar_init(&s_bar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     WarpList<E> list;
     list.init();
-    const float radius_key = (float)h.radius_key;
 
-    const uint32_t npairs = (a.nblk + 1) >> 1;
-    const uint32_t total_warps = gridDim.x * kScanWarps;
-    for (uint32_t pair = blockIdx.x * kScanWarps + warp; pair < npairs; pair += total_warps) {
-        const uint32_t blk0 = pair * 2;
-        const bool has1 = blk0 + 1 < a.nblk;
-        uint32_t live0 = a.live[blk0], live1 = has1 ? a.live[blk0 + 1] : 0u;
-        if (a.mask) {
-            live0 &= a.mask[blk0];
-            if (has1) live1 &= a.mask[blk0 + 1];
+    // ---- streaming: this warp's blocks are gw, gw + stride, ...; tiles of Ct chunks
+    const uint32_t stride = gridDim.x * nwarps;
+    const uint32_t T = (C + Ct - 1) / Ct;
+    const uint32_t stage_bytes = Ct * 512u;
+    unsigned char *ring = smem + a.ring_off + (size_t)warp * S * stage_bytes;
+    RingMeta &meta = s_meta[warp];
+    uint64_t *bars = s_bar[warp];
+
+    // issue iterator (warp-uniform): next (block, tile) to fetch
+    uint32_t iblk = blockIdx.x * nwarps + warp, itile = 0, ilive = 0;
+    auto seek_live = [&]() { // advance iblk to the next block with a live, unfiltered row
+        while (iblk < a.nblk) {
+            uint32_t w = __ldg(a.live + iblk);
+            if (a.mask) w &= __ldg(a.mask + iblk);
+            if (w) { ilive = w; return; }
+            iblk += stride;
         }
-        if ((live0 | live1) == 0u) continue; // warp-uniform
-        const uint4 *p0 = a.codes + ((size_t)blk0 * a.C) * 32 + lane;
-        const uint4 *p1 = has1 ? p0 + (size_t)a.C * 32 : p0;
-        const uint32_t slot0 = blk0 * 32 + lane, slot1 = has1 ? slot0 + 32 : slot0;
-        float key[2];
-        Scorer<QT>::run(a, smem, h, p0, p1, slot0, slot1, key);
-        const bool ok0 = (live0 >> lane) & 1u, ok1 = (live1 >> lane) & 1u;
-        if (MODE == MODE_RADIUS) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const bool pass = (r ? ok1 : ok0) && key[r] <= radius_key;
+    };
+    seek_live();
+    auto issue = [&](uint32_t s) { // all lanes run it (uniform control), lane 0 talks to the hardware
+        if (iblk >= a.nblk) {
+            if (lane == 0) meta.blk[s] = 0xFFFFFFFFu;
+            return;
+        }
+        const uint32_t c0 = itile * Ct, n = min(Ct, C - c0);
+        if (lane == 0) {
+            meta.blk[s] = iblk; meta.tile[s] = itile; meta.live[s] = ilive;
+            mbar_expect_tx(&bars[s], n * 512u);
+            bulk_g2s(ring + (size_t)s * stage_bytes, a.codes + ((size_t)iblk * C + c0) * 32, n * 512u, &bars[s]);
+        }
+        if (++itile == T) { itile = 0; iblk += stride; seek_live(); }
+    };
+    for (uint32_t s = 0; s < S; ++s) issue(s);
+    __syncwarp();
+
+    typename Scorer<QT>::Acc acc;
+    Scorer<QT>::reset(acc);
+    RowAux aux;
+    aux.rn = 0.f; aux.s2 = 0.0;
+    uint32_t phases = 0, cs = 0;
+    const uint32_t bpc = (uint32_t)pq_bytes_per_chunk(QT);
+    while (true) {
+        const uint32_t blk = meta.blk[cs];
+        if (blk == 0xFFFFFFFFu) break;
+        const uint32_t tile = meta.tile[cs], lv = meta.live[cs];
+        const uint32_t slot = blk * 32 + lane;
+        if (tile == 0) {
+            Scorer<QT>::reset(acc);
+            aux = load_aux<QT>(a, slot);
+        }
+        mbar_wait(&bars[cs], (phases >> cs) & 1u);
+        phases ^= 1u << cs;
+        const uint32_t c0 = tile * Ct, n = min(Ct, C - c0);
+        Scorer<QT>::tile(acc, reinterpret_cast<const uint4 *>(ring + (size_t)cs * stage_bytes) + lane, n,
+                         smem + (size_t)c0 * bpc, (int)a.metric);
+        if (tile == T - 1) {
+            const float key = Scorer<QT>::finish(acc, a, h, aux);
+            const bool ok = (lv >> lane) & 1u;
+            if (MODE == MODE_RADIUS) {
+                const bool pass = ok && key <= (float)h.radius_key;
                 const unsigned m = __ballot_sync(0xffffffffu, pass);
                 if (m) {
                     uint32_t base = 0;
@@ -519,81 +614,90 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(const ScanArgs a) {
                     base = __shfl_sync(0xffffffffu, base, 0);
                     if (pass) {
                         uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                        if (pos < a.rad_cap) a.rad_slots[pos] = r ? slot1 : slot0;
+                        if (pos < a.rad_cap) a.rad_slots[pos] = slot;
                     }
                 }
+            } else {
+                list.offer(ok ? make_key64(key, slot) : kNoKey, lane);
             }
-        } else {
-            list.offer(ok0 ? make_key64(key[0], slot0) : kNoKey, lane);
-            list.offer(ok1 ? make_key64(key[1], slot1) : kNoKey, lane);
         }
+        __syncwarp(); // every lane is done reading stage cs (and its meta) before it is refilled
+        issue(cs);
+        __syncwarp(); // meta written by lane 0 is visible to the warp
+        cs = (cs + 1 == S) ? 0 : cs + 1;
     }
     if (MODE == MODE_RADIUS) return;
 
-    // ---- block merge in shared memory (the digit payload is dead from here on)
+    // ---- block merge in shared memory (payload and rings are dead from here on); the CTA's best
+    //      32*E keys go to this query's candidate area, finalize_kernel does the rest
     unsigned long long *pool = reinterpret_cast<unsigned long long *>(smem);
     __syncthreads();
-    block_merge<E>(list, pool, tid, lane, warp);
+    block_merge<E>(list, pool, tid, lane, warp, nwarps);
     if (tid < Kp) a.cand[(size_t)blockIdx.x * Kp + tid] = pool[tid];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-
-    // ---- last CTA: merge all CTA lists, re-score, emit
-    __threadfence();
-    list.init();
-    const uint32_t total = gridDim.x * Kp;
-    for (uint32_t base = warp * 32; base < total; base += kScanThreads) {
-        const uint32_t i = base + lane;
-        list.offer(i < total ? ld_cg_u64(a.cand + i) : kNoKey, lane);
-    }
-    __syncthreads();
-    block_merge<E>(list, pool, tid, lane, warp);
-    double *s_ex = reinterpret_cast<double *>(pool + kScanWarps * Kp);
-    unsigned long long *s_id = reinterpret_cast<unsigned long long *>(s_ex + Kp);
-    finalize_topk<QT>(a, pool, Kp, s_ex, s_id, tid);
-    if (tid == 0) *a.ticket = 0u; // self-cleaning for the next launch on this workspace
 }
 
-// dynamic shared memory a launch needs
-inline size_t scan_smem_bytes(int qt, uint32_t C, int mode) {
-    size_t payload = ((size_t)C * pq_bytes_per_chunk(qt) + 15) / 16 * 16;
-    if (mode == MODE_RADIUS) return payload;
-    size_t Kp = 32u << mode;
-    size_t pool = (size_t)kScanWarps * Kp * 8 + Kp * 16;
-    return payload > pool ? payload : pool;
+// ---- host-side launch plan: shared memory carve-up for (quantization, C, mode, warps, stages)
+struct ScanPlan {
+    uint32_t Ct, stages, ring_off, warps;
+    size_t smem;
+};
+inline size_t scan_payload_bytes(int qt, uint32_t C) { return ((size_t)C * pq_bytes_per_chunk(qt) + 127) / 128 * 128; }
+inline bool scan_plan(int qt, uint32_t C, int mode, uint32_t warps, uint32_t stages, uint32_t max_tile_chunks,
+                      size_t smem_limit, ScanPlan *p) {
+    const size_t payload = scan_payload_bytes(qt, C);
+    const size_t Kp = mode == MODE_RADIUS ? 32 : (32u << mode);
+    const size_t pool = (size_t)warps * Kp * 8;
+    if (payload + (size_t)warps * stages * 512 > smem_limit || pool > smem_limit) return false;
+    size_t per_stage = (smem_limit - payload) / ((size_t)warps * stages) / 512;
+    uint32_t Ct = (uint32_t)(per_stage < max_tile_chunks ? per_stage : max_tile_chunks);
+    if (Ct > C) Ct = C;
+    if (Ct > (uint32_t)kMaxTileChunks) Ct = kMaxTileChunks;
+    if (Ct < 1) return false;
+    // equalise tiles: the smallest Ct that keeps the same number of tiles per block
+    const uint32_t T = (C + Ct - 1) / Ct;
+    Ct = (C + T - 1) / T;
+    p->Ct = Ct; p->stages = stages; p->warps = warps;
+    p->ring_off = (uint32_t)payload;
+    size_t need = payload + (size_t)warps * stages * Ct * 512;
+    p->smem = need > pool ? need : pool;
+    return true;
 }
 
 // host-side launcher, instantiated per quantization in scan_<qt>.cu
 template <int QT>
-cudaError_t launch_scan_t(int mode, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
+cudaError_t launch_scan_t(int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
     switch (mode) {
-    case 0: scan_kernel<QT, 0><<<grid, kScanThreads, smem, st>>>(a); break;
-    case 1: scan_kernel<QT, 1><<<grid, kScanThreads, smem, st>>>(a); break;
-    case 2: scan_kernel<QT, 2><<<grid, kScanThreads, smem, st>>>(a); break;
-    case 3: scan_kernel<QT, 3><<<grid, kScanThreads, smem, st>>>(a); break;
-    case MODE_RADIUS: scan_kernel<QT, MODE_RADIUS><<<grid, kScanThreads, smem, st>>>(a); break;
+    case 0: scan_kernel<QT, 0><<<grid, threads, smem, st>>>(a); break;
+    case 1: scan_kernel<QT, 1><<<grid, threads, smem, st>>>(a); break;
+    case 2: scan_kernel<QT, 2><<<grid, threads, smem, st>>>(a); break;
+    case 3: scan_kernel<QT, 3><<<grid, threads, smem, st>>>(a); break;
+    case MODE_RADIUS: scan_kernel<QT, MODE_RADIUS><<<grid, threads, smem, st>>>(a); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 template <int QT>
-cudaError_t scan_configure_t(size_t max_smem, int *blocks_per_sm) {
-    cudaError_t e;
-    int best = 0;
-#define SZG_CFG(M)                                                                                                \
-    e = cudaFuncSetAttribute(scan_kernel<QT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);       \
-    if (e != cudaSuccess) return e;                                                                                \
-    if (M == 0) {                                                                                                  \
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&best, scan_kernel<QT, M>, kScanThreads, 8192);           \
-        if (e != cudaSuccess) return e;                                                                            \
+cudaError_t launch_finalize_t(int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a) {
+    const size_t smem = finalize_smem_bytes(mode);
+    switch (mode) {
+    case 0: finalize_kernel<QT, 0><<<nq, kFinalizeThreads, smem, st>>>(a); break;
+    case 1: finalize_kernel<QT, 1><<<nq, kFinalizeThreads, smem, st>>>(a); break;
+    case 2: finalize_kernel<QT, 2><<<nq, kFinalizeThreads, smem, st>>>(a); break;
+    case 3: finalize_kernel<QT, 3><<<nq, kFinalizeThreads, smem, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
     }
-    SZG_CFG(0) SZG_CFG(1) SZG_CFG(2) SZG_CFG(3) SZG_CFG(MODE_RADIUS)
-#undef SZG_CFG
-    *blocks_per_sm = best;
+    return cudaGetLastError();
+}
+
+template <int QT>
+cudaError_t scan_attr_t(size_t max_smem) {
+    cudaError_t e;
+#define SZG_ATTR(M)                                                                                            \
+    e = cudaFuncSetAttribute(scan_kernel<QT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);  \
+    if (e != cudaSuccess) return e;
+    SZG_ATTR(0) SZG_ATTR(1) SZG_ATTR(2) SZG_ATTR(3) SZG_ATTR(MODE_RADIUS)
+#undef SZG_ATTR
     return cudaSuccess;
 }
 

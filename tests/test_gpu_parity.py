@@ -273,10 +273,10 @@ def test_radius_overflowing_first_compaction_buffer():
     ids = np.arange(n, dtype=np.uint64)
     q = o.synth_queries(52, 0, 1, dims)[0]
     with _build(codes, ids, dims, bits, szg.EUCLIDEAN) as ix:
-        ri, rd, _ = o.search_exact(codes, ids, dims, bits, szg.EUCLIDEAN, q, radius=1.9)
+        ri, rd, _ = o.search_exact(codes, ids, dims, bits, szg.EUCLIDEAN, q, radius=2.6)
         assert ri.size > 4096
-        gi, gd, _ = ix.search_radius(q, 1.9)
-        assert_radius_match(gi, gd, ri, rd, 1.9, "wide radius")
+        gi, gd, _ = ix.search_radius(q, 2.6)
+        assert_radius_match(gi, gd, ri, rd, 2.6, "wide radius")
 
 
 # ------------------------------------------------------------------ rescoring (LSH candidate path)
