@@ -141,10 +141,13 @@ int szg_rescore(szg_index *h, const double *query, const uint64_t *ids, uint64_t
  * Used by the multi-GPU host and by the benchmark's resident-input leg.  All work is
  * enqueued on `stream` (a cudaStream_t, NULL = default stream) and its helper streams are
  * joined back into it before returning; nothing is synchronised with the host.
- * d_out_ids/d_out_dist are nq*k, d_out_n nq (uint32). */
+ * d_out_ids/d_out_dist are nq*k, d_out_n nq (uint32).  The device variant cannot re-run a query
+ * (no host synchronisation): queries whose candidate set could not be certified against the
+ * surrogate's error bound are reported in d_out_flags and the caller re-runs them through
+ * szg_search_topk (which escalates on its own). */
 int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id,
                         uint32_t flags, uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
-                        void *stream);
+                        uint32_t *d_out_flags /* optional, nq: bit0 = result not certified */, void *stream);
 
 /*
  * Final merge of row-sharded top-k lists: rank g's {ids nq*k, dist nq*k, n nq}
@@ -156,9 +159,10 @@ int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint
  * is single-process.
  */
 int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const double *d_gathered_dist,
-                       const uint32_t *d_gathered_n, uint64_t rank_stride_bytes, uint32_t nranks,
-                       uint32_t nq, uint32_t k, uint64_t *d_out_ids, double *d_out_dist,
-                       uint32_t *d_out_n, void *stream);
+                       const uint32_t *d_gathered_n, const uint32_t *d_gathered_flags /* optional */,
+                       uint64_t rank_stride_bytes, uint32_t nranks, uint32_t nq, uint32_t k,
+                       uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
+                       uint32_t *d_out_flags /* optional: OR of the ranks' flags */, void *stream);
 
 /* ---- synthetic data + introspection (bench/test helpers, no reference counterpart) ---- */
 
@@ -193,8 +197,10 @@ int szg_get_stats(szg_index *h, szg_stats *out);
                                         (default), 2 accumulate over calls until szg_last_scan_times_ms reads them */
 #define SZG_OPT_MIN_CANDIDATE_MODE 3 /* force candidate set >= 32<<v (v in 0..3; -1 = automatic) */
 #define SZG_OPT_SCAN_WARPS 4         /* warps per scan CTA: 8 or 16 (default 16) */
-#define SZG_OPT_SCAN_STAGES 5        /* ring stages per warp, 2..8 (default 3) */
+#define SZG_OPT_SCAN_STAGES 5        /* ring stages per warp, 2..8 (default 2) */
 #define SZG_OPT_SCAN_TILE_CHUNKS 6   /* upper bound of 16-byte chunks per tile, 1..32 (default 8) */
+#define SZG_OPT_DIGITS 7             /* fixed-point digits of the query: 0 automatic (2, re-run with 3 when the
+                                        result cannot be certified), 2 or 3 forced */
 int szg_set_option(szg_index *h, int option, int64_t value);
 
 /* Time of the most recent scan launches on this handle, measured with CUDA events on the

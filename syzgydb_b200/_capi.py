@@ -26,6 +26,7 @@ OPT_MIN_CANDIDATE_MODE = 3
 OPT_SCAN_WARPS = 4
 OPT_SCAN_STAGES = 5
 OPT_SCAN_TILE_CHUNKS = 6
+OPT_DIGITS = 7
 
 # every symbol include/syzgy_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -83,8 +84,8 @@ def load():
     L.szg_result_free.argtypes = [vp]
     L.szg_result_free.restype = None
     L.szg_rescore.argtypes = [vp, f64p, u64p, C.c_uint64, f64p]
-    L.szg_search_topk_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, vp, vp, vp, vp]
-    L.szg_merge_topk_dev.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+    L.szg_search_topk_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, vp, vp, vp, vp, vp]
+    L.szg_merge_topk_dev.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
     L.szg_fill_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
     L.szg_fetch_codes.argtypes = [vp, u64p, C.c_uint64, u8p]
     L.szg_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -232,14 +233,15 @@ class Index:
 
     # -- search (device-resident; pointers are raw device addresses, e.g. torch tensor.data_ptr())
     def search_topk_dev(self, d_queries: int, nq: int, k: int, d_out_ids: int, d_out_dist: int, d_out_n: int,
-                        stream: int = 0, mask_id: int = -1, flags: int = 0):
+                        stream: int = 0, mask_id: int = -1, flags: int = 0, d_out_flags: int = 0):
         _check(self._L.szg_search_topk_dev(self._h, d_queries, nq, k, mask_id, flags, d_out_ids, d_out_dist,
-                                           d_out_n, stream))
+                                           d_out_n, d_out_flags or None, stream))
 
     def merge_topk_dev(self, d_g_ids: int, d_g_dist: int, d_g_n: int, nranks: int, nq: int, k: int, d_out_ids: int,
-                       d_out_dist: int, d_out_n: int, stream: int = 0, rank_stride_bytes: int = 0):
-        _check(self._L.szg_merge_topk_dev(self._h, d_g_ids, d_g_dist, d_g_n, rank_stride_bytes, nranks, nq, k,
-                                          d_out_ids, d_out_dist, d_out_n, stream))
+                       d_out_dist: int, d_out_n: int, stream: int = 0, rank_stride_bytes: int = 0, d_g_flags: int = 0,
+                       d_out_flags: int = 0):
+        _check(self._L.szg_merge_topk_dev(self._h, d_g_ids, d_g_dist, d_g_n, d_g_flags or None, rank_stride_bytes,
+                                          nranks, nq, k, d_out_ids, d_out_dist, d_out_n, d_out_flags or None, stream))
 
     # -- introspection
     def stats(self) -> dict:

@@ -16,8 +16,11 @@ namespace szg {
 
 constexpr int kRowsPerBlock = 32;
 constexpr int kChunkBytes = 16;
-constexpr int ND = 3;              // signed base-128 digits of the fixed-point query
-constexpr int kDigitBits = 7 * ND; // |W| < 2^21
+// The fixed-point query coefficient W_i = round(q_i * 2^F) is split in ND signed base-128 digits
+// (|W| < 2^(7 ND)).  ND = 2 is the fast path (8 IDP.4A per 16 codes instead of 12: the integer-dot
+// pipe and board power, not HBM, limited the 3-digit kernel); ND = 3 is the precise path a query
+// is re-run with when the 2-digit error bound cannot certify its result.
+constexpr int kMaxDigits = 3;
 
 enum QuantType : int { Q4 = 0, Q8 = 1, Q16 = 2, F32 = 3, F64 = 4 };
 enum Metric : int { EUCLID = 0, COSINE = 1 };
@@ -26,25 +29,29 @@ __host__ __device__ inline int quant_bits(int qt) { return qt == Q4 ? 4 : qt == 
 // elements per 16-byte chunk
 __host__ __device__ inline int elems_per_chunk(int qt) { return 128 / quant_bits(qt); }
 // bytes of prepared-query payload per chunk (digits or converted query values)
-__host__ __device__ inline int pq_bytes_per_chunk(int qt) {
-    return qt == Q4 ? 2 * ND * 16 : qt == Q8 ? ND * 16 : qt == Q16 ? ND * 8 : 16;
+__host__ __device__ inline int pq_bytes_per_chunk(int qt, int nd) {
+    return qt == Q4 ? 2 * nd * 16 : qt == Q8 ? nd * 16 : qt == Q16 ? nd * 8 : 16;
 }
 
 // Header of one prepared query (device memory, followed by the per-chunk payload).
+// Quantized rows: x.q = num * c_dot with num = 2*I + numc, I = sum_i code_i * W_i (exact integer).
+//   cosine key  = -(num * c_key) * (1/||x||)            (c_key = c_dot / ||q||)
+//   euclid key  = ||x||^2 + qn2 - 2 * num * c_dot       (squared distance)
+// |key - true key| <= e_abs + e_rel * |key| is a rigorous bound (fixed-point rounding of the query,
+// fp32 rounding of aux values and of the key); finalize uses it to certify the candidate set.
 struct __align__(16) PQHeader {
-    double sumW;       // sum of fixed-point coefficients W_i (exact integer)
-    double sumW2;      // sum W_i^2
-    double numc;       // cosine: num = 2*I + numc          (numc = cW * sumW)
-    double c_key;      // scale from integer domain to key unit
-    double base;       // euclid: E = aux*pow2F2 - pow2F1*I + base   (base = sumW2)
-    double pow2F1;     // 2^(F+1)
-    double pow2F2;     // 2^(2F)
-    double qnorm;      // ||q|| (parallel reduction; surrogate only)
+    double numc;       // -M * sum(W) (4/8-bit), +sum(W) (16-bit, codes stored centred)
+    double c_dot;      // 1 / (M * 2^F); float rows: 1
+    double c_key;      // cosine: c_dot / ||q|| (0 for a zero query); euclid: unused
+    double qn2;        // ||q||^2
+    double e_abs;      // surrogate error bound, absolute part
+    double e_rel;      // surrogate error bound, relative part
     double radius_key; // radius mode: surrogate threshold (key <= radius_key is a candidate)
     double radius;     // radius mode: exact threshold
     int F;
     int zero_query;    // ||q|| == 0
-    int pad[2];
+    int nd;
+    int pad;
 };
 static_assert(sizeof(PQHeader) % 16 == 0, "payload must stay 16-byte aligned");
 

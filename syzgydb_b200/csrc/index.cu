@@ -82,9 +82,7 @@ struct PinBuf {
 struct Workspace {
     cudaStream_t main = nullptr; // owned for host calls; the caller's stream for *_dev calls
     bool owns_main = false;
-    cudaStream_t helper[kMaxStreams] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
-    DevBuf<double> d_q;
+    DevBuf<double> d_q, d_q2;
     DevBuf<unsigned char> d_pq;
     DevBuf<unsigned long long> d_cand; // [nq][scan CTAs][32*E] candidate keys, scan -> finalize
     DevBuf<unsigned int> d_ticket;     // radius hit counter
@@ -102,27 +100,19 @@ struct Workspace {
     int init(bool own) {
         owns_main = own;
         if (own) CK(cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking));
-        for (int i = 1; i < kMaxStreams; ++i) CK(cudaStreamCreateWithFlags(&helper[i], cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        for (int i = 1; i < kMaxStreams; ++i) CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
-        int rc = d_ticket.ensure(kMaxStreams + 4);
+        int rc = d_ticket.ensure(4);
         if (rc) return rc;
-        CK(cudaMemset(d_ticket.p, 0, (kMaxStreams + 4) * sizeof(unsigned int)));
+        CK(cudaMemset(d_ticket.p, 0, 4 * sizeof(unsigned int)));
         return SZG_OK;
     }
     void destroy() {
-        d_q.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
+        d_q.release(); d_q2.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
         d_out_n.release(); d_out_flags.release(); d_slots.release();
         d_cand.release();
         h_q.release(); h_out_ids.release(); h_out_dist.release(); h_out_n.release(); h_out_flags.release();
         h_slots.release();
         for (auto e : t0) cudaEventDestroy(e);
         for (auto e : t1) cudaEventDestroy(e);
-        for (int i = 1; i < kMaxStreams; ++i) {
-            if (helper[i]) cudaStreamDestroy(helper[i]);
-            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
-        }
-        if (ev_fork) cudaEventDestroy(ev_fork);
         if (owns_main && main) cudaStreamDestroy(main);
     }
 };
@@ -177,7 +167,8 @@ struct szg_index {
     uint64_t launches = 0, escalations = 0, uncertain = 0;
     std::vector<float> last_times;
     Workspace *last_timed_ws = nullptr;
-    int scan_warps = 16, scan_stages = 3, scan_tile_chunks = 8; // streaming geometry (SZG_OPT_SCAN_*)
+    int scan_warps = 16, scan_stages = 2, scan_tile_chunks = 8;
+    int digits = 0; // 0 = automatic (2-digit fast pass, 3-digit re-run when uncertain), 2 or 3 = forced // streaming geometry (SZG_OPT_SCAN_*)
 
     bool lookup(uint64_t id, uint32_t *slot) const {
         auto it = map.find(id);
@@ -271,16 +262,21 @@ int mode_for_k(const szg_index *h, uint32_t k) {
     return mode;
 }
 
+size_t pq_stride(const szg_index *h, int nd) {
+    size_t payload = ((size_t)h->C * pq_bytes_per_chunk(h->qt, nd) + 15) / 16 * 16;
+    return sizeof(PQHeader) + payload;
+}
+// digits of the first pass: 2 (fast) for quantized rows unless SZG_OPT_DIGITS forces 3
+int first_digits(const szg_index *h) { return (h->qt <= Q16 && h->digits != 3) ? 2 : 3; }
+
+constexpr size_t kCandBytes = 64u << 20;       // candidate lists of one scan launch (bounds queries per launch)
 constexpr size_t kScanSmemLimit = 224 * 1024; // dynamic; + ~3 KB static stays under the 227 KB CTA limit
 
 // Persistent launch: one CTA per SM (fewer when the collection has fewer row blocks than warps).
-int plan_scan(szg_index *h, int mode, ScanPlan *p, int *grid) {
-    uint32_t warps = (uint32_t)h->scan_warps, stages = (uint32_t)h->scan_stages;
-    while (!scan_plan(h->qt, h->C, mode, warps, stages, (uint32_t)h->scan_tile_chunks, kScanSmemLimit, p)) {
-        if (stages > 2) --stages;          // very long rows: the query payload crowds the rings out
-        else if (warps > 8) warps = 8;
-        else return fail(SZG_EINVAL, "dimension %d needs more shared memory than one SM has", h->dim);
-    }
+int plan_scan(szg_index *h, int nd, ScanPlan *p, int *grid) {
+    if (!scan_plan(h->C, (uint32_t)h->scan_warps, (uint32_t)h->scan_stages, (uint32_t)h->scan_tile_chunks,
+                   pq_stride(h, nd), kScanSmemLimit, p))
+        return fail(SZG_EINTERNAL, "scan geometry does not fit shared memory");
     const uint32_t nblk = (h->nslots + 31) / 32;
     uint32_t g = (nblk + p->warps - 1) / p->warps;
     g = std::max<uint32_t>(1, std::min<uint32_t>(g, (uint32_t)h->sm_count));
@@ -288,10 +284,6 @@ int plan_scan(szg_index *h, int mode, ScanPlan *p, int *grid) {
     return SZG_OK;
 }
 
-size_t pq_stride(const szg_index *h) {
-    size_t payload = ((size_t)h->C * pq_bytes_per_chunk(h->qt) + 15) / 16 * 16;
-    return sizeof(PQHeader) + payload;
-}
 
 void fill_scan_args(szg_index *h, ScanArgs &a, const uint32_t *mask) {
     memset(&a, 0, sizeof a);
@@ -307,39 +299,37 @@ void fill_scan_args(szg_index *h, ScanArgs &a, const uint32_t *mask) {
     a.metric = (uint32_t)h->metric;
 }
 
-// Enqueues prep + one scan launch per query.  Inputs/outputs are device pointers; `ws`
-// supplies scratch; work is forked over `ns` streams and joined back into ws->main.
+// Enqueues prep + scan + finalize for nq queries on ws->main.  One scan launch serves a whole chunk of
+// queries (persistent warps walk query after query); the chunk size is bounded by the candidate
+// buffer.  Inputs/outputs are device pointers; `ws` supplies scratch.
 int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32_t k, const uint32_t *mask,
-             uint32_t flags, int mode, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
+             uint32_t flags, int mode, int nd, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
              uint32_t *d_out_flags) {
-    const size_t stride = pq_stride(h);
+    const size_t stride = pq_stride(h, nd);
     int rc;
     if ((rc = ws->d_pq.ensure(stride * nq))) return rc;
     ScanPlan plan;
     int grid = 0;
-    if ((rc = plan_scan(h, mode, &plan, &grid))) return rc;
-    const int ns = std::max(1, std::min(h->nstreams, kMaxStreams));
+    if ((rc = plan_scan(h, nd, &plan, &grid))) return rc;
     const size_t Kp = 32u << mode;
-    if ((rc = ws->d_cand.ensure((size_t)nq * grid * Kp))) return rc;
+    const size_t nlists = (size_t)grid * plan.warps;
+    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / (nlists * Kp * 8)}));
+    if ((rc = ws->d_cand.ensure((size_t)chunk * nlists * Kp))) return rc;
 
     cudaStream_t main = ws->main;
     PrepArgs pa;
     pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
     pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
-    pa.qt = h->qt; pa.radius_mode = 0; pa.radius = 0.0;
+    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
     CK(launch_prep(nq, main, pa));
     h->launches++;
-    const int used = (int)std::min<uint32_t>(ns, nq);
-    if (used > 1) {
-        CK(cudaEventRecord(ws->ev_fork, main));
-        for (int s = 1; s < used; ++s) CK(cudaStreamWaitEvent(ws->helper[s], ws->ev_fork, 0));
-    }
     const bool timing = h->timing != 0;
+    const uint32_t nlaunch = (nq + chunk - 1) / chunk;
     // timing == 2 accumulates events over calls (bounded) until szg_last_scan_times_ms drains them
     uint32_t tbase = 0;
-    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nq <= 65536) tbase = ws->timed;
+    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nlaunch <= 65536) tbase = ws->timed;
     if (timing) {
-        while (ws->t0.size() < tbase + nq) {
+        while (ws->t0.size() < tbase + nlaunch) {
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a));
             CK(cudaEventCreate(&b));
@@ -349,33 +339,30 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
     }
     ScanArgs a;
     fill_scan_args(h, a, mask);
-    a.k = k;
-    a.flags = flags & SZG_F_NO_FP64_VERIFY;
-    a.Ct = plan.Ct; a.stages = plan.stages; a.ring_off = plan.ring_off;
-    for (uint32_t i = 0; i < nq; ++i) {
-        const int s = (int)(i % used);
-        cudaStream_t st = s == 0 ? main : ws->helper[s];
-        a.pq = ws->d_pq.p + stride * i;
-        a.q = d_q + (size_t)i * h->dim;
-        a.cand = ws->d_cand.p + (size_t)i * grid * Kp;
-        if (timing) CK(cudaEventRecord(ws->t0[tbase + i], st));
-        CK(launch_scan(h->qt, mode, grid, (int)plan.warps * 32, plan.smem, st, a));
-        if (timing) CK(cudaEventRecord(ws->t1[tbase + i], st));
-        h->launches++;
-    }
-    if (timing) { ws->timed = tbase + nq; h->last_timed_ws = ws; }
-    for (int s = 1; s < used; ++s) {
-        CK(cudaEventRecord(ws->ev_join[s], ws->helper[s]));
-        CK(cudaStreamWaitEvent(main, ws->ev_join[s], 0));
-    }
-    // one finalize launch for the whole call: merge of the per-CTA lists, fp64 re-score, ordered output
+    a.Ct = plan.Ct; a.stages = plan.stages; a.pq_smem_off = plan.pq_smem_off;
+    a.pq_stride = stride;
+    a.cand = ws->d_cand.p;
     FinalizeArgs f;
-    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.queries = d_q; f.cand = ws->d_cand.p;
+    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.cand = ws->d_cand.p;
+    f.pq_stride = stride;
     f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
-    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.ncta = (uint32_t)grid;
-    f.out_ids = d_out_ids; f.out_dist = d_out_dist; f.out_n = d_out_n; f.out_flags = d_out_flags;
-    CK(launch_finalize(h->qt, mode, nq, main, f));
-    h->launches++;
+    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.nlists = (uint32_t)nlists;
+    for (uint32_t l = 0, q0 = 0; q0 < nq; q0 += chunk, ++l) {
+        const uint32_t m = std::min(chunk, nq - q0);
+        a.pq = ws->d_pq.p + stride * q0;
+        a.nq = m;
+        if (timing) CK(cudaEventRecord(ws->t0[tbase + l], main));
+        CK(launch_scan(h->qt, mode, nd, grid, (int)plan.warps * 32, plan.smem, main, a));
+        if (timing) CK(cudaEventRecord(ws->t1[tbase + l], main));
+        // merge of the per-warp lists, fp64 re-score, ordered output: one CTA per query
+        f.queries = d_q + (size_t)q0 * h->dim;
+        f.pq = a.pq;
+        f.out_ids = d_out_ids + (size_t)q0 * k; f.out_dist = d_out_dist + (size_t)q0 * k;
+        f.out_n = d_out_n + q0; f.out_flags = d_out_flags + q0;
+        CK(launch_finalize(h->qt, mode, m, main, f));
+        h->launches += 2;
+    }
+    if (timing) { ws->timed = tbase + nlaunch; h->last_timed_ws = ws; }
     return SZG_OK;
 }
 
@@ -490,6 +477,10 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
     case SZG_OPT_SCAN_TILE_CHUNKS:
         if (value < 1 || value > kMaxTileChunks) return fail(SZG_EINVAL, "tile chunks must be in [1, %d]", kMaxTileChunks);
         h->scan_tile_chunks = (int)value;
+        return SZG_OK;
+    case SZG_OPT_DIGITS:
+        if (value != 0 && value != 2 && value != 3) return fail(SZG_EINVAL, "digits must be 0 (auto), 2 or 3");
+        h->digits = (int)value;
         return SZG_OK;
     case SZG_OPT_MIN_CANDIDATE_MODE:
         if (value < -1 || value > 3) return fail(SZG_EINVAL, "candidate mode must be in [-1, 3]");
@@ -710,8 +701,8 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
     memcpy(ws->h_q.p, queries, qn * sizeof(double));
     cudaStream_t st = ws->main;
     CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st));
-    int mode = mode_for_k(h, k);
-    if ((rc = run_topk(h, ws, ws->d_q.p, nq, k, mask, flags, mode, ws->d_out_ids.p, ws->d_out_dist.p,
+    const int mode0 = mode_for_k(h, k), nd0 = first_digits(h);
+    if ((rc = run_topk(h, ws, ws->d_q.p, nq, k, mask, flags, mode0, nd0, ws->d_out_ids.p, ws->d_out_dist.p,
                        ws->d_out_n.p, ws->d_out_flags.p)))
         return rc;
     CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, on * 8, cudaMemcpyDeviceToHost, st));
@@ -722,33 +713,49 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
     memcpy(out_ids, ws->h_out_ids.p, on * 8);
     memcpy(out_dist, ws->h_out_dist.p, on * 8);
     memcpy(out_n, ws->h_out_n.p, nq * 4);
-    // escalate queries whose candidate margin was inside the tolerance band
+    // Queries whose candidate set could not be certified are re-run together, first with the
+    // 3-digit (precise) surrogate, then with larger candidate sets.
     if (!(flags & SZG_F_NO_FP64_VERIFY)) {
-        for (uint32_t i = 0; i < nq; ++i) {
-            int m = mode;
-            while ((ws->h_out_flags.p[i] & 1u) && m < 3) {
-                ++m;
-                h->escalations++;
-                if ((rc = run_topk(h, ws, ws->d_q.p + (size_t)i * h->dim, 1, k, mask, flags, m, ws->d_out_ids.p,
-                                   ws->d_out_dist.p, ws->d_out_n.p, ws->d_out_flags.p)))
-                    return rc;
-                CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(ws->h_out_flags.p + i, ws->d_out_flags.p, 4, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                memcpy(out_ids + (size_t)i * k, ws->h_out_ids.p, (size_t)k * 8);
-                memcpy(out_dist + (size_t)i * k, ws->h_out_dist.p, (size_t)k * 8);
-                out_n[i] = ws->h_out_n.p[0];
+        std::vector<uint32_t> pending;
+        for (uint32_t i = 0; i < nq; ++i)
+            if (ws->h_out_flags.p[i] & 1u) pending.push_back(i);
+        int nd = nd0, mode = mode0;
+        while (!pending.empty()) {
+            if (nd == 2) nd = 3;
+            else if (mode < 3) ++mode;
+            else break;
+            const uint32_t m = (uint32_t)pending.size();
+            h->escalations += m;
+            if ((rc = ws->d_q2.ensure((size_t)m * h->dim))) return rc;
+            for (uint32_t j = 0; j < m; ++j)
+                CK(cudaMemcpyAsync(ws->d_q2.p + (size_t)j * h->dim, ws->d_q.p + (size_t)pending[j] * h->dim,
+                                   (size_t)h->dim * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            if ((rc = run_topk(h, ws, ws->d_q2.p, m, k, mask, flags, mode, nd, ws->d_out_ids.p, ws->d_out_dist.p,
+                               ws->d_out_n.p, ws->d_out_flags.p)))
+                return rc;
+            CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::vector<uint32_t> still;
+            for (uint32_t j = 0; j < m; ++j) {
+                const uint32_t i = pending[j];
+                memcpy(out_ids + (size_t)i * k, ws->h_out_ids.p + (size_t)j * k, (size_t)k * 8);
+                memcpy(out_dist + (size_t)i * k, ws->h_out_dist.p + (size_t)j * k, (size_t)k * 8);
+                out_n[i] = ws->h_out_n.p[j];
+                if (ws->h_out_flags.p[j] & 1u) still.push_back(i);
             }
-            if (ws->h_out_flags.p[i] & 1u) h->uncertain++;
+            pending.swap(still);
         }
+        h->uncertain += pending.size();
     }
     return SZG_OK;
 }
 
 int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                        uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, void *stream) {
+                        uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags,
+                        void *stream) {
     GUARD(h);
     int rc;
     if ((rc = check_search(h, d_queries, nq))) return rc;
@@ -768,18 +775,25 @@ int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint
             h->dev_ws[stream] = ws;
         } else ws = it->second;
     }
-    if ((rc = ws->d_out_flags.ensure(nq))) return rc;
+    if (!d_out_flags) {
+        if ((rc = ws->d_out_flags.ensure(nq))) return rc;
+        d_out_flags = ws->d_out_flags.p;
+    }
     if (h->live_rows == 0) {
         CK(cudaMemsetAsync(d_out_n, 0, nq * 4, ws->main));
+        CK(cudaMemsetAsync(d_out_flags, 0, nq * 4, ws->main));
         return SZG_OK;
     }
-    return run_topk(h, ws, d_queries, nq, k, mask, flags, mode_for_k(h, k), (unsigned long long *)d_out_ids,
-                    d_out_dist, d_out_n, ws->d_out_flags.p);
+    // no host synchronisation here, hence no escalation: SZG_OPT_DIGITS = 2 (or automatic) runs the fast
+    // surrogate and reports uncertified queries in d_out_flags; the caller re-runs those with szg_search_topk
+    return run_topk(h, ws, d_queries, nq, k, mask, flags, mode_for_k(h, k), first_digits(h),
+                    (unsigned long long *)d_out_ids, d_out_dist, d_out_n, d_out_flags);
 }
 
 int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const double *d_gathered_dist,
-                       const uint32_t *d_gathered_n, uint64_t rank_stride_bytes, uint32_t nranks, uint32_t nq,
-                       uint32_t k, uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, void *stream) {
+                       const uint32_t *d_gathered_n, const uint32_t *d_gathered_flags, uint64_t rank_stride_bytes,
+                       uint32_t nranks, uint32_t nq, uint32_t k, uint64_t *d_out_ids, double *d_out_dist,
+                       uint32_t *d_out_n, uint32_t *d_out_flags, void *stream) {
     GUARD(h);
     if (!nq) return SZG_OK;
     if (!d_gathered_ids || !d_gathered_dist || !d_gathered_n || !d_out_ids || !d_out_dist || !d_out_n)
@@ -788,6 +802,7 @@ int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const doubl
         return fail(SZG_EINVAL, "merge of %u lists of k=%u is not supported", nranks, k);
     MergeArgs a;
     a.g_ids = (const unsigned long long *)d_gathered_ids; a.g_dist = d_gathered_dist; a.g_n = d_gathered_n;
+    a.g_flags = d_gathered_flags; a.out_flags = d_out_flags;
     a.rank_stride = (size_t)rank_stride_bytes;
     a.G = nranks; a.nq = nq; a.k = k;
     a.out_ids = (unsigned long long *)d_out_ids; a.out_dist = d_out_dist; a.out_n = d_out_n;
@@ -812,7 +827,8 @@ int szg_search_radius(szg_index *h, const double *query, double radius, int mask
     Workspace *ws;
     if ((rc = acquire_ws(h, &ws))) return rc;
     struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
-    const size_t stride = pq_stride(h);
+    const int nd = first_digits(h); // the radius threshold carries the surrogate error bound: no re-run needed
+    const size_t stride = pq_stride(h, nd);
     if ((rc = ws->h_q.ensure(h->dim)) || (rc = ws->d_q.ensure(h->dim)) || (rc = ws->d_pq.ensure(stride)) ||
         (rc = ws->h_out_n.ensure(1)))
         return rc;
@@ -822,12 +838,12 @@ int szg_search_radius(szg_index *h, const double *query, double radius, int mask
     PrepArgs pa;
     pa.queries = ws->d_q.p; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
     pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
-    pa.qt = h->qt; pa.radius_mode = 1; pa.radius = radius;
+    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 1; pa.radius = radius;
     CK(launch_prep(1, st, pa));
     h->launches++;
     ScanPlan plan;
     int grid = 0;
-    if ((rc = plan_scan(h, MODE_RADIUS, &plan, &grid))) return rc;
+    if ((rc = plan_scan(h, nd, &plan, &grid))) return rc;
     unsigned int *d_count = ws->d_ticket.p;
     uint32_t count = 0;
     size_t cap = std::max<size_t>(4096, h->nslots / 64);
@@ -836,10 +852,10 @@ int szg_search_radius(szg_index *h, const double *query, double radius, int mask
         CK(cudaMemsetAsync(d_count, 0, 4, st));
         ScanArgs a;
         fill_scan_args(h, a, mask);
-        a.pq = ws->d_pq.p; a.q = ws->d_q.p;
+        a.pq = ws->d_pq.p; a.pq_stride = stride; a.nq = 1;
         a.rad_count = d_count; a.rad_slots = ws->d_slots.p; a.rad_cap = (uint32_t)ws->d_slots.n;
-        a.Ct = plan.Ct; a.stages = plan.stages; a.ring_off = plan.ring_off;
-        CK(launch_scan(h->qt, MODE_RADIUS, grid, (int)plan.warps * 32, plan.smem, st, a));
+        a.Ct = plan.Ct; a.stages = plan.stages; a.pq_smem_off = plan.pq_smem_off;
+        CK(launch_scan(h->qt, MODE_RADIUS, nd, grid, (int)plan.warps * 32, plan.smem, st, a));
         h->launches++;
         CK(cudaMemcpyAsync(ws->h_out_n.p, d_count, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -941,7 +957,7 @@ int szg_get_stats(szg_index *h, szg_stats *out) {
     out->sm_count = (uint32_t)h->sm_count;
     int grid = 0;
     ScanPlan plan;
-    int rc = plan_scan(h, 0, &plan, &grid);
+    int rc = plan_scan(h, first_digits(h), &plan, &grid);
     if (rc) return rc;
     out->scan_grid = (uint32_t)grid;
     out->scan_block = plan.warps * 32;

@@ -7,86 +7,76 @@ namespace szg {
 // ======================================================================= query prep
 // One CTA per query.  Turns the float64 query (never quantized, collection.go:596) into
 // the payload the scan kernel streams against:
-//   4/8/16-bit rows: coefficient w_i (cosine: q_i; euclid: the unrounded code
-//   t_i = M(1+q_i)/2 of quantization.go:19-21, centred for 16-bit) -> W_i = round(w_i 2^F),
-//   |W_i| < 2^21, as three signed base-128 digits laid out per 16-byte chunk;
+//   4/8/16-bit rows: W_i = round(q_i 2^F), |W_i| < 2^(7 nd), as nd signed base-128 digits laid
+//   out per 16-byte chunk of codes (both metrics use the same payload: euclid is evaluated as
+//   ||x||^2 - 2 x.q + ||q||^2 with ||x||^2 precomputed per row);
 //   32/64-bit rows: the query converted to fp32 / kept fp64, padded per chunk.
-__device__ __forceinline__ double coeff(const PrepArgs &a, double qi) {
-    if (a.metric == COSINE) return qi;
-    double t = (double)a.maxint * (1.0 + qi) * 0.5;
-    return a.qt == Q16 ? t - 32768.0 : t;
-}
-
+// The header carries the scale factors and the rigorous surrogate error bound.
 __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
-    __shared__ double s_red[3][8];
-    __shared__ double s_out[3];
+    __shared__ double s_red[2][8];
+    __shared__ double s_out[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double *q = a.queries + (size_t)blockIdx.x * a.dims;
     unsigned char *out = a.pq + (size_t)blockIdx.x * a.pq_stride;
     PQHeader *h = reinterpret_cast<PQHeader *>(out);
     unsigned char *payload = out + sizeof(PQHeader);
     const bool quantized = a.qt <= Q16;
+    const int nd = a.nd;
 
-    const uint32_t n16 = (a.C * (uint32_t)pq_bytes_per_chunk(a.qt) + 15) / 16;
+    const uint32_t n16 = (a.C * (uint32_t)pq_bytes_per_chunk(a.qt, nd) + 15) / 16;
     for (uint32_t i = tid; i < n16; i += 256) reinterpret_cast<uint4 *>(payload)[i] = make_uint4(0, 0, 0, 0);
 
-    // pass 1: max |w|, max |q|, sum q^2
-    double mw = 0.0, mq = 0.0, sq = 0.0;
+    // pass 1: max |q|, sum q^2
+    double mq = 0.0, sq = 0.0;
     for (uint32_t i = tid; i < a.dims; i += 256) {
         double qi = q[i];
-        double w = fabs(coeff(a, qi));
-        if (w == w && w > mw) mw = w;
         double aq = fabs(qi);
         if (aq == aq && aq > mq) mq = aq;
         sq += qi * qi;
     }
     for (int o = 16; o; o >>= 1) {
-        mw = fmax(mw, __shfl_xor_sync(0xffffffffu, mw, o));
         mq = fmax(mq, __shfl_xor_sync(0xffffffffu, mq, o));
         sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
-    if (lane == 0) { s_red[0][warp] = mw; s_red[1][warp] = mq; s_red[2][warp] = sq; }
+    if (lane == 0) { s_red[0][warp] = mq; s_red[1][warp] = sq; }
     __syncthreads();
     if (tid == 0) {
-        double a0 = 0, a1 = 0, a2 = 0;
-        for (int w = 0; w < 8; ++w) { a0 = fmax(a0, s_red[0][w]); a1 = fmax(a1, s_red[1][w]); a2 += s_red[2][w]; }
-        s_out[0] = a0; s_out[1] = a1; s_out[2] = a2;
+        double a0 = 0, a1 = 0;
+        for (int w = 0; w < 8; ++w) { a0 = fmax(a0, s_red[0][w]); a1 += s_red[1][w]; }
+        s_out[0] = a0; s_out[1] = a1;
     }
     __syncthreads();
-    mw = s_out[0]; mq = s_out[1]; sq = s_out[2];
+    mq = s_out[0]; sq = s_out[1];
     __syncthreads();
 
     int F = 0;
-    if (quantized && mw > 0.0 && isfinite(mw)) {
-        F = (kDigitBits - 1) - ilogb(mw);
+    if (quantized && mq > 0.0 && isfinite(mq)) {
+        F = (7 * nd - 1) - ilogb(mq);
         F = F > 900 ? 900 : (F < -900 ? -900 : F);
     }
 
-    // pass 2: payload + sums of W
-    double sW = 0.0, sW2 = 0.0;
+    // pass 2: payload + sum of W
+    double sW = 0.0;
     for (uint32_t i = tid; i < a.dims; i += 256) {
         double qi = q[i];
         if (quantized) {
-            double w = coeff(a, qi);
-            long long W = (w == w && isfinite(w)) ? llrint(scalbn(w, F)) : 0;
-            const long long lim = 1ll << kDigitBits;
+            long long W = (qi == qi && isfinite(qi)) ? llrint(scalbn(qi, F)) : 0;
+            const long long lim = 1ll << (7 * nd);
             W = W >= lim ? lim - 1 : (W < -lim ? -lim : W);
             sW += (double)W;
-            sW2 += (double)W * (double)W;
-            signed char dg[ND];
+            signed char dg[kMaxDigits];
             long long t = W;
-#pragma unroll
-            for (int j = ND - 1; j >= 1; --j) { dg[j] = (signed char)(t & 127); t >>= 7; }
+            for (int j = nd - 1; j >= 1; --j) { dg[j] = (signed char)(t & 127); t >>= 7; }
             dg[0] = (signed char)t; // most significant, signed
             if (a.qt == Q8) {
                 uint32_t c = i >> 4, b = i & 15;
-                for (int j = 0; j < ND; ++j) payload[((size_t)c * ND + j) * 16 + b] = (unsigned char)dg[j];
+                for (int j = 0; j < nd; ++j) payload[((size_t)c * nd + j) * 16 + b] = (unsigned char)dg[j];
             } else if (a.qt == Q4) {
                 uint32_t byte = i >> 1, c = byte >> 4, b = byte & 15, arr = i & 1; // even dim = high nibble
-                for (int j = 0; j < ND; ++j) payload[(((size_t)c * 2 + arr) * ND + j) * 16 + b] = (unsigned char)dg[j];
+                for (int j = 0; j < nd; ++j) payload[(((size_t)c * 2 + arr) * nd + j) * 16 + b] = (unsigned char)dg[j];
             } else {
                 uint32_t c = i >> 3, e = i & 7;
-                for (int j = 0; j < ND; ++j) payload[((size_t)c * ND + j) * 8 + e] = (unsigned char)dg[j];
+                for (int j = 0; j < nd; ++j) payload[((size_t)c * nd + j) * 8 + e] = (unsigned char)dg[j];
             }
         } else if (a.qt == F32) {
             reinterpret_cast<float *>(payload)[i] = (float)qi;
@@ -94,42 +84,49 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
             reinterpret_cast<double *>(payload)[i] = qi;
         }
     }
-    for (int o = 16; o; o >>= 1) {
-        sW += __shfl_xor_sync(0xffffffffu, sW, o);
-        sW2 += __shfl_xor_sync(0xffffffffu, sW2, o);
-    }
-    if (lane == 0) { s_red[0][warp] = sW; s_red[1][warp] = sW2; }
+    for (int o = 16; o; o >>= 1) sW += __shfl_xor_sync(0xffffffffu, sW, o);
+    if (lane == 0) s_red[0][warp] = sW;
     __syncthreads();
     if (tid == 0) {
-        sW = 0; sW2 = 0;
-        for (int w = 0; w < 8; ++w) { sW += s_red[0][w]; sW2 += s_red[1][w]; }
-        const double M = (double)a.maxint;
+        sW = 0;
+        for (int w = 0; w < 8; ++w) sW += s_red[0][w];
+        const double M = (double)a.maxint, d = (double)a.dims;
         const double qn = sqrt(sq);
+        const double eps = 5.9604644775390625e-08; // 2^-24
         PQHeader hh;
-        hh.sumW = sW; hh.sumW2 = sW2;
-        hh.F = F; hh.zero_query = (sq == 0.0); hh.pad[0] = hh.pad[1] = 0;
-        hh.qnorm = qn;
-        hh.pow2F1 = scalbn(1.0, F + 1);
-        hh.pow2F2 = scalbn(1.0, 2 * F);
-        hh.base = sW2;
+        hh.F = F; hh.zero_query = (sq == 0.0); hh.nd = nd; hh.pad = 0;
+        hh.qn2 = sq;
         hh.numc = (a.qt == Q16 ? 1.0 : -M) * sW;
+        hh.c_dot = quantized ? scalbn(1.0, -F) / M : 1.0;
+        hh.c_key = (sq == 0.0) ? 0.0 : hh.c_dot / qn;
+        // ---- rigorous bound on |surrogate key - true key|
+        // fixed-point query: |q_i - W_i 2^-F| <= 2^-(F+1)  =>  |x.q error| <= ||x|| sqrt(d) 2^-(F+1), ||x|| <= sqrt(d)
+        const double dq = quantized ? scalbn(1.0, -(F + 1)) : 0.0;
         if (a.metric == COSINE) {
-            hh.c_key = (sq == 0.0) ? 0.0 : (quantized ? scalbn(1.0, -F) / (M * qn) : 1.0 / qn);
+            // key = -cos: fixed-point part / (||x|| ||q||) + fp32 roundings (two products, 1/||x|| itself)
+            hh.e_rel = 0.0;
+            hh.e_abs = (sq == 0.0 ? 0.0 : sqrt(d) * dq / qn) + 6.0 * eps;
+            if (a.qt == F32) hh.e_abs += (d + 8.0) * 2.0 * eps; // fp32 accumulation + fp32 copy of the query
+        } else if (quantized) {
+            // key = ||x||^2 (fp32 aux) + ||q||^2 - 2 x.q, rounded to fp32
+            hh.e_abs = 2.0 * d * dq + d * eps + 1e-30;
+            hh.e_rel = 2.0 * eps;
+        } else if (a.qt == F32) {
+            // fp32 sum of fp32 (q_i - x_i)^2 with an fp32 copy of the query
+            hh.e_rel = (d + 8.0) * 4.0 * eps;
+            hh.e_abs = 8.0 * eps * (sq + 1.0);
         } else {
-            hh.c_key = quantized ? 4.0 / (M * M) * scalbn(1.0, -2 * F) : 1.0;
+            hh.e_rel = 4.0 * eps; // fp64 sum, fp32 key
+            hh.e_abs = 1e-13 * (sq + 1.0);
         }
         hh.radius = a.radius;
         hh.radius_key = 0.0;
         if (a.radius_mode) {
+            // candidates: every row whose surrogate could belong to a true distance <= radius
             const double r = a.radius;
-            if (a.metric == COSINE) {
-                hh.radius_key = (r >= 1.0) ? 2.0 : -cos(3.141592653589793 * r) + 1e-5;
-            } else {
-                const double rel = a.qt == F32 ? 1e-3 : (a.qt == F64 ? 1e-6 : 1e-4);
-                const double ab = quantized ? 4e-6 * sqrt((double)a.dims) * fmax(1.0, mq) : 0.0;
-                const double t = r * (1.0 + rel) + ab;
-                hh.radius_key = t * t;
-            }
+            double t = a.metric == COSINE ? (r >= 1.0 ? 1.0 : -cospi(r)) : r * r;
+            t = t + hh.e_abs + hh.e_rel * fabs(t) * 1.000001 + 1e-7 * fabs(t);
+            hh.radius_key = (a.metric == COSINE && r >= 1.0) ? 2.0 : t;
         }
         *h = hh;
     }
@@ -239,15 +236,14 @@ cudaError_t launch_synth(const RowsArgs &a, unsigned long long seed, unsigned lo
     return cudaGetLastError();
 }
 
-// thread per row: per-row auxiliary value the surrogate needs (not streamed as payload):
-//   cosine           float 1/||x||   (0 for a zero-norm row -> distance 1.0, collection.go:828-830)
-//   euclid 4/8-bit   uint32 sum u^2 ; euclid 16-bit: uint64 sum (u-32768)^2 ; float rows: none
+// thread per row: per-row auxiliary values the surrogate needs (not streamed as payload):
+//   float2 { 1/||x|| (0 for a zero-norm row -> distance 1.0, collection.go:828-830), ||x||^2 }
+// from exact integer code sums for quantized rows, fp64 sums for float rows.
 __global__ void aux_kernel(const RowsArgs a, const uint32_t *__restrict__ slots, uint32_t slot0, uint32_t n) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint32_t slot = slots ? slots[r] : slot0 + r;
     if (slot == 0xFFFFFFFFu) return;
-    if (a.metric == EUCLID && a.qt > Q16) return;
     unsigned long long S1 = 0, S2 = 0; // quantized (unsigned code sums; Q16: S1 signed below)
     long long S1s = 0;
     double fs = 0.0;
@@ -288,19 +284,15 @@ __global__ void aux_kernel(const RowsArgs a, const uint32_t *__restrict__ slots,
             }
         }
     }
-    if (a.metric == COSINE) {
-        double nx2;
-        const double M = (double)a.maxint, d = (double)a.dims;
-        if (a.qt == Q16) nx2 = (4.0 * (double)S2 + 4.0 * (double)S1s + d) / (M * M);          // x = (2s+1)/M
-        else if (a.qt <= Q8) nx2 = (4.0 * (double)S2 - 4.0 * M * (double)S1 + M * M * d) / (M * M); // x = (2u-M)/M
-        else nx2 = fs;
-        float rn = (nx2 > 0.0 && isfinite(nx2)) ? (float)(1.0 / sqrt(nx2)) : 0.f;
-        reinterpret_cast<float *>(a.aux)[slot] = rn;
-    } else if (a.qt == Q16) {
-        reinterpret_cast<unsigned long long *>(a.aux)[slot] = S2;
-    } else {
-        reinterpret_cast<uint32_t *>(a.aux)[slot] = (uint32_t)S2;
-    }
+    double nx2;
+    const double M = (double)a.maxint, d = (double)a.dims;
+    if (a.qt == Q16) nx2 = (4.0 * (double)S2 + 4.0 * (double)S1s + d) / (M * M);                // x = (2s+1)/M
+    else if (a.qt <= Q8) nx2 = (4.0 * (double)S2 - 4.0 * M * (double)S1 + M * M * d) / (M * M); // x = (2u-M)/M
+    else nx2 = fs;
+    float2 o;
+    o.x = (nx2 > 0.0 && isfinite(nx2)) ? (float)(1.0 / sqrt(nx2)) : 0.f;
+    o.y = (float)nx2;
+    reinterpret_cast<float2 *>(a.aux)[slot] = o;
 }
 
 cudaError_t launch_aux(const RowsArgs &a, const uint32_t *slots, uint32_t slot0, uint32_t n, cudaStream_t st) {
@@ -432,7 +424,20 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
             a.out_dist[(size_t)q * a.k + rank] = d;
         }
     }
-    if (tid == 0) a.out_n[q] = s_total < a.k ? s_total : a.k;
+    if (tid == 0) {
+        a.out_n[q] = s_total < a.k ? s_total : a.k;
+        if (a.out_flags) {
+            uint32_t fl = 0;
+            if (a.g_flags)
+                for (uint32_t g = 0; g < a.G; ++g) {
+                    const uint32_t *f_g = a.rank_stride
+                        ? reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(a.g_flags) + g * a.rank_stride)
+                        : a.g_flags + (size_t)g * a.nq;
+                    fl |= f_g[q];
+                }
+            a.out_flags[q] = fl;
+        }
+    }
 }
 
 cudaError_t launch_merge(const MergeArgs &a, cudaStream_t st) {

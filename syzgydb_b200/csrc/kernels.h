@@ -10,13 +10,16 @@ struct PrepArgs {
     size_t pq_stride;
     uint32_t dims, C, metric, maxint;
     int qt;
+    int nd;          // digits (2 or 3) for quantized rows
     int radius_mode;
     double radius;
 };
 cudaError_t launch_prep(uint32_t nq, cudaStream_t st, const PrepArgs &a);
 
 // scan: one instantiation file per quantization
-cudaError_t launch_scan(int qt, int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a);
+// nd: digits of the fixed-point query (2 fast / 3 precise; ignored for float rows)
+cudaError_t launch_scan(int qt, int mode, int nd, int grid, int threads, size_t smem, cudaStream_t st,
+                        const ScanArgs &a);
 // one launch for all nq queries of a call: merges each query's per-CTA lists, fp64 re-score, ordered output
 cudaError_t launch_finalize(int qt, int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a);
 cudaError_t scan_configure(int qt, size_t max_smem);
@@ -63,11 +66,13 @@ struct MergeArgs {
     const unsigned long long *g_ids; // [G][nq][k]
     const double *g_dist;
     const uint32_t *g_n; // [G][nq]
+    const uint32_t *g_flags; // optional [G][nq]: bit0 = a rank could not certify its local list
     size_t rank_stride;  // bytes between ranks for all three arrays; 0 = each array tightly packed [G][...]
     uint32_t G, nq, k;
     unsigned long long *out_ids; // [nq][k]
     double *out_dist;
     uint32_t *out_n;
+    uint32_t *out_flags; // optional [nq]: OR of the ranks' flags
 };
 cudaError_t launch_merge(const MergeArgs &a, cudaStream_t st);
 

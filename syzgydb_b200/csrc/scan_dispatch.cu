@@ -4,19 +4,20 @@
 namespace szg {
 
 #define SZG_DECL(l)                                                                              \
-    cudaError_t launch_scan_##l(int, int, int, size_t, cudaStream_t, const ScanArgs &);          \
+    cudaError_t launch_scan_##l(int, int, int, int, size_t, cudaStream_t, const ScanArgs &);     \
     cudaError_t launch_finalize_##l(int, uint32_t, cudaStream_t, const FinalizeArgs &);           \
     cudaError_t scan_attr_##l(size_t);
 SZG_DECL(q4) SZG_DECL(q8) SZG_DECL(q16) SZG_DECL(f32) SZG_DECL(f64)
 #undef SZG_DECL
 
-cudaError_t launch_scan(int qt, int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
+cudaError_t launch_scan(int qt, int mode, int nd, int grid, int threads, size_t smem, cudaStream_t st,
+                        const ScanArgs &a) {
     switch (qt) {
-    case Q4: return launch_scan_q4(mode, grid, threads, smem, st, a);
-    case Q8: return launch_scan_q8(mode, grid, threads, smem, st, a);
-    case Q16: return launch_scan_q16(mode, grid, threads, smem, st, a);
-    case F32: return launch_scan_f32(mode, grid, threads, smem, st, a);
-    case F64: return launch_scan_f64(mode, grid, threads, smem, st, a);
+    case Q4: return launch_scan_q4(mode, nd, grid, threads, smem, st, a);
+    case Q8: return launch_scan_q8(mode, nd, grid, threads, smem, st, a);
+    case Q16: return launch_scan_q16(mode, nd, grid, threads, smem, st, a);
+    case F32: return launch_scan_f32(mode, nd, grid, threads, smem, st, a);
+    case F64: return launch_scan_f64(mode, nd, grid, threads, smem, st, a);
     }
     return cudaErrorInvalidValue;
 }

@@ -39,16 +39,17 @@ struct ScanArgs {
     const uint32_t *mask; // optional filter bitmask, same indexing (NULL = none)
     const unsigned long long *ids;
     const double *lut;          // dequantize table (4/8/16-bit)
-    const unsigned char *pq;    // PQHeader + payload of this query
-    const double *q;            // raw float64 query (re-score)
+    const unsigned char *pq;    // prepared queries: nq x (PQHeader + payload), pq_stride bytes apart
+    size_t pq_stride;
+    uint32_t nq;
     uint32_t C, nblk, dims, metric;
-    uint32_t k, flags;
     // streaming geometry (host-chosen, see scan_plan)
     uint32_t Ct;                // chunks per tile
     uint32_t stages;            // ring stages per warp
-    uint32_t ring_off;          // byte offset of the rings in dynamic shared memory
-    // top-k output: this query's per-CTA candidate lists, consumed by finalize_kernel
-    unsigned long long *cand;   // [gridDim.x][32*E]
+    uint32_t pq_smem_off;       // != 0: every warp keeps a private copy of its current prepared query at this
+                                // offset of dynamic shared memory (+ warp * pq_stride); 0: read it through L1
+    // top-k output: per-warp candidate lists, consumed by finalize_kernel
+    unsigned long long *cand;   // [nq][grid warps][32*E]
     // radius outputs
     uint32_t *rad_count;
     uint32_t *rad_slots;
@@ -62,8 +63,10 @@ struct FinalizeArgs {
     const unsigned long long *ids;
     const double *lut;
     const double *queries;            // [nq][dims] raw float64 queries
-    const unsigned long long *cand;   // [nq][ncta][32*E]
-    uint32_t C, dims, metric, k, flags, ncta;
+    const unsigned long long *cand;   // [nq][nlists][32*E]: one sorted list per scan warp
+    const unsigned char *pq;          // prepared queries (error bounds live in the header)
+    size_t pq_stride;
+    uint32_t C, dims, metric, k, flags, nlists;
     unsigned long long *out_ids;      // [nq][k]
     double *out_dist;                 // [nq][k]
     uint32_t *out_n;                  // [nq]
@@ -194,6 +197,7 @@ __device__ __forceinline__ void block_merge(const WarpList<E> &L, unsigned long 
 }
 
 // ------------------------------------------------------------------------- row scoring
+template <int ND>
 __device__ __forceinline__ double digits_total(const int (&a)[ND]) {
     double t = (double)a[0];
 #pragma unroll
@@ -201,40 +205,29 @@ __device__ __forceinline__ double digits_total(const int (&a)[ND]) {
     return t;
 }
 
-// aux value of one row, fetched when its block starts so that the latency hides behind the tiles
-struct RowAux {
-    float rn;      // cosine: 1/||x||
-    double s2;     // euclid, quantized: sum of squared (centred) codes
-};
-template <int QT>
-__device__ __forceinline__ RowAux load_aux(const ScanArgs &a, uint32_t slot) {
-    RowAux r;
-    r.rn = 0.f;
-    r.s2 = 0.0;
-    if (a.metric == COSINE) r.rn = reinterpret_cast<const float *>(a.aux)[slot];
-    else if (QT == Q16) r.s2 = (double)reinterpret_cast<const unsigned long long *>(a.aux)[slot];
-    else if (QT <= Q8) r.s2 = (double)reinterpret_cast<const uint32_t *>(a.aux)[slot];
-    return r;
+// aux values of one row {1/||x||, ||x||^2}, fetched when its block starts so that the latency hides
+// behind the tiles
+__device__ __forceinline__ float2 load_aux(const ScanArgs &a, uint32_t slot) {
+    return __ldg(reinterpret_cast<const float2 *>(a.aux) + slot);
 }
 
-__device__ __forceinline__ float finish_quant(const ScanArgs &a, const PQHeader &h, double I, const RowAux &x) {
+__device__ __forceinline__ float finish_quant(const ScanArgs &a, const PQHeader &h, double I, const float2 &x) {
+    const double num = 2.0 * I + h.numc;
     if (a.metric == COSINE) {
-        double num = 2.0 * I + h.numc;
-        float c = (float)(num * h.c_key) * x.rn;
-        return (h.zero_query || x.rn == 0.f) ? 1.0f : -c;
+        float c = (float)(num * h.c_key) * x.x;
+        return (h.zero_query || x.x == 0.f) ? 1.0f : -c;
     }
-    double Ev = fma(-h.pow2F1, I, fma(x.s2, h.pow2F2, h.base));
-    return (float)(Ev * h.c_key);
+    return (float)(((double)x.y + h.qn2) - 2.0 * (num * h.c_dot));
 }
 
 // A Scorer accumulates one row (one lane) over the tiles of its block:
-//   reset(acc); tile(acc, stage + lane, n, spq + c0 * bytes_per_chunk, metric) per tile; finish(...) -> key
-template <int QT>
+//   reset(acc); tile(acc, stage + lane, n, payload + c0 * bytes_per_chunk, metric) per tile; finish(...) -> key
+template <int QT, int ND>
 struct Scorer;
 
 // 8-bit codes: 16 dims per chunk, payload = ND uint4 of digits per chunk
-template <>
-struct Scorer<Q8> {
+template <int ND>
+struct Scorer<Q8, ND> {
     struct Acc { int a[ND]; };
     static __device__ __forceinline__ void reset(Acc &s) {
 #pragma unroll
@@ -267,15 +260,15 @@ struct Scorer<Q8> {
 #pragma unroll
         for (int j = 0; j < ND; ++j) s.a[j] += b[j];
     }
-    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
-        return finish_quant(a, h, digits_total(s.a), x);
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
+        return finish_quant(a, h, digits_total<ND>(s.a), x);
     }
 };
 
 // 4-bit codes: 32 dims per chunk; byte = (even dim << 4) | odd dim.  Payload per chunk =
 // ND uint4 for the even dims (applied to w & 0xF0F0F0F0, i.e. 16*u) + ND uint4 for the odd.
-template <>
-struct Scorer<Q4> {
+template <int ND>
+struct Scorer<Q4, ND> {
     struct Acc { int hi[ND], lo[ND]; };
     static __device__ __forceinline__ void reset(Acc &s) {
 #pragma unroll
@@ -304,17 +297,17 @@ struct Scorer<Q4> {
         }
         for (; c < n; ++c) step(sd[c * 32], dg + c * 2 * ND, s.hi, s.lo);
     }
-    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
         // hi accumulates 16 * u_even * W: I = hi/16 + lo (exact in double)
-        return finish_quant(a, h, digits_total(s.hi) * 0.0625 + digits_total(s.lo), x);
+        return finish_quant(a, h, digits_total<ND>(s.hi) * 0.0625 + digits_total<ND>(s.lo), x);
     }
 };
 
 // 16-bit codes, stored as little-endian int16 of (u - 32768): 8 dims per chunk, payload =
 // ND uint2 of digits per chunk.  |s16 * s8| <= 2^22, so int32 partials are flushed to
 // double at the end of every tile (<= 32 chunks = 256 dims).
-template <>
-struct Scorer<Q16> {
+template <int ND>
+struct Scorer<Q16, ND> {
     struct Acc { double I; };
     static __device__ __forceinline__ void reset(Acc &s) { s.I = 0.0; }
     static __device__ __forceinline__ void step(const uint4 &v, const uint2 *dg, int (&acc)[ND]) {
@@ -341,16 +334,16 @@ struct Scorer<Q16> {
             step(v3, dg + (c + 3) * ND, acc);
         }
         for (; c < n; ++c) step(sd[c * 32], dg + c * ND, acc);
-        s.I += digits_total(acc);
+        s.I += digits_total<ND>(acc);
     }
-    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
         return finish_quant(a, h, s.I, x);
     }
 };
 
 // 32-bit float rows: payload = the query as float4 per chunk
-template <>
-struct Scorer<F32> {
+template <int ND>
+struct Scorer<F32, ND> {
     struct Acc { float a[4]; };
     static __device__ __forceinline__ void reset(Acc &s) { s.a[0] = s.a[1] = s.a[2] = s.a[3] = 0.f; }
     template <int METRIC>
@@ -380,16 +373,16 @@ struct Scorer<F32> {
         if (metric == COSINE) loop<COSINE>(s, sd, n, sq);
         else loop<EUCLID>(s, sd, n, sq);
     }
-    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
         const float r = (s.a[0] + s.a[1]) + (s.a[2] + s.a[3]);
-        if (a.metric == COSINE) return (h.zero_query || x.rn == 0.f) ? 1.0f : -(r * (float)h.c_key) * x.rn;
+        if (a.metric == COSINE) return (h.zero_query || x.x == 0.f) ? 1.0f : -(r * (float)h.c_key) * x.x;
         return r;
     }
 };
 
 // 64-bit float rows: payload = the query as double2 per chunk
-template <>
-struct Scorer<F64> {
+template <int ND>
+struct Scorer<F64, ND> {
     struct Acc { double a[2]; };
     static __device__ __forceinline__ void reset(Acc &s) { s.a[0] = s.a[1] = 0.0; }
     template <int METRIC>
@@ -421,9 +414,9 @@ struct Scorer<F64> {
         if (metric == COSINE) loop<COSINE>(s, sd, n, sq);
         else loop<EUCLID>(s, sd, n, sq);
     }
-    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const RowAux &x) {
+    static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
         const double r = s.a[0] + s.a[1];
-        if (a.metric == COSINE) return (h.zero_query || x.rn == 0.f) ? 1.0f : -((float)(r * h.c_key)) * x.rn;
+        if (a.metric == COSINE) return (h.zero_query || x.x == 0.f) ? 1.0f : -((float)(r * h.c_key)) * x.x;
         return (float)r;
     }
 };
@@ -432,11 +425,11 @@ struct Scorer<F64> {
 // pool[0 .. K') holds the K' best (surrogate, slot) keys, ascending.  Re-scores them in
 // fp64, orders by (distance, lexicographic id) and writes min(k, #) results.
 template <int QT>
-__device__ void finalize_topk(const FinalizeArgs &a, const double *q, unsigned long long *out_ids, double *out_dist,
-                              uint32_t *out_n, uint32_t *out_flags, const unsigned long long *pool, int Kp,
-                              double *s_ex, unsigned long long *s_id, int tid) {
-    __shared__ double s_dk, s_dmax;
-    if (tid == 0) { s_dk = 0.0; s_dmax = 0.0; }
+__device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHeader *hdr, unsigned long long *out_ids,
+                              double *out_dist, uint32_t *out_n, uint32_t *out_flags, const unsigned long long *pool,
+                              int Kp, double *s_ex, unsigned long long *s_id, int tid) {
+    __shared__ double s_dk;
+    if (tid == 0) s_dk = 0.0;
     bool valid = false;
     double d = 0.0;
     unsigned long long id = 0;
@@ -466,15 +459,25 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, unsigned l
             out_dist[rank] = d;
         }
         if ((uint32_t)rank + 1 == a.k) s_dk = d;
-        if (rank == cnt - 1) s_dmax = d;
     }
     __syncthreads();
     if (tid == 0) {
         uint32_t n = (uint32_t)cnt < a.k ? (uint32_t)cnt : a.k;
         *out_n = n;
-        // all non-candidates have a surrogate no better than the worst candidate; the result is
-        // certain when that candidate is clearly (1e-4 relative) farther than the k-th result
-        bool uncertain = (nfull == Kp) && ((uint32_t)cnt >= a.k ? !(s_dmax > s_dk * (1.0 + 1e-4)) : true);
+        // Certification.  Every row outside the candidate set has a surrogate key >= s_last (the
+        // worst candidate's), hence a true key >= s_last - e_abs - e_rel |s_last| (PQHeader bound).
+        // The result is certain when that lower bound still exceeds the true key of the k-th
+        // result.  A candidate set that is not full holds every live row: always certain.
+        bool uncertain = false;
+        if (nfull == Kp) {
+            if ((uint32_t)cnt < a.k) uncertain = true; // NaN candidates displaced real ones
+            else {
+                const double s_last = (double)key_to_float((uint32_t)(pool[Kp - 1] >> 32));
+                const double lower = s_last - hdr->e_abs - hdr->e_rel * fabs(s_last);
+                const double t_k = a.metric == COSINE ? -cospi(s_dk) : s_dk * s_dk;
+                uncertain = !(lower > t_k);
+            }
+        }
         *out_flags = uncertain ? 1u : 0u;
     }
 }
@@ -490,19 +493,20 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
     unsigned long long *pool = reinterpret_cast<unsigned long long *>(fsm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t qi = blockIdx.x;
-    const unsigned long long *cand = a.cand + (size_t)qi * a.ncta * Kp;
+    const unsigned long long *cand = a.cand + (size_t)qi * a.nlists * Kp;
     WarpList<E> list;
     list.init();
-    const uint32_t total = a.ncta * Kp;
+    const uint32_t total = a.nlists * Kp;
     for (uint32_t base = warp * 32; base < total; base += kFinalizeThreads) {
         const uint32_t i = base + lane;
-        list.offer(i < total ? cand[i] : kNoKey, lane);
+        list.offer(i < total ? __ldg(cand + i) : kNoKey, lane);
     }
     block_merge<E>(list, pool, tid, lane, warp, NW);
     double *s_ex = reinterpret_cast<double *>(pool + NW * Kp);
     unsigned long long *s_id = reinterpret_cast<unsigned long long *>(s_ex + Kp);
-    finalize_topk<QT>(a, a.queries + (size_t)qi * a.dims, a.out_ids + (size_t)qi * a.k, a.out_dist + (size_t)qi * a.k,
-                      a.out_n + qi, a.out_flags + qi, pool, Kp, s_ex, s_id, tid);
+    finalize_topk<QT>(a, a.queries + (size_t)qi * a.dims,
+                      reinterpret_cast<const PQHeader *>(a.pq + (size_t)qi * a.pq_stride), a.out_ids + (size_t)qi * a.k,
+                      a.out_dist + (size_t)qi * a.k, a.out_n + qi, a.out_flags + qi, pool, Kp, s_ex, s_id, tid);
 }
 inline size_t finalize_smem_bytes(int mode) {
     const size_t Kp = 32u << mode;
@@ -510,14 +514,20 @@ inline size_t finalize_smem_bytes(int mode) {
 }
 
 // ------------------------------------------------------------------------ the scan kernel
-// per-warp streaming state of the tile ring: which (block, tile) each stage holds
+// per-warp streaming state of the tile ring: which (query, block, tile) each stage holds
 struct RingMeta {
     uint32_t blk[kMaxStages];   // 0xFFFFFFFF = no more tiles
-    uint32_t tile[kMaxStages];
+    uint32_t tile[kMaxStages];  // tile index | query index << 16
     uint32_t live[kMaxStages];  // live & filter word of that block
 };
 
-template <int QT, int MODE>
+// One launch serves all nq queries of a call: every warp walks the sequence
+// (query 0: its blocks), (query 1: its blocks), ... without any CTA-level synchronisation, so
+// the copy pipeline never drains between queries and there is no per-query launch gap.  Each
+// (query, block) pair is still streamed from HBM once: single-query GEMV semantics.  The
+// prepared query (digits) is read through L1 (warp-uniform 128-bit loads): a few KB per
+// query, resident next to the streaming traffic, which bypasses L1 via the bulk copies.
+template <int QT, int MODE, int ND>
 __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanArgs a) {
     constexpr int E = (MODE == MODE_RADIUS) ? 1 : (1 << MODE);
     constexpr int Kp = 32 * E;
@@ -525,55 +535,47 @@ __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanA
     __shared__ __align__(8) uint64_t s_bar[kMaxScanWarps][kMaxStages];
     __shared__ RingMeta s_meta[kMaxScanWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
+    const int nwarps = blockDim.x >> 5;
     const uint32_t S = a.stages, Ct = a.Ct, C = a.C;
 
-    __shared__ PQHeader s_hdr; // read at block ends only: keep it out of the register file
-    const PQHeader &h = s_hdr;
-    if (tid < (int)(sizeof(PQHeader) / 16))
-        reinterpret_cast<uint4 *>(&s_hdr)[tid] = reinterpret_cast<const uint4 *>(a.pq)[tid];
-    {
-        const uint32_t n16 = (C * (uint32_t)pq_bytes_per_chunk(QT) + 15) / 16;
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.pq + sizeof(PQHeader));
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (uint32_t i = tid; i < n16; i += nthreads) dst[i] = src[i];
-    }
     if (lane == 0) {
         for (uint32_t s = 0; s < S; ++s) mbar_init(&s_bar[warp][s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-
-    WarpList<E> list;
-    list.init();
+    __syncwarp();
 
     // ---- streaming: this warp's blocks are gw, gw + stride, ...; tiles of Ct chunks
     const uint32_t stride = gridDim.x * nwarps;
+    const uint32_t gw = blockIdx.x * nwarps + warp;
     const uint32_t T = (C + Ct - 1) / Ct;
     const uint32_t stage_bytes = Ct * 512u;
-    unsigned char *ring = smem + a.ring_off + (size_t)warp * S * stage_bytes;
+    unsigned char *ring = smem + (size_t)warp * S * stage_bytes;
     RingMeta &meta = s_meta[warp];
     uint64_t *bars = s_bar[warp];
 
-    // issue iterator (warp-uniform): next (block, tile) to fetch
-    uint32_t iblk = blockIdx.x * nwarps + warp, itile = 0, ilive = 0;
-    auto seek_live = [&]() { // advance iblk to the next block with a live, unfiltered row
-        while (iblk < a.nblk) {
-            uint32_t w = __ldg(a.live + iblk);
-            if (a.mask) w &= __ldg(a.mask + iblk);
-            if (w) { ilive = w; return; }
-            iblk += stride;
+    // issue iterator (warp-uniform): next (query, block, tile) to fetch
+    uint32_t iq = 0, iblk = gw, itile = 0, ilive = 0;
+    auto seek_live = [&]() { // advance (iq, iblk) to the next block with a live, unfiltered row
+        while (iq < a.nq) {
+            while (iblk < a.nblk) {
+                uint32_t w = __ldg(a.live + iblk);
+                if (a.mask) w &= __ldg(a.mask + iblk);
+                if (w) { ilive = w; return; }
+                iblk += stride;
+            }
+            ++iq;
+            iblk = gw;
         }
     };
     seek_live();
     auto issue = [&](uint32_t s) { // all lanes run it (uniform control), lane 0 talks to the hardware
-        if (iblk >= a.nblk) {
+        if (iq >= a.nq) {
             if (lane == 0) meta.blk[s] = 0xFFFFFFFFu;
             return;
         }
         const uint32_t c0 = itile * Ct, n = min(Ct, C - c0);
         if (lane == 0) {
-            meta.blk[s] = iblk; meta.tile[s] = itile; meta.live[s] = ilive;
+            meta.blk[s] = iblk; meta.tile[s] = itile | (iq << 16); meta.live[s] = ilive;
             mbar_expect_tx(&bars[s], n * 512u);
             bulk_g2s(ring + (size_t)s * stage_bytes, a.codes + ((size_t)iblk * C + c0) * 32, n * 512u, &bars[s]);
         }
@@ -582,28 +584,61 @@ __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanA
     for (uint32_t s = 0; s < S; ++s) issue(s);
     __syncwarp();
 
-    typename Scorer<QT>::Acc acc;
-    Scorer<QT>::reset(acc);
-    RowAux aux;
-    aux.rn = 0.f; aux.s2 = 0.0;
-    uint32_t phases = 0, cs = 0;
-    const uint32_t bpc = (uint32_t)pq_bytes_per_chunk(QT);
+    WarpList<E> list;
+    list.init();
+    using Sc = Scorer<QT, ND>;
+    typename Sc::Acc acc;
+    Sc::reset(acc);
+    float2 aux = make_float2(0.f, 0.f);
+    uint32_t phases = 0, cs = 0, cq = 0;
+    const uint32_t bpc = (uint32_t)pq_bytes_per_chunk(QT, ND);
+    // prepared query cq (header + payload).  Normally a per-warp private copy in shared memory
+    // (digit loads are then warp-uniform LDS.128 broadcasts, 1 wavefront each; as global loads
+    // they cost ~4x the L1 data-pipe time and made that pipe the limiter); warps change query
+    // independently, so the copy needs no CTA-level synchronisation.
+    const unsigned char *gpq = a.pq;
+    unsigned char *spq = a.pq_smem_off ? smem + a.pq_smem_off + (size_t)warp * a.pq_stride : nullptr;
+    auto load_pq = [&]() {
+        if (!spq) return;
+        const uint4 *src = reinterpret_cast<const uint4 *>(gpq);
+        uint4 *dst = reinterpret_cast<uint4 *>(spq);
+        const uint32_t n16 = (uint32_t)(a.pq_stride / 16);
+        for (uint32_t i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
+        __syncwarp();
+    };
+    load_pq();
+    const unsigned char *pq = spq ? spq : gpq;
+    auto flush = [&]() {                                  // this warp's list of query cq -> finalize_kernel
+        if (MODE != MODE_RADIUS) {
+            unsigned long long *dst = a.cand + ((size_t)cq * stride + gw) * Kp + (size_t)lane * E;
+#pragma unroll
+            for (int e = 0; e < E; ++e) dst[e] = list.v[e];
+            list.init();
+        }
+    };
     while (true) {
         const uint32_t blk = meta.blk[cs];
         if (blk == 0xFFFFFFFFu) break;
-        const uint32_t tile = meta.tile[cs], lv = meta.live[cs];
+        const uint32_t tq = meta.tile[cs], lv = meta.live[cs];
+        const uint32_t tile = tq & 0xFFFFu, qn = tq >> 16;
+        if (cq < qn) {
+            while (cq < qn) { flush(); ++cq; gpq += a.pq_stride; }
+            load_pq();
+            pq = spq ? spq : gpq;
+        }
         const uint32_t slot = blk * 32 + lane;
         if (tile == 0) {
-            Scorer<QT>::reset(acc);
-            aux = load_aux<QT>(a, slot);
+            Sc::reset(acc);
+            aux = load_aux(a, slot);
         }
         mbar_wait(&bars[cs], (phases >> cs) & 1u);
         phases ^= 1u << cs;
         const uint32_t c0 = tile * Ct, n = min(Ct, C - c0);
-        Scorer<QT>::tile(acc, reinterpret_cast<const uint4 *>(ring + (size_t)cs * stage_bytes) + lane, n,
-                         smem + (size_t)c0 * bpc, (int)a.metric);
+        Sc::tile(acc, reinterpret_cast<const uint4 *>(ring + (size_t)cs * stage_bytes) + lane, n,
+                         pq + sizeof(PQHeader) + (size_t)c0 * bpc, (int)a.metric);
         if (tile == T - 1) {
-            const float key = Scorer<QT>::finish(acc, a, h, aux);
+            const PQHeader &h = *reinterpret_cast<const PQHeader *>(pq);
+            const float key = Sc::finish(acc, a, h, aux);
             const bool ok = (lv >> lane) & 1u;
             if (MODE == MODE_RADIUS) {
                 const bool pass = ok && key <= (float)h.radius_key;
@@ -626,29 +661,24 @@ __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanA
         __syncwarp(); // meta written by lane 0 is visible to the warp
         cs = (cs + 1 == S) ? 0 : cs + 1;
     }
-    if (MODE == MODE_RADIUS) return;
-
-    // ---- block merge in shared memory (payload and rings are dead from here on); the CTA's best
-    //      32*E keys go to this query's candidate area, finalize_kernel does the rest
-    unsigned long long *pool = reinterpret_cast<unsigned long long *>(smem);
-    __syncthreads();
-    block_merge<E>(list, pool, tid, lane, warp, nwarps);
-    if (tid < Kp) a.cand[(size_t)blockIdx.x * Kp + tid] = pool[tid];
+    while (cq < a.nq) { flush(); ++cq; } // remaining queries (also the ones this warp had no block for)
 }
 
 // ---- host-side launch plan: shared memory carve-up for (quantization, C, mode, warps, stages)
 struct ScanPlan {
-    uint32_t Ct, stages, ring_off, warps;
+    uint32_t Ct, stages, warps, pq_smem_off;
     size_t smem;
 };
-inline size_t scan_payload_bytes(int qt, uint32_t C) { return ((size_t)C * pq_bytes_per_chunk(qt) + 127) / 128 * 128; }
-inline bool scan_plan(int qt, uint32_t C, int mode, uint32_t warps, uint32_t stages, uint32_t max_tile_chunks,
+inline bool scan_plan(uint32_t C, uint32_t warps, uint32_t stages, uint32_t max_tile_chunks, size_t pq_stride,
                       size_t smem_limit, ScanPlan *p) {
-    const size_t payload = scan_payload_bytes(qt, C);
-    const size_t Kp = mode == MODE_RADIUS ? 32 : (32u << mode);
-    const size_t pool = (size_t)warps * Kp * 8;
-    if (payload + (size_t)warps * stages * 512 > smem_limit || pool > smem_limit) return false;
-    size_t per_stage = (smem_limit - payload) / ((size_t)warps * stages) / 512;
+    if ((size_t)warps * stages * 512 > smem_limit) return false;
+    // per-warp private copies of the prepared query, unless they would squeeze the rings below 2 KB tiles
+    const size_t pq_all = (size_t)warps * pq_stride;
+    const uint32_t want = max_tile_chunks < C ? max_tile_chunks : C;
+    const uint32_t floor_ct = want < 4 ? want : 4;
+    const bool pq_in_smem = pq_all + (size_t)warps * stages * 512 * floor_ct <= smem_limit;
+    const size_t ring_budget = smem_limit - (pq_in_smem ? pq_all : 0);
+    size_t per_stage = ring_budget / ((size_t)warps * stages) / 512;
     uint32_t Ct = (uint32_t)(per_stage < max_tile_chunks ? per_stage : max_tile_chunks);
     if (Ct > C) Ct = C;
     if (Ct > (uint32_t)kMaxTileChunks) Ct = kMaxTileChunks;
@@ -657,24 +687,30 @@ inline bool scan_plan(int qt, uint32_t C, int mode, uint32_t warps, uint32_t sta
     const uint32_t T = (C + Ct - 1) / Ct;
     Ct = (C + T - 1) / T;
     p->Ct = Ct; p->stages = stages; p->warps = warps;
-    p->ring_off = (uint32_t)payload;
-    size_t need = payload + (size_t)warps * stages * Ct * 512;
-    p->smem = need > pool ? need : pool;
+    const size_t rings = (size_t)warps * stages * Ct * 512;
+    p->pq_smem_off = pq_in_smem ? (uint32_t)rings : 0; // rings start at 0, so a non-zero offset doubles as the flag
+    p->smem = rings + (pq_in_smem ? pq_all : 0);
     return true;
 }
 
-// host-side launcher, instantiated per quantization in scan_<qt>.cu
-template <int QT>
-cudaError_t launch_scan_t(int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
+// host-side launcher, instantiated per quantization in scan_<qt>.cu.  Float rows have no digits:
+// only the ND = 3 instantiation exists for them.
+template <int QT, int ND>
+cudaError_t launch_scan_nd(int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
     switch (mode) {
-    case 0: scan_kernel<QT, 0><<<grid, threads, smem, st>>>(a); break;
-    case 1: scan_kernel<QT, 1><<<grid, threads, smem, st>>>(a); break;
-    case 2: scan_kernel<QT, 2><<<grid, threads, smem, st>>>(a); break;
-    case 3: scan_kernel<QT, 3><<<grid, threads, smem, st>>>(a); break;
-    case MODE_RADIUS: scan_kernel<QT, MODE_RADIUS><<<grid, threads, smem, st>>>(a); break;
+    case 0: scan_kernel<QT, 0, ND><<<grid, threads, smem, st>>>(a); break;
+    case 1: scan_kernel<QT, 1, ND><<<grid, threads, smem, st>>>(a); break;
+    case 2: scan_kernel<QT, 2, ND><<<grid, threads, smem, st>>>(a); break;
+    case 3: scan_kernel<QT, 3, ND><<<grid, threads, smem, st>>>(a); break;
+    case MODE_RADIUS: scan_kernel<QT, MODE_RADIUS, ND><<<grid, threads, smem, st>>>(a); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
+}
+template <int QT>
+cudaError_t launch_scan_t(int mode, int nd, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
+    if (QT <= Q16 && nd == 2) return launch_scan_nd<QT, (QT <= Q16 ? 2 : 3)>(mode, grid, threads, smem, st, a);
+    return launch_scan_nd<QT, 3>(mode, grid, threads, smem, st, a);
 }
 
 template <int QT>
@@ -693,9 +729,14 @@ cudaError_t launch_finalize_t(int mode, uint32_t nq, cudaStream_t st, const Fina
 template <int QT>
 cudaError_t scan_attr_t(size_t max_smem) {
     cudaError_t e;
-#define SZG_ATTR(M)                                                                                            \
-    e = cudaFuncSetAttribute(scan_kernel<QT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);  \
-    if (e != cudaSuccess) return e;
+#define SZG_ATTR(M)                                                                                              \
+    e = cudaFuncSetAttribute(scan_kernel<QT, M, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem); \
+    if (e != cudaSuccess) return e;                                                                              \
+    if (QT <= Q16) {                                                                                             \
+        e = cudaFuncSetAttribute(scan_kernel<QT, M, (QT <= Q16 ? 2 : 3)>,                                        \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);                    \
+        if (e != cudaSuccess) return e;                                                                          \
+    }
     SZG_ATTR(0) SZG_ATTR(1) SZG_ATTR(2) SZG_ATTR(3) SZG_ATTR(MODE_RADIUS)
 #undef SZG_ATTR
     return cudaSuccess;

@@ -3,8 +3,8 @@
 
 namespace szg {
 
-cudaError_t launch_scan_q4(int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
-    return launch_scan_t<Q4>(mode, grid, threads, smem, st, a);
+cudaError_t launch_scan_q4(int mode, int nd, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
+    return launch_scan_t<Q4>(mode, nd, grid, threads, smem, st, a);
 }
 
 cudaError_t launch_finalize_q4(int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a) {

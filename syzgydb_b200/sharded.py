@@ -29,10 +29,15 @@ def shard_bounds(nrows: int, world: int) -> list[int]:
 
 def record_layout(nq: int, k: int) -> tuple[int, int, int, int]:
     """Packed per-rank record exchanged by the all-gather, in 8-byte words:
-    [ids nq*k u64][dist nq*k f64][n nq u32, padded to 8 bytes] -> (off_ids, off_dist, off_n, words)."""
+    [ids nq*k u64][dist nq*k f64][n nq u32, padded to 8 bytes][flags nq u32, padded]
+    -> (off_ids, off_dist, off_n, words); the flags start at off_n + (nq + 1) // 2."""
     off_ids, off_dist, off_n = 0, nq * k, 2 * nq * k
-    words = off_n + (nq + 1) // 2
+    words = off_n + 2 * ((nq + 1) // 2)
     return off_ids, off_dist, off_n, words
+
+
+def flags_offset(nq: int, k: int) -> int:
+    return 2 * nq * k + (nq + 1) // 2
 
 
 class CudaShard:
@@ -47,14 +52,16 @@ class CudaShard:
         base = rec.data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.index.search_topk_dev(tq.data_ptr(), nq, k, base + 8 * off_ids, base + 8 * off_dist, base + 8 * off_n,
-                                   stream, mask_id, flags)
+                                   stream, mask_id, flags, d_out_flags=base + 8 * flags_offset(nq, k))
 
     def merge_into(self, gathered: torch.Tensor, world: int, nq: int, k: int, out: torch.Tensor):
         off_ids, off_dist, off_n, words = record_layout(nq, k)
         g, o = gathered.data_ptr(), out.data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        off_f = flags_offset(nq, k)
         self.index.merge_topk_dev(g + 8 * off_ids, g + 8 * off_dist, g + 8 * off_n, world, nq, k, o + 8 * off_ids,
-                                  o + 8 * off_dist, o + 8 * off_n, stream, rank_stride_bytes=8 * words)
+                                  o + 8 * off_dist, o + 8 * off_n, stream, rank_stride_bytes=8 * words,
+                                  d_g_flags=g + 8 * off_f, d_out_flags=o + 8 * off_f)
 
     def close(self):
         self.index.close()
@@ -139,10 +146,31 @@ class ShardedIndex:
         h_out.copy_(out, non_blocking=True)
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
-        return unpack_record(h_out.numpy(), nq, k)
+        ids, dd, n = unpack_record(h_out.numpy(), nq, k)
+        unc = unpack_flags(h_out.numpy(), nq, k) & 1
+        if unc.any() and isinstance(self.shard, CudaShard):
+            # a rank could not certify its local candidate set with the fast surrogate: those queries are
+            # re-run through the escalating host call on every rank and merged again (rare; collective)
+            self.shard.index.set_option(_capi.OPT_DIGITS, 3)
+            try:
+                sel = np.nonzero(unc)[0]
+                out2 = self.search_topk_dev(tq[torch.from_numpy(sel).to(self.device)].contiguous(), k, mask_id, flags)
+                h2 = self._buffers(len(sel), k)[3]
+                h2.copy_(out2, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                i2, d2, n2 = unpack_record(h2.numpy(), len(sel), k)
+                ids[sel], dd[sel], n[sel] = i2, d2, n2
+            finally:
+                self.shard.index.set_option(_capi.OPT_DIGITS, 0)
+        return ids, dd, n
 
     def close(self):
         self.shard.close()
+
+
+def unpack_flags(words: np.ndarray, nq: int, k: int) -> np.ndarray:
+    w = np.ascontiguousarray(words[:record_layout(nq, k)[3]]).view(np.uint64)
+    return w[flags_offset(nq, k):].view(np.uint32)[:nq].copy()
 
 
 def unpack_record(words: np.ndarray, nq: int, k: int):
@@ -150,5 +178,5 @@ def unpack_record(words: np.ndarray, nq: int, k: int):
     w = np.ascontiguousarray(words[:total]).view(np.uint64)
     ids = w[off_ids:off_ids + nq * k].reshape(nq, k).copy()
     dd = w[off_dist:off_dist + nq * k].view(np.float64).reshape(nq, k).copy()
-    n = w[off_n:].view(np.uint32)[:nq].copy()
+    n = w[off_n:off_n + (nq + 1) // 2].view(np.uint32)[:nq].copy()
     return ids, dd, n

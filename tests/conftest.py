@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # keep the in-tree CUDA library and the oracle in step with their sources (no-ops when up to date)
+    import subprocess
+    for d in (os.path.join(ROOT, "syzgydb_b200", "csrc"), os.path.join(ROOT, "oracle")):
+        try:
+            subprocess.run(["make", "-C", d, "-j", str(os.cpu_count() or 2)], check=False, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL, timeout=900)
+        except Exception:
+            pass
 
 
 def _has_gpu():

@@ -118,10 +118,10 @@ def test_shard_bounds_and_record_layout():
     assert shard_bounds(10, 3) == [0, 4, 7, 10]
     assert shard_bounds(10_000_000, 8)[-1] == 10_000_000 and len(set(np.diff(shard_bounds(10_000_000, 8)))) == 1
     off_ids, off_dist, off_n, words = record_layout(5, 10)
-    assert (off_ids, off_dist, off_n, words) == (0, 50, 100, 103)
+    assert (off_ids, off_dist, off_n, words) == (0, 50, 100, 106)
     w = np.zeros(words, dtype=np.int64)
     w.view(np.uint64)[0:50] = np.arange(50)
     w.view(np.float64)[50:100] = np.arange(50) * 0.5
-    w[100:].view(np.uint32)[:5] = 10
+    w[100:103].view(np.uint32)[:5] = 10
     ids, dd, n = unpack_record(w, 5, 10)
     assert ids[4, 9] == 49 and dd[1, 0] == 5.0 and n.tolist() == [10] * 5

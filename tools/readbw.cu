@@ -77,6 +77,27 @@ int main(int argc, char **argv) {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     float ms;
+    if (argc > 2) { // sustained mode: argv[2] = iterations; prints the bandwidth of every 8th launch
+        int iters = atoi(argv[2]);
+        cudaFuncSetAttribute(bulk_ring<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+        for (int mode = 0; mode < 2; ++mode) {
+            printf("sustained %s:", mode ? "bulk ring 16w S3 4096B" : "ldg128 4xSM");
+            for (int it = 0; it < iters; ++it) {
+                cudaEventRecord(e0);
+                if (mode == 0) ldg_sum<<<sms * 4, 256>>>((const uint4 *)d, bytes / 16, out);
+                else bulk_ring<0><<<sms, 512, 16 * 3 * 4096>>>(d, bytes / 4096, 4096, 3, out);
+                cudaEventRecord(e1);
+                if (it % 8 == 7) {
+                    cudaEventSynchronize(e1);
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    printf(" %.0f", bytes / ms / 1e6);
+                }
+            }
+            cudaDeviceSynchronize();
+            printf("\n");
+        }
+        return 0;
+    }
     for (int blocks_per_sm : {2, 4, 8}) {
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(e0);

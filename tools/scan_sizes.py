@@ -8,13 +8,14 @@ dims, quant = 768, 8
 qs = np.random.default_rng(1).uniform(-1, 1, size=(16, dims))
 for flags in (0, 1):
     pts = []
-    for rows in (250_000, 500_000, 1_000_000, 2_000_000, 4_000_000, 8_000_000, 16_000_000):
+    for rows in [int(x) for x in os.environ.get('SIZES', '250000,500000,1000000,2000000,4000000,8000000,16000000').split(',')]:
         ix = szg.Index(dims, quant, szg.COSINE)
         ix.fill_synthetic(7, 0, rows)
         ix.set_option(_capi.OPT_STREAMS, 1)
         ix.search_topk(qs[:2], 10, flags=flags)
-        ix.search_topk(qs, 10, flags=flags)
-        ms = float(np.mean(ix.last_scan_times_ms()))
+        nq = int(os.environ.get('NQ', '16'))
+        ix.search_topk(qs[:nq], 10, flags=flags)
+        ms = float(np.mean(ix.last_scan_times_ms())) / nq  # one launch scans all nq queries
         pts.append((rows * 768 / 1e9, ms))
         print(json.dumps(dict(flags=flags, rows=rows, gb=rows * 768 / 1e9, ms=round(ms, 4), gbs=round(rows * 768 / ms / 1e6, 1))), flush=True)
         ix.close()

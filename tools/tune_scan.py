@@ -15,7 +15,7 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 dims = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 quant = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 metric = szg.COSINE if (sys.argv[4] if len(sys.argv) > 4 else "cosine") == "cosine" else szg.EUCLIDEAN
-nq = 12
+nq = int(os.environ.get("NQ", "12"))
 qs = np.random.default_rng(1).uniform(-1, 1, size=(nq, dims))
 ix = szg.Index(dims, quant, metric)
 ix.fill_synthetic(7, 0, rows)
@@ -33,7 +33,7 @@ for warps, stages, tc in itertools.product((8, 16), (2, 3, 4, 6), (4, 6, 8, 12, 
         ref = ids.copy()
     assert np.array_equal(ids, ref), "results changed with the geometry"
     t = ix.last_scan_times_ms()
-    ms = float(np.mean(t))
+    ms = float(np.mean(t)) / nq  # one launch scans all nq queries
     gbs = rows * ix.rowbytes / ms / 1e6
     rec = dict(warps=warps, stages=stages, tile_chunks=tc, tile_bytes=st["scan_tile_bytes"], eff_stages=st["scan_stages"],
                smem=st["scan_smem_bytes"], ms=round(ms, 4), gbs=round(gbs, 1))
