@@ -421,15 +421,128 @@ struct Scorer<F64, ND> {
     }
 };
 
-// ------------------------------------------------------- last-CTA finalisation (top-k)
+// ------------------------------------------------------------------- finalisation (top-k)
+constexpr int kFinalizeThreads = 512;
+constexpr size_t kFinalizeStageBytes = 64 * 1024; // staging area of the fp64 re-score
+
+// fp64 distances of the Kp candidates in pool[], in the reference's operation order (same element
+// order and the same un-fused multiply/add sequence as exact_distance_impl), but with the
+// operands staged through shared memory slab by slab: the whole CTA fetches the candidates'
+// chunks (one memory round trip per slab instead of one per chunk and candidate), then thread r
+// runs the sequential chain of candidate r out of shared memory.  dequantize: 4/8-bit through a
+// shared copy of the host-built table, 16-bit with the same three IEEE operations
+// ((v / maxInt) * 2 - 1, quantization.go:34-35).
+template <int QT, int METRIC>
+__device__ void exact_staged(const FinalizeArgs &a, const double *__restrict__ q, const unsigned long long *pool,
+                             int Kp, unsigned char *stage, double *s_out, int tid) {
+    constexpr int EPC = QT == Q4 ? 32 : QT == Q8 ? 16 : QT == Q16 ? 8 : QT == F32 ? 4 : 2;
+    constexpr int LUTN = QT == Q4 ? 16 : QT == Q8 ? 256 : 0;
+    double *s_lut = reinterpret_cast<double *>(stage);
+    unsigned char *body = stage + LUTN * sizeof(double);
+    const size_t budget = kFinalizeStageBytes - LUTN * sizeof(double);
+    // per chunk: Kp uint4 of codes + EPC doubles of the query; rows padded by one uint4 against bank conflicts
+    uint32_t SC = (uint32_t)((budget - (size_t)Kp * 16) / ((size_t)Kp * 16 + EPC * 8));
+    if (SC > a.C) SC = a.C;
+    uint4 *s_codes = reinterpret_cast<uint4 *>(body);
+    double *s_q = reinterpret_cast<double *>(body + (size_t)Kp * (SC + 1) * 16);
+    for (int i = tid; i < LUTN; i += kFinalizeThreads) s_lut[i] = a.lut[i];
+
+    const bool mine = tid < Kp && pool[tid < Kp ? tid : 0] != kNoKey;
+    ExactAcc acc = {0.0, 0.0, 0.0, 0.0};
+    for (uint32_t c0 = 0; c0 < a.C; c0 += SC) {
+        const uint32_t nc = min(SC, a.C - c0);
+        __syncthreads(); // previous slab fully consumed (and the table written)
+        for (uint32_t idx = tid; idx < (uint32_t)Kp * nc; idx += kFinalizeThreads) {
+            const uint32_t r = idx / nc, c = idx % nc;
+            const unsigned long long key = pool[r];
+            if (key != kNoKey) s_codes[(size_t)r * (SC + 1) + c] = __ldg(a.codes + chunk_index((uint32_t)key, a.C, c0 + c));
+        }
+        for (uint32_t e = tid; e < nc * EPC; e += kFinalizeThreads) {
+            const uint32_t i = c0 * EPC + e;
+            s_q[e] = i < a.dims ? q[i] : 0.0;
+        }
+        __syncthreads();
+        if (mine) {
+            const uint4 *row = s_codes + (size_t)tid * (SC + 1);
+            uint32_t i = c0 * EPC;
+            for (uint32_t c = 0; c < nc && i < a.dims; ++c) {
+                const uint4 v = row[c];
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                const double *qq = s_q + (size_t)c * EPC;
+                int e = 0;
+                if (QT == Q4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const uint32_t byte = (w[k] >> (8 * b)) & 0xFF;
+                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], s_lut[byte >> 4]);
+                            ++i; ++e;
+                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], s_lut[byte & 0x0F]);
+                            ++i; ++e;
+                        }
+                } else if (QT == Q8) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], s_lut[(w[k] >> (8 * b)) & 0xFF]);
+                            ++i; ++e;
+                        }
+                } else if (QT == Q16) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            const uint32_t u = ((w[k] >> (16 * hlf)) & 0xFFFF) ^ 0x8000u; // stored centred
+                            const double x = __dsub_rn(__dmul_rn(__ddiv_rn((double)u, 65535.0), 2.0), 1.0);
+                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], x);
+                            ++i; ++e;
+                        }
+                } else if (QT == F32) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (i < a.dims) exact_step<METRIC>(acc, qq[e], (double)__uint_as_float(w[k]));
+                        ++i; ++e;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (i < a.dims) exact_step<METRIC>(acc, qq[e], __hiloint2double((int)w[2 * k + 1], (int)w[2 * k]));
+                        ++i; ++e;
+                    }
+                }
+            }
+        }
+    }
+    if (mine) {
+        double d;
+        if (METRIC == COSINE) {
+            if (acc.m1 == 0.0 || acc.m2 == 0.0) d = 1.0; // collection.go:828-830
+            else {
+                const double r = __ddiv_rn(acc.dot, __dmul_rn(__dsqrt_rn(acc.m1), __dsqrt_rn(acc.m2)));
+                d = __ddiv_rn(acos(r), 3.141592653589793); // acos(r > 1) = NaN, as Go math.Acos
+            }
+        } else {
+            d = __dsqrt_rn(acc.sum);
+        }
+        s_out[tid] = d;
+    }
+    __syncthreads();
+}
+
 // pool[0 .. K') holds the K' best (surrogate, slot) keys, ascending.  Re-scores them in
-// fp64, orders by (distance, lexicographic id) and writes min(k, #) results.
+// fp64, orders by (distance, lexicographic id), writes min(k, #) results and certifies.
 template <int QT>
 __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHeader *hdr, unsigned long long *out_ids,
                               double *out_dist, uint32_t *out_n, uint32_t *out_flags, const unsigned long long *pool,
-                              int Kp, double *s_ex, unsigned long long *s_id, int tid) {
+                              int Kp, double *s_ex, unsigned long long *s_id, unsigned char *stage, int tid) {
     __shared__ double s_dk;
     if (tid == 0) s_dk = 0.0;
+    if (!(a.flags & 1u)) {
+        if (a.metric == COSINE) exact_staged<QT, COSINE>(a, q, pool, Kp, stage, s_ex, tid);
+        else exact_staged<QT, EUCLID>(a, q, pool, Kp, stage, s_ex, tid);
+    }
     bool valid = false;
     double d = 0.0;
     unsigned long long id = 0;
@@ -439,9 +552,12 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHe
             uint32_t slot = (uint32_t)key;
             id = a.ids[slot];
             if (a.flags & 1u) d = key_to_distance(a.metric, key_to_float((uint32_t)(key >> 32)));
-            else d = exact_distance<QT>(a.codes, a.C, a.dims, a.metric, a.lut, q, slot);
+            else d = s_ex[tid];
             valid = (d == d); // NaN is never returned
         }
+    }
+    __syncthreads();
+    if (tid < Kp) {
         s_ex[tid] = valid ? d : __longlong_as_double(0x7ff8000000000000ll);
         s_id[tid] = id;
     }
@@ -482,13 +598,12 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHe
     }
 }
 
-constexpr int kFinalizeThreads = 256;
-
 template <int QT, int MODE>
 __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const FinalizeArgs a) {
     constexpr int E = 1 << MODE;
     constexpr int Kp = 32 * E;
     constexpr int NW = kFinalizeThreads / 32;
+    constexpr int PF = 8; // candidate keys fetched ahead per lane: the merge is load-latency-bound otherwise
     extern __shared__ __align__(16) unsigned char fsm[];
     unsigned long long *pool = reinterpret_cast<unsigned long long *>(fsm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -497,20 +612,27 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
     WarpList<E> list;
     list.init();
     const uint32_t total = a.nlists * Kp;
-    for (uint32_t base = warp * 32; base < total; base += kFinalizeThreads) {
-        const uint32_t i = base + lane;
-        list.offer(i < total ? __ldg(cand + i) : kNoKey, lane);
+    for (uint32_t base = warp * 32; base < total; base += kFinalizeThreads * PF) {
+        unsigned long long v[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const uint32_t i = base + u * kFinalizeThreads + lane;
+            v[u] = i < total ? __ldg(cand + i) : kNoKey;
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) list.offer(v[u], lane);
     }
     block_merge<E>(list, pool, tid, lane, warp, NW);
     double *s_ex = reinterpret_cast<double *>(pool + NW * Kp);
     unsigned long long *s_id = reinterpret_cast<unsigned long long *>(s_ex + Kp);
+    unsigned char *stage = reinterpret_cast<unsigned char *>(s_id + Kp);
     finalize_topk<QT>(a, a.queries + (size_t)qi * a.dims,
                       reinterpret_cast<const PQHeader *>(a.pq + (size_t)qi * a.pq_stride), a.out_ids + (size_t)qi * a.k,
-                      a.out_dist + (size_t)qi * a.k, a.out_n + qi, a.out_flags + qi, pool, Kp, s_ex, s_id, tid);
+                      a.out_dist + (size_t)qi * a.k, a.out_n + qi, a.out_flags + qi, pool, Kp, s_ex, s_id, stage, tid);
 }
 inline size_t finalize_smem_bytes(int mode) {
     const size_t Kp = 32u << mode;
-    return (size_t)(kFinalizeThreads / 32) * Kp * 8 + Kp * 16;
+    return (size_t)(kFinalizeThreads / 32) * Kp * 8 + Kp * 16 + kFinalizeStageBytes;
 }
 
 // ------------------------------------------------------------------------ the scan kernel
@@ -729,6 +851,12 @@ cudaError_t launch_finalize_t(int mode, uint32_t nq, cudaStream_t st, const Fina
 template <int QT>
 cudaError_t scan_attr_t(size_t max_smem) {
     cudaError_t e;
+#define SZG_FATTR(M)                                                                                             \
+    e = cudaFuncSetAttribute(finalize_kernel<QT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                             (int)finalize_smem_bytes(M));                                                        \
+    if (e != cudaSuccess) return e;
+    SZG_FATTR(0) SZG_FATTR(1) SZG_FATTR(2) SZG_FATTR(3)
+#undef SZG_FATTR
 #define SZG_ATTR(M)                                                                                              \
     e = cudaFuncSetAttribute(scan_kernel<QT, M, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem); \
     if (e != cudaSuccess) return e;                                                                              \
