@@ -1,0 +1,587 @@
+// collection.cpp -- see collection.hpp.  Host logic only; every distance is computed on the GPU through
+// the C ABI (include/syzgy_b200.h).  No CPU distance code lives here (lshtree.go's hyperplane
+// arithmetic, which is tree navigation rather than the search hot path, stays on the host as in the
+// reference).
+#include "collection.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <random>
+#include <shared_mutex>
+#include <stdexcept>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "../../include/syzgy_b200.h"
+
+namespace syzgydb {
+
+// ------------------------------------------------------------------------------------ codec
+uint64_t quantize(double value, int bits) { // quantization.go:5-23
+    if (bits == 32) {
+        float f = (float)value;
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        return u;
+    }
+    if (bits == 64) {
+        uint64_t u;
+        std::memcpy(&u, &value, 8);
+        return u;
+    }
+    if (value < -1) value = -1;
+    else if (value > 1) value = 1;
+    const int64_t maxInt = ((int64_t)1 << bits) - 1;
+    return (uint64_t)std::round((value + 1) / 2 * (double)maxInt); // math.Round: half away from zero
+}
+
+double dequantize(uint64_t value, int bits) { // quantization.go:25-36
+    if (bits == 32) {
+        uint32_t u = (uint32_t)value;
+        float f;
+        std::memcpy(&f, &u, 4);
+        return (double)f;
+    }
+    if (bits == 64) {
+        double d;
+        std::memcpy(&d, &value, 8);
+        return d;
+    }
+    const int64_t maxInt = ((int64_t)1 << bits) - 1;
+    return ((double)value / (double)maxInt) * 2 - 1;
+}
+
+int getVectorSize(int quantization, int dimensions) { // collection.go:796-811
+    switch (quantization) {
+    case 4: return (dimensions + 1) / 2;
+    case 8: return dimensions;
+    case 16: return dimensions * 2;
+    case 32: return dimensions * 4;
+    case 64: return dimensions * 8;
+    }
+    throw std::invalid_argument("Unsupported quantization level");
+}
+
+std::vector<uint8_t> encodeDocument(const std::vector<double> &vector, int quantization) { // collection.go:713-744
+    const int dims = (int)vector.size();
+    std::vector<uint8_t> data((size_t)getVectorSize(quantization, dims), 0);
+    size_t off = 0;
+    for (int i = 0; i < dims; ++i) {
+        const uint64_t q = quantize(vector[(size_t)i], quantization);
+        switch (quantization) {
+        case 4:
+            if (i % 2 == 0) data[off] = (uint8_t)(q << 4); // even index: high nibble
+            else { data[off] |= (uint8_t)(q & 0x0F); ++off; }
+            break;
+        case 8: data[off++] = (uint8_t)q; break;
+        default: {
+            const int nb = quantization / 8;
+            for (int b = 0; b < nb; ++b) data[off++] = (uint8_t)(q >> (8 * (nb - 1 - b))); // big-endian
+        }
+        }
+    }
+    return data;
+}
+
+std::vector<double> decodeVector(const uint8_t *data, int dimensions, int quantization) { // collection.go:768-794
+    std::vector<double> v((size_t)dimensions);
+    size_t off = 0;
+    for (int i = 0; i < dimensions; ++i) {
+        uint64_t q = 0;
+        switch (quantization) {
+        case 4:
+            if (i % 2 == 0) q = data[off] >> 4;
+            else { q = data[off] & 0x0F; ++off; }
+            break;
+        case 8: q = data[off++]; break;
+        default: {
+            const int nb = quantization / 8;
+            for (int b = 0; b < nb; ++b) q = (q << 8) | data[off++];
+        }
+        }
+        v[(size_t)i] = dequantize(q, quantization);
+    }
+    return v;
+}
+
+namespace {
+
+[[noreturn]] void gpu_fail(const char *what) { // the reference panics on storage faults (collection.go:667, 683)
+    throw std::runtime_error(std::string("syzgy_b200 ") + what + ": " + szg_last_error());
+}
+#define GPU(call, what) do { if ((call) != SZG_OK) gpu_fail(what); } while (0)
+
+// sort.Strings order of decimal ids (spanfile.go:540-560)
+bool lex_less(uint64_t a, uint64_t b) { return std::to_string(a) < std::to_string(b); }
+
+// ----------------------------------------------------------------- container/heap, restated
+// Go's container/heap over a slice with a user Less: Push = append + up, Pop = swap(0, n-1) +
+// down(0, n-1) + remove last.  Needed to reproduce pop order among equal priorities.
+template <typename T, typename Less>
+struct GoHeap {
+    std::vector<T> a;
+    Less less;
+    void up(size_t j) {
+        while (j > 0) {
+            size_t i = (j - 1) / 2;
+            if (i == j || !less(a[j], a[i])) break;
+            std::swap(a[i], a[j]);
+            j = i;
+        }
+    }
+    void down(size_t i0, size_t n) {
+        size_t i = i0;
+        for (;;) {
+            size_t j1 = 2 * i + 1;
+            if (j1 >= n) break;
+            size_t j = j1, j2 = j1 + 1;
+            if (j2 < n && less(a[j2], a[j1])) j = j2;
+            if (!less(a[j], a[i])) break;
+            std::swap(a[i], a[j]);
+            i = j;
+        }
+    }
+    void push(T x) { a.push_back(std::move(x)); up(a.size() - 1); }
+    T pop() {
+        const size_t n = a.size() - 1;
+        std::swap(a[0], a[n]);
+        down(0, n);
+        T x = std::move(a.back());
+        a.pop_back();
+        return x;
+    }
+    size_t size() const { return a.size(); }
+};
+
+struct ResultItem { uint64_t id; double priority; };
+struct ResultLess { bool operator()(const ResultItem &x, const ResultItem &y) const { return x.priority > y.priority; } }; // collection.go:545-547
+
+// ----------------------------------------------------------------------------- lshtree.go
+struct LshNode { // lshtree.go:46-52 (radius is tracked by the reference but never read by search)
+    std::vector<double> normal;
+    double b = 0;
+    std::unique_ptr<LshNode> left, right;
+    std::vector<uint64_t> ids;
+    bool isLeaf() const { return !left; } // lshtree.go:55-57
+};
+
+double dotProduct(const std::vector<double> &a, const std::vector<double> &b) {
+    double dot = 0.0;
+    for (size_t i = 0; i < a.size(); ++i) dot += a[i] * b[i];
+    return dot;
+}
+double vectorLength(const std::vector<double> &v) { return std::sqrt(dotProduct(v, v)); } // lshtree.go:30-36
+
+// lshtree.go:59-77
+void distanceToHyperplane(int method, const std::vector<double> &v, double length, const std::vector<double> &normal,
+                          double b, double *dist, bool *right) {
+    double d = dotProduct(v, normal) - b;
+    *right = false;
+    if (method == Euclidean) {
+        if (d > 0) *right = true;
+        else d = -d;
+        *dist = d;
+        return;
+    }
+    d = std::acos(d / length) / M_PI;
+    if (d > 0.5) { *right = true; d = 1 - d; }
+    *dist = d;
+}
+
+struct NodeItem { LshNode *node; double priority; };
+struct NodeLess { bool operator()(const NodeItem &x, const NodeItem &y) const { return x.priority > y.priority; } }; // lshtree.go:362-364
+
+} // namespace
+
+// ================================================================================ Collection
+struct Collection::Impl {
+    CollectionOptions opt;
+    szg_index *gpu = nullptr;
+    int rowbytes = 0;
+    struct Rec { std::string meta; std::vector<uint8_t> codes; };
+    std::unordered_map<uint64_t, Rec> store; // stands in for the span file (id -> {stream 0, stream 1})
+    mutable std::shared_mutex mu;
+    // lsh tree (newLSHTree(c, 100, 5), collection.go:292)
+    std::vector<std::unique_ptr<LshNode>> roots;
+    int threshold = 100;
+    std::mt19937_64 rng;
+    std::normal_distribution<double> gauss{0.0, 1.0};
+    // test hooks
+    std::vector<uint64_t> last_visit;
+    int last_batches = 0;
+
+    std::vector<double> docVector(uint64_t id) const { // getDocument's decode (collection.go:470-484)
+        auto it = store.find(id);
+        if (it == store.end()) throw std::runtime_error("error getting document");
+        return decodeVector(it->second.codes.data(), opt.DimensionCount, opt.Quantization);
+    }
+
+    std::vector<double> randomNormalizedVector(int dim) { // lshtree.go:38-44, 10-28
+        std::vector<double> v((size_t)dim);
+        double norm = 0;
+        for (auto &x : v) { x = gauss(rng); norm += x * x; }
+        if (norm == 0) return v;
+        norm = std::sqrt(norm);
+        for (auto &x : v) x /= norm;
+        return v;
+    }
+
+    std::unique_ptr<LshNode> split(std::unique_ptr<LshNode> node) { // lshtree.go:172-248
+        const size_t n = node->ids.size();
+        const size_t i1 = (size_t)(rng() % n);
+        size_t i2;
+        do { i2 = (size_t)(rng() % n); } while (i2 == i1);
+        const std::vector<double> v1 = docVector(node->ids[i1]), v2 = docVector(node->ids[i2]);
+        bool same = true; // aboutEqual, tolerance 1e-9 (lshtree.go:158-170)
+        for (size_t i = 0; i < v1.size(); ++i)
+            if (std::fabs(v1[i] - v2[i]) > 1e-9) { same = false; break; }
+        if (same) return node;
+        std::vector<double> mid(v1.size());
+        for (size_t i = 0; i < v1.size(); ++i) mid[i] = (v1[i] + v2[i]) / 2;
+        std::vector<double> normal = randomNormalizedVector((int)mid.size());
+        double b = 0;
+        if (opt.DistanceMethod == Euclidean) b = std::sqrt(dotProduct(mid, mid));
+        std::vector<uint64_t> leftIDs, rightIDs;
+        for (uint64_t id : node->ids) {
+            const std::vector<double> v = docVector(id);
+            double dist;
+            bool right;
+            distanceToHyperplane(opt.DistanceMethod, v, vectorLength(v), normal, b, &dist, &right);
+            (right ? rightIDs : leftIDs).push_back(id);
+        }
+        if (leftIDs.empty() || rightIDs.empty()) return node;
+        auto parent = std::make_unique<LshNode>();
+        parent->normal = std::move(normal);
+        parent->b = b;
+        parent->left = std::make_unique<LshNode>();
+        parent->left->ids = std::move(leftIDs);
+        parent->right = std::make_unique<LshNode>();
+        parent->right->ids = std::move(rightIDs);
+        return parent;
+    }
+
+    std::unique_ptr<LshNode> insert(std::unique_ptr<LshNode> node, uint64_t id, const std::vector<double> &v,
+                                    double length) { // lshtree.go:116-134
+        if (node->isLeaf()) {
+            node->ids.push_back(id);
+            if ((int)node->ids.size() > threshold) node = split(std::move(node));
+            return node;
+        }
+        double dist;
+        bool right;
+        distanceToHyperplane(opt.DistanceMethod, v, length, node->normal, node->b, &dist, &right);
+        if (!right) node->left = insert(std::move(node->left), id, v, length);
+        else node->right = insert(std::move(node->right), id, v, length);
+        return node;
+    }
+
+    std::unique_ptr<LshNode> remove(std::unique_ptr<LshNode> node, uint64_t id, const std::vector<double> &v,
+                                    double length) { // lshtree.go:257-281
+        if (!node) return node;
+        if (node->isLeaf()) {
+            auto it = std::find(node->ids.begin(), node->ids.end(), id);
+            if (it != node->ids.end()) node->ids.erase(it);
+            if (node->ids.empty()) return nullptr;
+            return node;
+        }
+        double dist;
+        bool right;
+        distanceToHyperplane(opt.DistanceMethod, v, length, node->normal, node->b, &dist, &right);
+        if (!right) node->left = remove(std::move(node->left), id, v, length);
+        else node->right = remove(std::move(node->right), id, v, length);
+        return node;
+    }
+
+    void addPoint(uint64_t id, const std::vector<double> &v) { // lshtree.go:101-114 (sequential here)
+        const double length = vectorLength(v);
+        for (auto &root : roots) root = insert(std::move(root), id, v, length);
+    }
+    void removePoint(uint64_t id, const std::vector<double> &v) { // lshtree.go:250-255
+        const double length = vectorLength(v);
+        for (auto &root : roots) {
+            root = remove(std::move(root), id, v, length);
+            if (!root) root = std::make_unique<LshNode>();
+        }
+    }
+
+    int buildMask(const FilterFn &filter) { // FilterFn outcome -> GPU bitmask (collection.go:592-594 applied per record)
+        std::vector<uint64_t> ids;
+        std::vector<uint8_t> pass;
+        ids.reserve(store.size());
+        pass.reserve(store.size());
+        for (const auto &kv : store) {
+            ids.push_back(kv.first);
+            pass.push_back(filter(kv.first, kv.second.meta) ? 1 : 0);
+        }
+        int mask = -1;
+        GPU(szg_mask_create(gpu, ids.data(), pass.data(), ids.size(), &mask), "mask_create");
+        return mask;
+    }
+
+    SearchResults search(SearchArgs &args);
+    SearchResults searchIndex(const SearchArgs &args);
+};
+
+Collection::Collection(const CollectionOptions &options) : p_(new Impl) {
+    p_->opt = options;
+    if (p_->opt.Quantization == 0) p_->opt.Quantization = 64; // collection.go:254-256
+    p_->rowbytes = getVectorSize(p_->opt.Quantization, p_->opt.DimensionCount);
+    if (p_->opt.DistanceMethod != Euclidean && p_->opt.DistanceMethod != Cosine)
+        throw std::invalid_argument("Unsupported distance method"); // collection.go:281-282 panics
+    if (szg_create(p_->opt.DimensionCount, p_->opt.Quantization, p_->opt.DistanceMethod, p_->opt.Device, &p_->gpu) != SZG_OK)
+        throw std::runtime_error(std::string("syzgy_b200 create: ") + szg_last_error());
+    p_->rng.seed(options.Seed);
+    for (int i = 0; i < 5; ++i) p_->roots.push_back(std::make_unique<LshNode>());
+}
+
+Collection::~Collection() { Close(); }
+
+void Collection::Close() {
+    std::unique_lock<std::shared_mutex> lk(p_->mu);
+    if (p_->gpu) { szg_destroy(p_->gpu); p_->gpu = nullptr; }
+}
+
+const CollectionOptions &Collection::Options() const { return p_->opt; }
+const std::vector<uint64_t> &Collection::LastVisitSequence() const { return p_->last_visit; }
+int Collection::LastRescoreBatches() const { return p_->last_batches; }
+
+void Collection::AddDocument(uint64_t id, const std::vector<double> &vector, const std::string &metadata) {
+    std::unique_lock<std::shared_mutex> lk(p_->mu);
+    if ((int)vector.size() != p_->opt.DimensionCount)
+        throw std::invalid_argument("vector size does not match the expected number of dimensions"); // 431-434 panics
+    Impl::Rec rec{metadata, encodeDocument(vector, p_->opt.Quantization)};
+    GPU(szg_upsert(p_->gpu, &id, rec.codes.data(), 1), "upsert"); // right after WriteRecord (446-453)
+    p_->store[id] = std::move(rec);
+    p_->addPoint(id, vector); // 456: the raw vector, not the decoded one
+}
+
+void Collection::AddDocuments(const std::vector<uint64_t> &ids, const std::vector<std::vector<double>> &vectors,
+                              const std::vector<std::string> &metadata) {
+    std::unique_lock<std::shared_mutex> lk(p_->mu);
+    if (ids.size() != vectors.size() || (!metadata.empty() && metadata.size() != ids.size()))
+        throw std::invalid_argument("ids, vectors and metadata must have the same length");
+    std::vector<uint8_t> all((size_t)p_->rowbytes * ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        if ((int)vectors[i].size() != p_->opt.DimensionCount)
+            throw std::invalid_argument("vector size does not match the expected number of dimensions");
+        Impl::Rec rec{metadata.empty() ? std::string() : metadata[i], encodeDocument(vectors[i], p_->opt.Quantization)};
+        std::memcpy(all.data() + i * (size_t)p_->rowbytes, rec.codes.data(), (size_t)p_->rowbytes);
+        p_->store[ids[i]] = std::move(rec);
+    }
+    GPU(szg_upsert(p_->gpu, ids.data(), all.data(), ids.size()), "upsert");
+    for (size_t i = 0; i < ids.size(); ++i) p_->addPoint(ids[i], vectors[i]);
+}
+
+bool Collection::GetDocument(uint64_t id, Document *out) const {
+    std::shared_lock<std::shared_mutex> lk(p_->mu);
+    auto it = p_->store.find(id);
+    if (it == p_->store.end()) return false;
+    if (out) {
+        out->ID = id;
+        out->Metadata = it->second.meta;
+        out->Vector = decodeVector(it->second.codes.data(), p_->opt.DimensionCount, p_->opt.Quantization);
+    }
+    return true;
+}
+
+bool Collection::UpdateDocument(uint64_t id, const std::string &metadata) { // vector unchanged: the mirror is untouched
+    std::unique_lock<std::shared_mutex> lk(p_->mu);
+    auto it = p_->store.find(id);
+    if (it == p_->store.end()) return false;
+    it->second.meta = metadata;
+    return true;
+}
+
+bool Collection::removeDocument(uint64_t id) {
+    std::unique_lock<std::shared_mutex> lk(p_->mu);
+    auto it = p_->store.find(id);
+    if (it == p_->store.end()) return false;
+    p_->removePoint(id, decodeVector(it->second.codes.data(), p_->opt.DimensionCount, p_->opt.Quantization));
+    GPU(szg_remove(p_->gpu, &id, 1, nullptr), "remove");
+    p_->store.erase(it);
+    return true;
+}
+
+int Collection::GetDocumentCount() const {
+    std::shared_lock<std::shared_mutex> lk(p_->mu);
+    return (int)p_->store.size();
+}
+
+SearchResults Collection::Search(SearchArgs args) {
+    std::shared_lock<std::shared_mutex> lk(p_->mu); // RLock, collection.go:570
+    return p_->search(args);
+}
+
+SearchResults Collection::Impl::search(SearchArgs &args) {
+    if (args.Precision.empty()) args.Precision = "medium"; // 573-575
+    SearchResults ret;
+    const size_t numRecords = store.size();
+    size_t pointsSearched = 0;
+
+    if (args.Radius == 0 && args.K == 0) { // list mode, 633-668
+        std::vector<uint64_t> ids;
+        ids.reserve(numRecords);
+        for (const auto &kv : store) ids.push_back(kv.first);
+        std::sort(ids.begin(), ids.end(), lex_less); // IterateSortedRecords
+        for (uint64_t id : ids) {
+            const std::string &meta = store.at(id).meta;
+            if (args.Filter && !args.Filter(id, meta)) continue;
+            ++pointsSearched;
+            if (args.Offset > 0 && (int)pointsSearched <= args.Offset) continue;
+            ret.Results.push_back(SearchResult{id, meta, 0.0});
+            if (args.Limit > 0 && (int)ret.Results.size() >= args.Limit) break;
+        }
+    } else {
+        if ((int)args.Vector.size() != opt.DimensionCount) // appendix B-12: the reference would read out of bounds
+            throw std::invalid_argument("query dimension does not match the collection");
+        if (args.Precision == "exact") { // 672-684 -> one GPU scan
+            int mask = -1;
+            if (args.Filter) mask = buildMask(args.Filter);
+            std::vector<uint64_t> ids;
+            std::vector<double> dist;
+            uint64_t scanned = 0;
+            if (args.Radius > 0) { // Radius overrides K, inclusive (598-605)
+                szg_result *r = nullptr;
+                GPU(szg_search_radius(gpu, args.Vector.data(), args.Radius, mask, SZG_F_DEFAULT, &r, &scanned), "search_radius");
+                uint64_t n = 0;
+                szg_result_count(r, &n);
+                ids.resize(n);
+                dist.resize(n);
+                if (n) szg_result_fetch(r, 0, n, ids.data(), dist.data());
+                szg_result_free(r);
+            } else {
+                if (args.K > (int)SZG_MAX_K) throw std::invalid_argument("K exceeds SZG_MAX_K on the GPU path");
+                ids.resize((size_t)args.K);
+                dist.resize((size_t)args.K);
+                uint32_t n = 0;
+                GPU(szg_search_topk(gpu, args.Vector.data(), 1, (uint32_t)args.K, mask, SZG_F_DEFAULT, ids.data(), dist.data(),
+                                    &n, &scanned), "search_topk");
+                ids.resize(n);
+                dist.resize(n);
+            }
+            if (mask >= 0) szg_mask_destroy(gpu, mask);
+            pointsSearched = scanned; // filtered rows count as searched (589 precedes 592)
+            for (size_t i = 0; i < ids.size(); ++i) ret.Results.push_back(SearchResult{ids[i], store.at(ids[i]).meta, dist[i]});
+        } else {
+            SearchResults r = searchIndex(args);
+            ret.Results = std::move(r.Results);
+            pointsSearched = (size_t)r.PercentSearched; // carries the count, converted below
+        }
+    }
+    ret.PercentSearched = numRecords == 0 ? 0.0 : (double)pointsSearched / (double)numRecords * 100; // 700-710
+    return ret;
+}
+
+// lshTree.search (lshtree.go:283-351) driving `consider` (collection.go:583-629), with the distances
+// computed on the GPU.  Only leaves are ever pruned and inner nodes always expand, so the order in
+// which nodes pop does not depend on distances: the host pops ahead, gathers the ids of upcoming
+// leaves, rescoring them in one szg_rescore call, then replays the reference's loop over them.
+SearchResults Collection::Impl::searchIndex(const SearchArgs &args) {
+    const std::vector<double> &vector = args.Vector;
+    const double length = vectorLength(vector);
+    double radius = args.Radius > 0 ? args.Radius : 1.7976931348623157e308; // 686-689
+    std::unordered_set<uint64_t> visited;
+    const int search_k = 200;
+    int k_counter = 0;
+    bool pointAccepted = false;
+    size_t pointsSearched = 0;
+    GoHeap<ResultItem, ResultLess> results;
+    GoHeap<NodeItem, NodeLess> pq;
+    for (auto &root : roots) pq.push(NodeItem{root.get(), 0.0}); // 295-297
+    last_visit.clear();
+    last_batches = 0;
+
+    std::unordered_map<uint64_t, double> cache; // id -> GPU distance
+    struct Leaf { LshNode *node; double priority; };
+    std::vector<Leaf> ahead;
+    size_t ahead_pos = 0;
+    const size_t kBatchIds = 2048;
+    bool stop = false;
+
+    auto consider = [&](uint64_t id, double d, double *rad) -> int { // collection.go:583-629
+        if (d == SZG_MISSING_DISTANCE) return StopSearch;             // getDocument failed (585-587)
+        auto it = store.find(id);
+        if (it == store.end()) return StopSearch;
+        ++pointsSearched;
+        if (args.Filter && !args.Filter(id, it->second.meta)) return PointIgnored;
+        if (args.Radius > 0 && d <= args.Radius) {
+            results.push(ResultItem{id, d});
+            return PointAccepted;
+        } else if (args.Radius > 0) {
+            return PointChecked;
+        } else if (args.K > 0) {
+            if ((int)results.size() <= args.K) {
+                if ((int)results.size() < args.K || results.a[0].priority > d) {
+                    results.push(ResultItem{id, d});
+                    if ((int)results.size() > args.K) results.pop();
+                    *rad = results.a[0].priority;
+                    return PointAccepted;
+                }
+            }
+        }
+        return PointChecked;
+    };
+
+    while (!stop) {
+        // ---- pop ahead: leaves in the reference's pop order, until a batch of unseen ids is gathered
+        if (ahead_pos == ahead.size()) {
+            ahead.clear();
+            ahead_pos = 0;
+            std::vector<uint64_t> need;
+            std::unordered_set<uint64_t> in_batch;
+            while (pq.size() > 0 && need.size() < kBatchIds) {
+                NodeItem item = pq.pop();
+                LshNode *node = item.node;
+                if (node->isLeaf()) {
+                    ahead.push_back(Leaf{node, item.priority});
+                    for (uint64_t id : node->ids)
+                        if (!cache.count(id) && in_batch.insert(id).second) need.push_back(id);
+                } else { // 337-348
+                    double dist;
+                    bool right;
+                    distanceToHyperplane(opt.DistanceMethod, vector, length, node->normal, node->b, &dist, &right);
+                    if (right) {
+                        pq.push(NodeItem{node->right.get(), dist});
+                        pq.push(NodeItem{node->left.get(), -dist});
+                    } else {
+                        pq.push(NodeItem{node->left.get(), dist});
+                        pq.push(NodeItem{node->right.get(), -dist});
+                    }
+                }
+            }
+            if (ahead.empty()) break; // queue exhausted
+            if (!need.empty()) {
+                std::vector<double> dist(need.size());
+                GPU(szg_rescore(gpu, vector.data(), need.data(), need.size(), dist.data()), "rescore");
+                ++last_batches;
+                for (size_t i = 0; i < need.size(); ++i) cache.emplace(need[i], dist[i]);
+            }
+        }
+        // ---- replay lshtree.go:299-336 over the next leaf
+        const Leaf lf = ahead[ahead_pos++];
+        if (lf.priority < 0 && -lf.priority > radius) continue; // far side of the hyperplane, beyond the radius (304-309)
+        if (k_counter >= search_k) break;                        // 311-313
+        for (uint64_t id : lf.node->ids) {
+            if (visited.count(id)) continue;
+            visited.insert(id);
+            last_visit.push_back(id);
+            const int signal = consider(id, cache.at(id), &radius);
+            if (signal == StopSearch) { stop = true; break; }
+            if (signal == PointAccepted) { k_counter = 0; pointAccepted = true; }
+            else if (signal == PointChecked) { if (pointAccepted) ++k_counter; }
+        }
+    }
+
+    SearchResults out;
+    out.Results.resize(results.size()); // 693-697: pop back to front => ascending
+    for (size_t i = out.Results.size(); i-- > 0;) {
+        ResultItem it = results.pop();
+        out.Results[i] = SearchResult{it.id, store.at(it.id).meta, it.priority};
+    }
+    out.PercentSearched = (double)pointsSearched; // the caller converts the count
+    return out;
+}
+
+} // namespace syzgydb
