@@ -117,6 +117,17 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
                     uint64_t *scanned);
 
 /*
+ * Batched exact top-k: the results of nq independent szg_search_topk calls, computed as one dense
+ * contraction on the tensor cores (tcgen05.mma kind::i8 over the digit planes of the fixed-point
+ * queries, fused threshold top-k epilogue) when the collection is 8-bit, k <= 112 and a row fits
+ * shared memory; otherwise the call is served by the streaming scan.  Replaces: B concurrent Search
+ * calls under the RLock (collection.go:569-570).  Same outputs, same certification / escalation.
+ */
+int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id,
+                     uint32_t flags, uint64_t *out_ids, double *out_dist, uint32_t *out_n,
+                     uint64_t *scanned);
+
+/*
  * Radius search: every record with distance <= radius (inclusive, K ignored), ascending.
  * Replaces: Search with Radius>0, Precision=="exact" (collection.go:598-605).
  */
@@ -177,6 +188,7 @@ typedef struct szg_stats {
     uint64_t kernel_launches;   /* kernels this handle launched since creation */
     uint64_t escalations;       /* top-k calls re-run with a larger candidate set */
     uint64_t uncertain_results; /* top-k queries whose candidate margin stayed below tolerance */
+    uint64_t batch_queries;     /* queries served by the tensor-core batched path */
     uint64_t device_bytes;      /* HBM held by the mirror */
     uint64_t live_rows;
     uint64_t slots;             /* rows of HBM layout in use (live + tombstones) */
@@ -201,6 +213,7 @@ int szg_get_stats(szg_index *h, szg_stats *out);
 #define SZG_OPT_SCAN_TILE_CHUNKS 6   /* upper bound of 16-byte chunks per tile, 1..32 (default 8) */
 #define SZG_OPT_DIGITS 7             /* fixed-point digits of the query: 0 automatic (2, re-run with 3 when the
                                         result cannot be certified), 2 or 3 forced */
+#define SZG_OPT_BATCH_TENSOR 8       /* 0: szg_search_batch uses the streaming scan; 1 (default): tensor cores */
 int szg_set_option(szg_index *h, int option, int64_t value);
 
 /* Time of the most recent scan launches on this handle, measured with CUDA events on the

@@ -27,11 +27,12 @@ OPT_SCAN_WARPS = 4
 OPT_SCAN_STAGES = 5
 OPT_SCAN_TILE_CHUNKS = 6
 OPT_DIGITS = 7
+OPT_BATCH_TENSOR = 8
 
 # every symbol include/syzgy_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "szg_last_error", "szg_create", "szg_destroy", "szg_reserve", "szg_upsert", "szg_remove", "szg_count",
-    "szg_mask_create", "szg_mask_destroy", "szg_search_topk", "szg_search_radius", "szg_result_count",
+    "szg_mask_create", "szg_mask_destroy", "szg_search_topk", "szg_search_batch", "szg_search_radius", "szg_result_count",
     "szg_result_fetch", "szg_result_free", "szg_rescore", "szg_search_topk_dev", "szg_merge_topk_dev",
     "szg_fill_synthetic", "szg_fetch_codes", "szg_get_stats", "szg_set_option", "szg_last_scan_times_ms",
 ]
@@ -46,6 +47,7 @@ class SzgError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint64), ("escalations", C.c_uint64), ("uncertain_results", C.c_uint64),
+        ("batch_queries", C.c_uint64),
         ("device_bytes", C.c_uint64), ("live_rows", C.c_uint64), ("slots", C.c_uint64),
         ("rowbytes", C.c_uint32), ("pitch", C.c_uint32), ("sm_count", C.c_uint32), ("scan_grid", C.c_uint32),
         ("scan_block", C.c_uint32), ("scan_stages", C.c_uint32), ("scan_tile_bytes", C.c_uint32),
@@ -78,6 +80,7 @@ def load():
     L.szg_mask_create.argtypes = [vp, u64p, u8p, C.c_uint64, C.POINTER(C.c_int)]
     L.szg_mask_destroy.argtypes = [vp, C.c_int]
     L.szg_search_topk.argtypes = [vp, f64p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u64p, f64p, u32p, u64p]
+    L.szg_search_batch.argtypes = L.szg_search_topk.argtypes
     L.szg_search_radius.argtypes = [vp, f64p, C.c_double, C.c_int, C.c_uint32, C.POINTER(vp), u64p]
     L.szg_result_count.argtypes = [vp, u64p]
     L.szg_result_fetch.argtypes = [vp, C.c_uint64, C.c_uint64, u64p, f64p]
@@ -200,6 +203,23 @@ class Index:
         scanned = C.c_uint64(0)
         _check(self._L.szg_search_topk(self._h, _p(q, C.c_double), nq, int(k), mask_id, flags, _p(ids, C.c_uint64),
                                        _p(dist, C.c_double), _p(n, C.c_uint32), C.byref(scanned)))
+        return ids, dist, n, scanned.value
+
+    def search_batch(self, queries, k: int, mask_id: int = -1, flags: int = 0):
+        """Batched form of search_topk (tensor-core contraction for 8-bit collections).  Same return value."""
+        q = np.ascontiguousarray(queries, dtype=np.float64)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            raise ValueError(f"query has {q.shape[1]} dimensions, collection has {self.dim}")
+        nq = q.shape[0]
+        kk = max(int(k), 1)
+        ids = np.zeros((nq, kk), dtype=np.uint64)
+        dist = np.zeros((nq, kk), dtype=np.float64)
+        n = np.zeros(nq, dtype=np.uint32)
+        scanned = C.c_uint64(0)
+        _check(self._L.szg_search_batch(self._h, _p(q, C.c_double), nq, int(k), mask_id, flags, _p(ids, C.c_uint64),
+                                        _p(dist, C.c_double), _p(n, C.c_uint32), C.byref(scanned)))
         return ids, dist, n, scanned.value
 
     def search_radius(self, query, radius: float, mask_id: int = -1, flags: int = 0):

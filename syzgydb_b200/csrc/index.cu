@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -85,6 +86,7 @@ struct Workspace {
     DevBuf<double> d_q, d_q2;
     DevBuf<unsigned char> d_pq;
     DevBuf<unsigned long long> d_cand; // [nq][scan CTAs][32*E] candidate keys, scan -> finalize
+    DevBuf<unsigned char> d_img;       // batched path: A operand images (query digit planes)
     DevBuf<unsigned int> d_ticket;     // radius hit counter
     DevBuf<unsigned long long> d_out_ids;
     DevBuf<double> d_out_dist;
@@ -108,7 +110,7 @@ struct Workspace {
     void destroy() {
         d_q.release(); d_q2.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
         d_out_n.release(); d_out_flags.release(); d_slots.release();
-        d_cand.release();
+        d_cand.release(); d_img.release();
         h_q.release(); h_out_ids.release(); h_out_dist.release(); h_out_n.release(); h_out_flags.release();
         h_slots.release();
         for (auto e : t0) cudaEventDestroy(e);
@@ -168,6 +170,8 @@ struct szg_index {
     std::vector<float> last_times;
     Workspace *last_timed_ws = nullptr;
     int scan_warps = 16, scan_stages = 2, scan_tile_chunks = 8;
+    int batch_disabled = 0; // SZG_OPT_BATCH_TENSOR = 0 routes szg_search_batch to the streaming scan
+    uint64_t batch_queries = 0;
     int digits = 0; // 0 = automatic (2-digit fast pass, 3-digit re-run when uncertain), 2 or 3 = forced // streaming geometry (SZG_OPT_SCAN_*)
 
     bool lookup(uint64_t id, uint32_t *slot) const {
@@ -381,6 +385,62 @@ int check_search(szg_index *h, const void *q, uint32_t nq) {
     return SZG_OK;
 }
 
+// Copies the results of the first pass (already enqueued on ws->main into ws->d_out_*) to the host and
+// re-runs, together, the queries whose candidate set could not be certified: first with the 3-digit
+// (precise) surrogate, then with larger candidate sets.
+int collect_and_escalate(szg_index *h, Workspace *ws, uint32_t nq, uint32_t k, const uint32_t *mask, uint32_t flags,
+                         int nd0, int mode0, uint64_t *out_ids, double *out_dist, uint32_t *out_n) {
+    int rc;
+    cudaStream_t st = ws->main;
+    const size_t on = (size_t)nq * k;
+    CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, on * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, on * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out_ids, ws->h_out_ids.p, on * 8);
+    memcpy(out_dist, ws->h_out_dist.p, on * 8);
+    memcpy(out_n, ws->h_out_n.p, nq * 4);
+    // Queries whose candidate set could not be certified are re-run together, first with the
+    // 3-digit (precise) surrogate, then with larger candidate sets.
+    if (!(flags & SZG_F_NO_FP64_VERIFY)) {
+        std::vector<uint32_t> pending;
+        for (uint32_t i = 0; i < nq; ++i)
+            if (ws->h_out_flags.p[i] & 1u) pending.push_back(i);
+        int nd = nd0, mode = mode0;
+        while (!pending.empty()) {
+            if (nd == 2) nd = 3;
+            else if (mode < 3) ++mode;
+            else break;
+            const uint32_t m = (uint32_t)pending.size();
+            h->escalations += m;
+            if ((rc = ws->d_q2.ensure((size_t)m * h->dim))) return rc;
+            for (uint32_t j = 0; j < m; ++j)
+                CK(cudaMemcpyAsync(ws->d_q2.p + (size_t)j * h->dim, ws->d_q.p + (size_t)pending[j] * h->dim,
+                                   (size_t)h->dim * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            if ((rc = run_topk(h, ws, ws->d_q2.p, m, k, mask, flags, mode, nd, ws->d_out_ids.p, ws->d_out_dist.p,
+                               ws->d_out_n.p, ws->d_out_flags.p)))
+                return rc;
+            CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::vector<uint32_t> still;
+            for (uint32_t j = 0; j < m; ++j) {
+                const uint32_t i = pending[j];
+                memcpy(out_ids + (size_t)i * k, ws->h_out_ids.p + (size_t)j * k, (size_t)k * 8);
+                memcpy(out_dist + (size_t)i * k, ws->h_out_dist.p + (size_t)j * k, (size_t)k * 8);
+                out_n[i] = ws->h_out_n.p[j];
+                if (ws->h_out_flags.p[j] & 1u) still.push_back(i);
+            }
+            pending.swap(still);
+        }
+        h->uncertain += pending.size();
+    }
+    return SZG_OK;
+}
+
 } // namespace
 
 // ====================================================================== C ABI
@@ -478,6 +538,7 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
         if (value < 1 || value > kMaxTileChunks) return fail(SZG_EINVAL, "tile chunks must be in [1, %d]", kMaxTileChunks);
         h->scan_tile_chunks = (int)value;
         return SZG_OK;
+    case SZG_OPT_BATCH_TENSOR: h->batch_disabled = value == 0; return SZG_OK;
     case SZG_OPT_DIGITS:
         if (value != 0 && value != 2 && value != 3) return fail(SZG_EINVAL, "digits must be 0 (auto), 2 or 3");
         h->digits = (int)value;
@@ -705,53 +766,96 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
     if ((rc = run_topk(h, ws, ws->d_q.p, nq, k, mask, flags, mode0, nd0, ws->d_out_ids.p, ws->d_out_dist.p,
                        ws->d_out_n.p, ws->d_out_flags.p)))
         return rc;
-    CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, on * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, on * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, nq * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    memcpy(out_ids, ws->h_out_ids.p, on * 8);
-    memcpy(out_dist, ws->h_out_dist.p, on * 8);
-    memcpy(out_n, ws->h_out_n.p, nq * 4);
-    // Queries whose candidate set could not be certified are re-run together, first with the
-    // 3-digit (precise) surrogate, then with larger candidate sets.
-    if (!(flags & SZG_F_NO_FP64_VERIFY)) {
-        std::vector<uint32_t> pending;
-        for (uint32_t i = 0; i < nq; ++i)
-            if (ws->h_out_flags.p[i] & 1u) pending.push_back(i);
-        int nd = nd0, mode = mode0;
-        while (!pending.empty()) {
-            if (nd == 2) nd = 3;
-            else if (mode < 3) ++mode;
-            else break;
-            const uint32_t m = (uint32_t)pending.size();
-            h->escalations += m;
-            if ((rc = ws->d_q2.ensure((size_t)m * h->dim))) return rc;
-            for (uint32_t j = 0; j < m; ++j)
-                CK(cudaMemcpyAsync(ws->d_q2.p + (size_t)j * h->dim, ws->d_q.p + (size_t)pending[j] * h->dim,
-                                   (size_t)h->dim * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            if ((rc = run_topk(h, ws, ws->d_q2.p, m, k, mask, flags, mode, nd, ws->d_out_ids.p, ws->d_out_dist.p,
-                               ws->d_out_n.p, ws->d_out_flags.p)))
-                return rc;
-            CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            std::vector<uint32_t> still;
-            for (uint32_t j = 0; j < m; ++j) {
-                const uint32_t i = pending[j];
-                memcpy(out_ids + (size_t)i * k, ws->h_out_ids.p + (size_t)j * k, (size_t)k * 8);
-                memcpy(out_dist + (size_t)i * k, ws->h_out_dist.p + (size_t)j * k, (size_t)k * 8);
-                out_n[i] = ws->h_out_n.p[j];
-                if (ws->h_out_flags.p[j] & 1u) still.push_back(i);
-            }
-            pending.swap(still);
-        }
-        h->uncertain += pending.size();
-    }
-    return SZG_OK;
+    return collect_and_escalate(h, ws, nq, k, mask, flags, nd0, mode0, out_ids, out_dist, out_n);
 }
+
+// Batched search: same results as szg_search_topk for every query, computed by the tensor-core
+// contraction kernel (batch_q8.cu) when the collection is 8-bit and the geometry fits; every other
+// case is routed to the streaming scan (still on the GPU).
+int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
+                     uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
+    GUARD(h);
+    int rc;
+    // shared memory: `stages` stages of one super tile (4 blocks of C * 512 B); the query digits live in TMEM
+    uint32_t stages = 3;
+    while (stages > 2 && batch_smem_bytes(h->C, stages) > kScanSmemLimit - 4096) --stages;
+    const bool tensor_path = h->qt == Q8 && h->digits != 3 && (h->C % 2) == 0 && h->C <= batch_max_chunks() && k >= 1 &&
+                             k <= 112 && batch_smem_bytes(h->C, stages) <= kScanSmemLimit - 4096 && nq >= 1;
+    if (!tensor_path || h->live_rows == 0 || h->batch_disabled)
+        return szg_search_topk(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n, scanned);
+    if ((rc = check_search(h, queries, nq))) return rc;
+    if (!out_ids || !out_dist || !out_n) return fail(SZG_EINVAL, "null output");
+    if (scanned) *scanned = h->live_rows;
+    const uint32_t *mask;
+    if ((rc = get_mask(h, mask_id, &mask))) return rc;
+    Workspace *ws;
+    if ((rc = acquire_ws(h, &ws))) return rc;
+    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
+    const size_t qn = (size_t)nq * h->dim, on = (size_t)nq * k;
+    if ((rc = ws->h_q.ensure(qn)) || (rc = ws->d_q.ensure(qn)) || (rc = ws->d_out_ids.ensure(on)) ||
+        (rc = ws->d_out_dist.ensure(on)) || (rc = ws->d_out_n.ensure(nq)) || (rc = ws->d_out_flags.ensure(nq)) ||
+        (rc = ws->h_out_ids.ensure(on)) || (rc = ws->h_out_dist.ensure(on)) || (rc = ws->h_out_n.ensure(nq)) ||
+        (rc = ws->h_out_flags.ensure(nq)))
+        return rc;
+    memcpy(ws->h_q.p, queries, qn * sizeof(double));
+    cudaStream_t st = ws->main;
+    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st));
+
+    const int nd = 2, mode = 2; // 2 digit planes = the M dimension; 128 survivors per list = finalize MODE 2
+    const size_t stride = pq_stride(h, nd);
+    const uint32_t ngroups_all = (nq + 63) / 64;
+    const uint32_t gpl = std::min<uint32_t>(ngroups_all, 16);                      // groups per launch
+    const uint32_t nblk = (h->nslots + 31) / 32;
+    const uint32_t nranges = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)h->sm_count / gpl, nblk));
+    const uint32_t nlists = nranges * batch_lists_per_range();
+    if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * nlists * 128)))
+        return rc;
+    PrepArgs pa;
+    pa.queries = ws->d_q.p; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
+    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
+    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
+    CK(launch_prep(nq, st, pa));
+    h->launches++;
+    CK(batch_configure(kScanSmemLimit));
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.codes = h->codes.p; b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
+    b.pq = ws->d_pq.p; b.pq_stride = stride; b.img = nullptr; b.cand = ws->d_cand.p;
+    b.C = h->C; b.nblk = nblk; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
+    b.nranges = nranges; b.nlists = nlists; b.stages = stages;
+    if (const char *dbg = getenv("SZG_BATCH_DEBUG")) b.debug = (uint32_t)atoi(dbg);
+    const bool timing = h->timing != 0;
+    const uint32_t nlaunch = (ngroups_all + gpl - 1) / gpl;
+    if (timing) {
+        while (ws->t0.size() < nlaunch) {
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreate(&e0));
+            CK(cudaEventCreate(&e1));
+            ws->t0.push_back(e0);
+            ws->t1.push_back(e1);
+        }
+    }
+    for (uint32_t l = 0, g0 = 0; g0 < ngroups_all; g0 += gpl, ++l) {
+        b.group0 = g0;
+        b.ngroups = std::min(gpl, ngroups_all - g0);
+        if (timing) CK(cudaEventRecord(ws->t0[l], st));
+        CK(launch_batch(b, st));
+        if (timing) CK(cudaEventRecord(ws->t1[l], st));
+        h->launches++;
+    }
+    if (timing) { ws->timed = nlaunch; h->last_timed_ws = ws; }
+    FinalizeArgs f;
+    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.cand = ws->d_cand.p;
+    f.pq = ws->d_pq.p; f.pq_stride = stride; f.queries = ws->d_q.p;
+    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
+    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.nlists = nlists;
+    f.out_ids = ws->d_out_ids.p; f.out_dist = ws->d_out_dist.p; f.out_n = ws->d_out_n.p; f.out_flags = ws->d_out_flags.p;
+    CK(launch_finalize(h->qt, mode, nq, st, f));
+    h->launches++;
+    h->batch_queries += nq;
+    return collect_and_escalate(h, ws, nq, k, mask, flags, nd, mode_for_k(h, k), out_ids, out_dist, out_n);
+}
+
 
 int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
                         uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags,
@@ -948,6 +1052,7 @@ int szg_get_stats(szg_index *h, szg_stats *out) {
     out->kernel_launches = h->launches;
     out->escalations = h->escalations;
     out->uncertain_results = h->uncertain;
+    out->batch_queries = h->batch_queries;
     out->device_bytes = h->codes.n * sizeof(uint4) + h->ids.n * 8 + h->aux.n * 8 + h->live.n * 4 +
                         h->lut.n * 8 + h->masks.size() * (h->capacity / 32) * 4;
     out->live_rows = h->live_rows;

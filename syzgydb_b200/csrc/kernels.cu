@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
         if (a.metric == COSINE) {
             // key = -cos: fixed-point part / (||x|| ||q||) + fp32 roundings (two products, 1/||x|| itself)
             hh.e_rel = 0.0;
-            hh.e_abs = (sq == 0.0 ? 0.0 : sqrt(d) * dq / qn) + 6.0 * eps;
+            hh.e_abs = (sq == 0.0 ? 0.0 : sqrt(d) * dq / qn) + 12.0 * eps; // incl. the all-fp32 tail of the batched epilogue
             if (a.qt == F32) hh.e_abs += (d + 8.0) * 2.0 * eps; // fp32 accumulation + fp32 copy of the query
         } else if (quantized) {
             // key = ||x||^2 (fp32 aux) + ||q||^2 - 2 x.q, rounded to fp32
-            hh.e_abs = 2.0 * d * dq + d * eps + 1e-30;
+            hh.e_abs = 2.0 * d * dq + (d + 8.0 * (d + sq)) * eps + 1e-30; // incl. the fp32 tail of the batched epilogue
             hh.e_rel = 2.0 * eps;
         } else if (a.qt == F32) {
             // fp32 sum of fp32 (q_i - x_i)^2 with an fp32 copy of the query

@@ -62,6 +62,30 @@ struct RescoreArgs {
 };
 cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st);
 
+// K4: batched-query tensor-core contraction (batch_q8.cu), 8-bit rows
+struct BatchArgs {
+    const uint4 *codes;
+    const void *aux;
+    const uint32_t *live;
+    const uint32_t *mask;
+    const unsigned char *pq;   // prepared queries (2 digits), pq_stride apart
+    size_t pq_stride;
+    const unsigned char *img;  // A operand images, one per 64-query group (launch_batch_pack)
+    unsigned long long *cand;  // [nq][nlists][128] candidate keys for finalize_kernel (MODE 2)
+    uint32_t C, nblk, metric, nq, dims;
+    uint32_t group0, ngroups;  // query groups [group0, group0 + ngroups) run in this launch
+    uint32_t nranges, nlists;  // row ranges (CTAs per group); nlists = nranges * batch_lists_per_range()
+    uint32_t stages;           // shared-memory stages of one super tile (4 blocks) each
+    uint32_t debug;            // profiling aid: bit0 skip the epilogue math, bit1 skip aux loads, bit2 skip the MMAs
+};
+size_t batch_smem_bytes(uint32_t C, uint32_t stages);
+uint32_t batch_max_chunks();
+uint32_t batch_lists_per_range();
+cudaError_t batch_configure(size_t max_smem);
+cudaError_t launch_batch_pack(const unsigned char *pq, size_t pq_stride, uint32_t nq, uint32_t C, unsigned char *img,
+                              cudaStream_t st);
+cudaError_t launch_batch(const BatchArgs &a, cudaStream_t st);
+
 struct MergeArgs {
     const unsigned long long *g_ids; // [G][nq][k]
     const double *g_dist;
