@@ -6,18 +6,29 @@
 //     D[query-digit, row] = sum_i W_digit[query][i] * u[row][i]          (s8 x u8 -> s32, exact)
 // which is what tensor cores are for (a single query is a memory-bound GEMV and stays on the streaming
 // scan kernel).  Per CTA:
-//   A (M = 128) : 64 queries x 2 base-128 digit planes of the fixed-point query, resident in shared memory
-//                 in the canonical K-major no-swizzle core-matrix layout (prepared by batch_pack_kernel);
-//   B (N = 32)  : one 32-row block of the column-blocked mirror; its HBM image IS the canonical K-major
-//                 layout (8 rows x 16 B core matrices), so a block lands in shared memory with one
-//                 cp.async.bulk and is consumed by tcgen05.mma without any reshuffle;
-//   D           : 128 x 32 s32 accumulators in TMEM, double buffered (2 x 32 columns).
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-5 = epilogue
-// (tcgen05.ld, combine the two digit planes, key, per-query threshold, append to the query's candidate
-// buffer, occasional warp-level compaction by bitonic sort).  Pipelines: block ring (full/empty
-// mbarriers), accumulator ring (tcgen05.commit -> epilogue -> release).
-// CTAs are (query group g, row range r): the 16 groups of a 1024-query batch walk the same row range at
-// the same time, so HBM is read once per range and the other 15 reads hit L2.
+//   A (M = 128) : 64 queries x 2 base-128 digit planes of the fixed-point query, resident in TMEM for the
+//                 whole kernel (written once with tcgen05.st, C * 4 columns);
+//   B (N = 128) : one "super tile" = 4 consecutive 32-row blocks of the column-blocked mirror.  The HBM
+//                 image of a block IS the canonical K-major no-swizzle layout (8 rows x 16 B core matrices),
+//                 so TMA lands K slices of a super tile in shared memory ([chunk][block][512 B]) and
+//                 tcgen05.mma consumes them without any reshuffle;
+//   D           : 128 x 128 s32 accumulators in TMEM, double buffered.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-9 = epilogue (8 queries each).
+// Pipelines: a ring of K slices (full/empty mbarriers; the ring never drains between super tiles) and the
+// two accumulator buffers (tcgen05.commit -> epilogue -> release).
+//
+// Epilogue.  TMEM lane L holds (query, plane) with the two planes of a query 8 lanes apart, so that
+// tcgen05.ld.16x256b hands thread t BOTH planes of query t/4 for 2 columns (= rows) per 8-column group
+// (layout measured with tools/tmem_probe.cu): no exchange between threads is needed.  Per (query, row) the
+// thread combines the planes in exact integer arithmetic, converts once, and compares against a per-query
+// pre-transformed threshold (cosine: num * (1/||x||) > T;  euclid: num * c - ||x||^2 > T) that is slightly
+// conservative; the few survivors recompute the exact surrogate key of the streaming scan and append it to
+// the query's candidate buffer.  Every query belongs to exactly one epilogue warp, so appends, the
+// occasional compaction (bitonic sort in registers) and threshold updates need warp-level
+// synchronisation only.  Liveness / filter bits are folded into the staged per-row operand (NaN / +inf
+// never pass).
+// CTAs are (query group g, row range r): the groups of a batch walk the same row range at the same time,
+// so HBM is read once per range and the other reads hit L2.
 // The candidate buffers feed the same finalize_kernel as the scan path (fp64 re-score, ordering,
 // certification against the surrogate error bound), so results are identical to single queries.
 #include <cuda.h>
@@ -29,10 +40,14 @@ namespace szg {
 namespace {
 
 constexpr int kBatchQueries = 64;          // queries per CTA (x 2 digit planes = M 128)
-constexpr int kBatchThreads = 192;         // producer, MMA, 4 epilogue warps
-constexpr int kBatchCap = 512;             // candidate buffer entries per (CTA, query)
-constexpr int kBatchKp = 128;              // survivors of a compaction (= finalize MODE 2)
+constexpr int kBatchThreads = 320;         // producer, MMA, 8 epilogue warps
 constexpr uint32_t kNoBlock = 0xFFFFFFFFu;
+constexpr uint32_t kNB = 4;                // blocks per super tile (N = 4 x 32 = 128 rows)
+constexpr uint32_t kTileRows = kNB * 32;
+constexpr uint32_t kAccCols = kTileRows;   // columns of one accumulator buffer
+constexpr uint32_t kTmemCols = 512;        // 2 accumulator buffers + up to 256 columns of A
+constexpr int kBatchMaxStages = 13;
+constexpr uint32_t kAuxSlots = 6;          // ring of per-tile side data (aux pairs, live words)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -43,19 +58,14 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// 16 TMEM lanes x 64 columns: thread t receives lanes (t/4, t/4 + 8) x columns 8 * rep + 2 * (t%4) + {0, 1}:
+//   r[4 rep + 0/1] = lane t/4 (plane 0), r[4 rep + 2/3] = lane t/4 + 8 (plane 1)
+__device__ __forceinline__ void tmem_ld_16x64(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
         "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -63,53 +73,209 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// waits for every tcgen05.ld of this thread; the registers are passed through the statement so that no use of
+// them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+    asm volatile(""
+                 : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
+// per-query state of the epilogue (shared memory; owned by one epilogue warp)
+struct __align__(16) QState {
+    unsigned long long thr;   // admission threshold: min(last key of the query's list, gbound)
+    unsigned long long gbound; // bound shared by the row ranges of this query (see poll_bounds), kNoKey = none yet
+    long long numc;
+    float c_key, inv_ckey, c_dot2, qn2; // surrogate constants (PQHeader)
+    float T;                  // pre-transformed, conservative threshold of the fast test
+    float slack;              // euclid: bound of the rounding differences between fast test and exact key
+    uint32_t zero;            // zero query
+    uint32_t valid;
+    uint32_t pub;             // smallest mth-best key this range has published for the query (0xFFFFFFFF = none)
+};
+
+// threshold of the fast test "v > T" such that every key <= thr passes (see the file comment); fp32 arithmetic
+// with margins far above its own rounding
+template <bool COS>
+__device__ __forceinline__ float fast_threshold(const QState &s) {
+    if (s.thr == kNoKey) return -INFINITY;
+    const float thr_f = key_to_float((uint32_t)(s.thr >> 32));
+    if (thr_f != thr_f) return -INFINITY;
+    if (COS) {
+        // rows arrive in ascending slot order, so among equal keys nothing later can displace the threshold entry
+        if (s.zero || s.c_key <= 0.f) return thr_f > 1.0f ? -INFINITY : INFINITY;
+        const float t = -thr_f * s.inv_ckey;
+        return t - fabsf(t) * 3.814697265625e-6f - 1e-30f; // 2^-18
+    }
+    const float t = (s.qn2 - thr_f) - s.slack - fabsf(thr_f) * 9.5367431640625e-7f;
+    return t - fabsf(t) * 4.76837158203125e-7f - 1e-30f;
+}
+
+template <int E>
+__device__ __forceinline__ unsigned long long pick(const unsigned long long (&v)[E], uint32_t idx) {
+    unsigned long long r = v[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e)
+        if (idx == (uint32_t)e) r = v[e];
+    return r;
+}
+
+// sorted insert of nk (< the key at rank capm1) into a query's candidate list in shared memory; lane i holds ranks
+// [i E, i E + E).  Publishes the range's mth-best key when it improved and returns the key at rank capm1
+// (warp-uniform): capm1 = Kp - 1 normally, mth - 1 while the range is seeding the shared bound.
+template <int E>
+__device__ __forceinline__ unsigned long long list_insert(unsigned long long *l, unsigned long long nk, int lane, uint32_t capm1,
+                                                          uint32_t mthm1, uint32_t *gm, uint32_t *pub) {
+    unsigned long long v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = l[lane * E + e];
+    const unsigned gt = __ballot_sync(0xffffffffu, v[E - 1] > nk);
+    const int p = __ffs(gt) - 1;
+    const unsigned long long carry = __shfl_up_sync(0xffffffffu, v[E - 1], 1);
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) cnt += (v[e] < nk);
+#pragma unroll
+    for (int e = E - 1; e >= 1; --e) {
+        const unsigned long long prev = v[e - 1];
+        if (lane > p) v[e] = prev;
+        else if (lane == p) {
+            if (e > cnt) v[e] = prev;
+            else if (e == cnt) v[e] = nk;
+        }
+    }
+    if (lane > p) v[0] = carry;
+    else if (lane == p && cnt == 0) v[0] = nk;
+    if (lane >= p) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) l[lane * E + e] = v[e];
+    }
+    if ((uint32_t)lane == mthm1 / E) {
+        const uint32_t pk = (uint32_t)(pick<E>(v, mthm1 % E) >> 32);
+        if (pk < *pub) { *pub = pk; *reinterpret_cast<volatile uint32_t *>(gm) = pk; }
+    }
+    return __shfl_sync(0xffffffffu, pick<E>(v, capm1 % E), capm1 / E);
+}
+
+// Rows that passed the fast test for column index `colb + 2 * (lane & 3)` (one bit of m per lane): the whole warp
+// handles them one by one -- exact surrogate key of the streaming scan, sorted insert into the query's list,
+// new threshold.
+template <bool COS, int E>
+__device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, const float2 *xaux /*shared: aux pairs of the tile*/,
+                                        QState *wq /*the warp's 8 queries*/, unsigned long long *wl /*their lists*/, uint32_t slot0,
+                                        uint32_t *gmw /*gmth of the warp's first query, this range*/, uint32_t R, uint32_t mthm1,
+                                        uint32_t capm1) {
+    const int lane = threadIdx.x & 31;
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t j = (uint32_t)src >> 2;
+        const float nf = __shfl_sync(0xffffffffu, numf, src);
+        const uint32_t col = colb + 2 * ((uint32_t)src & 3u);
+        const float2 ax = xaux[col];
+        QState &s = wq[j];
+        float key;
+        if (COS) key = (s.zero || ax.x == 0.f) ? 1.0f : -((nf * s.c_key) * ax.x);
+        else key = (ax.y + s.qn2) - nf * s.c_dot2;
+        const unsigned long long k64 = make_key64(key, slot0 + col);
+        if (k64 < s.thr) {
+            const unsigned long long last = list_insert<E>(wl + j * (32 * E), k64, lane, capm1, mthm1, gmw + (size_t)j * R, &s.pub);
+            __syncwarp();
+            if (lane == 0) { s.thr = last < s.gbound ? last : s.gbound; s.T = fast_threshold<COS>(s); }
+            __syncwarp();
+        }
+    }
+}
+
+// 16 (query, row) pairs of one tcgen05.ld: 8 column groups x 2 rows.  The fast test of all 16 pairs is
+// straight-line code (independent chains, a max tree, one warp vote); only when some lane has a pair that
+// passes are the pairs looked at, group of four by group of four, by the whole warp.
+template <bool COS, bool FITS, int E>
+__device__ __forceinline__ float score16(const uint32_t (&r)[32], const float2 (&ax)[8], int numc32, long long numc64, float T, float c2,
+                                         uint32_t colp, const float2 *xaux, QState *wq, unsigned long long *wl,
+                                         uint32_t slot0, const float *Tsrc, uint32_t *gmw, uint32_t R, uint32_t mthm1, uint32_t capm1) {
+    float numf[16], v[16];
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const uint32_t hi = r[4 * rep + e], lo = r[4 * rep + 2 + e];
+            // num = 2 I + numc with I = 128 * D_hi + D_lo: exact in wrapping 32-bit arithmetic when |num| < 2^31
+            if (FITS) numf[2 * rep + e] = (float)(int)(hi * 256u + (2u * lo + (uint32_t)numc32));
+            else numf[2 * rep + e] = (float)(2 * ((long long)(int)hi * 128 + (long long)(int)lo) + numc64);
+            const float a = e ? ax[rep].y : ax[rep].x;
+            v[2 * rep + e] = COS ? numf[2 * rep + e] * a : fmaf(numf[2 * rep + e], c2, -a);
+        }
+    }
+    float m4[4];
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) m4[g4] = fmaxf(fmaxf(v[4 * g4], v[4 * g4 + 1]), fmaxf(v[4 * g4 + 2], v[4 * g4 + 3]));
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])); // fmaxf ignores NaN (dead rows)
+    if (__any_sync(0xffffffffu, mx > T)) {
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+            if (__any_sync(0xffffffffu, m4[g4] > T)) {
+#pragma unroll
+                for (int i = 4 * g4; i < 4 * g4 + 4; ++i) {
+                    const unsigned m = __ballot_sync(0xffffffffu, v[i] > T);
+                    if (m) batch_hits<COS, E>(m, numf[i], colp + (i >> 1) * 8 + (i & 1), xaux, wq, wl, slot0, gmw, R, mthm1, capm1);
+                }
+            }
+        }
+        T = *Tsrc; // thresholds may have tightened
+    }
+    return T;
+}
+
+
+// first super tile >= sup with a live, unfiltered row; lanes 0..3 return the live words of its blocks.
+// Producer and epilogue warps run the same walk over the same immutable bitmaps, so they agree on the
+// sequence of tiles without exchanging it.
+__device__ __forceinline__ uint32_t next_live_tile(const BatchArgs &a, uint32_t sup, uint32_t sup1, int lane, uint32_t *words) {
+    for (; sup < sup1; ++sup) {
+        uint32_t lv = 0;
+        if (lane < (int)kNB) {
+            const uint32_t blk = sup * kNB + lane;
+            if (blk < a.nblk) {
+                lv = __ldg(a.live + blk);
+                if (a.mask) lv &= __ldg(a.mask + blk);
+            }
+        }
+        if (__ballot_sync(0xffffffffu, lv != 0)) { *words = lv; return sup; }
+    }
+    *words = 0;
+    return sup1;
+}
 
 } // namespace
 
-// ---- query digits -> the A operand image of each 64-query group:
-//      img[g][c][16 row groups][8 rows][16 B], row m = plane * 64 + (query % 64), plane 0 = most significant digit
-__global__ void batch_pack_kernel(const unsigned char *__restrict__ pq, size_t pq_stride, uint32_t nq, uint32_t C,
-                                  unsigned char *__restrict__ img) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t ngroups = (nq + kBatchQueries - 1) / kBatchQueries;
-    const size_t total = (size_t)ngroups * 128 * C;
-    if (t >= total) return;
-    const uint32_t c = (uint32_t)(t % C), m = (uint32_t)((t / C) % 128), g = (uint32_t)(t / ((size_t)C * 128));
-    const uint32_t q = g * kBatchQueries + (m & 63), plane = m >> 6;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q < nq) v = *reinterpret_cast<const uint4 *>(pq + (size_t)q * pq_stride + sizeof(PQHeader) + ((size_t)c * 2 + plane) * 16);
-    *reinterpret_cast<uint4 *>(img + (size_t)g * C * 2048 + ((size_t)c * 16 + (m >> 3)) * 128 + (m & 7) * 16) = v;
-}
-
-// One "super tile" = kNB = 4 consecutive 32-row blocks = N 128: a tcgen05.mma costs ~64 cycles whether N is 32
-// or 128 (measured, tools/umma_test.cu), so the rows operand must be 128 wide.  The four blocks are laid out in
-// shared memory chunk-major, [chunk][block][8-row group][128 B], by 512-byte bulk copies (one per block and
-// chunk, issued by all 32 producer lanes), which gives the 16 row groups the uniform 128-byte stride the
-// K-major no-swizzle descriptor needs.  The query digit planes (A, M = 128) live in TMEM (192 columns,
-// written once per CTA with tcgen05.st: lane = row, 4 K-bytes per column), so no shared memory or bandwidth
-// is spent on A and both accumulator buffers (2 x 128 columns) fit beside it.
-constexpr uint32_t kNB = 4;                     // blocks per super tile (N = 4 x 32)
-constexpr uint32_t kAccCols = kNB * 32;         // columns of one accumulator buffer
-constexpr uint32_t kTmemCols = 512;             // 2 accumulator buffers + up to 256 columns of A
-
-struct SuperMeta { uint32_t blk, live[kNB]; };
-
+template <bool COS, int E>
 __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs a, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t b_full[kMaxStages], b_empty[kMaxStages], d_full[2], d_empty[2];
-    __shared__ SuperMeta s_meta[kMaxStages], s_dmeta[2];
-    __shared__ unsigned long long s_thr[kBatchQueries];
-    __shared__ uint32_t s_cnt[kBatchQueries];
+    __shared__ __align__(8) uint64_t b_full[kBatchMaxStages], b_empty[kBatchMaxStages], d_full[2], d_empty[2];
+    __shared__ uint32_t s_first[kBatchMaxStages]; // first block of the super tile a stage belongs to (kNoBlock = end)
+    __shared__ QState s_q[kBatchQueries];
+    __shared__ float s_aux[8][kTileRows];         // per epilogue warp: staged per-row operand of the current tile
+    // per-tile side data, producer -> epilogue: the rows' aux pairs (bulk copy), the live words, the tile index
+    __shared__ __align__(16) float2 s_xaux[kAuxSlots][kTileRows];
+    __shared__ uint32_t s_xwords[kAuxSlots][kNB], s_xsup[kAuxSlots];
+    __shared__ __align__(8) uint64_t x_full[kAuxSlots], x_empty[kAuxSlots];
     __shared__ uint32_t s_tmem;
+    __shared__ int s_fits;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t C = a.C, S = a.stages;
-    const uint32_t stage_bytes = kNB * C * 512u;
+    const uint32_t slc = a.slice;                        // chunks per K slice (= TMA box)
+    const uint32_t nsl = (C + slc - 1) / slc;            // slices per super tile
+    const uint32_t stage_bytes = kNB * slc * 512u;
     unsigned char *sB = smem;
-    int32_t *s_x = reinterpret_cast<int32_t *>(sB + (size_t)S * stage_bytes); // [2][128][17] plane exchange
 
     const uint32_t g = blockIdx.x % a.ngroups, r = blockIdx.x / a.ngroups; // (query group, row range)
     const uint32_t nsup = (a.nblk + kNB - 1) / kNB;
@@ -119,10 +285,32 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
 
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int d = 0; d < 2; ++d) { mbar_init(&d_full[d], 1); mbar_init(&d_empty[d], 4); }
+        for (int d = 0; d < 2; ++d) { mbar_init(&d_full[d], 1); mbar_init(&d_empty[d], 8); }
+        for (uint32_t x = 0; x < kAuxSlots; ++x) { mbar_init(&x_full[x], 1); mbar_init(&x_empty[x], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_fits = 1;
     }
-    if (tid < kBatchQueries) { s_thr[tid] = (q0 + tid < a.nq) ? kNoKey : 0ull; s_cnt[tid] = 0; }
+    __syncthreads();
+    if (tid < kBatchQueries) {
+        const uint32_t q = q0 + tid;
+        QState &s = s_q[tid];
+        s.valid = q < a.nq;
+        const PQHeader *hdr = reinterpret_cast<const PQHeader *>(a.pq + (size_t)(s.valid ? q : 0) * a.pq_stride);
+        s.thr = s.valid ? kNoKey : 0ull;
+        s.gbound = kNoKey;
+        s.pub = 0xFFFFFFFFu;
+        s.numc = (long long)hdr->numc;
+        s.c_key = (float)hdr->c_key; s.c_dot2 = (float)(2.0 * hdr->c_dot); s.qn2 = (float)hdr->qn2;
+        s.inv_ckey = hdr->c_key > 0.0 ? (float)(1.0 / hdr->c_key) : 0.f;
+        s.zero = hdr->zero_query != 0;
+        // |s| <= d + ||q||^2, |p| <= 2 sqrt(d) ||q|| (+ fixed-point rounding): 8 eps of their sum
+        s.slack = (float)(4.76837158203125e-7 * ((double)a.dims + hdr->qn2 + 2.0 * sqrt((double)a.dims * hdr->qn2) + 1.0));
+        s.T = s.valid ? -INFINITY : INFINITY;
+        // |num| = M 2^F |x.q| <= M 2^F sqrt(d) ||q||: when that fits 31 bits the whole sum can run in wrapping
+        // 32-bit arithmetic (exact mod 2^32, and the true value fits)
+        const bool fits = 255.0 * ldexp(1.0, hdr->F) * sqrt((double)a.dims * hdr->qn2) < 2.0e9;
+        if (s.valid && !fits) atomicAnd(&s_fits, 0);
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -133,10 +321,10 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     const uint32_t tmem = s_tmem;
     const uint32_t tmemA = tmem + 2 * kAccCols;
 
-    // ---- A operand: the epilogue threads own TMEM lanes; lane L = plane * 64 + query holds that digit plane
-    if (warp >= 2) {
+    // ---- A operand: TMEM lane L = 32 lq + 16 h + 8 plane + j holds digit plane `plane` of query 16 lq + 8 h + j
+    if (warp >= 2 && warp < 6) {
         const uint32_t lq = (uint32_t)(warp & 3), L = lq * 32 + lane;
-        const uint32_t q = q0 + (L & 63), plane = L >> 6;
+        const uint32_t q = q0 + lq * 16 + ((L >> 4) & 1u) * 8 + (L & 7u), plane = (L >> 3) & 1u;
         const unsigned char *src = a.pq + (size_t)(q < a.nq ? q : 0) * a.pq_stride + sizeof(PQHeader);
         for (uint32_t ks = 0; ks < C / 2; ++ks) { // 2 chunks = 32 K-bytes = 8 columns = one MMA K step
             uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
@@ -156,41 +344,52 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp == 0) {
-        // ================================================================ TMA producer (whole warp)
-        uint32_t t = 0; // stage counter
-        for (uint32_t sup = sup0; sup <= sup1; ++sup) {
-            uint32_t lv = 0;
-            if (sup < sup1 && lane < (int)kNB) {
-                const uint32_t blk = sup * kNB + lane;
-                if (blk < a.nblk) {
-                    lv = __ldg(a.live + blk);
-                    if (a.mask) lv &= __ldg(a.mask + blk);
-                }
-            }
-            const uint32_t any = __ballot_sync(0xffffffffu, lv != 0);
-            if (sup < sup1 && !any) continue; // nothing live in these blocks: never fetched
-            const uint32_t s = t % S;
-            if (t >= S) mbar_wait(&b_empty[s], ((t / S) - 1) & 1u);
-            if (lane < (int)kNB) s_meta[s].live[lane] = lv;
-            __syncwarp(); // the meta words are in place before lane 0 arms / arrives on the barrier
-            if (sup < sup1) {
-                if (lane == 0) {
-                    // one TMA tensor copy per stage: box (512 B, 4 blocks, C chunks) of the 3-D view
-                    // (512 B | block, stride C*512 | chunk, stride 512) lands chunk-major, [chunk][block][512 B];
-                    // blocks past the end of the mirror are zero-filled by the copy engine
-                    s_meta[s].blk = sup * kNB;
-                    mbar_expect_tx(&b_full[s], stage_bytes);
-                    asm volatile(
-                        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                            smem_u32(sB + (size_t)s * stage_bytes)),
-                        "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(smem_u32(&b_full[s])), "r"(0), "r"((int)(sup * kNB)), "r"(0)
-                        : "memory");
-                }
-            } else { // end of the range: a sentinel travels through both pipelines
-                if (lane == 0) { s_meta[s].blk = kNoBlock; mbar_arrive(&b_full[s]); }
-            }
+        // ================================================================ TMA producer
+        uint32_t t = 0, xt = 0, words; // stage counter, tile counter
+        bool again = a.nranges > 1; // the first tile of a range is sent twice (seeding pass, see the epilogue)
+        for (uint32_t sup = next_live_tile(a, sup0, sup1, lane, &words);;
+             sup = again ? sup : next_live_tile(a, sup + 1, sup1, lane, &words), again = false, ++xt) {
+            // side data of the tile (or the end marker) for the epilogue warps
+            const uint32_t x = xt % kAuxSlots;
+            if (xt >= kAuxSlots) mbar_wait(&x_empty[x], ((xt / kAuxSlots) - 1) & 1u);
+            if (lane < (int)kNB) s_xwords[x][lane] = words;
             __syncwarp();
-            ++t;
+            if (lane == 0) {
+                if (sup < sup1) {
+                    const uint32_t row0 = sup * kTileRows, nrows = min(kTileRows, a.nblk * 32 - row0);
+                    s_xsup[x] = sup;
+                    mbar_expect_tx(&x_full[x], nrows * 8u);
+                    bulk_g2s(&s_xaux[x][0], reinterpret_cast<const float2 *>(a.aux) + row0, nrows * 8u, &x_full[x]);
+                } else {
+                    s_xsup[x] = kNoBlock;
+                    mbar_arrive(&x_full[x]);
+                }
+            }
+            const uint32_t n = sup < sup1 ? nsl : 1u; // the end of the range travels through the ring as a sentinel stage
+            for (uint32_t sl = 0; sl < n; ++sl, ++t) {
+                const uint32_t s = t % S;
+                if (lane == 0) {
+                    if (t >= S) mbar_wait(&b_empty[s], ((t / S) - 1) & 1u);
+                    if (sup < sup1) {
+                        // one TMA tensor copy per stage: box (512 B, 4 blocks, slc chunks) of the 3-D view
+                        // (512 B | block, stride C * 512 | chunk, stride 512) lands chunk-major, [chunk][block][512 B];
+                        // blocks past the end of the mirror and chunks past the end of a row are zero-filled
+                        s_first[s] = sup * kNB;
+                        mbar_expect_tx(&b_full[s], stage_bytes);
+                        asm volatile(
+                            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                                smem_u32(sB + (size_t)s * stage_bytes)),
+                            "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(smem_u32(&b_full[s])), "r"(0), "r"((int)(sup * kNB)),
+                            "r"((int)(sl * slc))
+                            : "memory");
+                    } else {
+                        s_first[s] = kNoBlock;
+                        mbar_arrive(&b_full[s]);
+                    }
+                }
+                __syncwarp();
+            }
+            if (sup >= sup1) break;
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
@@ -198,167 +397,165 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             // D = S32, A = S8 (query digits, TMEM), B = U8 (codes, smem K-major), N = 128, M = 128
             const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((kAccCols >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t sb = smem_u32(sB);
-            for (uint32_t t = 0;; ++t) {
-                const uint32_t s = t % S, d = t & 1u;
-                mbar_wait(&b_full[s], (t / S) & 1u);
-                const uint32_t blk = *reinterpret_cast<volatile uint32_t *>(&s_meta[s].blk);
-                if (t >= 2) mbar_wait(&d_empty[d], ((t >> 1) - 1) & 1u);
-                s_dmeta[d].blk = blk;
-                for (uint32_t j = 0; j < kNB; ++j) s_dmeta[d].live[j] = *reinterpret_cast<volatile uint32_t *>(&s_meta[s].live[j]);
-                __threadfence_block();
-                if (blk == kNoBlock) { mbar_arrive(&d_full[d]); break; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (!(a.debug & 4u))
-                    for (uint32_t ks = 0; ks < C / 2; ++ks) {
-                        const uint64_t db = umma_desc(sb + s * stage_bytes + ks * (2 * kNB * 512u), kNB * 512u, 128);
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(
-                                tmem + d * kAccCols),
-                            "r"(tmemA + ks * 8), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)), "r"(0u)
-                            : "memory");
+            uint32_t t = 0;
+            for (uint32_t tile = 0;; ++tile) {
+                const uint32_t d = tile & 1u;
+                bool end = false;
+                for (uint32_t sl = 0; sl < nsl; ++sl, ++t) {
+                    const uint32_t s = t % S;
+                    mbar_wait(&b_full[s], (t / S) & 1u);
+                    if (sl == 0) {
+                        if (*reinterpret_cast<volatile uint32_t *>(&s_first[s]) == kNoBlock) { end = true; break; }
+                        if (tile >= 2) mbar_wait(&d_empty[d], ((tile >> 1) - 1) & 1u);
                     }
-                umma_commit(&b_empty[s]); // the stage may be refilled once these MMAs have read it
-                umma_commit(&d_full[d]);  // accumulators complete
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t ks0 = sl * slc / 2, ks1 = min(C / 2, ks0 + slc / 2);
+                    if (!(a.debug & 4u))
+                        for (uint32_t ks = ks0; ks < ks1; ++ks) {
+                            const uint64_t db = umma_desc(sb + s * stage_bytes + (ks - ks0) * (2 * kNB * 512u), kNB * 512u, 128);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(
+                                    tmem + d * kAccCols),
+                                "r"(tmemA + ks * 8), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)), "r"(0u)
+                                : "memory");
+                        }
+                    umma_commit(&b_empty[s]); // the stage may be refilled once these MMAs have read it
+                }
+                if (end) break;
+                umma_commit(&d_full[d]); // accumulators complete
             }
         }
     } else {
-        // ================================================================ epilogue (128 threads)
-        const int ew = warp - 2;                        // 0..3, compaction work split
+        // ================================================================ epilogue (8 warps, 8 queries each)
+        // warp = (TMEM lane quarter lq, half hh): TMEM lanes 32 lq + 16 hh + {0..15} = both planes of 8 queries
+        const int ew = warp - 2;                        // private staging buffer
         const uint32_t lq = (uint32_t)(warp & 3);       // TMEM lane quarter this warp may read
-        const uint32_t L = lq * 32 + lane;              // TMEM lane = A row: plane * 64 + query
-        const uint32_t qi = L & 63, upper = L >> 6;     // upper half holds the least significant digit plane
-        const uint32_t q = q0 + qi;
-        const bool qvalid = q < a.nq;
-        const PQHeader *hdr = reinterpret_cast<const PQHeader *>(a.pq + (size_t)(qvalid ? q : 0) * a.pq_stride);
-        // the cancellation num = 2 I + numc happens in exact 64-bit integers; everything after it is fp32
-        const long long numc = (long long)hdr->numc;
-        // |num| = M 2^F |x.q| <= M 2^F sqrt(d) ||q||: when that fits 31 bits the whole sum can run in wrapping
-        // 32-bit arithmetic (exact mod 2^32, and the true value fits), which spares the 64-bit ops and the slow
-        // s64 -> f32 conversion
-        const bool fits32 = 255.0 * ldexp(1.0, hdr->F) * sqrt((double)a.dims * hdr->qn2) < 2.0e9;
-        const int numc32 = (int)numc;
-        const float c_key = (float)hdr->c_key, c_dot2 = (float)(2.0 * hdr->c_dot), qn2 = (float)hdr->qn2;
-        const bool zero_query = hdr->zero_query != 0;
-        const bool cosine = a.metric == COSINE;
-        unsigned long long *gbuf = a.cand + ((size_t)(qvalid ? q : 0) * a.nlists + (size_t)r * (kBatchCap / kBatchKp)) * kBatchKp;
-        const float2 *aux = reinterpret_cast<const float2 *>(a.aux);
-        const uint32_t partner = upper ? L - 64 : L + 64;
-        const uint32_t slot_max = a.nblk * 32 - 1; // the last super tile may reach past the mirror: clamp aux reads
-        uint32_t xb = 0; // exchange buffer parity
-
-        for (uint32_t tile = 0;; ++tile) {
-            const uint32_t d = tile & 1u;
-            mbar_wait(&d_full[d], (tile >> 1) & 1u);
-            const uint32_t blk_base = *reinterpret_cast<volatile uint32_t *>(&s_dmeta[d].blk);
-            if (blk_base == kNoBlock) break;
-            uint32_t lives[kNB];
-#pragma unroll
-            for (uint32_t j = 0; j < kNB; ++j) lives[j] = *reinterpret_cast<volatile uint32_t *>(&s_dmeta[d].live[j]);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned long long thr = s_thr[qi];
-#pragma unroll 1
-            for (uint32_t j = 0; j < kNB; ++j) {
-                uint32_t acc[32];
-                tmem_ld32(tmem + ((lq * 32u) << 16) + d * kAccCols + j * 32, acc);
-                if (j == kNB - 1) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&d_empty[d]); // this warp's quarter of the buffer is in registers
-                }
-                if (a.debug & 1u) continue;
-                // exchange the halves: lower threads (digit 1) handle rows 0..15, upper threads (digit 0) rows 16..31
-                int32_t *xw = s_x + xb * (128 * 17);
-                xb ^= 1u;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) xw[L * 17 + i] = (int32_t)acc[upper ? i : 16 + i];
-                epi_barrier();
-                const uint32_t slot0 = (blk_base + j) * 32 + (upper ? 16 : 0);
-                const uint32_t live = lives[j] >> (upper ? 16 : 0);
-                unsigned long long k64[16];
-                unsigned long long best = kNoKey;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int32_t other = xw[partner * 17 + i];
-                    const int32_t d1 = upper ? other : (int32_t)acc[i];
-                    const int32_t d0 = upper ? (int32_t)acc[16 + i] : other;
-                    float numf;
-                    if (fits32) numf = (float)(2 * (d1 * 128 + d0) + numc32);
-                    else numf = (float)(2 * ((long long)d1 * 128 + (long long)d0) + numc);
-                    const float2 ax = (a.debug & 2u) ? make_float2(0.1f, 1.f) : __ldg(aux + min(slot0 + i, slot_max));
-                    float key;
-                    if (cosine) key = (zero_query || ax.x == 0.f) ? 1.0f : -((numf * c_key) * ax.x);
-                    else key = (ax.y + qn2) - numf * c_dot2;
-                    const bool ok = (live >> i) & 1u;
-                    k64[i] = ok ? make_key64(key, slot0 + i) : kNoKey;
-                    best = k64[i] < best ? k64[i] : best;
-                }
-                if (best < thr) { // rare once the threshold has tightened
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (k64[i] < thr) {
-                            const uint32_t pos = atomicAdd(&s_cnt[qi], 1u);
-                            if (pos < (uint32_t)kBatchCap) gbuf[pos] = k64[i];
-                        }
-                }
-            }
-            if (a.debug & 1u) continue;
-            epi_barrier();
-            // compaction: a super tile appends at most kNB * 32 keys per query
-            for (uint32_t cq = ew; cq < (uint32_t)kBatchQueries; cq += 4) {
-                const uint32_t n = s_cnt[cq];
-                if (n <= (uint32_t)(kBatchCap - kNB * 32)) continue;
-                unsigned long long *gb = a.cand + ((size_t)(q0 + cq) * a.nlists + (size_t)r * (kBatchCap / kBatchKp)) * kBatchKp;
-                // 512 keys = 16 per lane in registers (element e = lane * 16 + r): bitonic network, register
-                // compare-exchanges for partner distance < 16, shuffles above
-                unsigned long long v[16];
-#pragma unroll
-                for (int rr = 0; rr < 16; ++rr) { const uint32_t e = (uint32_t)lane * 16 + rr; v[rr] = e < n ? gb[e] : kNoKey; }
-#pragma unroll
-                for (int k = 2; k <= kBatchCap; k <<= 1) {
-#pragma unroll
-                    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                        if (jj >= 16) {
-                            const int lj = jj >> 4;
-                            const bool lower = (lane & lj) == 0;
-#pragma unroll
-                            for (int rr = 0; rr < 16; ++rr) {
-                                const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[rr], lj);
-                                const bool up = (((lane * 16 + rr) & k) == 0);
-                                const bool keep_min = (lower == up);
-                                v[rr] = keep_min ? (v[rr] < o ? v[rr] : o) : (v[rr] > o ? v[rr] : o);
-                            }
-                        } else {
-#pragma unroll
-                            for (int rr = 0; rr < 16; ++rr) {
-                                if ((rr & jj) == 0) {
-                                    const int r2 = rr | jj;
-                                    const bool up = (((lane * 16 + rr) & k) == 0);
-                                    const unsigned long long x = v[rr], y = v[r2];
-                                    const bool sw = (x > y) == up;
-                                    v[rr] = sw ? y : x;
-                                    v[r2] = sw ? x : y;
-                                }
-                            }
-                        }
+        const uint32_t hh = (uint32_t)(warp - 2) >> 2;  // which 16 lanes of the quarter
+        const uint32_t c4 = (uint32_t)lane & 3u;        // column pair within each group of 8 columns
+        const uint32_t qw = lq * 16 + hh * 8;           // the warp's first query within the group
+        QState *qs = &s_q[qw + (lane >> 2)];
+        const bool fits = s_fits != 0;
+        const long long numc64 = qs->numc;
+        const int numc32 = (int)numc64;
+        const float c2 = qs->c_dot2;
+        float T = qs->T;
+        constexpr uint32_t Kp = 32 * E;
+        float *sa = s_aux[ew];
+        QState *wq = &s_q[qw];
+        // the warp's 8 candidate lists (sorted, Kp keys each) live behind the ring in dynamic shared memory
+        unsigned long long *wl = reinterpret_cast<unsigned long long *>(smem + (size_t)S * stage_bytes) + (size_t)qw * Kp;
+        for (uint32_t i = lane; i < 8 * Kp; i += 32) wl[i] = kNoKey;
+        __syncwarp();
+        // Bound shared by the R row ranges of a query: every range publishes the key of its mth-best row so far
+        // (mth = ceil(Kp / R)); once all have one, at least R * mth >= Kp rows lie at or below the largest of them,
+        // so that value bounds the query's Kp-th best key and no row above it can reach the candidate set.  This
+        // keeps the number of rows that pass the fast test near Kp (1 + ln) per QUERY instead of per range.
+        // To have the bound from the start, the first tile of a range is processed twice: once "seeding"
+        // (admission by the mth-best key, cheap), then -- after every range of the group has published -- for real.
+        const uint32_t R = a.nranges, mthm1 = a.mth - 1;
+        uint32_t *gmw = a.gmth + ((size_t)min(q0 + qw, a.nq - 1) * R + r);
+        const uint32_t poll_mask = R <= 16 ? 3u : R <= 64 ? 15u : 63u; // poll every 4 / 16 / 64 tiles (+ at powers of two)
+        // returns true when every range has published for all of the warp's queries
+        auto poll_bounds = [&]() -> bool {
+            bool have = true;
+            if (lane < 8 && wq[lane].valid) {
+                const volatile uint32_t *g = a.gmth + (size_t)(q0 + qw + lane) * R;
+                uint32_t b = 0;
+                for (uint32_t rr = 0; rr < R; ++rr) b = max(b, g[rr]);
+                have = b != 0xFFFFFFFFu;
+                if (have) {
+                    const unsigned long long gb = ((unsigned long long)b << 32) | 0xFFFFFFFFull;
+                    QState &s = wq[lane];
+                    if (gb < s.gbound) {
+                        s.gbound = gb;
+                        if (gb < s.thr) { s.thr = gb; s.T = fast_threshold<COS>(s); }
                     }
                 }
-                // ranks [lane*16, lane*16+16): the first 128 ranks live in lanes 0..7
-                if (lane < kBatchKp / 16) {
-#pragma unroll
-                    for (int rr = 0; rr < 16; ++rr) gb[lane * 16 + rr] = v[rr];
-                }
-                if (lane == kBatchKp / 16 - 1) { s_cnt[cq] = kBatchKp; s_thr[cq] = v[15]; }
-                __syncwarp();
             }
-            epi_barrier();
+            return __all_sync(0xffffffffu, have);
+        };
+        bool seeding = R > 1;
+        for (uint32_t tile = 0;; ++tile) {
+            const uint32_t d = tile & 1u, x = tile % kAuxSlots;
+            // side data of the tile: per-row operand staged per warp (cosine 1/||x||, euclid ||x||^2; dead or
+            // filtered rows get a value that never passes); lane stages rows lane + 32 j
+            mbar_wait(&x_full[x], (tile / kAuxSlots) & 1u);
+            const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&s_xsup[x]);
+            if (cur == kNoBlock) break;
+            __syncwarp();
+#pragma unroll
+            for (uint32_t j = 0; j < kNB; ++j) {
+                const float2 axr = s_xaux[x][j * 32 + lane];
+                const bool ok = (s_xwords[x][j] >> lane) & 1u;
+                sa[j * 32 + lane] = COS ? (ok ? axr.x : __int_as_float(0x7FC00000)) : (ok ? axr.y : INFINITY);
+            }
+            __syncwarp();
+            if (R > 1 && tile >= 2 && ((tile & (tile - 1)) == 0 || (tile & poll_mask) == 0)) {
+                poll_bounds();
+                T = qs->T;
+            }
+            const uint32_t capm1 = seeding ? mthm1 : Kp - 1;
+            mbar_wait(&d_full[d], (tile >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tbase = tmem + ((lq * 32u + hh * 16u) << 16) + d * kAccCols;
+            if (a.debug & 1u) { // profiling aid: drain the accumulators, skip the arithmetic
+                uint32_t ra[32];
+                for (int i = 0; i < 2; ++i) { tmem_ld_16x64(tbase + i * 64, ra); tmem_ld_wait(ra); }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&d_empty[d]); mbar_arrive(&x_empty[x]); }
+                continue;
+            }
+            uint32_t ra[32], rb[32];
+            float2 ax[8];
+            auto load_ax = [&](uint32_t part) {
+#pragma unroll
+                for (int rep = 0; rep < 8; ++rep) ax[rep] = *reinterpret_cast<const float2 *>(sa + part * 64 + rep * 8 + 2 * c4);
+            };
+            const uint32_t slot0 = cur * kTileRows;
+            auto score = [&](const uint32_t (&rr)[32], uint32_t part) {
+                if (fits) T = score16<COS, true, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                else T = score16<COS, false, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+            };
+            // the second half of the columns is in flight while the first is scored
+            tmem_ld_16x64(tbase, ra);
+            load_ax(0);
+            tmem_ld_wait(ra);
+            tmem_ld_16x64(tbase + 64, rb);
+            score(ra, 0);
+            load_ax(1);
+            tmem_ld_wait(rb);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[d]); // this warp's part of the buffer is in registers
+            score(rb, 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&x_empty[x]); // the tile's aux pairs are no longer needed
+            if (seeding) {
+                // end of the seeding pass over the first tile: a range that could not seed publishes "no bound"
+                seeding = false;
+                if (lane < 8 && wq[lane].valid && wq[lane].pub == 0xFFFFFFFFu) {
+                    wq[lane].pub = 0xFFFFFFFEu;
+                    *reinterpret_cast<volatile uint32_t *>(gmw + (size_t)lane * R) = 0xFFFFFFFEu;
+                }
+                __syncwarp();
+                for (uint32_t i = lane; i < 8 * Kp; i += 32) wl[i] = kNoKey; // the tile comes again
+                if (lane < 8) { wq[lane].thr = wq[lane].valid ? kNoKey : 0ull; wq[lane].T = wq[lane].valid ? -INFINITY : INFINITY; }
+                __syncwarp();
+                while (!poll_bounds()) __nanosleep(200); // all ranges of the group are co-resident (grid <= SM count)
+                T = qs->T;
+            }
         }
-        // pad the unused tail of every candidate buffer so that finalize sees (cap / Kp) well-formed lists
-        epi_barrier();
-        for (uint32_t cq = ew; cq < (uint32_t)kBatchQueries; cq += 4) {
-            if (q0 + cq >= a.nq) continue;
-            unsigned long long *gb = a.cand + ((size_t)(q0 + cq) * a.nlists + (size_t)r * (kBatchCap / kBatchKp)) * kBatchKp;
-            for (uint32_t i = s_cnt[cq] + lane; i < (uint32_t)kBatchCap; i += 32) gb[i] = kNoKey;
+        __syncwarp();
+        if (seeding && lane < 8 && wq[lane].valid) // a range without live rows: tell the others not to wait for it
+            *reinterpret_cast<volatile uint32_t *>(gmw + (size_t)lane * R) = 0xFFFFFFFEu;
+        // hand the lists to finalize_kernel: cand[query][row range][Kp]
+        __syncwarp();
+        for (uint32_t j = 0; j < 8; ++j) {
+            if (!wq[j].valid) continue;
+            unsigned long long *gb = a.cand + ((size_t)(q0 + qw + j) * a.nranges + r) * Kp;
+            for (uint32_t i = lane; i < Kp; i += 32) gb[i] = wl[j * Kp + i];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -366,20 +563,40 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
 
-size_t batch_smem_bytes(uint32_t C, uint32_t stages) { return (size_t)stages * kNB * C * 512 + 2 * 128 * 17 * 4; }
+// chunks per ring stage: measured on B200, the fewer stage hand-offs per super tile the better (a whole tile per
+// stage with 2 stages beats 6 slices with 13 stages by 2x), so: the largest slice that still leaves >= 2 stages
+uint32_t batch_slice_chunks(uint32_t C, uint32_t want, size_t smem_limit) {
+    uint32_t s = want ? want : C;
+    if (s > C) s = C;
+    if (!want)
+        while (s > 2 && (size_t)2 * kNB * s * 512u > smem_limit) s = ((s + 1) / 2 + 1) & ~1u;
+    s &= ~1u;
+    return s < 2 ? 2 : s;
+}
+uint32_t batch_stages(uint32_t slice, size_t smem_limit) {
+    uint32_t s = (uint32_t)(smem_limit / (kNB * slice * 512u));
+    return s > (uint32_t)kBatchMaxStages ? (uint32_t)kBatchMaxStages : s;
+}
+size_t batch_list_bytes(uint32_t keep) { return (size_t)kBatchQueries * keep * 8; }
+size_t batch_smem_bytes(uint32_t slice, uint32_t stages, uint32_t keep) { return (size_t)stages * kNB * slice * 512u + batch_list_bytes(keep); }
 uint32_t batch_max_chunks() { return 256 * 4 / 16; } // A lives in <= 256 TMEM columns: rows of at most 1024 bytes
-uint32_t batch_lists_per_range() { return kBatchCap / kBatchKp; }
 
-cudaError_t batch_configure(size_t max_smem) {
-    return cudaFuncSetAttribute(batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+// dynamic shared memory available to the ring: the CTA limit minus the kernel's static shared memory
+size_t batch_dynamic_limit() {
+    cudaFuncAttributes fa;
+    size_t stat = 16 * 1024;
+    if (cudaFuncGetAttributes(&fa, batch_kernel<true, 4>) == cudaSuccess) stat = fa.sharedSizeBytes;
+    return 227 * 1024 - stat - 1024;
 }
 
-cudaError_t launch_batch_pack(const unsigned char *pq, size_t pq_stride, uint32_t nq, uint32_t C, unsigned char *img,
-                              cudaStream_t st) {
-    const uint32_t ngroups = (nq + kBatchQueries - 1) / kBatchQueries;
-    const size_t total = (size_t)ngroups * 128 * C;
-    batch_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pq, pq_stride, nq, C, img);
-    return cudaGetLastError();
+cudaError_t batch_configure(size_t max_smem) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    return cudaFuncSetAttribute(batch_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
 }
 
 // 3-D tensor map over the column-blocked mirror: (64 x u64 = one chunk of a block's 32 rows | block | chunk)
@@ -398,7 +615,7 @@ static cudaError_t make_tmap(const BatchArgs &a, CUtensorMap *tm) {
     }
     const cuuint64_t gdim[3] = {64, a.nblk, a.C};
     const cuuint64_t gstride[2] = {(cuuint64_t)a.C * 512, 512}; // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {64, kNB, a.C};
+    const cuuint32_t box[3] = {64, kNB, a.slice};
     const cuuint32_t estride[3] = {1, 1, 1};
     CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint4 *>(a.codes), gdim, gstride, box, estride,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -410,7 +627,21 @@ cudaError_t launch_batch(const BatchArgs &a, cudaStream_t st) {
     CUtensorMap tm;
     cudaError_t e = make_tmap(a, &tm);
     if (e != cudaSuccess) return e;
-    batch_kernel<<<a.ngroups * a.nranges, kBatchThreads, batch_smem_bytes(a.C, a.stages), st>>>(a, tm);
+    if (a.stages < 2 || a.stages > (uint32_t)kBatchMaxStages || (a.keep != 32 && a.keep != 64 && a.keep != 128)) return cudaErrorInvalidValue;
+    if (a.slice < 2 || a.slice > a.C || (a.slice & 1u)) return cudaErrorInvalidValue;
+    const size_t smem = batch_smem_bytes(a.slice, a.stages, a.keep);
+    const dim3 grid(a.ngroups * a.nranges);
+    const bool cos = a.metric == COSINE;
+    if (a.keep == 32) {
+        if (cos) batch_kernel<true, 1><<<grid, kBatchThreads, smem, st>>>(a, tm);
+        else batch_kernel<false, 1><<<grid, kBatchThreads, smem, st>>>(a, tm);
+    } else if (a.keep == 64) {
+        if (cos) batch_kernel<true, 2><<<grid, kBatchThreads, smem, st>>>(a, tm);
+        else batch_kernel<false, 2><<<grid, kBatchThreads, smem, st>>>(a, tm);
+    } else {
+        if (cos) batch_kernel<true, 4><<<grid, kBatchThreads, smem, st>>>(a, tm);
+        else batch_kernel<false, 4><<<grid, kBatchThreads, smem, st>>>(a, tm);
+    }
     return cudaGetLastError();
 }
 

@@ -86,7 +86,7 @@ struct Workspace {
     DevBuf<double> d_q, d_q2;
     DevBuf<unsigned char> d_pq;
     DevBuf<unsigned long long> d_cand; // [nq][scan CTAs][32*E] candidate keys, scan -> finalize
-    DevBuf<unsigned char> d_img;       // batched path: A operand images (query digit planes)
+    DevBuf<unsigned int> d_gmth;       // batched path: per (query, row range) shared bound keys
     DevBuf<unsigned int> d_ticket;     // radius hit counter
     DevBuf<unsigned long long> d_out_ids;
     DevBuf<double> d_out_dist;
@@ -110,7 +110,7 @@ struct Workspace {
     void destroy() {
         d_q.release(); d_q2.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
         d_out_n.release(); d_out_flags.release(); d_slots.release();
-        d_cand.release(); d_img.release();
+        d_cand.release(); d_gmth.release();
         h_q.release(); h_out_ids.release(); h_out_dist.release(); h_out_n.release(); h_out_flags.release();
         h_slots.release();
         for (auto e : t0) cudaEventDestroy(e);
@@ -776,11 +776,16 @@ int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t 
                      uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
     GUARD(h);
     int rc;
-    // shared memory: `stages` stages of one super tile (4 blocks of C * 512 B); the query digits live in TMEM
-    uint32_t stages = 3;
-    while (stages > 2 && batch_smem_bytes(h->C, stages) > kScanSmemLimit - 4096) --stages;
+    // shared memory: a ring of K slices of super tiles (4 blocks x <= 8 chunks each); the query digits live in TMEM
+    const int mode = mode_for_k(h, k); // candidates per list = 32 << mode, as in the streaming scan
+    const size_t ring_limit = batch_dynamic_limit();
+    uint32_t want_slice = 0;
+    if (const char *e = getenv("SZG_BATCH_SLICE")) want_slice = (uint32_t)atoi(e);
+    const size_t stage_limit = ring_limit - batch_list_bytes(32u << (mode <= 2 ? mode : 2));
+    const uint32_t slice = batch_slice_chunks(h->C, want_slice, stage_limit);
+    const uint32_t stages = batch_stages(slice, stage_limit);
     const bool tensor_path = h->qt == Q8 && h->digits != 3 && (h->C % 2) == 0 && h->C <= batch_max_chunks() && k >= 1 &&
-                             k <= 112 && batch_smem_bytes(h->C, stages) <= kScanSmemLimit - 4096 && nq >= 1;
+                             mode <= 2 && stages >= 2 && nq >= 1;
     if (!tensor_path || h->live_rows == 0 || h->batch_disabled)
         return szg_search_topk(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n, scanned);
     if ((rc = check_search(h, queries, nq))) return rc;
@@ -801,14 +806,16 @@ int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t 
     cudaStream_t st = ws->main;
     CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st));
 
-    const int nd = 2, mode = 2; // 2 digit planes = the M dimension; 128 survivors per list = finalize MODE 2
+    const int nd = 2; // 2 digit planes x 64 queries = the M dimension
+    const uint32_t keep = 32u << mode;
     const size_t stride = pq_stride(h, nd);
     const uint32_t ngroups_all = (nq + 63) / 64;
     const uint32_t gpl = std::min<uint32_t>(ngroups_all, 16);                      // groups per launch
     const uint32_t nblk = (h->nslots + 31) / 32;
     const uint32_t nranges = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)h->sm_count / gpl, nblk));
-    const uint32_t nlists = nranges * batch_lists_per_range();
-    if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * nlists * 128)))
+    const uint32_t nlists = nranges; // one sorted list of `keep` keys per row range
+    if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * nranges * keep)) ||
+        (rc = ws->d_gmth.ensure((size_t)nq * nranges)))
         return rc;
     PrepArgs pa;
     pa.queries = ws->d_q.p; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
@@ -816,13 +823,15 @@ int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t 
     pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
     CK(launch_prep(nq, st, pa));
     h->launches++;
-    CK(batch_configure(kScanSmemLimit));
+    CK(batch_configure(ring_limit));
     BatchArgs b;
     memset(&b, 0, sizeof b);
     b.codes = h->codes.p; b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
-    b.pq = ws->d_pq.p; b.pq_stride = stride; b.img = nullptr; b.cand = ws->d_cand.p;
+    b.pq = ws->d_pq.p; b.pq_stride = stride; b.cand = ws->d_cand.p; b.keep = keep;
     b.C = h->C; b.nblk = nblk; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
-    b.nranges = nranges; b.nlists = nlists; b.stages = stages;
+    b.nranges = nranges; b.nlists = nlists; b.stages = stages; b.slice = slice;
+    b.gmth = ws->d_gmth.p; b.mth = (keep + nranges - 1) / nranges;
+    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, (size_t)nq * nranges * sizeof(unsigned int), st));
     if (const char *dbg = getenv("SZG_BATCH_DEBUG")) b.debug = (uint32_t)atoi(dbg);
     const bool timing = h->timing != 0;
     const uint32_t nlaunch = (ngroups_all + gpl - 1) / gpl;
@@ -853,7 +862,7 @@ int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t 
     CK(launch_finalize(h->qt, mode, nq, st, f));
     h->launches++;
     h->batch_queries += nq;
-    return collect_and_escalate(h, ws, nq, k, mask, flags, nd, mode_for_k(h, k), out_ids, out_dist, out_n);
+    return collect_and_escalate(h, ws, nq, k, mask, flags, nd, mode, out_ids, out_dist, out_n);
 }
 
 

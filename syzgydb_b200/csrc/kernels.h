@@ -70,20 +70,24 @@ struct BatchArgs {
     const uint32_t *mask;
     const unsigned char *pq;   // prepared queries (2 digits), pq_stride apart
     size_t pq_stride;
-    const unsigned char *img;  // A operand images, one per 64-query group (launch_batch_pack)
-    unsigned long long *cand;  // [nq][nlists][128] candidate keys for finalize_kernel (MODE 2)
+    unsigned long long *cand;  // [nq][nranges][keep] candidate keys for finalize_kernel
     uint32_t C, nblk, metric, nq, dims;
     uint32_t group0, ngroups;  // query groups [group0, group0 + ngroups) run in this launch
-    uint32_t nranges, nlists;  // row ranges (CTAs per group); nlists = nranges * batch_lists_per_range()
-    uint32_t stages;           // shared-memory stages of one super tile (4 blocks) each
+    uint32_t nranges, nlists;  // row ranges (CTAs per group); nlists = what finalize sees per query
+    uint32_t stages;           // shared-memory ring stages (one K slice of a super tile each)
+    uint32_t slice;            // chunks per K slice (even, <= C)
+    uint32_t *gmth;            // [nq][nranges] ordered key of each range's mth-best row so far (0xFFFFFFFF = none yet)
+    uint32_t mth;              // ceil(keep / nranges)
+    uint32_t keep;             // candidates per (query, row range) list handed to finalize (32, 64, 128)
     uint32_t debug;            // profiling aid: bit0 skip the epilogue math, bit1 skip aux loads, bit2 skip the MMAs
 };
-size_t batch_smem_bytes(uint32_t C, uint32_t stages);
+uint32_t batch_slice_chunks(uint32_t C, uint32_t want, size_t smem_limit); // chunks per K slice (ring stage); want = 0: automatic
+size_t batch_list_bytes(uint32_t keep);                   // shared memory of the 64 candidate lists
+size_t batch_smem_bytes(uint32_t slice, uint32_t stages, uint32_t keep);
+uint32_t batch_stages(uint32_t slice, size_t smem_limit); // ring stages that fit
 uint32_t batch_max_chunks();
-uint32_t batch_lists_per_range();
 cudaError_t batch_configure(size_t max_smem);
-cudaError_t launch_batch_pack(const unsigned char *pq, size_t pq_stride, uint32_t nq, uint32_t C, unsigned char *img,
-                              cudaStream_t st);
+size_t batch_dynamic_limit();
 cudaError_t launch_batch(const BatchArgs &a, cudaStream_t st);
 
 struct MergeArgs {
