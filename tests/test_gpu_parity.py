@@ -554,3 +554,122 @@ def test_device_variant_reports_uncertified_queries():
         torch.cuda.synchronize()
     assert out_f[0].item() == 1  # thousands of rows within the surrogate error of each other
     assert out_n.tolist() == [k, k]
+
+
+# ------------------------------------------------------------------ batched queries on the tensor cores (szg_search_batch)
+def _batch_vs_oracle(ix, codes, ids, dims, metric, queries, k, mask_id=-1, passmask=None, what=""):
+    before = ix.stats()["batch_queries"]
+    gi, gd, gn, scanned = ix.search_batch(queries, k, mask_id=mask_id)
+    assert ix.stats()["batch_queries"] == before + len(queries), "the tensor-core path did not run"
+    flt = None if passmask is None else (lambda i, m: bool(passmask[int(i)]))
+    for qi, q in enumerate(queries):
+        if flt is None:
+            ri, rd, _ = o.search_exact(codes, ids, dims, 8, metric, q, k=k)
+        else:
+            keep = passmask.astype(bool)
+            ri, rd, _ = o.search_exact(codes[keep], ids[keep], dims, 8, metric, q, k=k)
+        if np.isnan(rd).any():
+            continue
+        assert gn[qi] == ri.size, f"{what} q{qi}: {gn[qi]} results, oracle {ri.size}"
+        assert_results_match(gi[qi, :gn[qi]], gd[qi, :gn[qi]], ri, rd, _true_dist(codes, ids, dims, 8, metric, q),
+                             f"{what} q{qi}")
+    return gi, gd, gn, scanned
+
+
+@pytest.mark.parametrize("metric", [szg.COSINE, szg.EUCLIDEAN])
+@pytest.mark.parametrize("dims,n,nq,k", [(768, 3000, 70, 10), (128, 9000, 130, 10), (384, 5001, 64, 50), (96, 4100, 3, 100),
+                                         (32, 700, 65, 1)])
+def test_batch_matches_oracle(metric, dims, n, nq, k):
+    """szg_search_batch (tcgen05 contraction + fused top-k) returns what nq single Search calls return."""
+    seed = 400 + dims + k
+    codes = o.synth_rows(seed, 0, n, dims, 8)
+    ids = np.arange(n, dtype=np.uint64) * 7 + 3
+    queries = o.synth_queries(seed + 1, 0, nq, dims)
+    with _build(codes, ids, dims, 8, metric) as ix:
+        gi, gd, gn, scanned = _batch_vs_oracle(ix, codes, ids, dims, metric, queries, k, what=f"batch m{metric} d{dims} k{k}")
+        assert scanned == n
+        # and bit-identical to the streaming scan (same candidates, same fp64 re-score)
+        si, sd, sn, _ = ix.search_topk(queries, k)
+        assert np.array_equal(gn, sn) and np.array_equal(gi, si) and np.array_equal(gd, sd)
+
+
+def test_batch_with_filter_mask_and_tombstones():
+    n, dims, nq, k = 6000, 256, 96, 10
+    codes = o.synth_rows(909, 0, n, dims, 8)
+    ids = np.arange(n, dtype=np.uint64)
+    queries = o.synth_queries(910, 0, nq, dims)
+    with _build(codes, ids, dims, 8, szg.COSINE) as ix:
+        dead = ids[(ids % 5 == 1)]
+        ix.remove(dead)
+        alive = (ids % 5 != 1)
+        passmask = ((ids % 10 < 3) & alive).astype(np.uint8)   # 30 % density (cfg3's filter), minus tombstones
+        mask = ix.mask_create(ids[alive], passmask[alive])
+        gi, gd, gn, scanned = _batch_vs_oracle(ix, codes, ids, dims, szg.COSINE, queries, k, mask_id=mask, passmask=passmask,
+                                               what="batch filtered")
+        assert scanned == int(alive.sum())  # filtered rows count as searched, removed ones do not
+        # a filter that leaves whole 128-row tiles empty and fewer than k rows in total
+        few = np.zeros(n, dtype=np.uint8)
+        few[[10, 4000, 4001, 5999]] = 1
+        few &= alive.astype(np.uint8)
+        mask2 = ix.mask_create(ids[alive], few[alive])
+        gi, gd, gn, _ = ix.search_batch(queries, k, mask_id=mask2)
+        assert np.all(gn == int(few.sum()))
+        assert set(gi[0, :gn[0]].tolist()) == set(ids[few.astype(bool)].tolist())
+
+
+def test_batch_zero_and_degenerate_queries():
+    n, dims = 2500, 64
+    codes = o.synth_rows(31, 0, n, dims, 8)
+    codes[100] = 128  # decodes to +0.0039..., fine; a true zero-norm row cannot exist with 8-bit codes
+    ids = np.arange(n, dtype=np.uint64)
+    queries = o.synth_queries(32, 0, 66, dims)
+    queries[5] = 0.0                      # zero query: every cosine distance is exactly 1.0 (collection.go:828-830)
+    queries[6] = queries[7]               # duplicate queries in one batch
+    queries[8] *= 1e-9                    # tiny norm
+    for metric in (szg.COSINE, szg.EUCLIDEAN):
+        with _build(codes, ids, dims, 8, metric) as ix:
+            gi, gd, gn, _ = _batch_vs_oracle(ix, codes, ids, dims, metric, queries, 10, what=f"batch degenerate m{metric}")
+            assert np.array_equal(gi[6], gi[7]) and np.array_equal(gd[6], gd[7])
+            if metric == szg.COSINE:
+                assert np.all(gd[5] == 1.0)  # 2500-way exact tie: any members (north_star tie rule)
+
+
+def test_batch_falls_back_to_the_scan_when_the_geometry_does_not_fit():
+    """Non-8-bit collections, odd chunk counts and k beyond the list sizes are served by the streaming scan, on the GPU."""
+    for bits, dims, k in [(4, 64, 10), (16, 48, 10), (8, 40, 10), (8, 64, 200)]:
+        n = 1500
+        codes = o.synth_rows(5, 0, n, dims, bits)
+        ids = np.arange(n, dtype=np.uint64)
+        queries = o.synth_queries(6, 0, 5, dims)
+        with _build(codes, ids, dims, bits, szg.EUCLIDEAN) as ix:
+            gi, gd, gn, _ = ix.search_batch(queries, k)
+            assert ix.stats()["batch_queries"] == 0
+            si, sd, sn, _ = ix.search_topk(queries, k)
+            assert np.array_equal(gi, si) and np.array_equal(gd, sd) and np.array_equal(gn, sn)
+
+
+def test_batch_near_duplicate_rows_escalate_like_the_scan():
+    """Rows closer to each other than the 2-digit surrogate can resolve: the batch path must flag and re-run them."""
+    n, dims = 4000, 128
+    rng = np.random.default_rng(3)
+    base = rng.integers(0, 256, size=dims, dtype=np.uint8)
+    codes = np.tile(base, (n, 1))
+    flip = rng.integers(0, dims, size=n)
+    codes[np.arange(n), flip] ^= 1  # every row differs from the base in one least-significant bit
+    ids = np.arange(n, dtype=np.uint64)
+    queries = o.synth_queries(44, 0, 64, dims)
+    with _build(codes, ids, dims, 8, szg.COSINE) as ix:
+        _batch_vs_oracle(ix, codes, ids, dims, szg.COSINE, queries[:8], 10, what="batch near-dup")
+
+
+def test_batch_cfg5_shape_against_streaming_scan():
+    """1024 queries, k = 100 (BASELINE.json configs[4] shape, 8-bit, one shard-sized slice): identical to the scan."""
+    rows, dims, nq, k = 200000, 768, 1024, 100
+    qs = np.random.default_rng(11).uniform(-1, 1, size=(nq, dims))
+    with szg.Index(dims, 8, szg.EUCLIDEAN) as ix:
+        ix.fill_synthetic(0x5A590005, 0, rows)
+        bi, bd, bn, _ = ix.search_batch(qs, k)
+        assert ix.stats()["batch_queries"] == nq
+        si, sd, sn, _ = ix.search_topk(qs, k)
+        assert np.array_equal(bn, sn) and np.array_equal(bi, si) and np.array_equal(bd, sd)
+        assert np.all(np.diff(bd, axis=1) >= 0)
