@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=250_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--batch-nq", type=int, default=1024,
+                    help="queries of the secondary, batched (tensor-core) measurement; 0 = skip")
+    ap.add_argument("--batch-steps", type=int, default=4)
     return ap.parse_args()
 
 
@@ -320,6 +323,53 @@ def run_b200(a):
             peaks = json.load(f)
     except Exception:
         pass
+
+    # ---- secondary: the same searches as ONE batch on the tensor cores (szg_search_batch_dev: tcgen05 kind::i8
+    #      contraction + fused top-k), then the same all-gather + merge.  Reported beside the headline, not as it.
+    batched = None
+    if a.batch_nq > 0 and a.quant == 8:
+        bq_h = np.random.default_rng(SEED + 2).uniform(-1.0, 1.0, size=(a.batch_nq, a.dims))
+        bq = torch.from_numpy(bq_h).to(dev)
+        for _ in range(3):
+            outb = sh.search_topk_dev(bq, a.k, batched=True)
+        sync_all()
+        ix.last_scan_times_ms(65536)
+        bq0 = ix.stats()["batch_queries"]
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(a.batch_steps):
+            outb = sh.search_topk_dev(bq, a.k, batched=True)
+        b1.record()
+        sync_all()
+        bms = b0.elapsed_time(b1)
+        kern_ms = ix.last_scan_times_ms(65536)
+        tb = torch.tensor([bms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        bms = float(tb.item())
+        served = ix.stats()["batch_queries"] - bq0
+        # the batch returns what single queries return: compare a few with the streaming scan
+        nchk = min(8, a.batch_nq)
+        single = sh.search_topk_dev(bq[:nchk].contiguous(), a.k)
+        torch.cuda.synchronize(dev)
+        bi, bd, bn = unpack_record(outb.cpu().numpy(), a.batch_nq, a.k)
+        si, sd, sn = unpack_record(single.cpu().numpy(), nchk, a.k)
+        same = bool((bi[:nchk] == si).all() and (bd[:nchk] == sd).all() and (bn[:nchk] == sn).all())
+        kern_s = float(np.sum(kern_ms)) / 1e3 / max(a.batch_steps, 1)  # batch_kernel time per batch on this rank
+        ops = 2.0 * 2 * my_rows * a.dims * (-(-a.batch_nq // 64) * 64)  # 2 digit planes, M padded to 64-query groups
+        tpeak = 2.0 * float(peaks.get("bf16_tflops_sustained", 1405.0))
+        batched = {
+            "metric": "exact_k%d_qps_batched" % a.k, "value": a.batch_nq * a.batch_steps / (bms / 1e3), "unit": UNIT,
+            "queries_per_batch": a.batch_nq, "ms_per_batch": bms / a.batch_steps, "steps": a.batch_steps,
+            "served_by_tensor_path": int(served) == a.batch_nq * a.batch_steps,
+            "identical_to_single_query_scan": same,
+            "roofline": {"bound": "tensor", "achieved": ops / kern_s / 1e12 if kern_s > 0 else None, "peak": tpeak,
+                         "unit": "TOP/s (int8)", "frac": (ops / kern_s / 1e12 / tpeak) if kern_s > 0 else None,
+                         "kernel": "batch_kernel (tcgen05.mma kind::i8, 2 digit planes x 64 queries x 128 rows per MMA)",
+                         "kernel_ms_per_batch": kern_s * 1e3,
+                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2 x bf16 dense on B200)",
+                         "hbm_floor_ms": my_rows * rb / (float(peaks.get("hbm_gbs", 6650.0)) * 1e9) * 1e3},
+        }
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     alg_bytes = my_rows * rb * a.nq  # one scan launch streams the shard once per query of the step
@@ -347,7 +397,7 @@ def run_b200(a):
                          "kernel": f"scan_kernel<Q{a.quant}, top-k> (one launch per step = {a.nq} queries x shard)",
                          "alg_bytes_per_launch": alg_bytes,
                          "mean_launch_ms": mean_scan_ms, "launches_timed": int(len(scan_ms)), "peak_source": peak_src},
-            "cpu_baseline": cpu, "clocks": clocks,
+            "cpu_baseline": cpu, "clocks": clocks, "batched": batched,
             "library": {"escalations": stats["escalations"], "uncertain_results": stats["uncertain_results"],
                         "scan_grid": stats["scan_grid"], "scan_block": stats["scan_block"]},
         }

@@ -160,6 +160,12 @@ int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint
                         uint32_t flags, uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
                         uint32_t *d_out_flags /* optional, nq: bit0 = result not certified */, void *stream);
 
+/* Device-resident form of szg_search_batch (tensor-core contraction when the geometry fits, the streaming scan
+ * otherwise); same contract as szg_search_topk_dev. */
+int szg_search_batch_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id,
+                         uint32_t flags, uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
+                         uint32_t *d_out_flags /* optional */, void *stream);
+
 /*
  * Final merge of row-sharded top-k lists: rank g's {ids nq*k, dist nq*k, n nq}
  * as gathered by ncclAllGather; writes the global top-k per query (ascending distance, ties

@@ -33,7 +33,7 @@ OPT_BATCH_TENSOR = 8
 EXPORTS = [
     "szg_last_error", "szg_create", "szg_destroy", "szg_reserve", "szg_upsert", "szg_remove", "szg_count",
     "szg_mask_create", "szg_mask_destroy", "szg_search_topk", "szg_search_batch", "szg_search_radius", "szg_result_count",
-    "szg_result_fetch", "szg_result_free", "szg_rescore", "szg_search_topk_dev", "szg_merge_topk_dev",
+    "szg_result_fetch", "szg_result_free", "szg_rescore", "szg_search_topk_dev", "szg_search_batch_dev", "szg_merge_topk_dev",
     "szg_fill_synthetic", "szg_fetch_codes", "szg_get_stats", "szg_set_option", "szg_last_scan_times_ms",
 ]
 
@@ -88,6 +88,7 @@ def load():
     L.szg_result_free.restype = None
     L.szg_rescore.argtypes = [vp, f64p, u64p, C.c_uint64, f64p]
     L.szg_search_topk_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, vp, vp, vp, vp, vp]
+    L.szg_search_batch_dev.argtypes = L.szg_search_topk_dev.argtypes
     L.szg_merge_topk_dev.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
     L.szg_fill_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64]
     L.szg_fetch_codes.argtypes = [vp, u64p, C.c_uint64, u8p]
@@ -256,6 +257,11 @@ class Index:
                         stream: int = 0, mask_id: int = -1, flags: int = 0, d_out_flags: int = 0):
         _check(self._L.szg_search_topk_dev(self._h, d_queries, nq, k, mask_id, flags, d_out_ids, d_out_dist,
                                            d_out_n, d_out_flags or None, stream))
+
+    def search_batch_dev(self, d_queries: int, nq: int, k: int, d_out_ids: int, d_out_dist: int, d_out_n: int,
+                         stream: int = 0, mask_id: int = -1, flags: int = 0, d_out_flags: int = 0):
+        _check(self._L.szg_search_batch_dev(self._h, d_queries, nq, k, mask_id, flags, d_out_ids, d_out_dist,
+                                            d_out_n, d_out_flags or None, stream))
 
     def merge_topk_dev(self, d_g_ids: int, d_g_dist: int, d_g_n: int, nranks: int, nq: int, k: int, d_out_ids: int,
                        d_out_dist: int, d_out_n: int, stream: int = 0, rank_stride_bytes: int = 0, d_g_flags: int = 0,

@@ -58,6 +58,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -393,38 +398,61 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
-        if (lane == 0) {
-            // D = S32, A = S8 (query digits, TMEM), B = U8 (codes, smem K-major), N = 128, M = 128
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((kAccCols >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t sb = smem_u32(sB);
-            uint32_t t = 0;
-            for (uint32_t tile = 0;; ++tile) {
-                const uint32_t d = tile & 1u;
-                bool end = false;
-                for (uint32_t sl = 0; sl < nsl; ++sl, ++t) {
-                    const uint32_t s = t % S;
-                    mbar_wait(&b_full[s], (t / S) & 1u);
-                    if (sl == 0) {
-                        if (*reinterpret_cast<volatile uint32_t *>(&s_first[s]) == kNoBlock) { end = true; break; }
-                        if (tile >= 2) mbar_wait(&d_empty[d], ((tile >> 1) - 1) & 1u);
-                    }
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t ks0 = sl * slc / 2, ks1 = min(C / 2, ks0 + slc / 2);
-                    if (!(a.debug & 4u))
-                        for (uint32_t ks = ks0; ks < ks1; ++ks) {
-                            const uint64_t db = umma_desc(sb + s * stage_bytes + (ks - ks0) * (2 * kNB * 512u), kNB * 512u, 128);
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(
-                                    tmem + d * kAccCols),
-                                "r"(tmemA + ks * 8), "l"(db), "r"(idesc), "r"((uint32_t)(ks > 0)), "r"(0u)
-                                : "memory");
-                        }
-                    umma_commit(&b_empty[s]); // the stage may be refilled once these MMAs have read it
+        // The whole warp walks the pipeline in uniform control flow (operands of tcgen05.mma live in uniform
+        // registers; computed by one divergent thread they cost a register-to-uniform "waterfall" per MMA, and
+        // that issue loop, not the tensor core, paced the kernel); one elected lane issues.
+        // D = S32, A = S8 (query digits, TMEM), B = U8 (codes, smem K-major), N = 128, M = 128
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((kAccCols >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t sb = smem_u32(sB);
+        uint32_t t = 0;
+        for (uint32_t tile = 0;; ++tile) {
+            const uint32_t d = tile & 1u;
+            bool end = false;
+            for (uint32_t sl = 0; sl < nsl; ++sl, ++t) {
+                const uint32_t s = t % S;
+                mbar_wait(&b_full[s], (t / S) & 1u);
+                if (sl == 0) {
+                    if (*reinterpret_cast<volatile uint32_t *>(&s_first[s]) == kNoBlock) { end = true; break; }
+                    if (tile >= 2) mbar_wait(&d_empty[d], ((tile >> 1) - 1) & 1u);
                 }
-                if (end) break;
-                umma_commit(&d_full[d]); // accumulators complete
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ks0 = sl * slc / 2, ks1 = min(C / 2, ks0 + slc / 2);
+                const uint64_t db0 = umma_desc(sb + s * stage_bytes, kNB * 512u, 128);
+                const uint32_t dacc = tmem + d * kAccCols;
+                if (elect_one()) {
+                    if (!(a.debug & 4u)) {
+                        // one descriptor per stage, advanced by adding the K-step offset to its address field;
+                        // the accumulate flag is an immediate (the first K step of a tile overwrites)
+                        uint64_t db = db0;
+                        uint32_t ta = tmemA + ks0 * 8;
+                        uint32_t ks = ks0;
+                        if (ks0 == 0) {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n\t}\n" ::"r"(dacc),
+                                "r"(ta), "l"(db), "r"(idesc), "r"(0u)
+                                : "memory");
+                            db += (2 * kNB * 512u) >> 4;
+                            ta += 8;
+                            ++ks;
+                        }
+#pragma unroll 4
+                        for (; ks < ks1; ++ks) {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%4, %4, %4, %4}, p;\n\t}\n" ::"r"(dacc),
+                                "r"(ta), "l"(db), "r"(idesc), "r"(0u)
+                                : "memory");
+                            db += (2 * kNB * 512u) >> 4;
+                            ta += 8;
+                        }
+                    }
+                    umma_commit(&b_empty[s]); // the stage may be refilled once these MMAs have read it
+                    if (sl == nsl - 1) umma_commit(&d_full[d]); // accumulators complete
+                }
+                __syncwarp();
             }
+            if (end) break;
         }
     } else {
         // ================================================================ epilogue (8 warps, 8 queries each)

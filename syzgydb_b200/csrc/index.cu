@@ -769,6 +769,94 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
     return collect_and_escalate(h, ws, nq, k, mask, flags, nd0, mode0, out_ids, out_dist, out_n);
 }
 
+// ---- batched queries on the tensor cores (batch_q8.cu)
+struct BatchPlan { uint32_t slice, stages, keep, nranges, gpl, ngroups; int mode; };
+
+// true when the tensor-core path can serve (collection, k): 8-bit rows, an even number of 16-byte chunks that
+// fits the TMEM columns reserved for the query digits, candidate lists of at most 128 keys, 2-digit queries
+static bool plan_batch(const szg_index *h, uint32_t nq, uint32_t k, BatchPlan *p) {
+    if (h->qt != Q8 || h->digits == 3 || (h->C % 2) != 0 || h->C > batch_max_chunks() || k < 1 || nq < 1 || h->batch_disabled ||
+        h->live_rows == 0)
+        return false;
+    p->mode = mode_for_k(h, k); // candidates per list = 32 << mode, as in the streaming scan
+    if (p->mode > 2) return false;
+    p->keep = 32u << p->mode;
+    const size_t ring_limit = batch_dynamic_limit();
+    if (ring_limit <= batch_list_bytes(p->keep)) return false;
+    const size_t stage_limit = ring_limit - batch_list_bytes(p->keep);
+    uint32_t want_slice = 0;
+    if (const char *e = getenv("SZG_BATCH_SLICE")) want_slice = (uint32_t)atoi(e);
+    p->slice = batch_slice_chunks(h->C, want_slice, stage_limit);
+    p->stages = batch_stages(p->slice, stage_limit);
+    if (p->stages < 2) return false;
+    p->ngroups = (nq + 63) / 64;
+    p->gpl = std::min<uint32_t>(p->ngroups, 16); // query groups per launch (they share the L2 copy of a row range)
+    const uint32_t nblk = (h->nslots + 31) / 32;
+    p->nranges = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)h->sm_count / p->gpl, (nblk + 3) / 4));
+    return true;
+}
+
+// prep -> batch_kernel (one launch per 16 query groups) -> finalize, all on ws->main; outputs on the device
+static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const double *d_q, uint32_t nq, uint32_t k,
+                     const uint32_t *mask, uint32_t flags, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
+                     uint32_t *d_out_flags) {
+    int rc;
+    cudaStream_t st = ws->main;
+    const int nd = 2; // 2 digit planes x 64 queries = the M dimension
+    const size_t stride = pq_stride(h, nd);
+    if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * p.nranges * p.keep)) ||
+        (rc = ws->d_gmth.ensure((size_t)nq * p.nranges)))
+        return rc;
+    PrepArgs pa;
+    pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
+    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
+    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
+    CK(launch_prep(nq, st, pa));
+    h->launches++;
+    CK(batch_configure(batch_dynamic_limit()));
+    BatchArgs b;
+    memset(&b, 0, sizeof b);
+    b.codes = h->codes.p; b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
+    b.pq = ws->d_pq.p; b.pq_stride = stride; b.cand = ws->d_cand.p; b.keep = p.keep;
+    b.C = h->C; b.nblk = (h->nslots + 31) / 32; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
+    b.nranges = p.nranges; b.nlists = p.nranges; b.stages = p.stages; b.slice = p.slice;
+    b.gmth = ws->d_gmth.p; b.mth = (p.keep + p.nranges - 1) / p.nranges;
+    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, (size_t)nq * p.nranges * sizeof(unsigned int), st));
+    if (const char *dbg = getenv("SZG_BATCH_DEBUG")) b.debug = (uint32_t)atoi(dbg);
+    const bool timing = h->timing != 0;
+    const uint32_t nlaunch = (p.ngroups + p.gpl - 1) / p.gpl;
+    uint32_t tbase = 0;
+    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nlaunch <= 65536) tbase = ws->timed;
+    if (timing) {
+        while (ws->t0.size() < tbase + nlaunch) {
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreate(&e0));
+            CK(cudaEventCreate(&e1));
+            ws->t0.push_back(e0);
+            ws->t1.push_back(e1);
+        }
+    }
+    for (uint32_t l = 0, g0 = 0; g0 < p.ngroups; g0 += p.gpl, ++l) {
+        b.group0 = g0;
+        b.ngroups = std::min(p.gpl, p.ngroups - g0);
+        if (timing) CK(cudaEventRecord(ws->t0[tbase + l], st));
+        CK(launch_batch(b, st));
+        if (timing) CK(cudaEventRecord(ws->t1[tbase + l], st));
+        h->launches++;
+    }
+    if (timing) { ws->timed = tbase + nlaunch; h->last_timed_ws = ws; }
+    FinalizeArgs f;
+    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.cand = ws->d_cand.p;
+    f.pq = ws->d_pq.p; f.pq_stride = stride; f.queries = d_q;
+    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
+    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.nlists = p.nranges; // one sorted list of `keep` keys per row range
+    f.out_ids = d_out_ids; f.out_dist = d_out_dist; f.out_n = d_out_n; f.out_flags = d_out_flags;
+    CK(launch_finalize(h->qt, p.mode, nq, st, f));
+    h->launches++;
+    h->batch_queries += nq;
+    return SZG_OK;
+}
+
 // Batched search: same results as szg_search_topk for every query, computed by the tensor-core
 // contraction kernel (batch_q8.cu) when the collection is 8-bit and the geometry fits; every other
 // case is routed to the streaming scan (still on the GPU).
@@ -776,18 +864,8 @@ int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t 
                      uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
     GUARD(h);
     int rc;
-    // shared memory: a ring of K slices of super tiles (4 blocks x <= 8 chunks each); the query digits live in TMEM
-    const int mode = mode_for_k(h, k); // candidates per list = 32 << mode, as in the streaming scan
-    const size_t ring_limit = batch_dynamic_limit();
-    uint32_t want_slice = 0;
-    if (const char *e = getenv("SZG_BATCH_SLICE")) want_slice = (uint32_t)atoi(e);
-    const size_t stage_limit = ring_limit - batch_list_bytes(32u << (mode <= 2 ? mode : 2));
-    const uint32_t slice = batch_slice_chunks(h->C, want_slice, stage_limit);
-    const uint32_t stages = batch_stages(slice, stage_limit);
-    const bool tensor_path = h->qt == Q8 && h->digits != 3 && (h->C % 2) == 0 && h->C <= batch_max_chunks() && k >= 1 &&
-                             mode <= 2 && stages >= 2 && nq >= 1;
-    if (!tensor_path || h->live_rows == 0 || h->batch_disabled)
-        return szg_search_topk(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n, scanned);
+    BatchPlan p;
+    if (!plan_batch(h, nq, k, &p)) return szg_search_topk(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n, scanned);
     if ((rc = check_search(h, queries, nq))) return rc;
     if (!out_ids || !out_dist || !out_n) return fail(SZG_EINVAL, "null output");
     if (scanned) *scanned = h->live_rows;
@@ -803,68 +881,44 @@ int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t 
         (rc = ws->h_out_flags.ensure(nq)))
         return rc;
     memcpy(ws->h_q.p, queries, qn * sizeof(double));
-    cudaStream_t st = ws->main;
-    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st));
-
-    const int nd = 2; // 2 digit planes x 64 queries = the M dimension
-    const uint32_t keep = 32u << mode;
-    const size_t stride = pq_stride(h, nd);
-    const uint32_t ngroups_all = (nq + 63) / 64;
-    const uint32_t gpl = std::min<uint32_t>(ngroups_all, 16);                      // groups per launch
-    const uint32_t nblk = (h->nslots + 31) / 32;
-    const uint32_t nranges = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)h->sm_count / gpl, nblk));
-    const uint32_t nlists = nranges; // one sorted list of `keep` keys per row range
-    if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * nranges * keep)) ||
-        (rc = ws->d_gmth.ensure((size_t)nq * nranges)))
+    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, ws->main));
+    if ((rc = run_batch(h, ws, p, ws->d_q.p, nq, k, mask, flags, ws->d_out_ids.p, ws->d_out_dist.p, ws->d_out_n.p,
+                        ws->d_out_flags.p)))
         return rc;
-    PrepArgs pa;
-    pa.queries = ws->d_q.p; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
-    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
-    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
-    CK(launch_prep(nq, st, pa));
-    h->launches++;
-    CK(batch_configure(ring_limit));
-    BatchArgs b;
-    memset(&b, 0, sizeof b);
-    b.codes = h->codes.p; b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
-    b.pq = ws->d_pq.p; b.pq_stride = stride; b.cand = ws->d_cand.p; b.keep = keep;
-    b.C = h->C; b.nblk = nblk; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
-    b.nranges = nranges; b.nlists = nlists; b.stages = stages; b.slice = slice;
-    b.gmth = ws->d_gmth.p; b.mth = (keep + nranges - 1) / nranges;
-    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, (size_t)nq * nranges * sizeof(unsigned int), st));
-    if (const char *dbg = getenv("SZG_BATCH_DEBUG")) b.debug = (uint32_t)atoi(dbg);
-    const bool timing = h->timing != 0;
-    const uint32_t nlaunch = (ngroups_all + gpl - 1) / gpl;
-    if (timing) {
-        while (ws->t0.size() < nlaunch) {
-            cudaEvent_t e0, e1;
-            CK(cudaEventCreate(&e0));
-            CK(cudaEventCreate(&e1));
-            ws->t0.push_back(e0);
-            ws->t1.push_back(e1);
-        }
-    }
-    for (uint32_t l = 0, g0 = 0; g0 < ngroups_all; g0 += gpl, ++l) {
-        b.group0 = g0;
-        b.ngroups = std::min(gpl, ngroups_all - g0);
-        if (timing) CK(cudaEventRecord(ws->t0[l], st));
-        CK(launch_batch(b, st));
-        if (timing) CK(cudaEventRecord(ws->t1[l], st));
-        h->launches++;
-    }
-    if (timing) { ws->timed = nlaunch; h->last_timed_ws = ws; }
-    FinalizeArgs f;
-    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.cand = ws->d_cand.p;
-    f.pq = ws->d_pq.p; f.pq_stride = stride; f.queries = ws->d_q.p;
-    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
-    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.nlists = nlists;
-    f.out_ids = ws->d_out_ids.p; f.out_dist = ws->d_out_dist.p; f.out_n = ws->d_out_n.p; f.out_flags = ws->d_out_flags.p;
-    CK(launch_finalize(h->qt, mode, nq, st, f));
-    h->launches++;
-    h->batch_queries += nq;
-    return collect_and_escalate(h, ws, nq, k, mask, flags, nd, mode, out_ids, out_dist, out_n);
+    return collect_and_escalate(h, ws, nq, k, mask, flags, 2, p.mode, out_ids, out_dist, out_n);
 }
 
+// Device-resident form of szg_search_batch (queries and outputs in HBM, everything enqueued on `stream`, no host
+// synchronisation): what a row-sharded deployment calls before its all-gather + szg_merge_topk_dev.
+int szg_search_batch_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
+                         uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags, void *stream) {
+    GUARD(h);
+    BatchPlan p;
+    if (!plan_batch(h, nq, k, &p))
+        return szg_search_topk_dev(h, d_queries, nq, k, mask_id, flags, d_out_ids, d_out_dist, d_out_n, d_out_flags, stream);
+    int rc;
+    if ((rc = check_search(h, d_queries, nq))) return rc;
+    if (k > SZG_MAX_K) return fail(SZG_EINVAL, "k=%u outside [1, %u]", k, SZG_MAX_K);
+    if (!d_out_ids || !d_out_dist || !d_out_n) return fail(SZG_EINVAL, "null output");
+    const uint32_t *mask;
+    if ((rc = get_mask(h, mask_id, &mask))) return rc;
+    Workspace *ws;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        auto it = h->dev_ws.find(stream);
+        if (it == h->dev_ws.end()) {
+            ws = new Workspace();
+            if ((rc = ws->init(false))) { ws->destroy(); delete ws; return rc; }
+            ws->main = (cudaStream_t)stream;
+            h->dev_ws[stream] = ws;
+        } else ws = it->second;
+    }
+    if (!d_out_flags) {
+        if ((rc = ws->d_out_flags.ensure(nq))) return rc;
+        d_out_flags = ws->d_out_flags.p;
+    }
+    return run_batch(h, ws, p, d_queries, nq, k, mask, flags, (unsigned long long *)d_out_ids, d_out_dist, d_out_n, d_out_flags);
+}
 
 int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
                         uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags,

@@ -47,12 +47,14 @@ class CudaShard:
         self.index = _capi.Index(dim, quant, metric, device)
         self.device = torch.device("cuda", device)
 
-    def topk_into(self, tq: torch.Tensor, k: int, rec: torch.Tensor, nq: int, mask_id: int = -1, flags: int = 0):
+    def topk_into(self, tq: torch.Tensor, k: int, rec: torch.Tensor, nq: int, mask_id: int = -1, flags: int = 0,
+                  batched: bool = False):
         off_ids, off_dist, off_n, _ = record_layout(nq, k)
         base = rec.data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        self.index.search_topk_dev(tq.data_ptr(), nq, k, base + 8 * off_ids, base + 8 * off_dist, base + 8 * off_n,
-                                   stream, mask_id, flags, d_out_flags=base + 8 * flags_offset(nq, k))
+        fn = self.index.search_batch_dev if batched else self.index.search_topk_dev
+        fn(tq.data_ptr(), nq, k, base + 8 * off_ids, base + 8 * off_dist, base + 8 * off_n,
+           stream, mask_id, flags, d_out_flags=base + 8 * flags_offset(nq, k))
 
     def merge_into(self, gathered: torch.Tensor, world: int, nq: int, k: int, out: torch.Tensor):
         off_ids, off_dist, off_n, words = record_layout(nq, k)
@@ -113,20 +115,24 @@ class ShardedIndex:
             self._bufs[key] = (rec, gathered, out, h_out)
         return self._bufs[key]
 
-    def search_topk_dev(self, tq: torch.Tensor, k: int, mask_id: int = -1, flags: int = 0) -> torch.Tensor:
+    def search_topk_dev(self, tq: torch.Tensor, k: int, mask_id: int = -1, flags: int = 0, batched: bool = False) -> torch.Tensor:
         """Queries resident on the device ([nq, dim] float64).  Enqueues local scan -> all-gather ->
         merge on the current stream and returns the packed result record (device int64 words,
-        see record_layout); nothing is synchronised with the host."""
+        see record_layout); nothing is synchronised with the host.  batched=True serves the local step with the
+        tensor-core contraction (szg_search_batch_dev) instead of nq single-query scans."""
         nq = tq.shape[0]
         rec, gathered, out, _ = self._buffers(nq, k)
-        self.shard.topk_into(tq, k, rec, nq, mask_id, flags)
+        if batched:
+            self.shard.topk_into(tq, k, rec, nq, mask_id, flags, batched=True)
+        else:
+            self.shard.topk_into(tq, k, rec, nq, mask_id, flags)
         if self.world == 1:
             return rec
         dist.all_gather_into_tensor(gathered, rec, group=self.group)
         self.shard.merge_into(gathered, self.world, nq, k, out)
         return out
 
-    def search_topk(self, queries, k: int, mask_id: int = -1, flags: int = 0):
+    def search_topk(self, queries, k: int, mask_id: int = -1, flags: int = 0, batched: bool = False):
         """Host buffers in, host buffers out (the call a user of the C ABI makes).  Returns
         (ids [nq,k] uint64, dist [nq,k] float64, n [nq] uint32)."""
         q = np.ascontiguousarray(queries, dtype=np.float64)
@@ -136,12 +142,13 @@ class ShardedIndex:
             raise ValueError(f"query has {q.shape[1]} dimensions, collection has {self.dim}")
         nq = q.shape[0]
         if self.world == 1 and isinstance(self.shard, CudaShard):
-            ids, dd, n, _ = self.shard.index.search_topk(q, k, mask_id, flags)
+            fn = self.shard.index.search_batch if batched else self.shard.index.search_topk
+            ids, dd, n, _ = fn(q, k, mask_id, flags)
             return ids, dd, n
         tq = torch.from_numpy(q)
         if self.device.type == "cuda":
             tq = tq.pin_memory().to(self.device, non_blocking=True)
-        out = self.search_topk_dev(tq, k, mask_id, flags)
+        out = self.search_topk_dev(tq, k, mask_id, flags, batched=batched)
         h_out = self._buffers(nq, k)[3]
         h_out.copy_(out, non_blocking=True)
         if self.device.type == "cuda":

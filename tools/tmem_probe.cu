@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128, 1) layout_kernel(uint32_t *out /*[2 bases
 
 // ---------------------------------------------------------------- 2. MMA pacing vs concurrent tcgen05.ld
 // warp 0 lane 0 issues `reps` x (K / 32) MMAs; warps 1..4 (if nld > 0) each run nld tcgen05.ld.32x32b.x32.
-__global__ void __launch_bounds__(160, 1) pace_kernel(int ts, int N, int K, int reps, int nld, int ld16, long long *cycles) {
+__global__ void __launch_bounds__(160, 1) pace_kernel(int ts, int N, int K, int reps, int nld, int ld16, long long *cycles, int altd = 0) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(160, 1) pace_kernel(int ts, int N, int K, int 
                 if (ts) {
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tm),
-                        "r"(tA + ks * 8), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tm + (altd ? (ks & 1) * 128 : 0)),
+                        "r"(tA + ks * 8), "l"(db), "r"(idesc), "r"((uint32_t)(altd ? ks > 1 : acc)), "r"(0u)
                         : "memory");
                 } else {
                     const uint64_t da = make_desc(s32(sA) + ks * 2 * 2048, 2048, 128);
@@ -204,6 +204,22 @@ int main() {
                     printf("   loader warps: %lld %lld %lld %lld cycles, %.1f B/cycle/warp", c[1], c[2], c[3], c[4], bytes / (double)c[1]);
                 }
                 printf("\n");
+            }
+    // long runs (fixed costs amortised), one accumulator vs two alternating accumulators
+    for (int ts = 0; ts < 2; ++ts)
+        for (int N : {32, 64, 128, 256})
+            for (int altd = 0; altd < 2; ++altd) {
+                if (altd && (N > 128 || !ts)) continue;
+                const size_t smem = (size_t)(K / 16) * (2048 + N * 16);
+                cudaMemset(dcyc, 0, 16 * 8);
+                const int lreps = 256;
+                pace_kernel<<<1, 160, smem>>>(ts, N, K, lreps, 0, 0, dcyc, altd);
+                e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("pace kernel failed: %s\n", cudaGetErrorString(e)); return 2; }
+                long long c[8];
+                cudaMemcpy(c, dcyc, sizeof c, cudaMemcpyDeviceToHost);
+                printf("LONG %s N=%3d %s: %6.1f cycles/MMA (%d MMAs)\n", ts ? "TS" : "SS", N, altd ? "2 accumulators" : "1 accumulator ",
+                       (double)c[0] / (lreps * (K / 32)), lreps * (K / 32));
             }
     // loads alone
     for (int mode = 1; mode < 3; ++mode) {
