@@ -115,8 +115,10 @@ __device__ __forceinline__ float fast_threshold(const QState &s) {
     const float thr_f = key_to_float((uint32_t)(s.thr >> 32));
     if (thr_f != thr_f) return -INFINITY;
     if (COS) {
-        // rows arrive in ascending slot order, so among equal keys nothing later can displace the threshold entry
-        if (s.zero || s.c_key <= 0.f) return thr_f > 1.0f ? -INFINITY : INFINITY;
+        // every key is 1.0.  Against a list entry (real slot) nothing later can win the tie, rows arrive in ascending
+        // slot order; against the shared bound (slot part all ones) every such row is still admissible
+        if (s.zero || s.c_key <= 0.f)
+            return (thr_f > 1.0f || (thr_f == 1.0f && (uint32_t)s.thr == 0xFFFFFFFFu)) ? -INFINITY : INFINITY;
         const float t = -thr_f * s.inv_ckey;
         return t - fabsf(t) * 3.814697265625e-6f - 1e-30f; // 2^-18
     }
