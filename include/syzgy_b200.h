@@ -148,6 +148,42 @@ void szg_result_free(szg_result *r);
  */
 int szg_rescore(szg_index *h, const double *query, const uint64_t *ids, uint64_t m, double *out_dist);
 
+/* ---- span file -> mirror -------------------------------------------------------
+ * Direct reader of a collection's .dat file (grammar spanfile.go:1-22).  Replaces, for loading, OpenFile's
+ * scanFile (spanfile.go:282-357) and NewCollection's per-record reload loop (collection.go:298-311): the file is
+ * mapped read-only, every span is CRC-checked and parsed by all host threads, the highest sequence number per
+ * record id wins (first seen wins a tie), corrupt spans are skipped like the reference does, and stream 1 of every
+ * live document is uploaded to the mirror in bulk.  The file is never written; pointers returned by
+ * szg_spanfile_record point into the mapping and stay valid until szg_spanfile_close. */
+typedef struct szg_spanfile szg_spanfile;
+typedef struct szg_spanfile_info {
+    uint64_t file_bytes;
+    uint64_t records;          /* live documents: ids strconv.ParseUint accepts, canonical spelling (GetStats numRecords) */
+    uint64_t spans_active;     /* valid 'SPAN' spans, superseded versions included */
+    uint64_t spans_free;       /* 'FREE' spans */
+    uint64_t spans_corrupt;    /* 'SPAN' spans that failed the checksum or the parse: skipped (spanfile.go:313-329) */
+    uint64_t free_bytes;       /* free spans + the zero tail of the file */
+    uint64_t foreign_records;  /* record ids that are not documents (ignored by collection.go:299-302) */
+    uint32_t next_sequence;    /* highest sequence number + 1 (spanfile.go:355) */
+    int32_t has_header;        /* record "" with the CollectionOptions JSON was found (collection.go:241-252) */
+    int32_t distance_method;   /* 0 euclidean, 1 cosine; -1 without header */
+    int32_t dimension_count;
+    int32_t quantization;      /* 0 in the file means 64 (collection.go:254-256) */
+    char name[256];
+} szg_spanfile_info;
+int szg_spanfile_open(const char *path, szg_spanfile **out);
+int szg_spanfile_close(szg_spanfile *sf);
+int szg_spanfile_get_info(const szg_spanfile *sf, szg_spanfile_info *out);
+/* live document ids in IterateSortedRecords order (sort.Strings of the decimal ids, spanfile.go:540-560);
+ * *n = total, at most cap are written */
+int szg_spanfile_ids(const szg_spanfile *sf, uint64_t *out_ids, uint64_t cap, uint64_t *n);
+/* stream 1 (vector bytes) and stream 0 (metadata) of a document, SpanReader.getStream (spanfile.go:67-118);
+ * SZG_ENOTFOUND like ReadRecord (spanfile.go:513-519) */
+int szg_spanfile_record(const szg_spanfile *sf, uint64_t id, const uint8_t **vector, uint64_t *vector_len,
+                        const uint8_t **metadata, uint64_t *metadata_len);
+/* bulk szg_upsert of every live document into h (whose dimension / quantization must match the header) */
+int szg_spanfile_load(const szg_spanfile *sf, szg_index *h, uint64_t *loaded);
+
 /* ---- device-resident variants (inputs/outputs already in HBM on the handle's device) ----
  * Used by the multi-GPU host and by the benchmark's resident-input leg.  All work is
  * enqueued on `stream` (a cudaStream_t, NULL = default stream) and its helper streams are

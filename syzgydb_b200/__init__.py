@@ -7,6 +7,6 @@ this package holds its sources (csrc/), the ctypes binding tests and benchmarks 
 that computes needs a B200.
 """
 from . import _capi
-from ._capi import COSINE, EUCLIDEAN, Index, SzgError
+from ._capi import COSINE, EUCLIDEAN, Index, SpanFile, SzgError
 
-__all__ = ["_capi", "Index", "SzgError", "EUCLIDEAN", "COSINE"]
+__all__ = ["_capi", "Index", "SpanFile", "SzgError", "EUCLIDEAN", "COSINE"]

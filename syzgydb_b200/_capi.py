@@ -35,6 +35,8 @@ EXPORTS = [
     "szg_mask_create", "szg_mask_destroy", "szg_search_topk", "szg_search_batch", "szg_search_radius", "szg_result_count",
     "szg_result_fetch", "szg_result_free", "szg_rescore", "szg_search_topk_dev", "szg_search_batch_dev", "szg_merge_topk_dev",
     "szg_fill_synthetic", "szg_fetch_codes", "szg_get_stats", "szg_set_option", "szg_last_scan_times_ms",
+    "szg_spanfile_open", "szg_spanfile_close", "szg_spanfile_get_info", "szg_spanfile_ids", "szg_spanfile_record",
+    "szg_spanfile_load",
 ]
 
 
@@ -42,6 +44,15 @@ class SzgError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"syzgy_b200 error {code}: {msg}")
         self.code = code
+
+
+class SpanFileInfo(C.Structure):
+    _fields_ = [
+        ("file_bytes", C.c_uint64), ("records", C.c_uint64), ("spans_active", C.c_uint64), ("spans_free", C.c_uint64),
+        ("spans_corrupt", C.c_uint64), ("free_bytes", C.c_uint64), ("foreign_records", C.c_uint64),
+        ("next_sequence", C.c_uint32), ("has_header", C.c_int32), ("distance_method", C.c_int32),
+        ("dimension_count", C.c_int32), ("quantization", C.c_int32), ("name", C.c_char * 256),
+    ]
 
 
 class Stats(C.Structure):
@@ -87,6 +98,12 @@ def load():
     L.szg_result_free.argtypes = [vp]
     L.szg_result_free.restype = None
     L.szg_rescore.argtypes = [vp, f64p, u64p, C.c_uint64, f64p]
+    L.szg_spanfile_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.szg_spanfile_close.argtypes = [vp]
+    L.szg_spanfile_get_info.argtypes = [vp, C.POINTER(SpanFileInfo)]
+    L.szg_spanfile_ids.argtypes = [vp, u64p, C.c_uint64, u64p]
+    L.szg_spanfile_record.argtypes = [vp, C.c_uint64, C.POINTER(u8p), u64p, C.POINTER(u8p), u64p]
+    L.szg_spanfile_load.argtypes = [vp, vp, u64p]
     L.szg_search_topk_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, vp, vp, vp, vp, vp]
     L.szg_search_batch_dev.argtypes = L.szg_search_topk_dev.argtypes
     L.szg_merge_topk_dev.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
@@ -283,3 +300,67 @@ class Index:
         n = C.c_uint32(0)
         _check(self._L.szg_last_scan_times_ms(self._h, _p(out, C.c_float), cap, C.byref(n)))
         return out[:n.value].copy()
+
+
+class SpanFile:
+    """A collection's .dat file, read directly (include/syzgy_b200.h, "span file -> mirror").  Needs no GPU until load()."""
+
+    def __init__(self, path: str):
+        self._L = load()
+        self._h = C.c_void_p()
+        _check(self._L.szg_spanfile_open(os.fsencode(path), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._L.szg_spanfile_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def info(self) -> dict:
+        i = SpanFileInfo()
+        _check(self._L.szg_spanfile_get_info(self._h, C.byref(i)))
+        d = {f: getattr(i, f) for f, _ in SpanFileInfo._fields_}
+        d["name"] = d["name"].decode("utf-8", "replace")
+        return d
+
+    def ids(self) -> np.ndarray:
+        n = C.c_uint64(0)
+        _check(self._L.szg_spanfile_ids(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint64)
+        _check(self._L.szg_spanfile_ids(self._h, _p(out, C.c_uint64), n.value, C.byref(n)))
+        return out
+
+    def record(self, doc_id: int):
+        """(vector bytes or None, metadata bytes or None); KeyError like ReadRecord's "record not found"."""
+        vp_, mp_ = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint8)()
+        vl, ml = C.c_uint64(0), C.c_uint64(0)
+        rc = self._L.szg_spanfile_record(self._h, int(doc_id), C.byref(vp_), C.byref(vl), C.byref(mp_), C.byref(ml))
+        if rc == -4:
+            raise KeyError(doc_id)
+        _check(rc)
+        vec = C.string_at(vp_, vl.value) if vp_ else None
+        meta = C.string_at(mp_, ml.value) if mp_ else None
+        return vec, meta
+
+    def open_index(self, device: int = 0) -> "Index":
+        """szg_create with the header's options + szg_spanfile_load: the GPU mirror of the collection."""
+        i = self.info()
+        if not i["has_header"]:
+            raise SzgError(-1, "span file has no collection header")
+        ix = Index(i["dimension_count"], i["quantization"], i["distance_method"], device)
+        try:
+            self.load_into(ix)
+        except Exception:
+            ix.close()
+            raise
+        return ix
+
+    def load_into(self, ix: "Index") -> int:
+        n = C.c_uint64(0)
+        _check(self._L.szg_spanfile_load(self._h, ix._h, C.byref(n)))
+        return n.value

@@ -34,6 +34,15 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+} // namespace
+
+// error channel and geometry for the other translation units of the library (spanfile.cu)
+namespace szg {
+int set_error(int code, const char *msg) { return fail(code, "%s", msg); }
+} // namespace szg
+
+namespace {
+
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -442,6 +451,13 @@ int collect_and_escalate(szg_index *h, Workspace *ws, uint32_t nq, uint32_t k, c
 }
 
 } // namespace
+
+// geometry of a handle, for spanfile.cu
+namespace szg {
+void index_geometry(const szg_index *h, int *dim, int *quant, int *metric, uint32_t *rowbytes) {
+    *dim = h->dim; *quant = h->quant; *metric = h->metric; *rowbytes = h->rowbytes;
+}
+} // namespace szg
 
 // ====================================================================== C ABI
 extern "C" {
