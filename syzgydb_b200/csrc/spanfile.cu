@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cerrno>
 #include <cstdarg>
 #include <cstdio>
@@ -220,11 +221,18 @@ struct Doc {
     uint8_t has_vec, has_meta;
 };
 
-bool lex_less_dec(uint64_t a, uint64_t b) { // sort.Strings over the decimal spellings (spanfile.go:540-560)
-    char sa[24], sb[24];
-    const int la = snprintf(sa, sizeof sa, "%llu", (unsigned long long)a), lb = snprintf(sb, sizeof sb, "%llu", (unsigned long long)b);
-    const int c = memcmp(sa, sb, (size_t)std::min(la, lb));
-    return c < 0 || (c == 0 && la < lb);
+// sort.Strings over the decimal spellings (spanfile.go:540-560) without building strings: left-align the digits
+// (id * 10^(20 - digits) fits 128 bits); equal padded values differ only by trailing zeros, the shorter sorts first
+struct LexKey {
+    uint64_t hi, lo;
+    uint32_t digits, index;
+};
+LexKey lex_key(uint64_t id, uint32_t index) {
+    uint32_t digits = 1;
+    for (uint64_t v = id; v >= 10; v /= 10) ++digits;
+    unsigned __int128 p = id;
+    for (uint32_t i = digits; i < 20; ++i) p *= 10;
+    return {(uint64_t)(p >> 64), (uint64_t)p, digits, index};
 }
 
 } // namespace
@@ -233,8 +241,8 @@ struct szg_spanfile {
     int fd = -1;
     const uint8_t *map = nullptr;
     size_t size = 0;
-    std::vector<Doc> docs;                         // live documents, lexicographic decimal-id order
-    std::unordered_map<uint64_t, uint32_t> by_id;  // id -> index into docs
+    std::vector<Doc> by_num;     // live documents in ascending numeric id order (binary-searched by szg_spanfile_record)
+    std::vector<uint32_t> lex;   // indices into by_num in lexicographic decimal-id order (IterateSortedRecords)
     szg_spanfile_info info;
 };
 
@@ -253,7 +261,7 @@ int szg_spanfile_open(const char *path, szg_spanfile **out) {
     sf->fd = fd;
     sf->size = (size_t)st.st_size;
     if (sf->size) {
-        void *m = mmap(nullptr, sf->size, PROT_READ, MAP_PRIVATE, fd, 0);
+        void *m = mmap(nullptr, sf->size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
         if (m == MAP_FAILED) { close(fd); delete sf; return failf(SZG_EINTERNAL, "mmap(%s): %s", path, strerror(errno)); }
         sf->map = static_cast<const uint8_t *>(m);
         madvise(m, sf->size, MADV_SEQUENTIAL);
@@ -266,6 +274,10 @@ int szg_spanfile_open(const char *path, szg_spanfile **out) {
             }
         }
     }
+    const bool timing = getenv("SZG_SPANFILE_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     const uint8_t *map = sf->map;
     const size_t size = sf->size;
     // ---- phase 1: walk the span headers (scanFile's loop without the parsing)
@@ -284,18 +296,23 @@ int szg_spanfile_open(const char *path, szg_spanfile **out) {
         offset += length;
     }
     free_bytes += size - offset;
+    const auto t1 = now();
     // ---- phase 2: checksum + parse, all host threads
     std::vector<Parsed> parsed(active.size());
     parallel_for(active.size(), 4096, [&](size_t b, size_t e) {
         for (size_t i = b; i < e; ++i) parse_span(map, active[i], &parsed[i]);
     });
+    const auto t2 = now();
     // ---- phase 3: file-ordered merge: highest sequence number per id, first seen wins a tie (spanfile.go:337-341)
+    // sort-based (no hash maps): candidates ordered by (id, file position); per id the highest sequence number wins
+    // and, walking in file order, the first seen wins a tie
     uint64_t ncorrupt = 0, nforeign = 0;
     uint32_t highest = 0;
-    std::unordered_map<uint64_t, uint32_t> best; // document id -> index into parsed
-    best.reserve(active.size());
     long header = -1;
-    std::unordered_map<std::string, uint32_t> foreign; // ids that are not documents: only counted
+    struct Cand { uint64_t id; uint32_t span; };
+    std::vector<Cand> cands;
+    cands.reserve(parsed.size());
+    std::vector<std::string> foreign; // ids that are not documents: only counted (distinct spellings)
     for (size_t i = 0; i < parsed.size(); ++i) {
         const Parsed &p = parsed[i];
         if (!p.ok) { ++ncorrupt; continue; }
@@ -306,29 +323,48 @@ int szg_spanfile_open(const char *path, szg_spanfile **out) {
         }
         uint64_t id;
         if (!parse_doc_id(map + p.id_off, p.id_len, &id)) {
-            foreign.emplace(std::string(reinterpret_cast<const char *>(map + p.id_off), p.id_len), (uint32_t)i);
+            foreign.emplace_back(reinterpret_cast<const char *>(map + p.id_off), p.id_len);
             continue;
         }
-        auto it = best.find(id);
-        if (it == best.end()) best.emplace(id, (uint32_t)i);
-        else if (p.seq > parsed[it->second].seq) it->second = (uint32_t)i;
+        cands.push_back({id, (uint32_t)i});
     }
-    nforeign = foreign.size();
-    sf->docs.reserve(best.size());
-    for (const auto &kv : best) {
-        const Parsed &p = parsed[kv.second];
+    std::sort(foreign.begin(), foreign.end());
+    nforeign = (uint64_t)(std::unique(foreign.begin(), foreign.end()) - foreign.begin());
+    bool ordered = true; // a freshly written collection is already in ascending id order
+    for (size_t i = 1; i < cands.size() && ordered; ++i) ordered = cands[i - 1].id < cands[i].id;
+    if (!ordered)
+        std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.id != b.id ? a.id < b.id : a.span < b.span; });
+    sf->by_num.clear();
+    sf->by_num.reserve(cands.size());
+    for (size_t i = 0; i < cands.size();) {
+        size_t j = i, bestj = i;
+        for (; j < cands.size() && cands[j].id == cands[i].id; ++j)
+            if (parsed[cands[j].span].seq > parsed[cands[bestj].span].seq) bestj = j;
+        const Parsed &p = parsed[cands[bestj].span];
         Doc d;
-        d.id = kv.first; d.vec_off = p.vec_off; d.meta_off = p.meta_off; d.vec_len = p.vec_len; d.meta_len = p.meta_len;
+        d.id = cands[i].id; d.vec_off = p.vec_off; d.meta_off = p.meta_off; d.vec_len = p.vec_len; d.meta_len = p.meta_len;
         d.seq = p.seq; d.has_vec = p.has_vec; d.has_meta = p.has_meta;
-        sf->docs.push_back(d);
+        sf->by_num.push_back(d);
+        i = j;
     }
-    std::sort(sf->docs.begin(), sf->docs.end(), [](const Doc &a, const Doc &b) { return lex_less_dec(a.id, b.id); });
-    sf->by_id.reserve(sf->docs.size());
-    for (uint32_t i = 0; i < sf->docs.size(); ++i) sf->by_id.emplace(sf->docs[i].id, i);
-
+    // IterateSortedRecords order: indices into by_num sorted by the decimal spelling
+    {
+        std::vector<LexKey> keys(sf->by_num.size());
+        parallel_for(keys.size(), 65536, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) keys[i] = lex_key(sf->by_num[i].id, (uint32_t)i);
+        });
+        std::sort(keys.begin(), keys.end(), [](const LexKey &a, const LexKey &b) {
+            return a.hi != b.hi ? a.hi < b.hi : a.lo != b.lo ? a.lo < b.lo : a.digits < b.digits;
+        });
+        sf->lex.resize(keys.size());
+        for (size_t i = 0; i < keys.size(); ++i) sf->lex[i] = keys[i].index;
+    }
+    if (timing)
+        fprintf(stderr, "szg_spanfile_open: walk %.1f ms, crc+parse %.1f ms (%u threads), merge+sort %.1f ms\n", ms(t0, t1), ms(t1, t2),
+                worker_count(), ms(t2, now()));
     szg_spanfile_info &in = sf->info;
     in.file_bytes = size;
-    in.records = sf->docs.size();
+    in.records = sf->by_num.size();
     in.spans_active = active.size() - ncorrupt;
     in.spans_free = nfree;
     in.spans_corrupt = ncorrupt;
@@ -370,18 +406,18 @@ int szg_spanfile_get_info(const szg_spanfile *sf, szg_spanfile_info *out) {
 
 int szg_spanfile_ids(const szg_spanfile *sf, uint64_t *out_ids, uint64_t cap, uint64_t *n) {
     if (!sf || !n) return failf(SZG_EINVAL, "null argument");
-    *n = sf->docs.size();
+    *n = sf->lex.size();
     if (out_ids)
-        for (uint64_t i = 0; i < std::min<uint64_t>(cap, sf->docs.size()); ++i) out_ids[i] = sf->docs[i].id;
+        for (uint64_t i = 0; i < std::min<uint64_t>(cap, sf->lex.size()); ++i) out_ids[i] = sf->by_num[sf->lex[i]].id;
     return SZG_OK;
 }
 
 int szg_spanfile_record(const szg_spanfile *sf, uint64_t id, const uint8_t **vector, uint64_t *vector_len, const uint8_t **metadata,
                         uint64_t *metadata_len) {
     if (!sf) return failf(SZG_EINVAL, "null argument");
-    auto it = sf->by_id.find(id);
-    if (it == sf->by_id.end()) return failf(SZG_ENOTFOUND, "record not found"); // spanfile.go:516
-    const Doc &d = sf->docs[it->second];
+    auto it = std::lower_bound(sf->by_num.begin(), sf->by_num.end(), id, [](const Doc &a, uint64_t v) { return a.id < v; });
+    if (it == sf->by_num.end() || it->id != id) return failf(SZG_ENOTFOUND, "record not found"); // spanfile.go:516
+    const Doc &d = *it;
     if (vector) *vector = d.has_vec ? sf->map + d.vec_off : nullptr;
     if (vector_len) *vector_len = d.has_vec ? d.vec_len : 0;
     if (metadata) *metadata = d.has_meta ? sf->map + d.meta_off : nullptr;
@@ -397,13 +433,13 @@ int szg_spanfile_load(const szg_spanfile *sf, szg_index *h, uint64_t *loaded) {
     if (sf->info.has_header && (sf->info.dimension_count != dim || sf->info.quantization != quant))
         return failf(SZG_EINVAL, "collection file is %d x %d-bit, the mirror is %d x %d-bit", sf->info.dimension_count,
                      sf->info.quantization, dim, quant);
-    const size_t n = sf->docs.size();
+    const size_t n = sf->by_num.size();
     // decodeDocument panics when stream 1 is missing and decodeVector reads dimension-many values out of it
     // (collection.go:752-757, 768-794): a record whose stream 1 is not exactly one row is an error here
     for (size_t i = 0; i < n; ++i)
-        if (!sf->docs[i].has_vec || sf->docs[i].vec_len != rowbytes)
-            return failf(SZG_EINVAL, "record %llu: vector stream has %u bytes, a row has %u", (unsigned long long)sf->docs[i].id,
-                         sf->docs[i].has_vec ? sf->docs[i].vec_len : 0u, rowbytes);
+        if (!sf->by_num[i].has_vec || sf->by_num[i].vec_len != rowbytes)
+            return failf(SZG_EINVAL, "record %llu: vector stream has %u bytes, a row has %u", (unsigned long long)sf->by_num[i].id,
+                         sf->by_num[i].has_vec ? sf->by_num[i].vec_len : 0u, rowbytes);
     uint64_t have = 0;
     int rc = szg_count(h, &have);
     if (rc || (rc = szg_reserve(h, have + n))) return rc;
@@ -414,7 +450,7 @@ int szg_spanfile_load(const szg_spanfile *sf, szg_index *h, uint64_t *loaded) {
         const size_t m = std::min(batch, n - b);
         parallel_for(m, 8192, [&](size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; ++i) {
-                const Doc &d = sf->docs[b + i];
+                const Doc &d = sf->by_num[sf->lex[b + i]]; // upload in scan order: slot order = lexicographic id order
                 ids[i] = d.id;
                 memcpy(stage.data() + i * rowbytes, sf->map + d.vec_off, rowbytes);
             }
