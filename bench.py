@@ -373,6 +373,18 @@ def run_b200(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     alg_bytes = my_rows * rb * a.nq  # one scan launch streams the shard once per query of the step
+    # DRAM traffic of that launch from the committed ncu --set full capture of the same kernel and row shape
+    # (dram__bytes_read.sum + dram__bytes_write.sum per row and query), scaled to this launch
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+            tr = json.load(f)
+        key = f"q{a.quant}_d{a.dims}"
+        if key in tr:
+            traffic = tr[key]["dram_bytes_per_row_per_query"] * my_rows * a.nq
+            traffic_src = tr[key]["source"]
+    except Exception:
+        pass
     achieved = alg_bytes / (mean_scan_ms / 1e3) / 1e9 if mean_scan_ms == mean_scan_ms else None
 
     cpu = None
@@ -393,7 +405,7 @@ def run_b200(a):
                              if my_rows * rb > 2 * 126e6 else "WARNING: shard fits L2"},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": f"scan_kernel<Q{a.quant}, top-k> (one launch per step = {a.nq} queries x shard)",
                          "alg_bytes_per_launch": alg_bytes,
                          "mean_launch_ms": mean_scan_ms, "launches_timed": int(len(scan_ms)), "peak_source": peak_src},
