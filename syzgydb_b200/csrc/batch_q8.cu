@@ -25,8 +25,8 @@
 // conservative; the few survivors recompute the exact surrogate key of the streaming scan and append it to
 // the query's candidate buffer.  Every query belongs to exactly one epilogue warp, so appends, the
 // occasional compaction (bitonic sort in registers) and threshold updates need warp-level
-// synchronisation only.  Liveness / filter bits are folded into the staged per-row operand (NaN / +inf
-// never pass).
+// synchronisation only.  Liveness / filter bits are checked only for rows that pass the fast test (a removed or
+// filtered row passes it as rarely as a live one does).
 // CTAs are (query group g, row range r): the groups of a batch walk the same row range at the same time,
 // so HBM is read once per range and the other reads hit L2.
 // The candidate buffers feed the same finalize_kernel as the scan path (fp64 re-score, ordering,
@@ -177,6 +177,7 @@ __device__ __forceinline__ unsigned long long list_insert(unsigned long long *l,
 // new threshold.
 template <bool COS, int E>
 __device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, const float2 *xaux /*shared: aux pairs of the tile*/,
+                                        const uint32_t *xwords /*shared: live & filter words of the tile's 4 blocks*/,
                                         QState *wq /*the warp's 8 queries*/, unsigned long long *wl /*their lists*/, uint32_t slot0,
                                         uint32_t *gmw /*gmth of the warp's first query, this range*/, uint32_t R, uint32_t mthm1,
                                         uint32_t capm1) {
@@ -187,6 +188,7 @@ __device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, c
         const uint32_t j = (uint32_t)src >> 2;
         const float nf = __shfl_sync(0xffffffffu, numf, src);
         const uint32_t col = colb + 2 * ((uint32_t)src & 3u);
+        if (!((xwords[col >> 5] >> (col & 31u)) & 1u)) continue; // removed or filtered row (or past the end of the mirror)
         const float2 ax = xaux[col];
         QState &s = wq[j];
         float key;
@@ -206,8 +208,8 @@ __device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, c
 // straight-line code (independent chains, a max tree, one warp vote); only when some lane has a pair that
 // passes are the pairs looked at, group of four by group of four, by the whole warp.
 template <bool COS, bool FITS, int E>
-__device__ __forceinline__ float score16(const uint32_t (&r)[32], const float2 (&ax)[8], int numc32, long long numc64, float T, float c2,
-                                         uint32_t colp, const float2 *xaux, QState *wq, unsigned long long *wl,
+__device__ __forceinline__ float score16(const uint32_t (&r)[32], const float4 (&ax)[8], int numc32, long long numc64, float T, float c2,
+                                         uint32_t colp, const float2 *xaux, const uint32_t *xwords, QState *wq, unsigned long long *wl,
                                          uint32_t slot0, const float *Tsrc, uint32_t *gmw, uint32_t R, uint32_t mthm1, uint32_t capm1) {
     float numf[16], v[16];
 #pragma unroll
@@ -218,7 +220,8 @@ __device__ __forceinline__ float score16(const uint32_t (&r)[32], const float2 (
             // num = 2 I + numc with I = 128 * D_hi + D_lo: exact in wrapping 32-bit arithmetic when |num| < 2^31
             if (FITS) numf[2 * rep + e] = (float)(int)(hi * 256u + (2u * lo + (uint32_t)numc32));
             else numf[2 * rep + e] = (float)(2 * ((long long)(int)hi * 128 + (long long)(int)lo) + numc64);
-            const float a = e ? ax[rep].y : ax[rep].x;
+            // aux pairs {1/||x||, ||x||^2} of rows col, col + 1: cosine uses .x/.z, euclid .y/.w
+            const float a = COS ? (e ? ax[rep].z : ax[rep].x) : (e ? ax[rep].w : ax[rep].y);
             v[2 * rep + e] = COS ? numf[2 * rep + e] * a : fmaf(numf[2 * rep + e], c2, -a);
         }
     }
@@ -233,7 +236,7 @@ __device__ __forceinline__ float score16(const uint32_t (&r)[32], const float2 (
 #pragma unroll
                 for (int i = 4 * g4; i < 4 * g4 + 4; ++i) {
                     const unsigned m = __ballot_sync(0xffffffffu, v[i] > T);
-                    if (m) batch_hits<COS, E>(m, numf[i], colp + (i >> 1) * 8 + (i & 1), xaux, wq, wl, slot0, gmw, R, mthm1, capm1);
+                    if (m) batch_hits<COS, E>(m, numf[i], colp + (i >> 1) * 8 + (i & 1), xaux, xwords, wq, wl, slot0, gmw, R, mthm1, capm1);
                 }
             }
         }
@@ -270,7 +273,6 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     __shared__ __align__(8) uint64_t b_full[kBatchMaxStages], b_empty[kBatchMaxStages], d_full[2], d_empty[2];
     __shared__ uint32_t s_first[kBatchMaxStages]; // first block of the super tile a stage belongs to (kNoBlock = end)
     __shared__ QState s_q[kBatchQueries];
-    __shared__ float s_aux[8][kTileRows];         // per epilogue warp: staged per-row operand of the current tile
     // per-tile side data, producer -> epilogue: the rows' aux pairs (bulk copy), the live words, the tile index
     __shared__ __align__(16) float2 s_xaux[kAuxSlots][kTileRows];
     __shared__ uint32_t s_xwords[kAuxSlots][kNB], s_xsup[kAuxSlots];
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
 
     if (warp == 0) {
         // ================================================================ TMA producer
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
         uint32_t t = 0, xt = 0, words; // stage counter, tile counter
         bool again = a.nranges > 1; // the first tile of a range is sent twice (seeding pass, see the epilogue)
         for (uint32_t sup = next_live_tile(a, sup0, sup1, lane, &words);;
@@ -459,7 +462,6 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     } else {
         // ================================================================ epilogue (8 warps, 8 queries each)
         // warp = (TMEM lane quarter lq, half hh): TMEM lanes 32 lq + 16 hh + {0..15} = both planes of 8 queries
-        const int ew = warp - 2;                        // private staging buffer
         const uint32_t lq = (uint32_t)(warp & 3);       // TMEM lane quarter this warp may read
         const uint32_t hh = (uint32_t)(warp - 2) >> 2;  // which 16 lanes of the quarter
         const uint32_t c4 = (uint32_t)lane & 3u;        // column pair within each group of 8 columns
@@ -471,7 +473,6 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         const float c2 = qs->c_dot2;
         float T = qs->T;
         constexpr uint32_t Kp = 32 * E;
-        float *sa = s_aux[ew];
         QState *wq = &s_q[qw];
         // the warp's 8 candidate lists (sorted, Kp keys each) live behind the ring in dynamic shared memory
         unsigned long long *wl = reinterpret_cast<unsigned long long *>(smem + (size_t)S * stage_bytes) + (size_t)qw * Kp;
@@ -508,19 +509,11 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         bool seeding = R > 1;
         for (uint32_t tile = 0;; ++tile) {
             const uint32_t d = tile & 1u, x = tile % kAuxSlots;
-            // side data of the tile: per-row operand staged per warp (cosine 1/||x||, euclid ||x||^2; dead or
-            // filtered rows get a value that never passes); lane stages rows lane + 32 j
+            // side data of the tile (aux pairs, live words): read in place; removed / filtered rows are rejected only
+            // when they pass the fast test (as rare as for live rows), see batch_hits
             mbar_wait(&x_full[x], (tile / kAuxSlots) & 1u);
             const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&s_xsup[x]);
             if (cur == kNoBlock) break;
-            __syncwarp();
-#pragma unroll
-            for (uint32_t j = 0; j < kNB; ++j) {
-                const float2 axr = s_xaux[x][j * 32 + lane];
-                const bool ok = (s_xwords[x][j] >> lane) & 1u;
-                sa[j * 32 + lane] = COS ? (ok ? axr.x : __int_as_float(0x7FC00000)) : (ok ? axr.y : INFINITY);
-            }
-            __syncwarp();
             if (R > 1 && tile >= 2 && ((tile & (tile - 1)) == 0 || (tile & poll_mask) == 0)) {
                 poll_bounds();
                 T = qs->T;
@@ -538,27 +531,28 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 continue;
             }
             uint32_t ra[32], rb[32];
-            float2 ax[8];
-            auto load_ax = [&](uint32_t part) {
+            float4 ax[8];
+            auto load_ax = [&](uint32_t part) { // the aux pairs of this lane's two rows per 8-column group, straight from the side ring
 #pragma unroll
-                for (int rep = 0; rep < 8; ++rep) ax[rep] = *reinterpret_cast<const float2 *>(sa + part * 64 + rep * 8 + 2 * c4);
+                for (int rep = 0; rep < 8; ++rep) ax[rep] = *reinterpret_cast<const float4 *>(&s_xaux[x][part * 64 + rep * 8 + 2 * c4]);
             };
             const uint32_t slot0 = cur * kTileRows;
             auto score = [&](const uint32_t (&rr)[32], uint32_t part) {
-                if (fits) T = score16<COS, true, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
-                else T = score16<COS, false, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                if (fits) T = score16<COS, true, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                else T = score16<COS, false, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
             };
-            // the second half of the columns is in flight while the first is scored
+            // both halves of this warp's part of the accumulator go to registers first, so the buffer returns to the
+            // MMA warp before any scoring (a warp that has rows to insert would otherwise hold it)
             tmem_ld_16x64(tbase, ra);
+            tmem_ld_16x64(tbase + 64, rb);
             load_ax(0);
             tmem_ld_wait(ra);
-            tmem_ld_16x64(tbase + 64, rb);
-            score(ra, 0);
-            load_ax(1);
             tmem_ld_wait(rb);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[d]); // this warp's part of the buffer is in registers
+            score(ra, 0);
+            load_ax(1);
             score(rb, 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[x]); // the tile's aux pairs are no longer needed

@@ -673,3 +673,21 @@ def test_batch_cfg5_shape_against_streaming_scan():
         si, sd, sn, _ = ix.search_topk(qs, k)
         assert np.array_equal(bn, sn) and np.array_equal(bi, si) and np.array_equal(bd, sd)
         assert np.all(np.diff(bd, axis=1) >= 0)
+
+
+def test_batch_gaussian_normalised_rows_cosine():
+    """all-MiniLM-like data (L2-normalised Gaussian rows use only ~+-14 codes around 128): candidate margins are far smaller
+    than with uniform codes; the batch must certify or escalate exactly like the scan."""
+    n, dims, nq, k = 20000, 384, 80, 10
+    rng = np.random.default_rng(21)
+    x = rng.normal(size=(n, dims))
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    codes = o.encode_rows(x, 8)
+    ids = np.arange(n, dtype=np.uint64)
+    q = rng.normal(size=(nq, dims))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    with _build(codes, ids, dims, 8, szg.COSINE) as ix:
+        _batch_vs_oracle(ix, codes, ids, dims, szg.COSINE, q[:6], k, what="batch gaussian")
+        bi, bd, bn, _ = ix.search_batch(q, k)
+        si, sd, sn, _ = ix.search_topk(q, k)
+        assert np.array_equal(bi, si) and np.array_equal(bd, sd) and np.array_equal(bn, sn)
