@@ -327,7 +327,7 @@ def run_b200(a):
     # ---- secondary: the same searches as ONE batch on the tensor cores (szg_search_batch_dev: tcgen05 kind::i8
     #      contraction + fused top-k), then the same all-gather + merge.  Reported beside the headline, not as it.
     batched = None
-    if a.batch_nq > 0 and a.quant == 8:
+    if a.batch_nq > 0 and a.quant in (8, 16):
         bq_h = np.random.default_rng(SEED + 2).uniform(-1.0, 1.0, size=(a.batch_nq, a.dims))
         bq = torch.from_numpy(bq_h).to(dev)
         for _ in range(3):
@@ -356,7 +356,8 @@ def run_b200(a):
         si, sd, sn = unpack_record(single.cpu().numpy(), nchk, a.k)
         same = bool((bi[:nchk] == si).all() and (bd[:nchk] == sd).all() and (bn[:nchk] == sn).all())
         kern_s = float(np.sum(kern_ms)) / 1e3 / max(a.batch_steps, 1)  # batch_kernel time per batch on this rank
-        ops = 2.0 * 2 * my_rows * a.dims * (-(-a.batch_nq // 64) * 64)  # 2 digit planes, M padded to 64-query groups
+        byte_planes = 2 if a.quant == 16 else 1  # 16-bit rows are contracted as a high-byte and a low-byte plane
+        ops = 2.0 * 2 * byte_planes * my_rows * a.dims * (-(-a.batch_nq // 64) * 64)  # 2 digit planes, M padded to 64-query groups
         tpeak = 2.0 * float(peaks.get("bf16_tflops_sustained", 1405.0))
         batched = {
             "metric": "exact_k%d_qps_batched" % a.k, "value": a.batch_nq * a.batch_steps / (bms / 1e3), "unit": UNIT,
@@ -365,7 +366,8 @@ def run_b200(a):
             "identical_to_single_query_scan": same,
             "roofline": {"bound": "tensor", "achieved": ops / kern_s / 1e12 if kern_s > 0 else None, "peak": tpeak,
                          "unit": "TOP/s (int8)", "frac": (ops / kern_s / 1e12 / tpeak) if kern_s > 0 else None,
-                         "kernel": "batch_kernel (tcgen05.mma kind::i8, 2 digit planes x 64 queries x 128 rows per MMA)",
+                         "kernel": "batch_kernel (tcgen05.mma kind::i8, 2 digit planes x 64 queries x 128 rows per MMA"
+                                   + (", high-byte and low-byte planes of the 16-bit codes)" if a.quant == 16 else ")"),
                          "kernel_ms_per_batch": kern_s * 1e3,
                          "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 dense = 2 x bf16 dense on B200)",
                          "hbm_floor_ms": my_rows * rb / (float(peaks.get("hbm_gbs", 6650.0)) * 1e9) * 1e3},

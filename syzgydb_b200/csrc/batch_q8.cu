@@ -207,8 +207,9 @@ __device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, c
 // 16 (query, row) pairs of one tcgen05.ld: 8 column groups x 2 rows.  The fast test of all 16 pairs is
 // straight-line code (independent chains, a max tree, one warp vote); only when some lane has a pair that
 // passes are the pairs looked at, group of four by group of four, by the whole warp.
-template <bool COS, bool FITS, int E>
-__device__ __forceinline__ float score16(const uint32_t (&r)[32], const float4 (&ax)[8], int numc32, long long numc64, float T, float c2,
+template <bool COS, bool FITS, int E, bool P16 = false>
+__device__ __forceinline__ float score16(const uint32_t (&r)[32], const uint32_t (&rl)[32], const float4 (&ax)[8], int numc32, long long numc64,
+                                         float T, float c2,
                                          uint32_t colp, const float2 *xaux, const uint32_t *xwords, QState *wq, unsigned long long *wl,
                                          uint32_t slot0, const float *Tsrc, uint32_t *gmw, uint32_t R, uint32_t mthm1, uint32_t capm1) {
     float numf[16], v[16];
@@ -218,7 +219,13 @@ __device__ __forceinline__ float score16(const uint32_t (&r)[32], const float4 (
         for (int e = 0; e < 2; ++e) {
             const uint32_t hi = r[4 * rep + e], lo = r[4 * rep + 2 + e];
             // num = 2 I + numc with I = 128 * D_hi + D_lo: exact in wrapping 32-bit arithmetic when |num| < 2^31
-            if (FITS) numf[2 * rep + e] = (float)(int)(hi * 256u + (2u * lo + (uint32_t)numc32));
+            if (P16) {
+                // 16-bit rows: r = contraction with the HIGH bytes, rl = with the LOW bytes of the uncentred codes;
+                // I = 256 I_H + I_L, num = 2 I + numc (numc = -65535 sum W), exact in 64-bit integers
+                const long long ih = (long long)(int)hi * 128 + (long long)(int)lo;
+                const long long il = (long long)(int)rl[4 * rep + e] * 128 + (long long)(int)rl[4 * rep + 2 + e];
+                numf[2 * rep + e] = (float)(2 * (256 * ih + il) + numc64);
+            } else if (FITS) numf[2 * rep + e] = (float)(int)(hi * 256u + (2u * lo + (uint32_t)numc32));
             else numf[2 * rep + e] = (float)(2 * ((long long)(int)hi * 128 + (long long)(int)lo) + numc64);
             // aux pairs {1/||x||, ||x||^2} of rows col, col + 1: cosine uses .x/.z, euclid .y/.w
             const float a = COS ? (e ? ax[rep].z : ax[rep].x) : (e ? ax[rep].w : ax[rep].y);
@@ -267,8 +274,10 @@ __device__ __forceinline__ uint32_t next_live_tile(const BatchArgs &a, uint32_t 
 
 } // namespace
 
-template <bool COS, int E>
-__global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs a, const __grid_constant__ CUtensorMap tmap) {
+template <bool COS, int E, bool P16>
+__global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs a, const __grid_constant__ CUtensorMap tmap,
+                                                                 const __grid_constant__ CUtensorMap tmapL) {
+    constexpr uint32_t kHalves = P16 ? 2u : 1u; // 16-bit rows: every super tile is contracted twice (high bytes, low bytes)
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t b_full[kBatchMaxStages], b_empty[kBatchMaxStages], d_full[2], d_empty[2];
     __shared__ uint32_t s_first[kBatchMaxStages]; // first block of the super tile a stage belongs to (kNoBlock = end)
@@ -308,7 +317,8 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         s.thr = s.valid ? kNoKey : 0ull;
         s.gbound = kNoKey;
         s.pub = 0xFFFFFFFFu;
-        s.numc = (long long)hdr->numc;
+        // 16-bit: the header's numc belongs to centred codes (+sum W); the byte planes hold uncentred ones: -65535 sum W
+        s.numc = P16 ? -65535ll * (long long)hdr->numc : (long long)hdr->numc;
         s.c_key = (float)hdr->c_key; s.c_dot2 = (float)(2.0 * hdr->c_dot); s.qn2 = (float)hdr->qn2;
         s.inv_ckey = hdr->c_key > 0.0 ? (float)(1.0 / hdr->c_key) : 0.f;
         s.zero = hdr->zero_query != 0;
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         // |num| = M 2^F |x.q| <= M 2^F sqrt(d) ||q||: when that fits 31 bits the whole sum can run in wrapping
         // 32-bit arithmetic (exact mod 2^32, and the true value fits)
         const bool fits = 255.0 * ldexp(1.0, hdr->F) * sqrt((double)a.dims * hdr->qn2) < 2.0e9;
-        if (s.valid && !fits) atomicAnd(&s_fits, 0);
+        if (s.valid && (!fits || P16)) atomicAnd(&s_fits, 0);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols));
@@ -354,7 +364,10 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
 
     if (warp == 0) {
         // ================================================================ TMA producer
-        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+            if (P16) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapL)) : "memory");
+        }
         uint32_t t = 0, xt = 0, words; // stage counter, tile counter
         bool again = a.nranges > 1; // the first tile of a range is sent twice (seeding pass, see the epilogue)
         for (uint32_t sup = next_live_tile(a, sup0, sup1, lane, &words);;
@@ -375,9 +388,10 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                     mbar_arrive(&x_full[x]);
                 }
             }
-            const uint32_t n = sup < sup1 ? nsl : 1u; // the end of the range travels through the ring as a sentinel stage
-            for (uint32_t sl = 0; sl < n; ++sl, ++t) {
+            const uint32_t n = sup < sup1 ? nsl * kHalves : 1u; // the end of the range travels through the ring as a sentinel stage
+            for (uint32_t i = 0; i < n; ++i, ++t) {
                 const uint32_t s = t % S;
+                const uint32_t half = i / nsl, sl = i % nsl;
                 if (lane == 0) {
                     if (t >= S) mbar_wait(&b_empty[s], ((t / S) - 1) & 1u);
                     if (sup < sup1) {
@@ -389,7 +403,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                         asm volatile(
                             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                                 smem_u32(sB + (size_t)s * stage_bytes)),
-                            "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(smem_u32(&b_full[s])), "r"(0), "r"((int)(sup * kNB)),
+                            "l"(reinterpret_cast<uint64_t>(half ? &tmapL : &tmap)), "r"(smem_u32(&b_full[s])), "r"(0), "r"((int)(sup * kNB)),
                             "r"((int)(sl * slc))
                             : "memory");
                     } else {
@@ -411,19 +425,23 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         const uint32_t sb = smem_u32(sB);
         uint32_t t = 0;
         for (uint32_t tile = 0;; ++tile) {
-            const uint32_t d = tile & 1u;
+            // 8-bit: two accumulator buffers alternate; 16-bit: the two buffers hold the high-byte and the low-byte
+            // contraction of ONE tile (the epilogue drains them to registers before it scores, so the wait is short)
+            const uint32_t d = P16 ? 0u : (tile & 1u);
             bool end = false;
-            for (uint32_t sl = 0; sl < nsl; ++sl, ++t) {
+            for (uint32_t i = 0; i < nsl * kHalves; ++i, ++t) {
                 const uint32_t s = t % S;
+                const uint32_t half = i / nsl, sl = i % nsl;
                 mbar_wait(&b_full[s], (t / S) & 1u);
-                if (sl == 0) {
+                if (i == 0) {
                     if (*reinterpret_cast<volatile uint32_t *>(&s_first[s]) == kNoBlock) { end = true; break; }
-                    if (tile >= 2) mbar_wait(&d_empty[d], ((tile >> 1) - 1) & 1u);
+                    if (P16) { if (tile >= 1) mbar_wait(&d_empty[0], (tile - 1) & 1u); }
+                    else if (tile >= 2) mbar_wait(&d_empty[d], ((tile >> 1) - 1) & 1u);
                 }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ks0 = sl * slc / 2, ks1 = min(C / 2, ks0 + slc / 2);
                 const uint64_t db0 = umma_desc(sb + s * stage_bytes, kNB * 512u, 128);
-                const uint32_t dacc = tmem + d * kAccCols;
+                const uint32_t dacc = tmem + (P16 ? half : d) * kAccCols;
                 if (elect_one()) {
                     if (!(a.debug & 4u)) {
                         // one descriptor per stage, advanced by adding the K-step offset to its address field;
@@ -453,7 +471,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                         }
                     }
                     umma_commit(&b_empty[s]); // the stage may be refilled once these MMAs have read it
-                    if (sl == nsl - 1) umma_commit(&d_full[d]); // accumulators complete
+                    if (i == nsl * kHalves - 1) umma_commit(&d_full[d]); // accumulators complete
                 }
                 __syncwarp();
             }
@@ -508,7 +526,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         };
         bool seeding = R > 1;
         for (uint32_t tile = 0;; ++tile) {
-            const uint32_t d = tile & 1u, x = tile % kAuxSlots;
+            const uint32_t d = P16 ? 0u : (tile & 1u), x = tile % kAuxSlots;
             // side data of the tile (aux pairs, live words): read in place; removed / filtered rows are rejected only
             // when they pass the fast test (as rare as for live rows), see batch_hits
             mbar_wait(&x_full[x], (tile / kAuxSlots) & 1u);
@@ -519,12 +537,12 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 T = qs->T;
             }
             const uint32_t capm1 = seeding ? mthm1 : Kp - 1;
-            mbar_wait(&d_full[d], (tile >> 1) & 1u);
+            mbar_wait(&d_full[d], (P16 ? tile : (tile >> 1)) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tbase = tmem + ((lq * 32u + hh * 16u) << 16) + d * kAccCols;
             if (a.debug & 1u) { // profiling aid: drain the accumulators, skip the arithmetic
                 uint32_t ra[32];
-                for (int i = 0; i < 2; ++i) { tmem_ld_16x64(tbase + i * 64, ra); tmem_ld_wait(ra); }
+                for (int i = 0; i < (P16 ? 4 : 2); ++i) { tmem_ld_16x64(tbase + i * 64, ra); tmem_ld_wait(ra); }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&d_empty[d]); mbar_arrive(&x_empty[x]); }
@@ -538,9 +556,27 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             };
             const uint32_t slot0 = cur * kTileRows;
             auto score = [&](const uint32_t (&rr)[32], uint32_t part) {
-                if (fits) T = score16<COS, true, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
-                else T = score16<COS, false, E>(rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                if (fits) T = score16<COS, true, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                else T = score16<COS, false, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
             };
+            if (P16) {
+                // high-byte accumulators in columns [0, 128), low-byte ones in [128, 256); half of the columns at a time
+                tmem_ld_16x64(tbase, ra);
+                tmem_ld_16x64(tbase + kAccCols, rb);
+                load_ax(0);
+                tmem_ld_wait(ra);
+                tmem_ld_wait(rb);
+                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                tmem_ld_16x64(tbase + 64, ra);
+                tmem_ld_16x64(tbase + kAccCols + 64, rb);
+                load_ax(1);
+                tmem_ld_wait(ra);
+                tmem_ld_wait(rb);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[0]); // both accumulators of the tile are in registers
+                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+            } else {
             // both halves of this warp's part of the accumulator go to registers first, so the buffer returns to the
             // MMA warp before any scoring (a warp that has rows to insert would otherwise hold it)
             tmem_ld_16x64(tbase, ra);
@@ -554,6 +590,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             score(ra, 0);
             load_ax(1);
             score(rb, 1);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&x_empty[x]); // the tile's aux pairs are no longer needed
             if (seeding) {
@@ -609,22 +646,27 @@ uint32_t batch_max_chunks() { return 256 * 4 / 16; } // A lives in <= 256 TMEM c
 size_t batch_dynamic_limit() {
     cudaFuncAttributes fa;
     size_t stat = 16 * 1024;
-    if (cudaFuncGetAttributes(&fa, batch_kernel<true, 4>) == cudaSuccess) stat = fa.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fa, batch_kernel<true, 4, true>) == cudaSuccess) stat = fa.sharedSizeBytes;
     return 227 * 1024 - stat - 1024;
 }
 
-cudaError_t batch_configure(size_t max_smem) {
+template <bool P16>
+static cudaError_t configure_all(size_t max_smem) {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(batch_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
-    if ((e = cudaFuncSetAttribute(batch_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
-    if ((e = cudaFuncSetAttribute(batch_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
-    if ((e = cudaFuncSetAttribute(batch_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
-    if ((e = cudaFuncSetAttribute(batch_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
-    return cudaFuncSetAttribute(batch_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    if ((e = cudaFuncSetAttribute(batch_kernel<true, 1, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<true, 2, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<true, 4, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<false, 1, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    if ((e = cudaFuncSetAttribute(batch_kernel<false, 2, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem))) return e;
+    return cudaFuncSetAttribute(batch_kernel<false, 4, P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+}
+cudaError_t batch_configure(size_t max_smem) {
+    cudaError_t e = configure_all<false>(max_smem);
+    return e ? e : configure_all<true>(max_smem);
 }
 
 // 3-D tensor map over the column-blocked mirror: (64 x u64 = one chunk of a block's 32 rows | block | chunk)
-static cudaError_t make_tmap(const BatchArgs &a, CUtensorMap *tm) {
+static cudaError_t make_tmap(const BatchArgs &a, const uint4 *codes, CUtensorMap *tm) {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -641,31 +683,38 @@ static cudaError_t make_tmap(const BatchArgs &a, CUtensorMap *tm) {
     const cuuint64_t gstride[2] = {(cuuint64_t)a.C * 512, 512}; // bytes, dims 1 and 2
     const cuuint32_t box[3] = {64, kNB, a.slice};
     const cuuint32_t estride[3] = {1, 1, 1};
-    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint4 *>(a.codes), gdim, gstride, box, estride,
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint4 *>(codes), gdim, gstride, box, estride,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+template <bool P16>
+static void launch_variant(const BatchArgs &a, const CUtensorMap &tm, const CUtensorMap &tl, dim3 grid, size_t smem, cudaStream_t st) {
+    const bool cos = a.metric == COSINE;
+    if (a.keep == 32) {
+        if (cos) batch_kernel<true, 1, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
+        else batch_kernel<false, 1, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
+    } else if (a.keep == 64) {
+        if (cos) batch_kernel<true, 2, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
+        else batch_kernel<false, 2, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
+    } else {
+        if (cos) batch_kernel<true, 4, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
+        else batch_kernel<false, 4, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
+    }
+}
+
 cudaError_t launch_batch(const BatchArgs &a, cudaStream_t st) {
-    CUtensorMap tm;
-    cudaError_t e = make_tmap(a, &tm);
+    CUtensorMap tm, tl;
+    cudaError_t e = make_tmap(a, a.codes, &tm);
     if (e != cudaSuccess) return e;
+    if ((e = make_tmap(a, a.codes_lo ? a.codes_lo : a.codes, &tl)) != cudaSuccess) return e;
     if (a.stages < 2 || a.stages > (uint32_t)kBatchMaxStages || (a.keep != 32 && a.keep != 64 && a.keep != 128)) return cudaErrorInvalidValue;
     if (a.slice < 2 || a.slice > a.C || (a.slice & 1u)) return cudaErrorInvalidValue;
     const size_t smem = batch_smem_bytes(a.slice, a.stages, a.keep);
     const dim3 grid(a.ngroups * a.nranges);
-    const bool cos = a.metric == COSINE;
-    if (a.keep == 32) {
-        if (cos) batch_kernel<true, 1><<<grid, kBatchThreads, smem, st>>>(a, tm);
-        else batch_kernel<false, 1><<<grid, kBatchThreads, smem, st>>>(a, tm);
-    } else if (a.keep == 64) {
-        if (cos) batch_kernel<true, 2><<<grid, kBatchThreads, smem, st>>>(a, tm);
-        else batch_kernel<false, 2><<<grid, kBatchThreads, smem, st>>>(a, tm);
-    } else {
-        if (cos) batch_kernel<true, 4><<<grid, kBatchThreads, smem, st>>>(a, tm);
-        else batch_kernel<false, 4><<<grid, kBatchThreads, smem, st>>>(a, tm);
-    }
+    if (a.codes_lo) launch_variant<true>(a, tm, tl, grid, smem, st);
+    else launch_variant<false>(a, tm, tl, grid, smem, st);
     return cudaGetLastError();
 }
 

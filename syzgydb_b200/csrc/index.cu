@@ -180,6 +180,10 @@ struct szg_index {
     Workspace *last_timed_ws = nullptr;
     int scan_warps = 16, scan_stages = 2, scan_tile_chunks = 8;
     int batch_disabled = 0; // SZG_OPT_BATCH_TENSOR = 0 routes szg_search_batch to the streaming scan
+    // 16-bit collections: byte-planar copy of the codes, the operand of the batched path (rebuilt lazily after mutations)
+    DevBuf<uint4> planar;
+    bool planar_dirty = true;
+    uint32_t planar_nblk = 0;
     uint64_t batch_queries = 0;
     int digits = 0; // 0 = automatic (2-digit fast pass, 3-digit re-run when uncertain), 2 or 3 = forced // streaming geometry (SZG_OPT_SCAN_*)
 
@@ -523,7 +527,7 @@ int szg_destroy(szg_index *h) {
     for (auto ws : h->free_ws) { ws->destroy(); delete ws; }
     for (auto &kv : h->dev_ws) { kv.second->destroy(); delete kv.second; }
     for (auto &m : h->masks) cudaFree(m.second);
-    h->codes.release(); h->ids.release(); h->aux.release(); h->live.release(); h->lut.release();
+    h->codes.release(); h->ids.release(); h->aux.release(); h->live.release(); h->lut.release(); h->planar.release();
     h->h_stage.release(); h->d_stage.release(); h->h_slots.release(); h->d_slots.release();
     h->h_ids.release(); h->d_ids_in.release();
     if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
@@ -581,6 +585,7 @@ int szg_count(szg_index *h, uint64_t *n) {
 int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t n) {
     GUARD(h);
     if (n && (!ids || !codes)) return fail(SZG_EINVAL, "null ids/codes");
+    h->planar_dirty = true;
     const uint64_t per = std::max<uint64_t>(1, kStageBytes / h->rowbytes);
     int rc;
     for (uint64_t off = 0; off < n; off += per) {
@@ -654,6 +659,7 @@ int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_remove
 int szg_fill_synthetic(szg_index *h, uint64_t seed, uint64_t row0, uint64_t nrows) {
     GUARD(h);
     if (!nrows) return SZG_OK;
+    h->planar_dirty = true;
     if ((uint64_t)h->nslots + nrows > 0xFFFFFF00ull) return fail(SZG_EINVAL, "too many rows");
     for (const auto &r : h->ranges)
         if (row0 < r.id0 + r.n && r.id0 < row0 + nrows) return fail(SZG_EINVAL, "synthetic range overlaps an existing one");
@@ -786,14 +792,16 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
 }
 
 // ---- batched queries on the tensor cores (batch_q8.cu)
-struct BatchPlan { uint32_t slice, stages, keep, nranges, gpl, ngroups; int mode; };
+struct BatchPlan { uint32_t slice, stages, keep, nranges, gpl, ngroups, Cb; int mode; bool p16; };
 
 // true when the tensor-core path can serve (collection, k): 8-bit rows, an even number of 16-byte chunks that
 // fits the TMEM columns reserved for the query digits, candidate lists of at most 128 keys, 2-digit queries
 static bool plan_batch(const szg_index *h, uint32_t nq, uint32_t k, BatchPlan *p) {
-    if (h->qt != Q8 || h->digits == 3 || (h->C % 2) != 0 || h->C > batch_max_chunks() || k < 1 || nq < 1 || h->batch_disabled ||
-        h->live_rows == 0)
-        return false;
+    if ((h->qt != Q8 && h->qt != Q16) || h->digits == 3 || k < 1 || nq < 1 || h->batch_disabled || h->live_rows == 0) return false;
+    // chunks of the contraction operand: the 8-bit row itself, or one byte plane of a 16-bit row (16 dimensions per chunk)
+    p->p16 = h->qt == Q16;
+    p->Cb = p->p16 ? (uint32_t)(h->dim + 15) / 16 : h->C;
+    if ((p->Cb % 2) != 0 || p->Cb > batch_max_chunks()) return false;
     p->mode = mode_for_k(h, k); // candidates per list = 32 << mode, as in the streaming scan
     if (p->mode > 2) return false;
     p->keep = 32u << p->mode;
@@ -802,7 +810,7 @@ static bool plan_batch(const szg_index *h, uint32_t nq, uint32_t k, BatchPlan *p
     const size_t stage_limit = ring_limit - batch_list_bytes(p->keep);
     uint32_t want_slice = 0;
     if (const char *e = getenv("SZG_BATCH_SLICE")) want_slice = (uint32_t)atoi(e);
-    p->slice = batch_slice_chunks(h->C, want_slice, stage_limit);
+    p->slice = batch_slice_chunks(p->Cb, want_slice, stage_limit);
     p->stages = batch_stages(p->slice, stage_limit);
     if (p->stages < 2) return false;
     p->ngroups = (nq + 63) / 64;
@@ -819,22 +827,42 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     int rc;
     cudaStream_t st = ws->main;
     const int nd = 2; // 2 digit planes x 64 queries = the M dimension
-    const size_t stride = pq_stride(h, nd);
+    // the query digits are laid out like an 8-bit row of Cb chunks in both cases
+    const size_t stride = sizeof(PQHeader) + (size_t)p.Cb * nd * 16;
     if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * p.nranges * p.keep)) ||
         (rc = ws->d_gmth.ensure((size_t)nq * p.nranges)))
         return rc;
+    const uint32_t nblk_now = (h->nslots + 31) / 32;
+    if (p.p16) {
+        // (re)build the byte-planar copy after a mutation: [high-byte plane | low-byte plane], each nblk x Cb x 32 uint4.
+        // Searches may run concurrently (RLock): the first one in rebuilds and waits, the others wait on the mutex.
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (h->planar_dirty || h->planar_nblk != nblk_now) {
+            const size_t plane = (size_t)nblk_now * p.Cb * 32;
+            if ((rc = h->planar.ensure(2 * plane))) return rc;
+            CK(cudaStreamSynchronize(h->mut_stream));
+            CK(launch_planar16(h->codes.p, h->C, h->planar.p, h->planar.p + plane, p.Cb, nblk_now, st));
+            CK(cudaStreamSynchronize(st));
+            h->launches++;
+            h->planar_dirty = false;
+            h->planar_nblk = nblk_now;
+        }
+    }
     PrepArgs pa;
     pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
-    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
+    pa.dims = (uint32_t)h->dim; pa.C = p.Cb; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
     pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
+    pa.planar16 = p.p16 ? 1 : 0;
     CK(launch_prep(nq, st, pa));
     h->launches++;
     CK(batch_configure(batch_dynamic_limit()));
     BatchArgs b;
     memset(&b, 0, sizeof b);
-    b.codes = h->codes.p; b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
+    b.codes = p.p16 ? h->planar.p : h->codes.p;
+    b.codes_lo = p.p16 ? h->planar.p + (size_t)nblk_now * p.Cb * 32 : nullptr;
+    b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
     b.pq = ws->d_pq.p; b.pq_stride = stride; b.cand = ws->d_cand.p; b.keep = p.keep;
-    b.C = h->C; b.nblk = (h->nslots + 31) / 32; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
+    b.C = p.Cb; b.nblk = nblk_now; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
     b.nranges = p.nranges; b.nlists = p.nranges; b.stages = p.stages; b.slice = p.slice;
     b.gmth = ws->d_gmth.p; b.mth = (p.keep + p.nranges - 1) / p.nranges;
     CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, (size_t)nq * p.nranges * sizeof(unsigned int), st));
@@ -1132,7 +1160,7 @@ int szg_get_stats(szg_index *h, szg_stats *out) {
     out->escalations = h->escalations;
     out->uncertain_results = h->uncertain;
     out->batch_queries = h->batch_queries;
-    out->device_bytes = h->codes.n * sizeof(uint4) + h->ids.n * 8 + h->aux.n * 8 + h->live.n * 4 +
+    out->device_bytes = h->codes.n * sizeof(uint4) + h->planar.n * sizeof(uint4) + h->ids.n * 8 + h->aux.n * 8 + h->live.n * 4 +
                         h->lut.n * 8 + h->masks.size() * (h->capacity / 32) * 4;
     out->live_rows = h->live_rows;
     out->slots = h->nslots;

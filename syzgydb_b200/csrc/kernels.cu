@@ -22,8 +22,11 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
     unsigned char *payload = out + sizeof(PQHeader);
     const bool quantized = a.qt <= Q16;
     const int nd = a.nd;
+    // payload layout: normally the collection's own; the batched 16-bit path wants the digits laid out like an
+    // 8-bit row (16 dimensions per chunk) because its operand is the byte-planar copy of the codes
+    const int lqt = a.planar16 ? (int)Q8 : a.qt;
 
-    const uint32_t n16 = (a.C * (uint32_t)pq_bytes_per_chunk(a.qt, nd) + 15) / 16;
+    const uint32_t n16 = (a.C * (uint32_t)pq_bytes_per_chunk(lqt, nd) + 15) / 16;
     for (uint32_t i = tid; i < n16; i += 256) reinterpret_cast<uint4 *>(payload)[i] = make_uint4(0, 0, 0, 0);
 
     // pass 1: max |q|, sum q^2
@@ -68,10 +71,10 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
             long long t = W;
             for (int j = nd - 1; j >= 1; --j) { dg[j] = (signed char)(t & 127); t >>= 7; }
             dg[0] = (signed char)t; // most significant, signed
-            if (a.qt == Q8) {
+            if (lqt == Q8) {
                 uint32_t c = i >> 4, b = i & 15;
                 for (int j = 0; j < nd; ++j) payload[((size_t)c * nd + j) * 16 + b] = (unsigned char)dg[j];
-            } else if (a.qt == Q4) {
+            } else if (lqt == Q4) {
                 uint32_t byte = i >> 1, c = byte >> 4, b = byte & 15, arr = i & 1; // even dim = high nibble
                 for (int j = 0; j < nd; ++j) payload[(((size_t)c * 2 + arr) * nd + j) * 16 + b] = (unsigned char)dg[j];
             } else {
@@ -448,6 +451,50 @@ cudaError_t launch_merge(const MergeArgs &a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
     }
     merge_kernel<<<a.nq, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ======================================================================= byte-planar copy of 16-bit codes
+// The batched tensor-core path contracts bytes (tcgen05 kind::i8).  A 16-bit collection gets a secondary copy in
+// which block b, chunk c (16 dimensions) holds the HIGH bytes of the uncentred codes u = c + 32768 of its 32 rows
+// in one array and the LOW bytes in another, both in the column-blocked layout of an 8-bit collection, so that
+// I = sum u_i W_i = 256 * sum hi_i W_i + sum lo_i W_i is two 8-bit contractions with the same query operand.
+__global__ void __launch_bounds__(256) planar16_kernel(const uint4 *__restrict__ codes, uint32_t C16, uint4 *__restrict__ hi,
+                                                       uint4 *__restrict__ lo, uint32_t C8, uint32_t nblk) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)nblk * C8 * 32;
+    if (t >= total) return;
+    const uint32_t lane = (uint32_t)(t & 31), c8 = (uint32_t)((t >> 5) % C8), b = (uint32_t)((t >> 5) / C8);
+    unsigned char h8[16], l8[16];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t c16 = 2 * c8 + half;
+        uint4 v = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u); // centred zero-padding -> u = 0
+        if (c16 < C16) v = codes[((size_t)b * C16 + c16) * 32 + lane];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const uint32_t s16 = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu; // little-endian int16 of (u - 32768)
+            const uint32_t u = s16 ^ 0x8000u;
+            h8[half * 8 + e] = (unsigned char)(u >> 8);
+            l8[half * 8 + e] = (unsigned char)(u & 0xFF);
+        }
+        if (c16 >= C16) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { h8[half * 8 + e] = 0; l8[half * 8 + e] = 0; }
+        }
+    }
+    uint4 H, L;
+    memcpy(&H, h8, 16);
+    memcpy(&L, l8, 16);
+    hi[((size_t)b * C8 + c8) * 32 + lane] = H;
+    lo[((size_t)b * C8 + c8) * 32 + lane] = L;
+}
+
+cudaError_t launch_planar16(const uint4 *codes, uint32_t C16, uint4 *hi, uint4 *lo, uint32_t C8, uint32_t nblk, cudaStream_t st) {
+    const size_t total = (size_t)nblk * C8 * 32;
+    if (!total) return cudaSuccess;
+    planar16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(codes, C16, hi, lo, C8, nblk);
     return cudaGetLastError();
 }
 

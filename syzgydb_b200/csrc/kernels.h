@@ -13,6 +13,7 @@ struct PrepArgs {
     int nd;          // digits (2 or 3) for quantized rows
     int radius_mode;
     double radius;
+    int planar16 = 0; // payload laid out like an 8-bit row (batched 16-bit path); C is then the planar chunk count
 };
 cudaError_t launch_prep(uint32_t nq, cudaStream_t st, const PrepArgs &a);
 
@@ -62,9 +63,13 @@ struct RescoreArgs {
 };
 cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st);
 
-// K4: batched-query tensor-core contraction (batch_q8.cu), 8-bit rows
+// byte-planar copy of a 16-bit collection's codes (operand of the batched path)
+cudaError_t launch_planar16(const uint4 *codes, uint32_t C16, uint4 *hi, uint4 *lo, uint32_t C8, uint32_t nblk, cudaStream_t st);
+
+// K4: batched-query tensor-core contraction (batch_q8.cu): 8-bit rows, or the byte planes of 16-bit rows
 struct BatchArgs {
-    const uint4 *codes;
+    const uint4 *codes;        // 8-bit rows; 16-bit: the plane of HIGH bytes
+    const uint4 *codes_lo;     // 16-bit: the plane of LOW bytes (NULL for 8-bit)
     const void *aux;
     const uint32_t *live;
     const uint32_t *mask;

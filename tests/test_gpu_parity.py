@@ -635,8 +635,8 @@ def test_batch_zero_and_degenerate_queries():
 
 
 def test_batch_falls_back_to_the_scan_when_the_geometry_does_not_fit():
-    """Non-8-bit collections, odd chunk counts and k beyond the list sizes are served by the streaming scan, on the GPU."""
-    for bits, dims, k in [(4, 64, 10), (16, 48, 10), (8, 40, 10), (8, 64, 200)]:
+    """4/32/64-bit collections, odd chunk counts and k beyond the list sizes are served by the streaming scan, on the GPU."""
+    for bits, dims, k in [(4, 64, 10), (16, 40, 10), (32, 48, 10), (8, 40, 10), (8, 64, 200)]:
         n = 1500
         codes = o.synth_rows(5, 0, n, dims, bits)
         ids = np.arange(n, dtype=np.uint64)
@@ -691,3 +691,64 @@ def test_batch_gaussian_normalised_rows_cosine():
         bi, bd, bn, _ = ix.search_batch(q, k)
         si, sd, sn, _ = ix.search_topk(q, k)
         assert np.array_equal(bi, si) and np.array_equal(bd, sd) and np.array_equal(bn, sn)
+
+
+# ------------------------------------------------------------------ 16-bit collections on the tensor cores (byte planes)
+@pytest.mark.parametrize("metric", [szg.COSINE, szg.EUCLIDEAN])
+@pytest.mark.parametrize("dims,n,nq,k", [(768, 3000, 70, 10), (96, 9000, 130, 100), (24, 5001, 64, 30), (32, 700, 3, 1)])
+def test_batch_16bit_matches_oracle(metric, dims, n, nq, k):
+    """16-bit rows: the batch is contracted as a high-byte and a low-byte plane of the uncentred codes (a secondary
+    byte-planar copy in HBM); results are what nq single Search calls return."""
+    seed = 900 + dims + k
+    codes = o.synth_rows(seed, 0, n, dims, 16)
+    ids = np.arange(n, dtype=np.uint64) * 5 + 2
+    queries = o.synth_queries(seed + 1, 0, nq, dims)
+    with _build(codes, ids, dims, 16, metric) as ix:
+        gi, gd, gn, scanned = ix.search_batch(queries, k)
+        assert ix.stats()["batch_queries"] == nq, "the tensor-core path did not run"
+        assert scanned == n
+        for qi in range(min(nq, 6)):
+            ri, rd, _ = o.search_exact(codes, ids, dims, 16, metric, queries[qi], k=k)
+            assert gn[qi] == ri.size
+            assert_results_match(gi[qi, :gn[qi]], gd[qi, :gn[qi]], ri, rd, _true_dist(codes, ids, dims, 16, metric, queries[qi]),
+                                 f"batch16 m{metric} d{dims} k{k} q{qi}")
+        si, sd, sn, _ = ix.search_topk(queries, k)
+        assert np.array_equal(gn, sn) and np.array_equal(gi, si) and np.array_equal(gd, sd)
+
+
+def test_batch_16bit_follows_mutations_and_masks():
+    """The byte-planar copy is rebuilt lazily after upsert / fill; removals and filter masks act through the live words."""
+    n, dims, nq, k = 4000, 64, 66, 10
+    codes = o.synth_rows(61, 0, n, dims, 16)
+    ids = np.arange(n, dtype=np.uint64)
+    queries = o.synth_queries(62, 0, nq, dims)
+    with _build(codes[:3000], ids[:3000], dims, 16, szg.EUCLIDEAN) as ix:
+        a = ix.search_batch(queries, k)
+        ix.upsert(ids[3000:], codes[3000:])                    # new rows: the copy must be rebuilt
+        newc = o.synth_rows(63, 0, 10, dims, 16)
+        ix.upsert(ids[:10], newc)                              # replaced rows
+        ix.remove(ids[100:200])
+        cur = codes.copy(); cur[:10] = newc
+        alive = np.ones(n, dtype=bool); alive[100:200] = False
+        passmask = ((ids % 4 != 0) & alive).astype(np.uint8)
+        mask = ix.mask_create(ids[alive], passmask[alive])
+        gi, gd, gn, scanned = ix.search_batch(queries, k, mask_id=mask)
+        assert ix.stats()["batch_queries"] == 2 * nq and scanned == int(alive.sum())
+        keep = passmask.astype(bool)
+        for qi in range(5):
+            ri, rd, _ = o.search_exact(cur[keep], ids[keep], dims, 16, szg.EUCLIDEAN, queries[qi], k=k)
+            assert_results_match(gi[qi, :gn[qi]], gd[qi, :gn[qi]], ri, rd, None, f"batch16 mutated q{qi}")
+        si, sd, sn, _ = ix.search_topk(queries, k, mask_id=mask)
+        assert np.array_equal(gi, si) and np.array_equal(gd, sd)
+
+
+def test_batch_cfg5_shape_16bit_euclid_k100():
+    """BASELINE.json configs[4] shape on one shard-sized slice: 1024 queries, k = 100, 16-bit, euclidean."""
+    rows, dims, nq, k = 150000, 768, 1024, 100
+    qs = np.random.default_rng(12).uniform(-1, 1, size=(nq, dims))
+    with szg.Index(dims, 16, szg.EUCLIDEAN) as ix:
+        ix.fill_synthetic(0x5A590005, 0, rows)
+        bi, bd, bn, _ = ix.search_batch(qs, k)
+        assert ix.stats()["batch_queries"] == nq
+        si, sd, sn, _ = ix.search_topk(qs, k)
+        assert np.array_equal(bn, sn) and np.array_equal(bi, si) and np.array_equal(bd, sd)
