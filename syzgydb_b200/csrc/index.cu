@@ -179,6 +179,7 @@ struct szg_index {
     std::vector<float> last_times;
     Workspace *last_timed_ws = nullptr;
     int scan_warps = 16, scan_stages = 2, scan_tile_chunks = 8;
+    bool scan_geometry_set = false; // SZG_OPT_SCAN_* given: no automatic choice
     int batch_disabled = 0; // SZG_OPT_BATCH_TENSOR = 0 routes szg_search_batch to the streaming scan
     // 16-bit collections: byte-planar copy of the codes, the operand of the batched path (rebuilt lazily after mutations)
     DevBuf<uint4> planar;
@@ -291,8 +292,14 @@ constexpr size_t kScanSmemLimit = 224 * 1024; // dynamic; + ~3 KB static stays u
 
 // Persistent launch: one CTA per SM (fewer when the collection has fewer row blocks than warps).
 int plan_scan(szg_index *h, int nd, ScanPlan *p, int *grid) {
-    if (!scan_plan(h->C, (uint32_t)h->scan_warps, (uint32_t)h->scan_stages, (uint32_t)h->scan_tile_chunks,
-                   pq_stride(h, nd), kScanSmemLimit, p))
+    // measured on B200 (profiles/r01_tune_scan_*): 16 warps x 4 KB tiles win on multi-GB shards (7.29 vs 7.04 TB/s at
+    // 7.7 GB), 8 warps x 8 KB tiles on ~1 GB shards (7.41 vs 7.04 TB/s at 0.96 GB: half as many per-warp lists per query)
+    uint32_t warps = (uint32_t)h->scan_warps, tile_chunks = (uint32_t)h->scan_tile_chunks;
+    if (!h->scan_geometry_set && h->qt == Q8 && (uint64_t)h->nslots * h->rowbytes < 1500000000ull && h->C >= 16) {
+        warps = 8;
+        tile_chunks = 16;
+    }
+    if (!scan_plan(h->C, warps, (uint32_t)h->scan_stages, tile_chunks, pq_stride(h, nd), kScanSmemLimit, p))
         return fail(SZG_EINTERNAL, "scan geometry does not fit shared memory");
     const uint32_t nblk = (h->nslots + 31) / 32;
     uint32_t g = (nblk + p->warps - 1) / p->warps;
@@ -549,14 +556,17 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
     case SZG_OPT_SCAN_WARPS:
         if (value != 8 && value != 16) return fail(SZG_EINVAL, "scan warps must be 8 or 16");
         h->scan_warps = (int)value;
+        h->scan_geometry_set = true;
         return SZG_OK;
     case SZG_OPT_SCAN_STAGES:
         if (value < 2 || value > kMaxStages) return fail(SZG_EINVAL, "scan stages must be in [2, %d]", kMaxStages);
         h->scan_stages = (int)value;
+        h->scan_geometry_set = true;
         return SZG_OK;
     case SZG_OPT_SCAN_TILE_CHUNKS:
         if (value < 1 || value > kMaxTileChunks) return fail(SZG_EINVAL, "tile chunks must be in [1, %d]", kMaxTileChunks);
         h->scan_tile_chunks = (int)value;
+        h->scan_geometry_set = true;
         return SZG_OK;
     case SZG_OPT_BATCH_TENSOR: h->batch_disabled = value == 0; return SZG_OK;
     case SZG_OPT_DIGITS:
