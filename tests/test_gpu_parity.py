@@ -470,6 +470,10 @@ def test_concurrent_searches_on_one_handle():
                     qi = (t + rep) % len(qs)
                     gi, gd, gn, _ = ix.search_topk(qs[qi], 10)
                     assert_results_match(gi[0], gd[0], want[qi][0], want[qi][1])
+                    if t % 2 == 0:  # the batched tensor-core path is a search too: same lock, same safety
+                        bi, bd, bn, _ = ix.search_batch(qs, 10)
+                        for j in range(len(qs)):
+                            assert_results_match(bi[j], bd[j], want[j][0], want[j][1])
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         th = [threading.Thread(target=work, args=(t,)) for t in range(6)]

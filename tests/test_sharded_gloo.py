@@ -41,7 +41,8 @@ class OracleShard:
         self.device = torch.device("cpu")
         self.dims, self.bits, self.metric = dims, bits, metric
 
-    def topk_into(self, tq, k, rec, nq, mask_id=-1, flags=0):
+    def topk_into(self, tq, k, rec, nq, mask_id=-1, flags=0, batched=False):
+        self.batched_calls = getattr(self, "batched_calls", 0) + int(batched)
         off_ids, off_dist, off_n, _ = record_layout(nq, k)
         w = rec.numpy().view(np.uint64)
         for qi in range(nq):
@@ -89,6 +90,9 @@ def _worker(rank, world, port, q):
         for qi in range(nq):
             ri, rd, _ = o.search_exact(allcodes, allids, dims, bits, metric, qs[qi], k=k)
             assert cnt[qi] == k and ids[qi].tolist() == ri.tolist() and np.array_equal(dd[qi], rd)
+        # batched=True takes the same collective path (local batch step -> all-gather -> merge)
+        ids2, dd2, cnt2 = sh.search_topk(qs, k, batched=True)
+        assert sh.shard.batched_calls == 1 and np.array_equal(ids2, ids) and np.array_equal(dd2, dd) and np.array_equal(cnt2, cnt)
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)))
