@@ -657,7 +657,9 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 for (uint32_t i = lane; i < 8 * Kp; i += 32) wl[i] = kNoKey; // the tile comes again
                 if (lane < 8) { wq[lane].thr = wq[lane].valid ? kNoKey : 0ull; wq[lane].T = wq[lane].valid ? -INFINITY : INFINITY; }
                 __syncwarp();
-                while (!poll_bounds()) __nanosleep(200); // all ranges of the group are co-resident (grid <= SM count)
+                // all ranges of the group are normally co-resident (grid <= SM count) and publish within a tile time; the
+                // bound is an optimisation only, so the wait is bounded (~4 ms) and the range simply goes on without it
+                for (int spin = 0; !poll_bounds() && spin < 20000; ++spin) __nanosleep(200);
                 T = qs->T;
             }
         }
