@@ -336,6 +336,79 @@ Collection::Collection(const CollectionOptions &options) : p_(new Impl) {
     for (int i = 0; i < 5; ++i) p_->roots.push_back(std::make_unique<LshNode>());
 }
 
+std::unique_ptr<Collection> Collection::Open(const std::string &path, int device, uint64_t seed) {
+    szg_spanfile *sf = nullptr;
+    if (szg_spanfile_open(path.c_str(), &sf) != SZG_OK) throw std::runtime_error(std::string("failed to open file: ") + szg_last_error());
+    struct Closer { szg_spanfile *f; ~Closer() { szg_spanfile_close(f); } } closer{sf};
+    szg_spanfile_info info;
+    szg_spanfile_get_info(sf, &info);
+    if (!info.has_header) throw std::runtime_error("failed to read header: record not found"); // collection.go:243-246
+    CollectionOptions o;
+    o.Name = info.name;
+    o.DistanceMethod = info.distance_method;
+    o.DimensionCount = info.dimension_count;
+    o.Quantization = info.quantization;
+    o.Device = device;
+    o.Seed = seed;
+    std::unique_ptr<Collection> c(new Collection(o));
+    Impl &p = *c->p_;
+    uint64_t loaded = 0;
+    GPU(szg_spanfile_load(sf, p.gpu, &loaded), "spanfile_load");
+    std::vector<uint64_t> ids((size_t)info.records);
+    uint64_t n = 0;
+    GPU(szg_spanfile_ids(sf, ids.data(), ids.size(), &n), "spanfile_ids");
+    for (uint64_t id : ids) { // IterateSortedRecords order (spanfile.go:540-560)
+        const uint8_t *vec = nullptr, *meta = nullptr;
+        uint64_t vl = 0, ml = 0;
+        GPU(szg_spanfile_record(sf, id, &vec, &vl, &meta, &ml), "spanfile_record");
+        Impl::Rec rec{std::string(reinterpret_cast<const char *>(meta), (size_t)ml), std::vector<uint8_t>(vec, vec + vl)};
+        const std::vector<double> v = decodeVector(rec.codes.data(), o.DimensionCount, o.Quantization);
+        p.store[id] = std::move(rec);
+        p.addPoint(id, v); // collection.go:304-305: the decoded vector
+    }
+    return c;
+}
+
+std::vector<SearchResults> Collection::SearchBatch(const std::vector<SearchArgs> &args) {
+    std::vector<SearchResults> out(args.size());
+    std::vector<size_t> batch; // exact, K > 0, no radius, no filter, one common K
+    int K = 0;
+    for (size_t i = 0; i < args.size(); ++i) {
+        const SearchArgs &a = args[i];
+        const bool fits = a.Precision == "exact" && a.K > 0 && a.K <= (int)SZG_MAX_K && a.Radius <= 0 && !a.Filter &&
+                          (int)a.Vector.size() == p_->opt.DimensionCount && (K == 0 || a.K == K);
+        if (fits) { K = a.K; batch.push_back(i); }
+    }
+    if (batch.size() >= 2) {
+        std::shared_lock<std::shared_mutex> lk(p_->mu);
+        const size_t nq = batch.size(), d = (size_t)p_->opt.DimensionCount;
+        std::vector<double> flat(nq * d), dist(nq * (size_t)K);
+        std::vector<uint64_t> ids(nq * (size_t)K);
+        std::vector<uint32_t> cnt(nq);
+        for (size_t j = 0; j < nq; ++j) std::copy(args[batch[j]].Vector.begin(), args[batch[j]].Vector.end(), flat.begin() + j * d);
+        uint64_t scanned = 0;
+        GPU(szg_search_batch(p_->gpu, flat.data(), (uint32_t)nq, (uint32_t)K, -1, SZG_F_DEFAULT, ids.data(), dist.data(), cnt.data(),
+                             &scanned), "search_batch");
+        const size_t numRecords = p_->store.size();
+        for (size_t j = 0; j < nq; ++j) {
+            SearchResults &r = out[batch[j]];
+            for (uint32_t e = 0; e < cnt[j]; ++e) {
+                const uint64_t id = ids[j * (size_t)K + e];
+                r.Results.push_back(SearchResult{id, p_->store.at(id).meta, dist[j * (size_t)K + e]});
+            }
+            r.PercentSearched = numRecords == 0 ? 0.0 : (double)scanned / (double)numRecords * 100;
+        }
+    } else {
+        batch.clear();
+    }
+    size_t b = 0;
+    for (size_t i = 0; i < args.size(); ++i) {
+        if (b < batch.size() && batch[b] == i) { ++b; continue; }
+        out[i] = Search(args[i]);
+    }
+    return out;
+}
+
 Collection::~Collection() { Close(); }
 
 void Collection::Close() {

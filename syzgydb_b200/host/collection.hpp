@@ -79,6 +79,11 @@ std::vector<double> decodeVector(const uint8_t *data, int dimensions, int quanti
 class Collection {
 public:
     explicit Collection(const CollectionOptions &options); // throws std::runtime_error without a B200
+    // NewCollection on an existing collection file (collection.go:241-252, 298-311): options from the header record,
+    // stream 1 of every live document bulk-loaded into the mirror by the library's span-file reader (szg_spanfile_*,
+    // the file is read, never written), metadata copied out of the mapping, the LSH trees rebuilt from the decoded
+    // vectors in IterateSortedRecords order like the reference's reload loop.
+    static std::unique_ptr<Collection> Open(const std::string &path, int device = 0, uint64_t seed = 1);
     ~Collection();
     Collection(const Collection &) = delete;
     Collection &operator=(const Collection &) = delete;
@@ -93,6 +98,10 @@ public:
     bool removeDocument(uint64_t id);                              // collection.go:511-521
     int GetDocumentCount() const;                                  // collection.go:54-61
     SearchResults Search(SearchArgs args);                         // collection.go:569-711
+    // The results of Search(args[i]) for every i.  Exact top-k queries without a filter (all with the same K) go to the
+    // GPU as ONE batch (szg_search_batch: the tensor-core contraction for 8/16-bit collections); everything else is
+    // answered one by one.  No reference counterpart: there the calls would run concurrently under the RLock (570).
+    std::vector<SearchResults> SearchBatch(const std::vector<SearchArgs> &args);
     void Close();                                                  // collection.go:408-421
 
     // test hooks: the ids the last index-driven Search fed to `consider`, in order, and how many GPU

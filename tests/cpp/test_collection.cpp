@@ -3,6 +3,7 @@
 // the CPU oracle.  `--cpu` runs only the codec checks (no GPU needed).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <random>
@@ -284,7 +285,49 @@ static void TestLSHQuantized() {
 }
 static void TestLSHRadiusWithFilter() { lsh_case("lsh_cos_f64_radius_filter", 30000, 48, 64, Cosine, 0, 0.46, true); } // cfg3 shape, small
 
+// --open <file.dat> <k> <q_0,0> <q_0,1> ... : opens a collection file written by the reference (or its restated writer),
+// prints its options and document count, then the exact top-k of the queries found on the command line (one
+// line per result: query index, id, distance as a hex float, metadata) answered as ONE SearchBatch and, for the
+// first query, once more through Search.  tests/test_host_cpp.py compares the output with the oracle.
+static int open_mode(int argc, char **argv) {
+    const std::string path = argv[2];
+    const int k = std::atoi(argv[3]);
+    auto c = Collection::Open(path);
+    const CollectionOptions &o = c->Options();
+    std::printf("OPTIONS %s %d %d %d\n", o.Name.c_str(), o.DistanceMethod, o.DimensionCount, o.Quantization);
+    std::printf("COUNT %d\n", c->GetDocumentCount());
+    std::vector<SearchArgs> batch;
+    for (int at = 4; at + o.DimensionCount <= argc; at += o.DimensionCount) {
+        SearchArgs a;
+        a.K = k;
+        a.Precision = "exact";
+        for (int i = 0; i < o.DimensionCount; ++i) a.Vector.push_back(std::strtod(argv[at + i], nullptr));
+        batch.push_back(a);
+    }
+    const auto res = c->SearchBatch(batch);
+    for (size_t q = 0; q < res.size(); ++q)
+        for (const auto &r : res[q].Results)
+            std::printf("RESULT %zu %llu %a %s\n", q, (unsigned long long)r.ID, r.Distance, r.Metadata.c_str());
+    const SearchResults one = c->Search(batch[0]);
+    for (const auto &r : one.Results) std::printf("SINGLE 0 %llu %a %s\n", (unsigned long long)r.ID, r.Distance, r.Metadata.c_str());
+    std::printf("PERCENT %.6f\n", res[0].PercentSearched);
+    // the medium-precision path over the rebuilt LSH trees still answers
+    SearchArgs m = batch[0];
+    m.Precision = "";
+    const SearchResults lsh = c->Search(m);
+    std::printf("LSH %zu %.6f\n", lsh.Results.size(), lsh.PercentSearched);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 4 && std::string(argv[1]) == "--open") {
+        try {
+            return open_mode(argc, argv);
+        } catch (const std::exception &e) {
+            std::printf("ERROR %s\n", e.what());
+            return 2;
+        }
+    }
     const bool cpu_only = argc > 1 && std::string(argv[1]) == "--cpu";
     struct T { const char *name; void (*fn)(); bool gpu; };
     const T tests[] = {

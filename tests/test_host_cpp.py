@@ -32,3 +32,56 @@ def test_host_mirror_collection_tests_on_gpu():
                  "TestVectorSearchWith4BitQuantization", "TestDocumentRoundTripUpdateRemove", "TestListModePagination",
                  "TestSearchExactVsLSH", "TestLSHQuantized", "TestLSHRadiusWithFilter"):
         assert f"PASS {name}" in out.stdout, out.stdout[-4000:]
+
+
+@pytest.mark.gpu
+def test_host_mirror_opens_a_collection_file_and_batches(tmp_path):
+    """Collection::Open over a span file written by the restated reference writer (updates and removals included),
+    then SearchBatch: the C++ mirror must return what the oracle returns, with the metadata of the file."""
+    import json
+
+    import numpy as np
+
+    from oracle import pyoracle as o
+    from oracle import spanfile as sfo
+    _build()
+    n, dims, bits, metric, k, nq = 600, 16, 8, 1, 5, 6
+    w = sfo.SpanFileWriter()
+    w.write_header("hosttest", metric, dims, bits)
+    codes = o.synth_rows(33, 0, n, dims, bits)
+    ids = np.arange(n, dtype=np.uint64) * 2 + 5
+    for i in range(n):
+        w.add_document(int(ids[i]), codes[i].tobytes(), json.dumps({"i": int(ids[i])}).encode())
+    new = o.synth_rows(34, 0, 20, dims, bits)
+    for j in range(20):                       # updates move the records and leave FREE spans behind
+        w.add_document(int(ids[j * 7]), new[j].tobytes(), json.dumps({"i": int(ids[j * 7]), "v": 2}).encode())
+        codes[j * 7] = new[j]
+    gone = set(int(x) for x in ids[100:130])
+    for x in gone:
+        w.remove_document(x)
+    keep = np.array([int(x) not in gone for x in ids])
+    path = os.path.join(tmp_path, "host.dat")
+    with open(path, "wb") as f:
+        f.write(w.tobytes())
+    qs = o.synth_queries(35, 0, nq, dims)
+    argv = [BIN, "--open", path, str(k)] + [repr(float(x)) for x in qs.reshape(-1)]
+    out = subprocess.run(argv, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert f"OPTIONS hosttest {metric} {dims} {bits}" in lines and f"COUNT {int(keep.sum())}" in lines
+    got = {}
+    for ln in lines:
+        if ln.startswith("RESULT "):
+            _, q, i, d, meta = ln.split(" ", 4)
+            got.setdefault(int(q), []).append((int(i), float.fromhex(d), meta))
+    for qi in range(nq):
+        ri, rd, _ = o.search_exact(codes[keep], ids[keep], dims, bits, metric, qs[qi], k=k)
+        assert [g[0] for g in got[qi]] == ri.tolist(), (qi, got[qi], ri)
+        assert np.allclose([g[1] for g in got[qi]], rd, rtol=1e-12, atol=0)
+        for g in got[qi]:
+            assert json.loads(g[2])["i"] == g[0]
+    single = [ln.split(" ", 4) for ln in lines if ln.startswith("SINGLE ")]
+    assert [int(s[2]) for s in single] == [g[0] for g in got[0]]
+    assert "PERCENT 100.000000" in lines
+    lsh = [ln for ln in lines if ln.startswith("LSH ")][0].split()
+    assert int(lsh[1]) == k
