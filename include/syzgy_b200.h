@@ -119,9 +119,11 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
 /*
  * Batched exact top-k: the results of nq independent szg_search_topk calls, computed as one dense
  * contraction on the tensor cores (tcgen05.mma kind::i8 over the digit planes of the fixed-point
- * queries, fused threshold top-k epilogue) when the collection is 8-bit, k <= 112 and a row fits
- * shared memory; otherwise the call is served by the streaming scan.  Replaces: B concurrent Search
- * calls under the RLock (collection.go:569-570).  Same outputs, same certification / escalation.
+ * queries, fused threshold top-k epilogue) when the collection is 4-, 8- or 16-bit (4-bit through a
+ * one-byte-per-code copy, 16-bit through a byte-planar copy kept next to the mirror), k <= 112 and the
+ * row has an even number of 16-dimension chunks (at most 64); otherwise the call is served by the
+ * streaming scan.  Replaces: B concurrent Search calls under the RLock (collection.go:569-570).
+ * Same outputs, same certification / escalation.
  */
 int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id,
                      uint32_t flags, uint64_t *out_ids, double *out_dist, uint32_t *out_n,

@@ -802,15 +802,17 @@ int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k
 }
 
 // ---- batched queries on the tensor cores (batch_q8.cu)
-struct BatchPlan { uint32_t slice, stages, keep, nranges, gpl, ngroups, Cb; int mode; bool p16; };
+struct BatchPlan { uint32_t slice, stages, keep, nranges, gpl, ngroups, Cb; int mode; bool p16, p4; };
 
 // true when the tensor-core path can serve (collection, k): 8-bit rows, an even number of 16-byte chunks that
 // fits the TMEM columns reserved for the query digits, candidate lists of at most 128 keys, 2-digit queries
 static bool plan_batch(const szg_index *h, uint32_t nq, uint32_t k, BatchPlan *p) {
-    if ((h->qt != Q8 && h->qt != Q16) || h->digits == 3 || k < 1 || nq < 1 || h->batch_disabled || h->live_rows == 0) return false;
-    // chunks of the contraction operand: the 8-bit row itself, or one byte plane of a 16-bit row (16 dimensions per chunk)
+    if (h->qt > Q16 || h->digits == 3 || k < 1 || nq < 1 || h->batch_disabled || h->live_rows == 0) return false;
+    // chunks of the contraction operand (16 dimensions each): the 8-bit row itself, one byte plane of a 16-bit row,
+    // or the one-byte-per-code copy of a 4-bit row
     p->p16 = h->qt == Q16;
-    p->Cb = p->p16 ? (uint32_t)(h->dim + 15) / 16 : h->C;
+    p->p4 = h->qt == Q4;
+    p->Cb = h->qt == Q8 ? h->C : (uint32_t)(h->dim + 15) / 16;
     if ((p->Cb % 2) != 0 || p->Cb > batch_max_chunks()) return false;
     p->mode = mode_for_k(h, k); // candidates per list = 32 << mode, as in the streaming scan
     if (p->mode > 2) return false;
@@ -843,15 +845,17 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
         (rc = ws->d_gmth.ensure((size_t)nq * p.nranges)))
         return rc;
     const uint32_t nblk_now = (h->nslots + 31) / 32;
-    if (p.p16) {
-        // (re)build the byte-planar copy after a mutation: [high-byte plane | low-byte plane], each nblk x Cb x 32 uint4.
-        // Searches may run concurrently (RLock): the first one in rebuilds and waits, the others wait on the mutex.
+    if (p.p16 || p.p4) {
+        // (re)build the byte copy after a mutation.  16-bit: [high-byte plane | low-byte plane], each nblk x Cb x 32 uint4;
+        // 4-bit: one plane, one byte per code.  Searches may run concurrently (RLock): the first one in rebuilds and
+        // waits, the others wait on the mutex.
         std::lock_guard<std::mutex> lk(h->mu);
         if (h->planar_dirty || h->planar_nblk != nblk_now) {
             const size_t plane = (size_t)nblk_now * p.Cb * 32;
-            if ((rc = h->planar.ensure(2 * plane))) return rc;
+            if ((rc = h->planar.ensure((p.p16 ? 2 : 1) * plane))) return rc;
             CK(cudaStreamSynchronize(h->mut_stream));
-            CK(launch_planar16(h->codes.p, h->C, h->planar.p, h->planar.p + plane, p.Cb, nblk_now, st));
+            if (p.p16) CK(launch_planar16(h->codes.p, h->C, h->planar.p, h->planar.p + plane, p.Cb, nblk_now, st));
+            else CK(launch_expand4(h->codes.p, h->C, h->planar.p, p.Cb, nblk_now, st));
             CK(cudaStreamSynchronize(st));
             h->launches++;
             h->planar_dirty = false;
@@ -862,13 +866,13 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
     pa.dims = (uint32_t)h->dim; pa.C = p.Cb; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
     pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
-    pa.planar16 = p.p16 ? 1 : 0;
+    pa.planar16 = (p.p16 || p.p4) ? 1 : 0; // digits laid out like an 8-bit row of Cb chunks
     CK(launch_prep(nq, st, pa));
     h->launches++;
     CK(batch_configure(batch_dynamic_limit()));
     BatchArgs b;
     memset(&b, 0, sizeof b);
-    b.codes = p.p16 ? h->planar.p : h->codes.p;
+    b.codes = (p.p16 || p.p4) ? h->planar.p : h->codes.p;
     b.codes_lo = p.p16 ? h->planar.p + (size_t)nblk_now * p.Cb * 32 : nullptr;
     b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
     b.pq = ws->d_pq.p; b.pq_stride = stride; b.cand = ws->d_cand.p; b.keep = p.keep;

@@ -491,6 +491,36 @@ __global__ void __launch_bounds__(256) planar16_kernel(const uint4 *__restrict__
     lo[((size_t)b * C8 + c8) * 32 + lane] = L;
 }
 
+// 4-bit collections: a secondary copy with one byte per code (0..15), in the column-blocked layout of an 8-bit
+// collection, is the operand of the batched path (tcgen05 has no 4-bit integer kind).  Chunk c8 (16 dimensions) of a
+// row is the first or second half of its 4-bit chunk c8 / 2; even dimensions sit in the high nibble (collection.go:774-779).
+__global__ void __launch_bounds__(256) expand4_kernel(const uint4 *__restrict__ codes, uint32_t C4, uint4 *__restrict__ out, uint32_t C8,
+                                                      uint32_t nblk) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)nblk * C8 * 32;
+    if (t >= total) return;
+    const uint32_t lane = (uint32_t)(t & 31), c8 = (uint32_t)((t >> 5) % C8), b = (uint32_t)((t >> 5) / C8);
+    const uint32_t c4 = c8 >> 1, half = c8 & 1u;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c4 < C4) v = codes[((size_t)b * C4 + c4) * 32 + lane];
+    const uint32_t w2[2] = {half ? v.z : v.x, half ? v.w : v.y}; // 8 bytes = 16 codes
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t two = (w2[k >> 1] >> (16 * (k & 1))) & 0xFFFFu; // 2 bytes = 4 codes: dims 4k .. 4k+3
+        const uint32_t b0 = two & 0xFF, b1 = two >> 8;
+        o[k] = (b0 >> 4) | ((b0 & 0xF) << 8) | ((b1 >> 4) << 16) | ((b1 & 0xF) << 24);
+    }
+    out[((size_t)b * C8 + c8) * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+cudaError_t launch_expand4(const uint4 *codes, uint32_t C4, uint4 *out, uint32_t C8, uint32_t nblk, cudaStream_t st) {
+    const size_t total = (size_t)nblk * C8 * 32;
+    if (!total) return cudaSuccess;
+    expand4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(codes, C4, out, C8, nblk);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_planar16(const uint4 *codes, uint32_t C16, uint4 *hi, uint4 *lo, uint32_t C8, uint32_t nblk, cudaStream_t st) {
     const size_t total = (size_t)nblk * C8 * 32;
     if (!total) return cudaSuccess;

@@ -64,6 +64,8 @@ struct RescoreArgs {
 cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st);
 
 // byte-planar copy of a 16-bit collection's codes (operand of the batched path)
+// one-byte-per-code copy of a 4-bit collection's codes (operand of the batched path)
+cudaError_t launch_expand4(const uint4 *codes, uint32_t C4, uint4 *out, uint32_t C8, uint32_t nblk, cudaStream_t st);
 cudaError_t launch_planar16(const uint4 *codes, uint32_t C16, uint4 *hi, uint4 *lo, uint32_t C8, uint32_t nblk, cudaStream_t st);
 
 // K4: batched-query tensor-core contraction (batch_q8.cu): 8-bit rows, or the byte planes of 16-bit rows
