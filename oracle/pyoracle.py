@@ -48,6 +48,10 @@ def lib():
         L.orc_euclidean.restype = C.c_double
         L.orc_euclidean.argtypes = [f64p, f64p, C.c_int64]
         L.orc_angular.restype = C.c_double
+        for fn in (L.orc_go_acos, L.orc_go_asin, L.orc_go_atan):
+            fn.restype = C.c_double
+            fn.argtypes = [C.c_double]
+        L.orc_libm_acos_mode.argtypes = [C.c_int]
         L.orc_angular.argtypes = [f64p, f64p, C.c_int64]
         L.orc_lex_order.argtypes = [u64p, C.c_int64, i64p]
         L.orc_search_exact.restype = C.c_int64
@@ -236,3 +240,17 @@ class LshTree:
             self.close()
         except Exception:
             pass
+
+
+def go_acos(x: float) -> float:
+    """Go's math.Acos restated (oracle/syzgy_oracle.c orc_go_acos)."""
+    return float(lib().orc_go_acos(float(x)))
+
+
+def go_atan(x: float) -> float:
+    return float(lib().orc_go_atan(float(x)))
+
+
+def libm_acos_mode(on: bool):
+    """Switches the oracle's angular distance between Go's Acos restatement (default) and libm acos."""
+    lib().orc_libm_acos_mode(1 if on else 0)

@@ -12,7 +12,9 @@
  * plus behavioural properties (collection_test.go:283-382, 549-612).  Those are
  * checked in tests/test_oracle.py.  Everything else (codec values, angular
  * distance values, tie order, NaN handling, LSH replay) is "parity unpinned": it is
- * pinned only by this line-by-line restatement of the cited Go lines.
+ * pinned only by this line-by-line restatement of the cited Go lines.  Go's math.Acos
+ * (standard library, not under /root/reference) is restated from its published Cephes
+ * algorithm below and cross-checked against libm (tests/test_oracle.py).
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (see oracle/Makefile).
  * -ffp-contract=off mirrors Go/amd64, which never fuses x*y+z.
@@ -146,8 +148,59 @@ double orc_euclidean(const double *a, const double *b, int64_t n) {
     return sqrt(sum);
 }
 
-/* collection.go:821-832.  Go math.Acos(x>1) = NaN, as is libm acos.  libm acos may
- * differ from Go's Cephes-style Acos in the last ulp. */
+/* ---- Go's math.Acos, restated (the Go standard library is a dependency that is not under /root/reference:
+ * go 1.21 per go.mod:3, src/math/asin.go and src/math/atan.go, pure Go on amd64).  Published algorithm (Cephes):
+ *   Acos(x) = Pi/2 - Asin(x)
+ *   Asin(x): x == 0 -> x; work on |x|; |x| > 1 -> NaN; t = Sqrt(1 - x*x);
+ *            |x| > 0.7 ? Pi/2 - satan(t/|x|) : satan(|x|/t); restore the sign
+ *   satan(x): x <= 0.66 -> xatan(x); x > tan(3pi/8) -> Pi/2 - xatan(1/x) + Morebits;
+ *             else Pi/4 + xatan((x-1)/(x+1)) + 0.5*Morebits
+ *   xatan(x): z = x*x; z = z * P(z)/Q(z) (degree 4 / degree 5, coefficients below); x*z + x
+ * The coefficients are the Cephes atan.c ones, written down from memory (the Go source is not available here to diff
+ * against): tests/test_oracle.py checks the restatement against libm atan/acos over dense sweeps -- a wrong
+ * coefficient would show as an error of many ulp, the observed maximum is reported there.  orc_angular and the
+ * cosine hyperplane distance use this function, so the oracle follows the reference's arithmetic to the last
+ * library call; orc_libm_acos_mode(1) switches back to libm for comparison. */
+static double go_xatan(double x) {
+    const double P0 = -8.750608600031904122785e-01, P1 = -1.615753718733365076637e+01, P2 = -7.500855792314704667340e+01,
+                 P3 = -1.228866684490136173410e+02, P4 = -6.485021904942025371773e+01;
+    const double Q0 = +2.485846490142306297962e+01, Q1 = +1.650270098316988542046e+02, Q2 = +4.328810604912902668951e+02,
+                 Q3 = +4.853903996359136964868e+02, Q4 = +1.945506571482613964425e+02;
+    double z = x * x;
+    z = z * ((((P0 * z + P1) * z + P2) * z + P3) * z + P4) / (((((z + Q0) * z + Q1) * z + Q2) * z + Q3) * z + Q4);
+    z = x * z + x;
+    return z;
+}
+static double go_satan(double x) {
+    const double Morebits = 6.123233995736765886130e-17; /* pi/2 = PIO2 + Morebits */
+    const double Tan3pio8 = 2.41421356237309504880;      /* tan(3*pi/8) */
+    if (x <= 0.66) return go_xatan(x);
+    if (x > Tan3pio8) return M_PI / 2 - go_xatan(1 / x) + Morebits;
+    return M_PI / 4 + go_xatan((x - 1) / (x + 1)) + 0.5 * Morebits;
+}
+double orc_go_atan(double x) { /* math.Atan */
+    if (x == 0) return x;
+    if (x > 0) return go_satan(x);
+    return -go_satan(-x);
+}
+double orc_go_asin(double x) { /* math.Asin */
+    if (x == 0) return x;
+    int sign = 0;
+    if (x < 0) { x = -x; sign = 1; }
+    if (x > 1) return NAN;
+    double temp = sqrt(1 - x * x);
+    if (x > 0.7) temp = M_PI / 2 - go_satan(temp / x);
+    else temp = go_satan(x / temp);
+    if (sign) temp = -temp;
+    return temp;
+}
+double orc_go_acos(double x) { return M_PI / 2 - orc_go_asin(x); } /* math.Acos; NaN for |x| > 1 and for NaN */
+
+static int g_libm_acos = 0;
+void orc_libm_acos_mode(int on) { g_libm_acos = on; }
+static double ref_acos(double x) { return g_libm_acos ? acos(x) : orc_go_acos(x); }
+
+/* collection.go:821-832.  math.Acos(x > 1) = NaN. */
 double orc_angular(const double *a, const double *b, int64_t n) {
     double dot = 0.0, m1 = 0.0, m2 = 0.0;
     for (int64_t i = 0; i < n; i++) {
@@ -156,7 +209,7 @@ double orc_angular(const double *a, const double *b, int64_t n) {
         m2 += b[i] * b[i];
     }
     if (m1 == 0 || m2 == 0) return 1.0;
-    return acos(dot / (sqrt(m1) * sqrt(m2))) / M_PI;
+    return ref_acos(dot / (sqrt(m1) * sqrt(m2))) / M_PI;
 }
 
 double orc_distance(int metric, const double *a, const double *b, int64_t n) {
@@ -504,7 +557,7 @@ static double distance_to_hyperplane(int method, const double *v, double length,
         else dist = -dist;
         return dist;
     }
-    dist = acos(dist / length) / M_PI;
+    dist = ref_acos(dist / length) / M_PI;
     if (dist > 0.5) {
         *right = 1;
         dist = 1 - dist;

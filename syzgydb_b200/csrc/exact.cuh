@@ -11,6 +11,51 @@
 
 namespace szg {
 
+// Go's math.Acos (go 1.21 standard library, src/math/asin.go + atan.go: the Cephes algorithm, pure Go on amd64), in the
+// same operation order with un-fused IEEE operations, so that the angular distance is the reference's to the last bit
+// -- including its loss of relative accuracy for nearly parallel vectors (Acos = Pi/2 - Asin cancels; Asin takes
+// Sqrt(1 - x*x) of a rounded product).  oracle/syzgy_oracle.c carries the same restatement and tests/test_oracle.py
+// pins it against libm.
+__device__ __forceinline__ double go_xatan(double x) {
+    const double P0 = -8.750608600031904122785e-01, P1 = -1.615753718733365076637e+01, P2 = -7.500855792314704667340e+01,
+                 P3 = -1.228866684490136173410e+02, P4 = -6.485021904942025371773e+01;
+    const double Q0 = +2.485846490142306297962e+01, Q1 = +1.650270098316988542046e+02, Q2 = +4.328810604912902668951e+02,
+                 Q3 = +4.853903996359136964868e+02, Q4 = +1.945506571482613964425e+02;
+    double z = __dmul_rn(x, x);
+    double p = __dadd_rn(__dmul_rn(P0, z), P1);
+    p = __dadd_rn(__dmul_rn(p, z), P2);
+    p = __dadd_rn(__dmul_rn(p, z), P3);
+    p = __dadd_rn(__dmul_rn(p, z), P4);
+    double q = __dadd_rn(z, Q0);
+    q = __dadd_rn(__dmul_rn(q, z), Q1);
+    q = __dadd_rn(__dmul_rn(q, z), Q2);
+    q = __dadd_rn(__dmul_rn(q, z), Q3);
+    q = __dadd_rn(__dmul_rn(q, z), Q4);
+    z = __ddiv_rn(__dmul_rn(z, p), q);
+    return __dadd_rn(__dmul_rn(x, z), x);
+}
+__device__ __forceinline__ double go_satan(double x) {
+    const double Morebits = 6.123233995736765886130e-17, Tan3pio8 = 2.41421356237309504880;
+    const double Pi = 3.141592653589793;
+    if (x <= 0.66) return go_xatan(x);
+    if (x > Tan3pio8) return __dadd_rn(__dsub_rn(Pi / 2, go_xatan(__ddiv_rn(1.0, x))), Morebits);
+    return __dadd_rn(__dadd_rn(Pi / 4, go_xatan(__ddiv_rn(__dsub_rn(x, 1.0), __dadd_rn(x, 1.0)))), 0.5 * Morebits);
+}
+__device__ __forceinline__ double go_acos(double x) {
+    const double Pi = 3.141592653589793;
+    double as;
+    if (x == 0.0) as = x;
+    else {
+        const bool sign = x < 0.0;
+        const double ax = sign ? -x : x;
+        if (!(ax <= 1.0)) return __longlong_as_double(0x7ff8000000000000ll); // |x| > 1 or NaN -> NaN (collection.go:831)
+        double t = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(ax, ax)));
+        t = ax > 0.7 ? __dsub_rn(Pi / 2, go_satan(__ddiv_rn(t, ax))) : go_satan(__ddiv_rn(ax, t));
+        as = sign ? -t : t;
+    }
+    return __dsub_rn(Pi / 2, as);
+}
+
 struct ExactAcc {
     double dot, m1, m2, sum;
 };
@@ -82,7 +127,7 @@ __device__ double exact_distance_impl(const uint4 *__restrict__ codes, uint32_t 
     if (METRIC == COSINE) {
         if (s.m1 == 0.0 || s.m2 == 0.0) return 1.0; // collection.go:828-830
         double r = __ddiv_rn(s.dot, __dmul_rn(__dsqrt_rn(s.m1), __dsqrt_rn(s.m2)));
-        return __ddiv_rn(acos(r), 3.141592653589793); // acos(r > 1) = NaN, as Go math.Acos
+        return __ddiv_rn(go_acos(r), 3.141592653589793); // math.Acos(r > 1) = NaN
     }
     return __dsqrt_rn(s.sum);
 }

@@ -521,7 +521,7 @@ __device__ void exact_staged(const FinalizeArgs &a, const double *__restrict__ q
             if (acc.m1 == 0.0 || acc.m2 == 0.0) d = 1.0; // collection.go:828-830
             else {
                 const double r = __ddiv_rn(acc.dot, __dmul_rn(__dsqrt_rn(acc.m1), __dsqrt_rn(acc.m2)));
-                d = __ddiv_rn(acos(r), 3.141592653589793); // acos(r > 1) = NaN, as Go math.Acos
+                d = __ddiv_rn(go_acos(r), 3.141592653589793); // math.Acos(r > 1) = NaN
             }
         } else {
             d = __dsqrt_rn(acc.sum);

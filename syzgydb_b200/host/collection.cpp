@@ -174,6 +174,38 @@ double dotProduct(const std::vector<double> &a, const std::vector<double> &b) {
 }
 double vectorLength(const std::vector<double> &v) { return std::sqrt(dotProduct(v, v)); } // lshtree.go:30-36
 
+// Go's math.Acos (standard library, Cephes algorithm: src/math/asin.go, atan.go), restated so that the hyperplane side
+// decisions of the LSH trees follow the reference to the last bit (same restatement as oracle/syzgy_oracle.c and
+// csrc/exact.cuh; compiled with -ffp-contract=off like the rest of this file).
+static double goXatan(double x) {
+    const double P0 = -8.750608600031904122785e-01, P1 = -1.615753718733365076637e+01, P2 = -7.500855792314704667340e+01,
+                 P3 = -1.228866684490136173410e+02, P4 = -6.485021904942025371773e+01;
+    const double Q0 = +2.485846490142306297962e+01, Q1 = +1.650270098316988542046e+02, Q2 = +4.328810604912902668951e+02,
+                 Q3 = +4.853903996359136964868e+02, Q4 = +1.945506571482613964425e+02;
+    double z = x * x;
+    z = z * ((((P0 * z + P1) * z + P2) * z + P3) * z + P4) / (((((z + Q0) * z + Q1) * z + Q2) * z + Q3) * z + Q4);
+    return x * z + x;
+}
+static double goSatan(double x) {
+    const double Morebits = 6.123233995736765886130e-17, Tan3pio8 = 2.41421356237309504880;
+    if (x <= 0.66) return goXatan(x);
+    if (x > Tan3pio8) return M_PI / 2 - goXatan(1 / x) + Morebits;
+    return M_PI / 4 + goXatan((x - 1) / (x + 1)) + 0.5 * Morebits;
+}
+static double goAcos(double x) {
+    double as;
+    if (x == 0) as = x;
+    else {
+        const bool sign = x < 0;
+        const double ax = sign ? -x : x;
+        if (!(ax <= 1)) return std::nan("");
+        double t = std::sqrt(1 - ax * ax);
+        t = ax > 0.7 ? M_PI / 2 - goSatan(t / ax) : goSatan(ax / t);
+        as = sign ? -t : t;
+    }
+    return M_PI / 2 - as;
+}
+
 // lshtree.go:59-77
 void distanceToHyperplane(int method, const std::vector<double> &v, double length, const std::vector<double> &normal,
                           double b, double *dist, bool *right) {
@@ -185,7 +217,7 @@ void distanceToHyperplane(int method, const std::vector<double> &v, double lengt
         *dist = d;
         return;
     }
-    d = std::acos(d / length) / M_PI;
+    d = goAcos(d / length) / M_PI; // lshtree.go:71 math.Acos
     if (d > 0.5) { *right = true; d = 1 - d; }
     *dist = d;
 }

@@ -3,8 +3,8 @@ against the CPU oracle on the same seeded inputs and against the committed golde
 
 Bar (BASELINE.json north_star): ids and order identical to the reference scan in
 lexicographic-decimal-id order, except among results whose float64 distances are within 1e-5
-relative of each other; returned distances are the fp64 re-score (every op IEEE-exact except
-acos, compared at 1e-12 relative).
+relative of each other; returned distances are the fp64 re-score and are compared bit for bit (every
+operation IEEE-exact and in the reference's order, math.Acos restated on both sides).
 """
 import math
 
