@@ -124,8 +124,8 @@ def cpu_arm(a, seconds: float, threads: int, steps: int | None = None, warmup: i
         ok = True
         for qi in range(4):
             ri, rd, _ = o.search_exact(codes, ids, a.dims, a.quant, metric, queries[qi], k=a.k, order=order)
-            ok = ok and gi[qi, :gn[qi]].tolist() == ri.tolist() and bool(np.allclose(gd[qi, :gn[qi]], rd, rtol=1e-12, atol=0))
-        parity = "ids+distances identical on 4 queries" if ok else "MISMATCH"
+            ok = ok and gi[qi, :gn[qi]].tolist() == ri.tolist() and bool(np.array_equal(gd[qi, :gn[qi]], rd))  # bit for bit
+        parity = "ids and fp64 distances bit-identical on 4 queries" if ok else "MISMATCH"
     detail = {
         "value": qps_full, "unit": UNIT, "cores": threads, "kind": "port",
         "sample": f"{threads} concurrent queries x {len(step_times)} rounds over the first {S} rows "
