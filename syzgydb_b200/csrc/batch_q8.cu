@@ -613,22 +613,25 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 else T = score16<COS, false, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
             };
             if (P16) {
-                // high-byte accumulators in columns [0, 128), low-byte ones in [128, 256); half of the columns at a time
+                // high-byte accumulators in columns [0, 128), low-byte ones in [128, 256).  The two buffers hold ONE tile,
+                // so the MMA warp waits for this drain: all four loads go to registers first and the buffers are released
+                // before any scoring
+                uint32_t rc[32], rd[32];
                 tmem_ld_16x64(tbase, ra);
                 tmem_ld_16x64(tbase + kAccCols, rb);
+                tmem_ld_16x64(tbase + 64, rc);
+                tmem_ld_16x64(tbase + kAccCols + 64, rd);
                 load_ax(0);
                 tmem_ld_wait(ra);
                 tmem_ld_wait(rb);
-                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
-                tmem_ld_16x64(tbase + 64, ra);
-                tmem_ld_16x64(tbase + kAccCols + 64, rb);
-                load_ax(1);
-                tmem_ld_wait(ra);
-                tmem_ld_wait(rb);
+                tmem_ld_wait(rc);
+                tmem_ld_wait(rd);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[0]); // both accumulators of the tile are in registers
-                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                load_ax(1);
+                T = score16<COS, false, E, true>(rc, rd, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
             } else {
             // both halves of this warp's part of the accumulator go to registers first, so the buffer returns to the
             // MMA warp before any scoring (a warp that has rows to insert would otherwise hold it)
