@@ -470,23 +470,24 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         const uint32_t sb = smem_u32(sB);
         uint32_t t = 0;
         for (uint32_t tile = 0;; ++tile) {
-            // 8-bit: two accumulator buffers alternate; 16-bit: the two buffers hold the high-byte and the low-byte
-            // contraction of ONE tile (the epilogue drains them to registers before it scores, so the wait is short)
-            const uint32_t d = P16 ? 0u : (tile & 1u);
             bool end = false;
             for (uint32_t i = 0; i < nsl * kHalves; ++i, ++t) {
                 const uint32_t s = t % S;
                 const uint32_t half = i / nsl, sl = i % nsl;
+                // 8-bit: the two accumulator buffers alternate between tiles.  16-bit: buffer 0 takes the high-byte
+                // contraction of every tile, buffer 1 the low-byte one; the epilogue drains each to registers as soon as
+                // it completes, so the next tile's high-byte pass starts while this tile is still being scored
+                const uint32_t d = P16 ? half : (tile & 1u);
                 mbar_wait(&b_full[s], (t / S) & 1u);
-                if (i == 0) {
-                    if (*reinterpret_cast<volatile uint32_t *>(&s_first[s]) == kNoBlock) { end = true; break; }
-                    if (P16) { if (tile >= 1) mbar_wait(&d_empty[0], (tile - 1) & 1u); }
+                if (i == 0 && *reinterpret_cast<volatile uint32_t *>(&s_first[s]) == kNoBlock) { end = true; break; }
+                if (sl == 0) {
+                    if (P16) { if (tile >= 1) mbar_wait(&d_empty[d], (tile - 1) & 1u); }
                     else if (tile >= 2) mbar_wait(&d_empty[d], ((tile >> 1) - 1) & 1u);
                 }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ks0 = sl * slc / 2, ks1 = min(C / 2, ks0 + slc / 2);
                 const uint64_t db0 = umma_desc(sb + s * stage_bytes, kNB * 512u, 128);
-                const uint32_t dacc = tmem + (P16 ? half : d) * kAccCols;
+                const uint32_t dacc = tmem + d * kAccCols;
                 if (elect_one()) {
                     if (!(a.debug & 4u)) {
                         // one descriptor per stage, advanced by adding the K-step offset to its address field;
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                         }
                     }
                     umma_commit(&b_empty[s]); // the stage may be refilled once these MMAs have read it
-                    if (i == nsl * kHalves - 1) umma_commit(&d_full[d]); // accumulators complete
+                    if (sl == nsl - 1) umma_commit(&d_full[d]); // this buffer's accumulators are complete
                 }
                 __syncwarp();
             }
@@ -590,15 +591,24 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 T = qs->T;
             }
             const uint32_t capm1 = seeding ? mthm1 : Kp - 1;
-            mbar_wait(&d_full[d], (P16 ? tile : (tile >> 1)) & 1u);
+            mbar_wait(&d_full[d], (P16 ? tile : (tile >> 1)) & 1u); // 16-bit: d = 0, the high-byte buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tbase = tmem + ((lq * 32u + hh * 16u) << 16) + d * kAccCols;
             if (a.debug & 1u) { // profiling aid: drain the accumulators, skip the arithmetic
                 uint32_t ra[32];
-                for (int i = 0; i < (P16 ? 4 : 2); ++i) { tmem_ld_16x64(tbase + i * 64, ra); tmem_ld_wait(ra); }
+                for (int i = 0; i < 2; ++i) { tmem_ld_16x64(tbase + i * 64, ra); tmem_ld_wait(ra); }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&d_empty[d]); mbar_arrive(&x_empty[x]); }
+                if (lane == 0) mbar_arrive(&d_empty[d]);
+                if (P16) {
+                    mbar_wait(&d_full[1], tile & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int i = 0; i < 2; ++i) { tmem_ld_16x64(tbase + kAccCols + i * 64, ra); tmem_ld_wait(ra); }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[1]);
+                }
+                if (lane == 0) mbar_arrive(&x_empty[x]);
                 continue;
             }
             uint32_t ra[32], rb[32];
@@ -613,22 +623,26 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 else T = score16<COS, false, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
             };
             if (P16) {
-                // high-byte accumulators in columns [0, 128), low-byte ones in [128, 256).  The two buffers hold ONE tile,
-                // so the MMA warp waits for this drain: all four loads go to registers first and the buffers are released
-                // before any scoring
+                // high-byte accumulators in buffer 0, low-byte ones in buffer 1: each is drained to registers and released
+                // as soon as it completes, the scoring follows
                 uint32_t rc[32], rd[32];
                 tmem_ld_16x64(tbase, ra);
-                tmem_ld_16x64(tbase + kAccCols, rb);
                 tmem_ld_16x64(tbase + 64, rc);
-                tmem_ld_16x64(tbase + kAccCols + 64, rd);
                 load_ax(0);
                 tmem_ld_wait(ra);
-                tmem_ld_wait(rb);
                 tmem_ld_wait(rc);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[0]); // high-byte accumulators are in registers
+                mbar_wait(&d_full[1], tile & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld_16x64(tbase + kAccCols, rb);
+                tmem_ld_16x64(tbase + kAccCols + 64, rd);
+                tmem_ld_wait(rb);
                 tmem_ld_wait(rd);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[0]); // both accumulators of the tile are in registers
+                if (lane == 0) mbar_arrive(&d_empty[1]); // low-byte accumulators too
                 T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
                 load_ax(1);
                 T = score16<COS, false, E, true>(rc, rd, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
