@@ -777,3 +777,26 @@ def test_batch_4bit_matches_oracle(metric, dims, n, nq, k):
                                  f"batch4 m{metric} d{dims} k{k} q{qi}")
         si, sd, sn, _ = ix.search_topk(queries, k)
         assert np.array_equal(gn, sn) and np.array_equal(gi, si) and np.array_equal(gd, sd)
+
+
+@pytest.mark.parametrize("bits", [4, 8, 16])
+def test_batch_tiny_and_emptied_collections(bits):
+    """Fewer rows than one 128-row tile, k larger than the collection, everything removed, nothing ever added."""
+    dims, nq = 32, 5
+    queries = o.synth_queries(71, 0, nq, dims)
+    for n in (1, 5, 127, 129):
+        codes = o.synth_rows(70 + n, 0, n, dims, bits)
+        ids = np.arange(n, dtype=np.uint64) + 100
+        with _build(codes, ids, dims, bits, szg.EUCLIDEAN) as ix:
+            gi, gd, gn, scanned = ix.search_batch(queries, 10)
+            assert scanned == n and np.all(gn == min(n, 10))
+            for qi in range(nq):
+                ri, rd, _ = o.search_exact(codes, ids, dims, bits, szg.EUCLIDEAN, queries[qi], k=10)
+                assert_results_match(gi[qi, :gn[qi]], gd[qi, :gn[qi]], ri, rd, None, f"tiny b{bits} n{n} q{qi}")
+            if n == 129:
+                ix.remove(ids)                       # emptied: K > N_pass returns nothing, PercentSearched 0 (collection.go:706-709)
+                gi, gd, gn, scanned = ix.search_batch(queries, 10)
+                assert scanned == 0 and np.all(gn == 0)
+    with szg.Index(dims, bits, szg.COSINE) as ix:   # never filled
+        gi, gd, gn, scanned = ix.search_batch(queries, 3)
+        assert scanned == 0 and np.all(gn == 0)
