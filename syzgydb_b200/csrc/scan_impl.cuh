@@ -649,7 +649,7 @@ struct RingMeta {
 // (query, block) pair is still streamed from HBM once: single-query GEMV semantics.  The
 // prepared query (digits) is read through L1 (warp-uniform 128-bit loads): a few KB per
 // query, resident next to the streaming traffic, which bypasses L1 via the bulk copies.
-template <int QT, int MODE, int ND>
+template <int QT, int MODE, int ND, bool SHARE = false>
 __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanArgs a) {
     constexpr int E = (MODE == MODE_RADIUS) ? 1 : (1 << MODE);
     constexpr int Kp = 32 * E;
@@ -664,13 +664,25 @@ __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanA
         for (uint32_t s = 0; s < S; ++s) mbar_init(&s_bar[warp][s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    // CTA-shared bound of short scans (see the use below): (query << 32 | key of the warp's mth-best row), 4 query slots
+    __shared__ unsigned long long s_pub[SHARE ? 4 : 1][kMaxScanWarps];
+    if (SHARE) {
+        if (lane < 4) s_pub[lane][warp] = ~0ull;
+        __syncthreads();
+    }
 
     // ---- streaming: this warp's blocks are gw, gw + stride, ...; tiles of Ct chunks
     const uint32_t stride = gridDim.x * nwarps;
     const uint32_t gw = blockIdx.x * nwarps + warp;
     const uint32_t T = (C + Ct - 1) / Ct;
     const uint32_t stage_bytes = Ct * 512u;
+    // When a warp sees only a few dozen blocks per query, most of its selection work is the warm-up of its own list
+    // (every one of the grid's lists starts empty: measured 35 % of the instructions at 13 blocks per warp, cfg2).
+    // The warps of a CTA then share a bound: each publishes the key of its mth-best row so far, mth = ceil(Kp / warps);
+    // once all have, warps * mth >= Kp rows of this CTA lie at or below the largest published key, so no row above it
+    // can be among the query's best Kp.  Warps move from query to query independently: entries carry the query index.
+    const uint32_t mth = ((uint32_t)Kp + (uint32_t)nwarps - 1) / (uint32_t)nwarps;
+    constexpr bool share_bound = SHARE; // a separate instantiation: the long-scan kernel keeps its code and registers
     unsigned char *ring = smem + (size_t)warp * S * stage_bytes;
     RingMeta &meta = s_meta[warp];
     uint64_t *bars = s_bar[warp];
@@ -775,7 +787,21 @@ __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanA
                     }
                 }
             } else {
+                if (share_bound) {
+                    const unsigned long long e = lane < nwarps ? s_pub[cq & 3u][lane] : ((unsigned long long)cq << 32);
+                    if (__all_sync(0xffffffffu, (uint32_t)(e >> 32) == cq)) {
+                        const unsigned long long b = ((unsigned long long)__reduce_max_sync(0xffffffffu, (uint32_t)e) << 32) | 0xFFFFFFFFull;
+                        if (b < list.thr) list.thr = b; // keys equal to the bound still pass
+                    }
+                }
                 list.offer(ok ? make_key64(key, slot) : kNoKey, lane);
+                if (share_bound && (uint32_t)lane == (mth - 1) / E) {
+                    unsigned long long mv = list.v[0];
+#pragma unroll
+                    for (int e2 = 1; e2 < E; ++e2)
+                        if ((mth - 1) % E == (uint32_t)e2) mv = list.v[e2];
+                    if (mv != kNoKey) s_pub[cq & 3u][warp] = ((unsigned long long)cq << 32) | (mv >> 32);
+                }
             }
         }
         __syncwarp(); // every lane is done reading stage cs (and its meta) before it is refilled
@@ -820,7 +846,11 @@ inline bool scan_plan(uint32_t C, uint32_t warps, uint32_t stages, uint32_t max_
 template <int QT, int ND>
 cudaError_t launch_scan_nd(int mode, int grid, int threads, size_t smem, cudaStream_t st, const ScanArgs &a) {
     switch (mode) {
-    case 0: scan_kernel<QT, 0, ND><<<grid, threads, smem, st>>>(a); break;
+    case 0:
+        // short per-warp streams (< 96 blocks per warp and query): the variant with the CTA-shared bound
+        if (a.nblk / ((uint32_t)grid * (uint32_t)(threads / 32)) < 96) scan_kernel<QT, 0, ND, true><<<grid, threads, smem, st>>>(a);
+        else scan_kernel<QT, 0, ND><<<grid, threads, smem, st>>>(a);
+        break;
     case 1: scan_kernel<QT, 1, ND><<<grid, threads, smem, st>>>(a); break;
     case 2: scan_kernel<QT, 2, ND><<<grid, threads, smem, st>>>(a); break;
     case 3: scan_kernel<QT, 3, ND><<<grid, threads, smem, st>>>(a); break;
@@ -860,6 +890,15 @@ cudaError_t scan_attr_t(size_t max_smem) {
 #define SZG_ATTR(M)                                                                                              \
     e = cudaFuncSetAttribute(scan_kernel<QT, M, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem); \
     if (e != cudaSuccess) return e;                                                                              \
+    if (M == 0) {                                                                                                \
+        e = cudaFuncSetAttribute(scan_kernel<QT, 0, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem); \
+        if (e != cudaSuccess) return e;                                                                          \
+        if (QT <= Q16) {                                                                                         \
+            e = cudaFuncSetAttribute(scan_kernel<QT, 0, (QT <= Q16 ? 2 : 3), true>,                              \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);                \
+            if (e != cudaSuccess) return e;                                                                      \
+        }                                                                                                        \
+    }                                                                                                            \
     if (QT <= Q16) {                                                                                             \
         e = cudaFuncSetAttribute(scan_kernel<QT, M, (QT <= Q16 ? 2 : 3)>,                                        \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);                    \
