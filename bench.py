@@ -116,6 +116,10 @@ def cpu_arm(a, seconds: float, threads: int, steps: int | None = None, warmup: i
     qps_full = qps_sample * S / a.rows
     # the faithful variant (per-record allocation like decodeVector's make([]float64)), one round
     _, tf = one_round(faithful=True)
+    # one core = what a single Search call costs in the reference (one goroutine per query)
+    t1 = time.perf_counter()
+    o.search_exact(codes, ids, a.dims, a.quant, metric, queries[0], k=a.k, order=order)
+    one_core_qps = 1.0 / (time.perf_counter() - t1) * S / a.rows
     parity = None
     if gpu_check is not None:  # the oracle as checker: the GPU scan of the same sample returns the same neighbours
         with gpu_check.Index(a.dims, a.quant, metric) as ix:
@@ -134,6 +138,7 @@ def cpu_arm(a, seconds: float, threads: int, steps: int | None = None, warmup: i
                   f"parse/CRC/alloc); QPS scaled by {S}/{a.rows} rows",
         "qps_on_sample": qps_sample,
         "faithful_alloc_variant_qps": threads / tf * S / a.rows,
+        "one_core_qps": one_core_qps,
         "gpu_parity_on_sample": parity,
         "ms_per_step": 1e3 * sum(step_times) / len(step_times),
     }
@@ -392,7 +397,7 @@ def run_b200(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         _, cpu = cpu_arm(a, a.cpu_seconds, os.cpu_count() or 1, gpu_check=szg)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "faithful_alloc_variant_qps",
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "faithful_alloc_variant_qps", "one_core_qps",
                                    "gpu_parity_on_sample")}
 
     if rank == 0:
