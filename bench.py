@@ -57,11 +57,27 @@ def parse():
     ap.add_argument("--batch-nq", type=int, default=1024,
                     help="queries of the secondary, batched (tensor-core) measurement; 0 = skip")
     ap.add_argument("--batch-steps", type=int, default=4)
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "gaussian"],
+                    help="uniform: codes uniform over the code range (device-generated, the headline); gaussian: L2-normalised "
+                         "Gaussian rows and queries through the reference's quantize (all-MiniLM-like: only ~+-14 codes around "
+                         "128 are used at d = 768), host-generated and uploaded; 8-bit, one GPU")
     return ap.parse_args()
 
 
 def workload_name(a):
     return f"{a.rows}x{a.dims} {a.quant}-bit {a.metric} exact k={a.k} (BASELINE.json configs[3])"
+
+
+def gaussian_codes(seed, row0, nrows, dims):
+    """Rows ~ N(0, I) L2-normalised, then quantize(v, 8) = round-half-away((v + 1) / 2 * 255) (quantization.go:5-23),
+    vectorised; the same function feeds the GPU mirror and the CPU arm, so both see identical bytes."""
+    import numpy as np
+    v = np.random.default_rng([seed, row0]).standard_normal((nrows, dims))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    x = (np.clip(v, -1.0, 1.0) + 1.0) / 2.0 * 255.0
+    r = np.floor(x)
+    r += (x - r) >= 0.5
+    return r.astype(np.uint8)
 
 
 def rowbytes(quant, dims):
@@ -79,10 +95,14 @@ def cpu_arm(a, seconds: float, threads: int, steps: int | None = None, warmup: i
     from oracle import pyoracle as o
     metric = o.COSINE if a.metric == "cosine" else o.EUCLIDEAN
     S = min(a.cpu_sample_rows, a.rows)
-    codes = o.synth_rows(SEED, 0, S, a.dims, a.quant)
+    gauss = getattr(a, "dist", "uniform") == "gaussian"
+    codes = gaussian_codes(SEED, 0, S, a.dims) if gauss else o.synth_rows(SEED, 0, S, a.dims, a.quant)
     ids = np.arange(S, dtype=np.uint64)
     order = np.arange(S, dtype=np.int64)  # ids == row index: lexicographic order precomputed once is not timed
     queries = o.synth_queries(SEED + 1, 0, max(64, threads), a.dims)
+    if gauss:
+        queries = np.random.default_rng(SEED + 1).standard_normal(queries.shape)
+        queries /= np.linalg.norm(queries, axis=1, keepdims=True)
     o.search_exact(codes[:1000], ids[:1000], a.dims, a.quant, metric, queries[0], k=a.k, order=order[:1000])
 
     def one_round(faithful=False):
@@ -123,7 +143,10 @@ def cpu_arm(a, seconds: float, threads: int, steps: int | None = None, warmup: i
     parity = None
     if gpu_check is not None:  # the oracle as checker: the GPU scan of the same sample returns the same neighbours
         with gpu_check.Index(a.dims, a.quant, metric) as ix:
-            ix.fill_synthetic(SEED, 0, S)
+            if gauss:
+                ix.upsert(ids, codes)
+            else:
+                ix.fill_synthetic(SEED, 0, S)
             gi, gd, gn, _ = ix.search_topk(queries[:4], a.k)
         ok = True
         for qi in range(4):
@@ -244,7 +267,17 @@ def run_b200(a):
 
     metric = szg.COSINE if a.metric == "cosine" else szg.EUCLIDEAN
     sh = ShardedIndex(a.dims, a.quant, metric, rank, world, local)
-    r0, r1 = sh.fill_synthetic(SEED, a.rows)
+    if a.dist == "gaussian":
+        if world != 1 or a.quant != 8:
+            raise SystemExit("bench.py --dist gaussian: 8-bit, one GPU")
+        r0, r1, chunk = 0, a.rows, 250_000  # chunk 0 is exactly the CPU arm's sample
+        sh.shard.index.reserve(a.rows)
+        for c0 in range(0, a.rows, chunk):
+            n = min(chunk, a.rows - c0)
+            sh.shard.index.upsert(np.arange(c0, c0 + n, dtype=np.uint64), gaussian_codes(SEED, c0, n, a.dims))
+        sh.total_rows = a.rows
+    else:
+        r0, r1 = sh.fill_synthetic(SEED, a.rows)
     my_rows = r1 - r0
     ix = sh.shard.index
     ix.set_option(_capi.OPT_TIMING, 2)
@@ -253,6 +286,9 @@ def run_b200(a):
     # distinct queries every step, uniform(-1,1)^d, never copied from the rows (same on every rank)
     total_steps = a.warmup + a.steps
     hq = np.random.default_rng(SEED + 1).uniform(-1.0, 1.0, size=(total_steps, a.nq, a.dims))
+    if a.dist == "gaussian":
+        hq = np.random.default_rng(SEED + 1).standard_normal((total_steps, a.nq, a.dims))
+        hq /= np.linalg.norm(hq, axis=2, keepdims=True)
     dq = torch.from_numpy(hq).to(dev)
     hq_pinned = torch.from_numpy(hq).pin_memory()
 
@@ -334,6 +370,9 @@ def run_b200(a):
     batched = None
     if a.batch_nq > 0 and a.quant in (8, 16):
         bq_h = np.random.default_rng(SEED + 2).uniform(-1.0, 1.0, size=(a.batch_nq, a.dims))
+        if a.dist == "gaussian":
+            bq_h = np.random.default_rng(SEED + 2).standard_normal((a.batch_nq, a.dims))
+            bq_h /= np.linalg.norm(bq_h, axis=1, keepdims=True)
         bq = torch.from_numpy(bq_h).to(dev)
         for _ in range(3):
             outb = sh.search_topk_dev(bq, a.k, batched=True)
@@ -404,7 +443,8 @@ def run_b200(a):
         line = {
             "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8" if a.quant == 8 else f"q{a.quant}", "data": "synthetic",
+            "dtype": "u8" if a.quant == 8 else f"q{a.quant}",
+            "data": "synthetic" if a.dist == "uniform" else "synthetic (L2-normalised Gaussian rows through the reference's quantize)",
             "config": {"workload": workload_name(a), "rows": a.rows, "dims": a.dims, "quantization": a.quant,
                        "distance": a.metric, "k": a.k, "queries_per_step": a.nq, "rows_per_gpu": my_rows,
                        "parallelism": f"row-sharded x{world}, one all-gather + merge per step",
