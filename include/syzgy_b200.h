@@ -84,6 +84,19 @@ int szg_reserve(szg_index *h, uint64_t nrows);
  */
 int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t n);
 
+/*
+ * Ingest-side quantization: encodes n float64 vectors (n * dim values, host memory) on
+ * the device exactly as encodeDocument does (collection.go:713-744) with quantize (quantization.go:5-23: clamp to
+ * [-1, 1], (v + 1) / 2 * (2^b - 1) in that operation order, math.Round = half away from zero; 32-bit =
+ * Float32bits(float32(v)), 64-bit = Float64bits(v); 4-bit pairs with the even element in the high nibble,
+ * 16/32/64-bit big-endian).  out_codes (optional, n * rowbytes bytes, caller-allocated) receives the stream-1
+ * bytes the caller hands to WriteRecord (collection.go:446-453); upsert != 0 also puts the rows into the mirror
+ * under ids[i], like szg_upsert.  Replaces the per-element Go loop of encodeDocument in AddDocument (427-457) for
+ * bulk ingest.  A NaN element of a 4/8/16-bit collection encodes as code 0 (what Go/amd64's uint64(NaN) leaves in
+ * the low bits); NaN payloads of 32-bit collections are not preserved.
+ */
+int szg_encode(szg_index *h, const uint64_t *ids, const double *vectors, uint64_t n, uint8_t *out_codes, int upsert);
+
 /* Replaces: removeDocument (collection.go:511-521).  *n_removed (optional) = ids that existed. */
 int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_removed);
 

@@ -31,7 +31,7 @@ OPT_BATCH_TENSOR = 8
 
 # every symbol include/syzgy_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "szg_last_error", "szg_create", "szg_destroy", "szg_reserve", "szg_upsert", "szg_remove", "szg_count",
+    "szg_last_error", "szg_create", "szg_destroy", "szg_reserve", "szg_upsert", "szg_encode", "szg_remove", "szg_count",
     "szg_mask_create", "szg_mask_destroy", "szg_search_topk", "szg_search_batch", "szg_search_radius", "szg_result_count",
     "szg_result_fetch", "szg_result_free", "szg_rescore", "szg_search_topk_dev", "szg_search_batch_dev", "szg_merge_topk_dev",
     "szg_fill_synthetic", "szg_fetch_codes", "szg_get_stats", "szg_set_option", "szg_last_scan_times_ms",
@@ -86,6 +86,7 @@ def load():
     L.szg_destroy.argtypes = [vp]
     L.szg_reserve.argtypes = [vp, C.c_uint64]
     L.szg_upsert.argtypes = [vp, u64p, u8p, C.c_uint64]
+    L.szg_encode.argtypes = [vp, u64p, f64p, C.c_uint64, u8p, C.c_int]
     L.szg_remove.argtypes = [vp, u64p, C.c_uint64, u64p]
     L.szg_count.argtypes = [vp, u64p]
     L.szg_mask_create.argtypes = [vp, u64p, u8p, C.c_uint64, C.POINTER(C.c_int)]
@@ -172,6 +173,20 @@ class Index:
         if codes.size != ids.size * self.rowbytes:
             raise ValueError(f"codes must hold {ids.size} x {self.rowbytes} bytes")
         _check(self._L.szg_upsert(self._h, _p(ids, C.c_uint64), _p(codes, C.c_uint8), ids.size))
+
+    def encode(self, vectors, ids=None, upsert: bool = False) -> np.ndarray:
+        """encodeDocument on the device (szg_encode): float64 vectors -> stream-1 bytes; upsert=True also mirrors
+        them under `ids`."""
+        v = np.ascontiguousarray(vectors, dtype=np.float64).reshape(-1, self.dim)
+        out = np.zeros((v.shape[0], self.rowbytes), dtype=np.uint8)
+        idp = None
+        if upsert:
+            ids = np.ascontiguousarray(ids, dtype=np.uint64)
+            if ids.size != v.shape[0]:
+                raise ValueError("one id per vector")
+            idp = _p(ids, C.c_uint64)
+        _check(self._L.szg_encode(self._h, idp, _p(v, C.c_double), v.shape[0], _p(out, C.c_uint8), 1 if upsert else 0))
+        return out
 
     def remove(self, ids) -> int:
         ids = np.ascontiguousarray(ids, dtype=np.uint64)

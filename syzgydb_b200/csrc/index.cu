@@ -162,6 +162,7 @@ struct szg_index {
     // staging for mutations
     PinBuf<unsigned char> h_stage;
     DevBuf<unsigned char> d_stage;
+    DevBuf<double> d_vec; // float64 vectors of an szg_encode batch
     PinBuf<uint32_t> h_slots;
     DevBuf<uint32_t> d_slots;
     PinBuf<unsigned long long> h_ids;
@@ -535,7 +536,7 @@ int szg_destroy(szg_index *h) {
     for (auto &kv : h->dev_ws) { kv.second->destroy(); delete kv.second; }
     for (auto &m : h->masks) cudaFree(m.second);
     h->codes.release(); h->ids.release(); h->aux.release(); h->live.release(); h->lut.release(); h->planar.release();
-    h->h_stage.release(); h->d_stage.release(); h->h_slots.release(); h->d_slots.release();
+    h->h_stage.release(); h->d_stage.release(); h->d_vec.release(); h->h_slots.release(); h->d_slots.release();
     h->h_ids.release(); h->d_ids_in.release();
     if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
     delete h;
@@ -592,11 +593,14 @@ int szg_count(szg_index *h, uint64_t *n) {
     return SZG_OK;
 }
 
-int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t n) {
-    GUARD(h);
-    if (n && (!ids || !codes)) return fail(SZG_EINVAL, "null ids/codes");
-    h->planar_dirty = true;
-    const uint64_t per = std::max<uint64_t>(1, kStageBytes / h->rowbytes);
+// One staged batch of rows into the mirror: slot assignment on the host, then scatter + aux on the device.  The
+// stream-1 bytes come either from the caller (codes) or from encode_kernel over the caller's float64 vectors, in
+// which case they are also handed back (out_codes) for the span file.
+static int upsert_rows(szg_index *h, const uint64_t *ids, const uint8_t *codes, const double *vectors, uint8_t *out_codes,
+                       uint64_t n, bool into_mirror) {
+    if (into_mirror) h->planar_dirty = true;
+    uint64_t per = std::max<uint64_t>(1, kStageBytes / h->rowbytes);
+    if (vectors) per = std::max<uint64_t>(1, std::min<uint64_t>(per, kStageBytes / ((uint64_t)h->dim * sizeof(double))));
     int rc;
     for (uint64_t off = 0; off < n; off += per) {
         const uint32_t m = (uint32_t)std::min<uint64_t>(per, n - off);
@@ -604,40 +608,67 @@ int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t
             (rc = h->d_ids_in.ensure(m)) || (rc = h->h_stage.ensure((size_t)m * h->rowbytes)) ||
             (rc = h->d_stage.ensure((size_t)m * h->rowbytes)))
             return rc;
-        // slot assignment.  A batch may name an id twice: the last one wins, like two
-        // AddDocument calls in a row; earlier duplicates are skipped (slot 0xFFFFFFFF).
-        if ((rc = grow(h, (uint64_t)h->nslots + m))) return rc;
-        std::unordered_map<uint64_t, uint32_t> last_in_batch;
-        last_in_batch.reserve(m);
-        for (uint32_t i = 0; i < m; ++i) last_in_batch[ids[off + i]] = i;
-        for (uint32_t i = 0; i < m; ++i) {
-            const uint64_t id = ids[off + i];
-            uint32_t slot = 0xFFFFFFFFu;
-            if (last_in_batch[id] == i && !h->lookup(id, &slot)) {
-                if (!h->free_slots.empty()) {
-                    slot = h->free_slots.back();
-                    h->free_slots.pop_back();
-                } else {
-                    slot = h->nslots++;
-                }
-                h->map[id] = slot; // shadows a (dead) synthetic-range entry of the same id
-                h->live_rows++;
-            }
-            h->h_slots.p[i] = slot;
-            h->h_ids.p[i] = id;
-        }
-        memcpy(h->h_stage.p, codes + off * h->rowbytes, (size_t)m * h->rowbytes);
+        if (vectors && (rc = h->d_vec.ensure((size_t)m * h->dim))) return rc;
         cudaStream_t st = h->mut_stream;
-        CK(cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, (size_t)m * h->rowbytes, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(h->d_ids_in.p, h->h_ids.p, (size_t)m * 8, cudaMemcpyHostToDevice, st));
         RowsArgs ra = h->rows_args();
-        CK(launch_scatter(ra, h->d_stage.p, h->d_slots.p, h->d_ids_in.p, m, st));
-        CK(launch_aux(ra, h->d_slots.p, 0, m, st));
-        h->launches += 2;
+        if (vectors) {
+            CK(cudaMemcpyAsync(h->d_vec.p, vectors + off * (uint64_t)h->dim, (size_t)m * h->dim * sizeof(double),
+                               cudaMemcpyHostToDevice, st));
+            CK(launch_encode(ra, h->d_vec.p, h->d_stage.p, m, st));
+            h->launches += 1;
+            if (out_codes)
+                CK(cudaMemcpyAsync(out_codes + off * h->rowbytes, h->d_stage.p, (size_t)m * h->rowbytes, cudaMemcpyDeviceToHost, st));
+        } else {
+            memcpy(h->h_stage.p, codes + off * h->rowbytes, (size_t)m * h->rowbytes);
+            CK(cudaMemcpyAsync(h->d_stage.p, h->h_stage.p, (size_t)m * h->rowbytes, cudaMemcpyHostToDevice, st));
+        }
+        if (into_mirror) {
+            // slot assignment.  A batch may name an id twice: the last one wins, like two
+            // AddDocument calls in a row; earlier duplicates are skipped (slot 0xFFFFFFFF).
+            if ((rc = grow(h, (uint64_t)h->nslots + m))) return rc;
+            std::unordered_map<uint64_t, uint32_t> last_in_batch;
+            last_in_batch.reserve(m);
+            for (uint32_t i = 0; i < m; ++i) last_in_batch[ids[off + i]] = i;
+            for (uint32_t i = 0; i < m; ++i) {
+                const uint64_t id = ids[off + i];
+                uint32_t slot = 0xFFFFFFFFu;
+                if (last_in_batch[id] == i && !h->lookup(id, &slot)) {
+                    if (!h->free_slots.empty()) {
+                        slot = h->free_slots.back();
+                        h->free_slots.pop_back();
+                    } else {
+                        slot = h->nslots++;
+                    }
+                    h->map[id] = slot; // shadows a (dead) synthetic-range entry of the same id
+                    h->live_rows++;
+                }
+                h->h_slots.p[i] = slot;
+                h->h_ids.p[i] = id;
+            }
+            ra = h->rows_args(); // grow() may have moved the arrays
+            CK(cudaMemcpyAsync(h->d_slots.p, h->h_slots.p, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(h->d_ids_in.p, h->h_ids.p, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+            CK(launch_scatter(ra, h->d_stage.p, h->d_slots.p, h->d_ids_in.p, m, st));
+            CK(launch_aux(ra, h->d_slots.p, 0, m, st));
+            h->launches += 2;
+        }
         CK(cudaStreamSynchronize(st));
     }
     return SZG_OK;
+}
+
+int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t n) {
+    GUARD(h);
+    if (n && (!ids || !codes)) return fail(SZG_EINVAL, "null ids/codes");
+    return upsert_rows(h, ids, codes, nullptr, nullptr, n, true);
+}
+
+int szg_encode(szg_index *h, const uint64_t *ids, const double *vectors, uint64_t n, uint8_t *out_codes, int upsert) {
+    GUARD(h);
+    if (n && !vectors) return fail(SZG_EINVAL, "null vectors");
+    if (n && upsert && !ids) return fail(SZG_EINVAL, "null ids");
+    if (!upsert && !out_codes) return fail(SZG_EINVAL, "nothing to do: no output buffer and no upsert");
+    return upsert_rows(h, ids, nullptr, vectors, out_codes, n, upsert != 0);
 }
 
 int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_removed) {

@@ -346,6 +346,83 @@ cudaError_t launch_fetch(const RowsArgs &a, const uint32_t *slots, uint32_t n, u
     return cudaGetLastError();
 }
 
+// ============================================================ ingest: encodeDocument on the device
+// quantization.go:5-23: clamp to [-1, 1], (value + 1) / 2 * maxInt in that operation order, math.Round (half away from
+// zero = round()), conversion to an unsigned integer (NaN converts to 0 here; Go/amd64 gives 1 << 63, whose low
+// 4/8/16 bits -- all the reference keeps -- are 0 as well).
+__device__ __forceinline__ uint32_t quantize_code(double v, double maxint) {
+    if (v < -1.0) v = -1.0;
+    else if (v > 1.0) v = 1.0;
+    const double q = __dmul_rn(__ddiv_rn(__dadd_rn(v, 1.0), 2.0), maxint);
+    return (uint32_t)(unsigned long long)round(q);
+}
+
+// thread per (document, 16-byte chunk of its stream-1 row): n vectors of float64 -> the bytes encodeDocument
+// (collection.go:713-744) produces: 4-bit pairs (even element in the high nibble), bytes, big-endian 16/32/64-bit words
+__global__ void encode_kernel(const RowsArgs a, const double *__restrict__ vec, unsigned char *__restrict__ staged, uint32_t n) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t row = (uint32_t)(t / a.C), c = (uint32_t)(t % a.C);
+    if (row >= n) return;
+    const double *v = vec + (size_t)row * a.dims;
+    const double mx = (double)a.maxint;
+    __align__(16) unsigned char b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) b[i] = 0;
+    if (a.qt == Q4) {
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t e = (c * 16 + i) * 2;
+            uint32_t hi = 0, lo = 0;
+            if (e < a.dims) hi = quantize_code(v[e], mx);
+            if (e + 1 < a.dims) lo = quantize_code(v[e + 1], mx);
+            b[i] = (unsigned char)((hi << 4) | (lo & 0x0Fu));
+        }
+    } else if (a.qt == Q8) {
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t e = c * 16 + i;
+            if (e < a.dims) b[i] = (unsigned char)quantize_code(v[e], mx);
+        }
+    } else if (a.qt == Q16) {
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t e = c * 8 + i;
+            if (e < a.dims) {
+                const uint32_t q = quantize_code(v[e], mx);
+                b[2 * i] = (unsigned char)(q >> 8);
+                b[2 * i + 1] = (unsigned char)q;
+            }
+        }
+    } else if (a.qt == F32) {
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t e = c * 4 + i;
+            if (e < a.dims) {
+                const uint32_t q = __float_as_uint(__double2float_rn(v[e])); // math.Float32bits(float32(value))
+                for (int k = 0; k < 4; ++k) b[4 * i + k] = (unsigned char)(q >> (24 - 8 * k));
+            }
+        }
+    } else {
+        for (int i = 0; i < 2; ++i) {
+            const uint32_t e = c * 2 + i;
+            if (e < a.dims) {
+                const unsigned long long q = (unsigned long long)__double_as_longlong(v[e]);
+                for (int k = 0; k < 8; ++k) b[8 * i + k] = (unsigned char)(q >> (56 - 8 * k));
+            }
+        }
+    }
+    unsigned char *dst = staged + (size_t)row * a.rowbytes + (size_t)c * 16;
+    const uint32_t remain = a.rowbytes - c * 16;
+    if (remain >= 16 && (((size_t)row * a.rowbytes) & 15u) == 0) {
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(b);
+    } else {
+        for (uint32_t i = 0; i < 16 && i < remain; ++i) dst[i] = b[i];
+    }
+}
+
+cudaError_t launch_encode(const RowsArgs &a, const double *vec, unsigned char *staged, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const size_t total = (size_t)n * a.C;
+    encode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, vec, staged, n);
+    return cudaGetLastError();
+}
+
 // ============================================================ K3: gather + fp64 re-score
 // thread per candidate, visit order preserved; replaces decodeVector + distance inside
 // `consider` (collection.go:584-596) for the ids an index (lshtree.go:316-335) or the

@@ -49,6 +49,9 @@ cudaError_t launch_mask_set(uint32_t *mask, const uint32_t *slots, const unsigne
 // records back to stream-1 bytes
 cudaError_t launch_fetch(const RowsArgs &a, const uint32_t *slots, uint32_t n, unsigned char *out, cudaStream_t st);
 
+// ingest: n float64 vectors -> stream-1 bytes (encodeDocument, collection.go:713-744 + quantize, quantization.go:5-23)
+cudaError_t launch_encode(const RowsArgs &a, const double *vec, unsigned char *staged, uint32_t n, cudaStream_t st);
+
 struct RescoreArgs {
     const uint4 *codes;
     const unsigned long long *ids;

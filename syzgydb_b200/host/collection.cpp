@@ -467,15 +467,20 @@ void Collection::AddDocuments(const std::vector<uint64_t> &ids, const std::vecto
     std::unique_lock<std::shared_mutex> lk(p_->mu);
     if (ids.size() != vectors.size() || (!metadata.empty() && metadata.size() != ids.size()))
         throw std::invalid_argument("ids, vectors and metadata must have the same length");
-    std::vector<uint8_t> all((size_t)p_->rowbytes * ids.size());
+    // bulk ingest: encodeDocument runs on the device (szg_encode); the bytes come back for the record store
+    const size_t d = (size_t)p_->opt.DimensionCount;
+    std::vector<double> flat(d * ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
-        if ((int)vectors[i].size() != p_->opt.DimensionCount)
+        if (vectors[i].size() != d)
             throw std::invalid_argument("vector size does not match the expected number of dimensions");
-        Impl::Rec rec{metadata.empty() ? std::string() : metadata[i], encodeDocument(vectors[i], p_->opt.Quantization)};
-        std::memcpy(all.data() + i * (size_t)p_->rowbytes, rec.codes.data(), (size_t)p_->rowbytes);
-        p_->store[ids[i]] = std::move(rec);
+        std::memcpy(flat.data() + i * d, vectors[i].data(), d * sizeof(double));
     }
-    GPU(szg_upsert(p_->gpu, ids.data(), all.data(), ids.size()), "upsert");
+    std::vector<uint8_t> all((size_t)p_->rowbytes * ids.size());
+    GPU(szg_encode(p_->gpu, ids.data(), flat.data(), ids.size(), all.data(), 1), "encode");
+    for (size_t i = 0; i < ids.size(); ++i) {
+        const uint8_t *row = all.data() + i * (size_t)p_->rowbytes;
+        p_->store[ids[i]] = Impl::Rec{metadata.empty() ? std::string() : metadata[i], std::vector<uint8_t>(row, row + p_->rowbytes)};
+    }
     for (size_t i = 0; i < ids.size(); ++i) p_->addPoint(ids[i], vectors[i]);
 }
 

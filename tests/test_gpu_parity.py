@@ -213,6 +213,50 @@ def test_mirror_roundtrip_and_synthetic_generator(bits):
                               o.synth_rows(21, 1000, 50, dims, bits))
 
 
+@pytest.mark.parametrize("bits", [4, 8, 16, 32, 64])
+@pytest.mark.parametrize("dims", [1, 7, 37, 384])
+def test_device_encode_is_encodeDocument(bits, dims):
+    # szg_encode = encodeDocument (collection.go:713-744) + quantize (quantization.go:5-23) on the device: byte-identical
+    # to the oracle's restatement, including the clamp, the exact .5 ties of math.Round and odd 4-bit tails
+    rng = np.random.default_rng(100 + bits + dims)
+    n = 257
+    x = rng.uniform(-1.3, 1.3, size=(n, dims))
+    if bits <= 16:  # values whose scaled image is an exact half (ties round away from zero), and the a7 check values
+        M = (1 << bits) - 1
+        ties = (np.arange(n * dims) % (M + 1) + 0.5) / M * 2 - 1
+        x[::3] = ties.reshape(n, dims)[::3]
+        kat = np.array([-1.5, -1, -.5, 0, .1, .5, 1, 2])
+        x[1, :min(dims, 8)] = kat[:min(dims, 8)]
+    want = o.encode_rows(x, bits)
+    ids = np.arange(n, dtype=np.uint64) * 3 + 1
+    with szg.Index(dims, bits, szg.EUCLIDEAN) as ix:
+        got = ix.encode(x)
+        assert ix.count() == 0  # encode only
+        assert np.array_equal(got, want)
+        got2 = ix.encode(x, ids=ids, upsert=True)
+        assert np.array_equal(got2, want) and ix.count() == n
+        assert np.array_equal(ix.fetch_codes(ids), want)  # the mirror holds the same rows
+        q = rng.uniform(-1, 1, size=dims)
+        gi, gd, gn, _ = ix.search_topk(q, 5)
+        ri, rd, _ = o.search_exact(want, ids, dims, bits, szg.EUCLIDEAN, q, k=5)
+        assert_results_match(gi[0, :gn[0]], gd[0, :gn[0]], ri, rd, what=f"encode b{bits}")
+    if bits == 8 and dims >= 8:
+        assert got[1, :8].tolist() == [0, 0, 64, 128, 140, 191, 255, 255]
+
+
+def test_device_encode_large_batch_spans_staging_chunks():
+    # more rows than one 64 MB staging chunk of float64 input holds (4-bit: 16 input bytes per code byte)
+    dims, n = 768, 30000
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(n, dims)) * 0.5
+    with szg.Index(dims, 4, szg.COSINE) as ix:
+        got = ix.encode(x, ids=np.arange(n, dtype=np.uint64), upsert=True)
+        rows = np.arange(0, n, 611)
+        assert np.array_equal(got[rows], o.encode_rows(x[rows], 4))
+        assert ix.count() == n
+        assert np.array_equal(ix.fetch_codes(rows.astype(np.uint64)), got[rows])
+
+
 def test_upsert_replaces_and_remove_hides():
     # appendix B-14: re-adding an id replaces its row (spanfile.go:459-472); removeDocument hides it
     dims, bits = 16, 8
