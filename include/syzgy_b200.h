@@ -113,6 +113,89 @@ int szg_mask_create(szg_index *h, const uint64_t *ids, const uint8_t *pass, uint
 int szg_mask_destroy(szg_index *h, int mask_id);
 
 /*
+ * Metadata filters evaluated on the device.  Replaces, for filters built by BuildFilter
+ * (collection.go:204-218), the per-document json.Unmarshal + closure walk of query/compiler.go:15-165, 477-497 that
+ * Search applies at collection.go:592-594: the shim mirrors the scalar metadata fields it wants to filter on into
+ * columns (once per AddDocument/UpdateDocument, where it holds the JSON anyway), lowers the filter's syntax tree
+ * (query/parser.go node types) to a postfix program, and szg_filter_mask evaluates it for every row into a mask
+ * usable as mask_id of every search call.  Filters the lowering does not cover (ANY/ALL, LENGTH, array indexing,
+ * comparisons between two fields) keep using szg_mask_create with the Go predicate.
+ *
+ * Value kinds mirror what encoding/json puts into an interface{}: a missing key reads as nil (getField,
+ * compiler.go:428-444); SZG_MV_OTHER = array or object; SZG_MV_ERROR = evaluating the (nested) field raises an error
+ * (compiler.go:222-233: key not found below the top level).
+ */
+#define SZG_MV_MISSING 0u
+#define SZG_MV_NULL 1u
+#define SZG_MV_BOOL 2u   /* num = 0 / 1 */
+#define SZG_MV_NUMBER 3u /* num */
+#define SZG_MV_STRING 4u /* str, str_len */
+#define SZG_MV_OTHER 5u
+#define SZG_MV_ERROR 6u
+/* per document: metadata that json.Unmarshal rejects never passes a filter (compiler.go:480-483) */
+#define SZG_DOC_INVALID 0u
+#define SZG_DOC_OBJECT 1u
+#define SZG_DOC_OTHER 2u /* valid JSON that is not an object: every field access is an error */
+#define SZG_MAX_META_COLUMNS 32u
+
+typedef struct szg_meta_value {
+    uint32_t kind;
+    uint32_t str_len;
+    double num;
+    const char *str;
+} szg_meta_value;
+
+/* Sets, for n documents already in the mirror, the document kind and the values of ncols columns
+ * (values[i * ncols + j] = column cols[j] of ids[i]).  Columns not listed keep their values; removing a document
+ * clears all of them.  Unknown ids are an error. */
+int szg_meta_upsert(szg_index *h, const uint64_t *ids, uint64_t n, const uint8_t *doc_kind, const uint32_t *cols,
+                    uint32_t ncols, const szg_meta_value *values);
+
+/* postfix program; operands are pushed left to right (IN: the tested value first, then the list's elements) */
+#define SZG_FOP_COL 1u        /* arg = column: IdentifierNode of a mirrored field */
+#define SZG_FOP_NUM 2u        /* ValueNode float64 (parser.go:472-479) */
+#define SZG_FOP_STR 3u        /* ValueNode string */
+#define SZG_FOP_BOOL 4u       /* ValueNode bool: num != 0 */
+#define SZG_FOP_NULL 5u       /* ValueNode nil */
+#define SZG_FOP_EQ 6u         /* compiler.go:172-175 reflect.DeepEqual */
+#define SZG_FOP_NE 7u
+#define SZG_FOP_LT 8u         /* compiler.go:266-326 compareValues */
+#define SZG_FOP_LE 9u
+#define SZG_FOP_GT 10u
+#define SZG_FOP_GE 11u
+#define SZG_FOP_AND 12u       /* compiler.go:178-184 */
+#define SZG_FOP_OR 13u        /* compiler.go:185-197 */
+#define SZG_FOP_NOT 14u       /* compiler.go:198-203 */
+#define SZG_FOP_IN 15u        /* arg = number of list elements; compiler.go:379-393 */
+#define SZG_FOP_NOT_IN 16u
+#define SZG_FOP_CONTAINS 17u    /* str = the literal right operand; compiler.go:395-420 */
+#define SZG_FOP_STARTS_WITH 18u
+#define SZG_FOP_ENDS_WITH 19u
+#define SZG_FOP_STR_TABLE 20u /* table[code] for every dictionary code (e.g. MATCHES, evaluated by the shim's regexp
+                                 over szg_meta_dictionary_get); a non-string operand is an error like 416-419 */
+#define SZG_FOP_EXISTS 21u      /* arg = column; compiler.go:340-345 */
+#define SZG_FOP_NOT_EXISTS 22u  /* arg = column; compiler.go:60-75 */
+
+typedef struct szg_filter_op {
+    uint32_t op;
+    uint32_t arg;
+    double num;
+    const char *str;
+    uint32_t str_len;
+    uint32_t table_len;
+    const uint8_t *table;
+} szg_filter_op;
+
+/* Evaluates the program for every row on the device; *mask_id is then valid for the search calls until
+ * szg_mask_destroy.  Like any mask it reflects the metadata at the time of the call. */
+int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *mask_id);
+
+/* the string dictionary of the metadata columns (codes 0 .. size-1), for predicates the shim tabulates itself */
+int szg_meta_dictionary_size(szg_index *h, uint32_t *size);
+int szg_meta_dictionary_get(szg_index *h, uint32_t code, const char **str, uint32_t *len);
+
+
+/*
  * Exact top-k for nq queries (each scans the whole mirror on its own: single-query GEMV
  * semantics, not the batched contraction).  Replaces: Search with Precision=="exact",
  * Radius==0, K>0 (collection.go:672-684 driving consider 583-629 and the drain 693-697).

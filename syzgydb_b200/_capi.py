@@ -29,6 +29,10 @@ OPT_SCAN_TILE_CHUNKS = 6
 OPT_DIGITS = 7
 OPT_BATCH_TENSOR = 8
 
+# szg_filter_op opcodes (include/syzgy_b200.h SZG_FOP_*)
+(FOP_COL, FOP_NUM, FOP_STR, FOP_BOOL, FOP_NULL, FOP_EQ, FOP_NE, FOP_LT, FOP_LE, FOP_GT, FOP_GE, FOP_AND, FOP_OR, FOP_NOT,
+ FOP_IN, FOP_NOT_IN, FOP_CONTAINS, FOP_STARTS_WITH, FOP_ENDS_WITH, FOP_STR_TABLE, FOP_EXISTS, FOP_NOT_EXISTS) = range(1, 23)
+
 # every symbol include/syzgy_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "szg_last_error", "szg_create", "szg_destroy", "szg_reserve", "szg_upsert", "szg_encode", "szg_remove", "szg_count",
@@ -36,7 +40,7 @@ EXPORTS = [
     "szg_result_fetch", "szg_result_free", "szg_rescore", "szg_search_topk_dev", "szg_search_batch_dev", "szg_merge_topk_dev",
     "szg_fill_synthetic", "szg_fetch_codes", "szg_get_stats", "szg_set_option", "szg_last_scan_times_ms",
     "szg_spanfile_open", "szg_spanfile_close", "szg_spanfile_get_info", "szg_spanfile_ids", "szg_spanfile_record",
-    "szg_spanfile_load",
+    "szg_spanfile_load", "szg_meta_upsert", "szg_filter_mask", "szg_meta_dictionary_size", "szg_meta_dictionary_get",
 ]
 
 
@@ -53,6 +57,15 @@ class SpanFileInfo(C.Structure):
         ("next_sequence", C.c_uint32), ("has_header", C.c_int32), ("distance_method", C.c_int32),
         ("dimension_count", C.c_int32), ("quantization", C.c_int32), ("name", C.c_char * 256),
     ]
+
+
+class MetaValue(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("str_len", C.c_uint32), ("num", C.c_double), ("str", C.c_void_p)]
+
+
+class FilterOp(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("arg", C.c_uint32), ("num", C.c_double), ("str", C.c_void_p), ("str_len", C.c_uint32),
+                ("table_len", C.c_uint32), ("table", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -91,6 +104,10 @@ def load():
     L.szg_count.argtypes = [vp, u64p]
     L.szg_mask_create.argtypes = [vp, u64p, u8p, C.c_uint64, C.POINTER(C.c_int)]
     L.szg_mask_destroy.argtypes = [vp, C.c_int]
+    L.szg_meta_upsert.argtypes = [vp, u64p, C.c_uint64, u8p, u32p, C.c_uint32, C.POINTER(MetaValue)]
+    L.szg_filter_mask.argtypes = [vp, C.POINTER(FilterOp), C.c_uint32, C.POINTER(C.c_int)]
+    L.szg_meta_dictionary_size.argtypes = [vp, u32p]
+    L.szg_meta_dictionary_get.argtypes = [vp, C.c_uint32, C.POINTER(C.c_void_p), u32p]
     L.szg_search_topk.argtypes = [vp, f64p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u64p, f64p, u32p, u64p]
     L.szg_search_batch.argtypes = L.szg_search_topk.argtypes
     L.szg_search_radius.argtypes = [vp, f64p, C.c_double, C.c_int, C.c_uint32, C.POINTER(vp), u64p]
@@ -216,6 +233,65 @@ class Index:
         mid = C.c_int(0)
         _check(self._L.szg_mask_create(self._h, _p(ids, C.c_uint64), _p(passed, C.c_uint8), ids.size, C.byref(mid)))
         return mid.value
+
+    # -- metadata columns and device-side filters (szg_meta_upsert / szg_filter_mask)
+    def meta_upsert(self, ids, doc_kinds, cols, values):
+        """values[i][j] = (kind, value) of column cols[j] for ids[i] (kinds: syzgydb_b200.filter.MV_*)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        dk = np.ascontiguousarray(doc_kinds, dtype=np.uint8)
+        cols = np.ascontiguousarray(cols, dtype=np.uint32)
+        n, m = ids.size, cols.size
+        arr = (MetaValue * max(n * m, 1))()
+        keep = []
+        for i in range(n):
+            for j in range(m):
+                kind, v = values[i][j]
+                mv = arr[i * m + j]
+                mv.kind = kind
+                if kind == 4:  # string
+                    b = v.encode("utf-8")
+                    buf = C.create_string_buffer(b, len(b) + 1)
+                    keep.append(buf)
+                    mv.str = C.cast(buf, C.c_void_p)
+                    mv.str_len = len(b)
+                elif kind in (2, 3):  # bool, number
+                    mv.num = float(v)
+        _check(self._L.szg_meta_upsert(self._h, _p(ids, C.c_uint64), n, _p(dk, C.c_uint8), _p(cols, C.c_uint32), m, arr))
+
+    def filter_mask(self, program) -> int:
+        """Runs a postfix filter program (list of dicts: op, arg, num, str, table) on the device; returns a mask id."""
+        ops = (FilterOp * max(len(program), 1))()
+        keep = []
+        for i, o in enumerate(program):
+            ops[i].op = o["op"]
+            ops[i].arg = o.get("arg", 0)
+            ops[i].num = o.get("num", 0.0)
+            if "str" in o:
+                b = o["str"].encode("utf-8")
+                buf = C.create_string_buffer(b, len(b) + 1)
+                keep.append(buf)
+                ops[i].str = C.cast(buf, C.c_void_p)
+                ops[i].str_len = len(b)
+            if "table" in o:
+                t = bytes(o["table"])
+                buf = C.create_string_buffer(t, len(t) + 1)
+                keep.append(buf)
+                ops[i].table = C.cast(buf, C.c_void_p)
+                ops[i].table_len = len(t)
+        mid = C.c_int(0)
+        _check(self._L.szg_filter_mask(self._h, ops, len(program), C.byref(mid)))
+        return mid.value
+
+    def meta_dictionary(self):
+        """The string dictionary of the metadata columns, by code."""
+        n = C.c_uint32(0)
+        _check(self._L.szg_meta_dictionary_size(self._h, C.byref(n)))
+        out = []
+        for code in range(n.value):
+            sp, ln = C.c_void_p(), C.c_uint32(0)
+            _check(self._L.szg_meta_dictionary_get(self._h, code, C.byref(sp), C.byref(ln)))
+            out.append(C.string_at(sp.value, ln.value).decode("utf-8", "replace") if ln.value else "")
+        return out
 
     def mask_destroy(self, mask_id: int):
         _check(self._L.szg_mask_destroy(self._h, mask_id))

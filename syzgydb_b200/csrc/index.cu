@@ -187,6 +187,13 @@ struct szg_index {
     bool planar_dirty = true;
     uint32_t planar_nblk = 0;
     uint64_t batch_queries = 0;
+    // metadata columns (filter.cu): allocated on first use, sized to `capacity`
+    DevBuf<unsigned char> doc_kind;
+    DevBuf<unsigned char> col_kind[kFilterMaxCols];
+    DevBuf<unsigned long long> col_val[kFilterMaxCols];
+    bool meta_used = false;
+    std::unordered_map<std::string, uint32_t> dict;
+    std::vector<std::string> dict_strs;
     int digits = 0; // 0 = automatic (2-digit fast pass, 3-digit re-run when uncertain), 2 or 3 = forced // streaming geometry (SZG_OPT_SCAN_*)
 
     bool lookup(uint64_t id, uint32_t *slot) const {
@@ -248,6 +255,20 @@ int grow(szg_index *h, uint64_t want_slots) {
         CK(cudaStreamSynchronize(st));
         cudaFree(m.second);
         m.second = np;
+    }
+    // metadata columns follow the capacity; new rows read as "no metadata"
+    auto grow_bytes = [&](DevBuf<unsigned char> &b) -> int {
+        const size_t old_n = b.n;
+        if (!old_n) return SZG_OK; // never used: allocated at first use
+        int r = b.ensure(cap, true, st);
+        if (r) return r;
+        CK(cudaMemsetAsync(b.p + old_n, 0, cap - old_n, st));
+        return SZG_OK;
+    };
+    if ((rc = grow_bytes(h->doc_kind))) return rc;
+    for (uint32_t c = 0; c < kFilterMaxCols; ++c) {
+        if ((rc = grow_bytes(h->col_kind[c]))) return rc;
+        if (h->col_val[c].n && (rc = h->col_val[c].ensure(cap, true, st))) return rc;
     }
     CK(cudaStreamSynchronize(st));
     h->capacity = (uint32_t)cap;
@@ -536,7 +557,9 @@ int szg_destroy(szg_index *h) {
     for (auto &kv : h->dev_ws) { kv.second->destroy(); delete kv.second; }
     for (auto &m : h->masks) cudaFree(m.second);
     h->codes.release(); h->ids.release(); h->aux.release(); h->live.release(); h->lut.release(); h->planar.release();
-    h->h_stage.release(); h->d_stage.release(); h->d_vec.release(); h->h_slots.release(); h->d_slots.release();
+    h->h_stage.release(); h->d_stage.release(); h->d_vec.release();
+    h->doc_kind.release();
+    for (uint32_t c = 0; c < kFilterMaxCols; ++c) { h->col_kind[c].release(); h->col_val[c].release(); } h->h_slots.release(); h->d_slots.release();
     h->h_ids.release(); h->d_ids_in.release();
     if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
     delete h;
@@ -693,6 +716,13 @@ int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_remove
     CK(cudaMemcpyAsync(h->d_slots.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, st));
     CK(launch_kill(h->live.p, h->d_slots.p, (uint32_t)slots.size(), st));
     h->launches++;
+    if (h->meta_used) { // a slot that is handed to another document later must not show this one's metadata
+        MetaPtrs mp;
+        mp.doc_kind = h->doc_kind.p;
+        for (uint32_t c = 0; c < kFilterMaxCols; ++c) mp.col_kind[c] = h->col_kind[c].p;
+        CK(launch_meta_clear(h->d_slots.p, (uint32_t)slots.size(), mp, st));
+        h->launches++;
+    }
     CK(cudaStreamSynchronize(st));
     return SZG_OK;
 }
@@ -784,6 +814,248 @@ int szg_mask_create(szg_index *h, const uint64_t *ids, const uint8_t *pass, uint
         if (e != cudaSuccess) rc = fail(SZG_ECUDA, "sync failed: %s", cudaGetErrorString(e));
     }
     if (rc) { cudaFree(mask); return rc; }
+    *mask_id = h->next_mask++;
+    h->masks[*mask_id] = mask;
+    return SZG_OK;
+}
+
+// ---------------------------------------------------------------- metadata columns and device-side filters
+static int meta_column_ready(szg_index *h, DevBuf<unsigned char> &kind, DevBuf<unsigned long long> *val) {
+    int rc;
+    cudaStream_t st = h->mut_stream;
+    if (!kind.n) {
+        if ((rc = kind.ensure(std::max<size_t>(h->capacity, 64)))) return rc;
+        CK(cudaMemsetAsync(kind.p, 0, kind.n, st));
+    }
+    if (val && !val->n) {
+        if ((rc = val->ensure(std::max<size_t>(h->capacity, 64)))) return rc;
+        CK(cudaMemsetAsync(val->p, 0, val->n * 8, st));
+    }
+    return SZG_OK;
+}
+
+static uint32_t dict_code(szg_index *h, const char *sp, uint32_t len, bool insert) {
+    std::string key(sp ? sp : "", sp ? len : 0);
+    auto it = h->dict.find(key);
+    if (it != h->dict.end()) return it->second;
+    if (!insert) return 0xFFFFFFFFu;
+    const uint32_t code = (uint32_t)h->dict_strs.size();
+    h->dict_strs.push_back(key);
+    h->dict.emplace(std::move(key), code);
+    return code;
+}
+
+int szg_meta_upsert(szg_index *h, const uint64_t *ids, uint64_t n, const uint8_t *doc_kind, const uint32_t *cols,
+                    uint32_t ncols, const szg_meta_value *values) {
+    GUARD(h);
+    if (n && (!ids || !doc_kind || (ncols && (!cols || !values)))) return fail(SZG_EINVAL, "null argument");
+    if (n > 0xFFFFFFFFull) return fail(SZG_EINVAL, "too many ids");
+    for (uint32_t j = 0; j < ncols; ++j)
+        if (cols[j] >= kFilterMaxCols) return fail(SZG_EINVAL, "metadata column %u out of range (max %u)", cols[j], kFilterMaxCols - 1);
+    if (!n) return SZG_OK;
+    int rc;
+    std::vector<uint32_t> slots(n);
+    if ((rc = map_ids(h, ids, n, slots.data(), true))) return rc;
+    h->meta_used = true;
+    cudaStream_t st = h->mut_stream;
+    if ((rc = meta_column_ready(h, h->doc_kind, nullptr))) return rc;
+    DevBuf<unsigned char> d_kinds;
+    DevBuf<unsigned long long> d_vals;
+    if ((rc = h->d_slots.ensure(n)) || (rc = d_kinds.ensure(n)) || (rc = d_vals.ensure(n))) return rc;
+    std::vector<unsigned char> kinds(n);
+    std::vector<unsigned long long> vals(n);
+    auto finish = [&](int code) { d_kinds.release(); d_vals.release(); return code; };
+#define CKF(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return finish(fail(SZG_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); \
+    } while (0)
+    CKF(cudaMemcpyAsync(h->d_slots.p, slots.data(), n * 4, cudaMemcpyHostToDevice, st));
+    for (uint64_t i = 0; i < n; ++i) {
+        if (doc_kind[i] > SZG_DOC_OTHER) return finish(fail(SZG_EINVAL, "bad document kind %u", doc_kind[i]));
+        kinds[i] = doc_kind[i];
+    }
+    CKF(cudaMemcpyAsync(d_kinds.p, kinds.data(), n, cudaMemcpyHostToDevice, st));
+    CKF(launch_meta_scatter(h->d_slots.p, d_kinds.p, nullptr, h->doc_kind.p, nullptr, (uint32_t)n, st));
+    CKF(cudaStreamSynchronize(st)); // the staging vectors are reused per column
+    h->launches++;
+    for (uint32_t j = 0; j < ncols; ++j) {
+        const uint32_t c = cols[j];
+        if ((rc = meta_column_ready(h, h->col_kind[c], &h->col_val[c]))) return finish(rc);
+        for (uint64_t i = 0; i < n; ++i) {
+            const szg_meta_value &v = values[i * ncols + j];
+            if (v.kind > SZG_MV_ERROR) return finish(fail(SZG_EINVAL, "bad value kind %u", v.kind));
+            kinds[i] = (unsigned char)v.kind;
+            unsigned long long bits = 0;
+            if (v.kind == SZG_MV_NUMBER) memcpy(&bits, &v.num, 8);
+            else if (v.kind == SZG_MV_BOOL) bits = v.num != 0.0;
+            else if (v.kind == SZG_MV_STRING) bits = dict_code(h, v.str, v.str_len, true);
+            vals[i] = bits;
+        }
+        CKF(cudaMemcpyAsync(d_kinds.p, kinds.data(), n, cudaMemcpyHostToDevice, st));
+        CKF(cudaMemcpyAsync(d_vals.p, vals.data(), n * 8, cudaMemcpyHostToDevice, st));
+        CKF(launch_meta_scatter(h->d_slots.p, d_kinds.p, d_vals.p, h->col_kind[c].p, h->col_val[c].p, (uint32_t)n, st));
+        CKF(cudaStreamSynchronize(st));
+        h->launches++;
+    }
+    return finish(SZG_OK);
+}
+
+int szg_meta_dictionary_size(szg_index *h, uint32_t *size) {
+    GUARD(h);
+    if (!size) return fail(SZG_EINVAL, "null argument");
+    *size = (uint32_t)h->dict_strs.size();
+    return SZG_OK;
+}
+
+int szg_meta_dictionary_get(szg_index *h, uint32_t code, const char **str, uint32_t *len) {
+    GUARD(h);
+    if (!str || !len) return fail(SZG_EINVAL, "null argument");
+    if (code >= h->dict_strs.size()) return fail(SZG_ENOTFOUND, "no string with code %u", code);
+    *str = h->dict_strs[code].data();
+    *len = (uint32_t)h->dict_strs[code].size();
+    return SZG_OK;
+}
+
+int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *mask_id) {
+    GUARD(h);
+    if (!ops || !nops || !mask_id) return fail(SZG_EINVAL, "null argument");
+    if (nops > 4096) return fail(SZG_EINVAL, "filter program too long");
+    int rc;
+    cudaStream_t st = h->mut_stream;
+    // ---- validate the stack discipline and lower the literals
+    const uint32_t D = (uint32_t)h->dict_strs.size();
+    std::vector<std::string> lits; // literal strings that are not in the dictionary get virtual codes D, D + 1, ...
+    auto literal_code = [&](const szg_filter_op &o) -> uint32_t {
+        uint32_t c = dict_code(h, o.str, o.str_len, false);
+        if (c != 0xFFFFFFFFu) return c;
+        std::string key(o.str ? o.str : "", o.str ? o.str_len : 0);
+        for (size_t i = 0; i < lits.size(); ++i)
+            if (lits[i] == key) return D + (uint32_t)i;
+        lits.push_back(key);
+        return D + (uint32_t)lits.size() - 1;
+    };
+    std::vector<FilterOp> prog(nops);
+    std::vector<std::vector<unsigned char>> tables(nops);
+    bool need_rank = false;
+    int sp = 0;
+    for (uint32_t i = 0; i < nops; ++i) {
+        const szg_filter_op &o = ops[i];
+        FilterOp &f = prog[i];
+        f.op = 0; f.arg = 0; f.bits = 0; f.table = nullptr;
+        int pops = 0, pushes = 1;
+        switch (o.op) {
+        case SZG_FOP_COL:
+        case SZG_FOP_EXISTS:
+        case SZG_FOP_NOT_EXISTS:
+            if (o.arg >= kFilterMaxCols) return fail(SZG_EINVAL, "op %u: column %u out of range", i, o.arg);
+            f.op = o.op == SZG_FOP_COL ? FOP_COL : (o.op == SZG_FOP_EXISTS ? FOP_EXISTS : FOP_NOT_EXISTS);
+            f.arg = o.arg;
+            if ((rc = meta_column_ready(h, h->col_kind[o.arg], &h->col_val[o.arg]))) return rc; // never set: all missing
+            break;
+        case SZG_FOP_NUM: f.op = FOP_NUM; memcpy(&f.bits, &o.num, 8); break;
+        case SZG_FOP_STR: f.op = FOP_STR; f.bits = literal_code(o); break;
+        case SZG_FOP_BOOL: f.op = FOP_BOOL; f.bits = o.num != 0.0; break;
+        case SZG_FOP_NULL: f.op = FOP_NULL; break;
+        case SZG_FOP_EQ: f.op = FOP_EQ; pops = 2; break;
+        case SZG_FOP_NE: f.op = FOP_NE; pops = 2; break;
+        case SZG_FOP_LT: f.op = FOP_LT; pops = 2; need_rank = true; break;
+        case SZG_FOP_LE: f.op = FOP_LE; pops = 2; need_rank = true; break;
+        case SZG_FOP_GT: f.op = FOP_GT; pops = 2; need_rank = true; break;
+        case SZG_FOP_GE: f.op = FOP_GE; pops = 2; need_rank = true; break;
+        case SZG_FOP_AND: f.op = FOP_AND; pops = 2; break;
+        case SZG_FOP_OR: f.op = FOP_OR; pops = 2; break;
+        case SZG_FOP_NOT: f.op = FOP_NOT; pops = 1; break;
+        case SZG_FOP_IN:
+        case SZG_FOP_NOT_IN:
+            f.op = o.op == SZG_FOP_IN ? FOP_IN : FOP_NOT_IN;
+            f.arg = o.arg;
+            if (o.arg >= (uint32_t)kFilterMaxStack) return fail(SZG_EINVAL, "op %u: list of %u elements is too long", i, o.arg);
+            pops = (int)o.arg + 1;
+            break;
+        case SZG_FOP_CONTAINS:
+        case SZG_FOP_STARTS_WITH:
+        case SZG_FOP_ENDS_WITH: {
+            // strings.Contains / HasPrefix / HasSuffix (compiler.go:395-420) over the dictionary, once per program
+            const std::string lit(o.str ? o.str : "", o.str ? o.str_len : 0);
+            std::vector<unsigned char> &t = tables[i];
+            t.resize(std::max<uint32_t>(D, 1));
+            for (uint32_t c = 0; c < D; ++c) {
+                const std::string &x = h->dict_strs[c];
+                bool r;
+                if (o.op == SZG_FOP_CONTAINS) r = x.find(lit) != std::string::npos;
+                else if (o.op == SZG_FOP_STARTS_WITH) r = x.size() >= lit.size() && x.compare(0, lit.size(), lit) == 0;
+                else r = x.size() >= lit.size() && x.compare(x.size() - lit.size(), lit.size(), lit) == 0;
+                t[c] = r;
+            }
+            f.op = FOP_STR_TABLE; f.arg = D; pops = 1;
+            break;
+        }
+        case SZG_FOP_STR_TABLE:
+            if (o.table_len && !o.table) return fail(SZG_EINVAL, "op %u: null table", i);
+            tables[i].assign(o.table, o.table + o.table_len);
+            if (tables[i].empty()) tables[i].push_back(0);
+            f.op = FOP_STR_TABLE; f.arg = o.table_len; pops = 1;
+            break;
+        default: return fail(SZG_EINVAL, "op %u: unknown opcode %u", i, o.op);
+        }
+        if (sp < pops) return fail(SZG_EINVAL, "op %u: value stack underflow", i);
+        sp += pushes - pops;
+        if (sp > kFilterMaxStack) return fail(SZG_EINVAL, "op %u: expression nests deeper than %d values", i, kFilterMaxStack);
+    }
+    if (sp != 1) return fail(SZG_EINVAL, "the program leaves %d values, not one", sp);
+    // ---- bytewise order of all string codes (Go compares strings bytewise, compiler.go:306-320)
+    std::vector<uint32_t> rank;
+    if (need_rank) {
+        const uint32_t total = D + (uint32_t)lits.size();
+        std::vector<uint32_t> order(total);
+        for (uint32_t i = 0; i < total; ++i) order[i] = i;
+        auto str_of = [&](uint32_t c) -> const std::string & { return c < D ? h->dict_strs[c] : lits[c - D]; };
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return str_of(x) < str_of(y); });
+        rank.resize(total);
+        for (uint32_t i = 0; i < total; ++i) rank[order[i]] = i;
+    }
+    if (rank.empty()) rank.push_back(0);
+    // ---- upload and run
+    if ((rc = meta_column_ready(h, h->doc_kind, nullptr))) return rc;
+    size_t table_bytes = 0;
+    for (auto &t : tables) table_bytes += (t.size() + 15) / 16 * 16;
+    DevBuf<unsigned char> d_blob; // [tables][program][ranks]
+    const size_t prog_off = table_bytes, rank_off = (prog_off + nops * sizeof(FilterOp) + 15) / 16 * 16;
+    const size_t blob_bytes = rank_off + rank.size() * 4;
+    if ((rc = d_blob.ensure(blob_bytes))) return rc;
+    std::vector<unsigned char> blob(blob_bytes, 0);
+    size_t off = 0;
+    for (uint32_t i = 0; i < nops; ++i) {
+        if (tables[i].empty()) continue;
+        memcpy(blob.data() + off, tables[i].data(), tables[i].size());
+        prog[i].table = d_blob.p + off;
+        off += (tables[i].size() + 15) / 16 * 16;
+    }
+    memcpy(blob.data() + prog_off, prog.data(), nops * sizeof(FilterOp));
+    memcpy(blob.data() + rank_off, rank.data(), rank.size() * 4);
+    const size_t words = h->capacity / 32;
+    uint32_t *mask = nullptr;
+    cudaError_t e = cudaMalloc(&mask, std::max<size_t>(words, 1) * 4);
+    if (e != cudaSuccess) { d_blob.release(); return fail(SZG_ENOMEM, "mask allocation failed: %s", cudaGetErrorString(e)); }
+    FilterArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.prog = reinterpret_cast<const FilterOp *>(d_blob.p + prog_off);
+    fa.nops = nops;
+    fa.doc_kind = h->doc_kind.p;
+    for (uint32_t c = 0; c < kFilterMaxCols; ++c) { fa.col_kind[c] = h->col_kind[c].p; fa.col_val[c] = h->col_val[c].p; }
+    fa.rank = reinterpret_cast<const uint32_t *>(d_blob.p + rank_off);
+    fa.nrank = (uint32_t)rank.size();
+    fa.mask = mask;
+    fa.nwords = (uint32_t)words;
+    fa.nslots = h->nslots;
+    e = cudaMemsetAsync(mask, 0, std::max<size_t>(words, 1) * 4, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_blob.p, blob.data(), blob_bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_filter(fa, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    d_blob.release();
+    h->launches++;
+    if (e != cudaSuccess) { cudaFree(mask); return fail(SZG_ECUDA, "filter evaluation failed: %s", cudaGetErrorString(e)); }
     *mask_id = h->next_mask++;
     h->masks[*mask_id] = mask;
     return SZG_OK;

@@ -100,6 +100,40 @@ cudaError_t batch_configure(size_t max_smem);
 size_t batch_dynamic_limit();
 cudaError_t launch_batch(const BatchArgs &a, cudaStream_t st);
 
+// ---- metadata filters on the device (filter.cu)
+constexpr uint32_t kFilterMaxCols = 32;   // metadata columns per collection
+constexpr int kFilterMaxStack = 16;       // value stack of the filter program
+enum MetaKind : uint32_t { MV_MISSING = 0, MV_NULL = 1, MV_BOOL = 2, MV_NUMBER = 3, MV_STRING = 4, MV_OTHER = 5, MV_ERROR = 6 };
+enum DocKind : uint32_t { DOC_INVALID = 0, DOC_OBJECT = 1, DOC_OTHER = 2 };
+enum FilterOpcode : uint32_t {
+    FOP_COL = 1, FOP_NUM, FOP_STR, FOP_BOOL, FOP_NULL, FOP_EQ, FOP_NE, FOP_LT, FOP_LE, FOP_GT, FOP_GE, FOP_AND, FOP_OR,
+    FOP_NOT, FOP_IN, FOP_NOT_IN, FOP_STR_TABLE, FOP_EXISTS, FOP_NOT_EXISTS
+};
+struct FilterOp {
+    uint32_t op, arg;              // arg: column (COL, EXISTS, NOT_EXISTS), list length (IN, NOT_IN), table length (STR_TABLE)
+    unsigned long long bits;       // literal: float64 bits, string code, bool
+    const unsigned char *table;    // STR_TABLE: one byte per string code
+};
+struct FilterArgs {
+    const FilterOp *prog;
+    uint32_t nops;
+    const unsigned char *doc_kind;
+    const unsigned char *col_kind[kFilterMaxCols];
+    const unsigned long long *col_val[kFilterMaxCols];
+    const uint32_t *rank;          // bytewise order of every string code (dictionary + this program's literals)
+    uint32_t nrank;
+    uint32_t *mask;                // out: bit per slot
+    uint32_t nwords, nslots;
+};
+cudaError_t launch_filter(const FilterArgs &a, cudaStream_t st);
+cudaError_t launch_meta_scatter(const uint32_t *slots, const unsigned char *kinds, const unsigned long long *vals,
+                                unsigned char *col_kind, unsigned long long *col_val, uint32_t n, cudaStream_t st);
+struct MetaPtrs {
+    unsigned char *doc_kind;
+    unsigned char *col_kind[kFilterMaxCols];
+};
+cudaError_t launch_meta_clear(const uint32_t *slots, uint32_t n, const MetaPtrs &p, cudaStream_t st);
+
 struct MergeArgs {
     const unsigned long long *g_ids; // [G][nq][k]
     const double *g_dist;
