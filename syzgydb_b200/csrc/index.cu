@@ -192,6 +192,7 @@ struct szg_index {
     DevBuf<unsigned char> col_kind[kFilterMaxCols];
     DevBuf<unsigned long long> col_val[kFilterMaxCols];
     bool meta_used = false;
+    DevBuf<unsigned char> d_filter_blob; // program + tables + ranks of the filter being evaluated (kept between calls)
     std::unordered_map<std::string, uint32_t> dict;
     std::vector<std::string> dict_strs;
     int digits = 0; // 0 = automatic (2-digit fast pass, 3-digit re-run when uncertain), 2 or 3 = forced // streaming geometry (SZG_OPT_SCAN_*)
@@ -558,7 +559,7 @@ int szg_destroy(szg_index *h) {
     for (auto &m : h->masks) cudaFree(m.second);
     h->codes.release(); h->ids.release(); h->aux.release(); h->live.release(); h->lut.release(); h->planar.release();
     h->h_stage.release(); h->d_stage.release(); h->d_vec.release();
-    h->doc_kind.release();
+    h->doc_kind.release(); h->d_filter_blob.release();
     for (uint32_t c = 0; c < kFilterMaxCols; ++c) { h->col_kind[c].release(); h->col_val[c].release(); } h->h_slots.release(); h->d_slots.release();
     h->h_ids.release(); h->d_ids_in.release();
     if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
@@ -1020,7 +1021,7 @@ int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *
     if ((rc = meta_column_ready(h, h->doc_kind, nullptr))) return rc;
     size_t table_bytes = 0;
     for (auto &t : tables) table_bytes += (t.size() + 15) / 16 * 16;
-    DevBuf<unsigned char> d_blob; // [tables][program][ranks]
+    DevBuf<unsigned char> &d_blob = h->d_filter_blob; // [tables][program][ranks]
     const size_t prog_off = table_bytes, rank_off = (prog_off + nops * sizeof(FilterOp) + 15) / 16 * 16;
     const size_t blob_bytes = rank_off + rank.size() * 4;
     if ((rc = d_blob.ensure(blob_bytes))) return rc;
@@ -1037,7 +1038,7 @@ int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *
     const size_t words = h->capacity / 32;
     uint32_t *mask = nullptr;
     cudaError_t e = cudaMalloc(&mask, std::max<size_t>(words, 1) * 4);
-    if (e != cudaSuccess) { d_blob.release(); return fail(SZG_ENOMEM, "mask allocation failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) return fail(SZG_ENOMEM, "mask allocation failed: %s", cudaGetErrorString(e));
     FilterArgs fa;
     memset(&fa, 0, sizeof fa);
     fa.prog = reinterpret_cast<const FilterOp *>(d_blob.p + prog_off);
@@ -1053,7 +1054,6 @@ int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_blob.p, blob.data(), blob_bytes, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = launch_filter(fa, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    d_blob.release();
     h->launches++;
     if (e != cudaSuccess) { cudaFree(mask); return fail(SZG_ECUDA, "filter evaluation failed: %s", cudaGetErrorString(e)); }
     *mask_id = h->next_mask++;
