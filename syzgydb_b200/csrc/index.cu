@@ -17,6 +17,7 @@
 
 #include "../../include/syzgy_b200.h"
 #include "kernels.h"
+#include "scan_small.cuh"
 
 using namespace szg;
 
@@ -346,6 +347,72 @@ void fill_scan_args(szg_index *h, ScanArgs &a, const uint32_t *mask) {
     a.metric = (uint32_t)h->metric;
 }
 
+// run_topk for short rows: the launch is cut in (query, part) items handled by one CTA each (scan_small.cuh)
+int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32_t k, const uint32_t *mask, uint32_t flags,
+                   int nd, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags) {
+    const size_t stride = pq_stride(h, nd);
+    int rc;
+    if ((rc = ws->d_pq.ensure(stride * nq))) return rc;
+    const uint32_t nblk = (h->nslots + 31) / 32;
+    const uint32_t sms = (uint32_t)h->sm_count;
+    cudaStream_t main = ws->main;
+    PrepArgs pa;
+    pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
+    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
+    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
+    CK(launch_prep(nq, main, pa));
+    h->launches++;
+    // queries per launch: bounded by the candidate buffer (parts <= SM count lists of 16 warps x 32 keys per query)
+    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / ((size_t)sms * kSmallWarps * 32 * 8)}));
+    const bool timing = h->timing != 0;
+    const uint32_t nlaunch = (nq + chunk - 1) / chunk;
+    uint32_t tbase = 0;
+    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nlaunch <= 65536) tbase = ws->timed;
+    if (timing) {
+        while (ws->t0.size() < tbase + nlaunch) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            ws->t0.push_back(a);
+            ws->t1.push_back(b);
+        }
+    }
+    ScanArgs a;
+    fill_scan_args(h, a, mask);
+    a.pq_stride = stride;
+    FinalizeArgs f;
+    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p;
+    f.pq_stride = stride;
+    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
+    f.flags = flags & SZG_F_NO_FP64_VERIFY;
+    for (uint32_t l = 0, q0 = 0; q0 < nq; q0 += chunk, ++l) {
+        const uint32_t m = std::min(chunk, nq - q0);
+        // parts per query: as many as keep every CTA busy, but no part shorter than one block per warp
+        uint32_t parts = small_parts(m, sms);
+        parts = std::max<uint32_t>(1, std::min<uint32_t>(parts, (nblk + kSmallWarps - 1) / kSmallWarps));
+        const uint32_t nlists = parts * kSmallWarps;
+        const int grid = (int)std::min<uint64_t>((uint64_t)m * parts, sms);
+        if ((rc = ws->d_cand.ensure((size_t)m * nlists * 32))) return rc;
+        a.pq = ws->d_pq.p + stride * q0;
+        a.nq = m;
+        a.parts = parts;
+        a.cand = ws->d_cand.p;
+        if (timing) CK(cudaEventRecord(ws->t0[tbase + l], main));
+        CK(launch_scan_small(h->qt, nd, h->C, grid, stride, main, a));
+        if (timing) CK(cudaEventRecord(ws->t1[tbase + l], main));
+        f.cand = ws->d_cand.p;
+        f.nlists = nlists;
+        f.queries = d_q + (size_t)q0 * h->dim;
+        f.pq = a.pq;
+        f.out_ids = d_out_ids + (size_t)q0 * k; f.out_dist = d_out_dist + (size_t)q0 * k;
+        f.out_n = d_out_n + q0; f.out_flags = d_out_flags + q0;
+        CK(launch_finalize(h->qt, 0, m, main, f));
+        h->launches += 2;
+    }
+    if (timing) { ws->timed = tbase + nlaunch; h->last_timed_ws = ws; }
+    return SZG_OK;
+}
+
 // Enqueues prep + scan + finalize for nq queries on ws->main.  One scan launch serves a whole chunk of
 // queries (persistent warps walk query after query); the chunk size is bounded by the candidate
 // buffer.  Inputs/outputs are device pointers; `ws` supplies scratch.
@@ -359,6 +426,12 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
     int grid = 0;
     if ((rc = plan_scan(h, nd, &plan, &grid))) return rc;
     const size_t Kp = 32u << mode;
+    // short rows, k <= 24: the kernel of scan_small.cuh (SZG_SCAN_SMALL=0 keeps the general kernel, for comparisons)
+    static const bool small_ok = !(getenv("SZG_SCAN_SMALL") && atoi(getenv("SZG_SCAN_SMALL")) == 0);
+    static const uint32_t small_maxc = getenv("SZG_SCAN_SMALL_MAXC") ? (uint32_t)atoi(getenv("SZG_SCAN_SMALL_MAXC")) : 48u;
+    const bool small = small_ok && mode == 0 && !h->scan_geometry_set && scan_small_supported(h->qt, h->C) && h->C <= small_maxc &&
+                       h->nslots >= 32;
+    if (small) return run_topk_small(h, ws, d_q, nq, k, mask, flags, nd, d_out_ids, d_out_dist, d_out_n, d_out_flags);
     const size_t nlists = (size_t)grid * plan.warps;
     const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / (nlists * Kp * 8)}));
     if ((rc = ws->d_cand.ensure((size_t)chunk * nlists * Kp))) return rc;

@@ -21,6 +21,8 @@ cudaError_t launch_prep(uint32_t nq, cudaStream_t st, const PrepArgs &a);
 // nd: digits of the fixed-point query (2 fast / 3 precise; ignored for float rows)
 cudaError_t launch_scan(int qt, int mode, int nd, int grid, int threads, size_t smem, cudaStream_t st,
                         const ScanArgs &a);
+// short quantized rows (C = 2, 4, 8), k <= 24: scan_small.cuh; a.parts = work items per query, lists per query = parts * 16
+cudaError_t launch_scan_small(int qt, int nd, uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a);
 // one launch for all nq queries of a call: merges each query's per-CTA lists, fp64 re-score, ordered output
 cudaError_t launch_finalize(int qt, int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a);
 cudaError_t scan_configure(int qt, size_t max_smem);

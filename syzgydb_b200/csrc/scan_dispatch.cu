@@ -22,6 +22,18 @@ cudaError_t launch_scan(int qt, int mode, int nd, int grid, int threads, size_t 
     return cudaErrorInvalidValue;
 }
 
+cudaError_t launch_scan_small_q4(int, uint32_t, int, size_t, cudaStream_t, const ScanArgs &);
+cudaError_t launch_scan_small_q8(int, uint32_t, int, size_t, cudaStream_t, const ScanArgs &);
+cudaError_t launch_scan_small_q16(int, uint32_t, int, size_t, cudaStream_t, const ScanArgs &);
+cudaError_t launch_scan_small(int qt, int nd, uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
+    switch (qt) {
+    case Q4: return launch_scan_small_q4(nd, C, grid, smem, st, a);
+    case Q8: return launch_scan_small_q8(nd, C, grid, smem, st, a);
+    case Q16: return launch_scan_small_q16(nd, C, grid, smem, st, a);
+    }
+    return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_finalize(int qt, int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a) {
     switch (qt) {
     case Q4: return launch_finalize_q4(mode, nq, st, a);

@@ -1,5 +1,6 @@
 // scan_q16.cu -- instantiates the scan kernel (scan_impl.cuh) for Q16 records.
 #include "kernels.h"
+#include "scan_small.cuh"
 
 namespace szg {
 
@@ -12,5 +13,9 @@ cudaError_t launch_finalize_q16(int mode, uint32_t nq, cudaStream_t st, const Fi
 }
 
 cudaError_t scan_attr_q16(size_t max_smem) { return scan_attr_t<Q16>(max_smem); }
+
+cudaError_t launch_scan_small_q16(int nd, uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
+    return launch_scan_small_t<Q16>(nd, C, grid, smem, st, a);
+}
 
 } // namespace szg

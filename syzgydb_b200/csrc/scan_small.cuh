@@ -1,0 +1,212 @@
+// scan_small.cuh -- the top-k scan for SHORT quantized rows (C = 2 .. 24 chunks of 16 bytes per row: at most
+// 384 bytes; BASELINE configs[1]: 1M x 128 4-bit = 64-byte rows, configs[0]: 100k x 384 8-bit) and k <= 24.
+//
+// Why a second kernel: a 32-row block of such rows is only C * 512 bytes.  The general kernel (scan_impl.cuh)
+// spends ~420 instructions per block on them, of which the arithmetic is ~150 -- ring stages, barriers, per-tile
+// bookkeeping, run-time chunk loops and per-chunk digit loads are sized for rows of kilobytes -- and with every warp
+// of the grid walking every query it ends a query after a dozen blocks (2368 candidate lists per query, each warmed
+// up from empty).  Measured (profiles/r01_small_rows_*): 20 us per query for 64 MB that sit in L2, issue-bound.
+//
+// What is different here:
+//  * chunk count, digit count and blocks per step are compile-time: everything is unrolled, no ring, no barriers --
+//    a lane loads its row's chunks with plain coalesced 128-bit loads (the collection fits L2 at these row sizes or
+//    streams with a dozen warps' worth of 8 KB steps in flight per SM), 16 uint4 (U = 16 / C blocks) per step;
+//  * the query's digits are read from shared memory once per chunk and applied to the U rows a lane holds;
+//  * queries are dealt to CTAs: a launch of nq queries is cut in nq x P work items (query, part), an item is
+//    processed by ONE CTA whose warps stride over the part's blocks, so a query ends in P x warps lists (16 when
+//    nq >= SM count) and a warp sees hundreds of blocks per query; all warps of the CTA share one bound (the same
+//    argument as the general kernel's short-scan variant).  P = SM count for a single query: the decomposition the
+//    general kernel has.
+// Keys are computed by the same Scorer<QT, ND>::step / finish as the general kernel: identical surrogate keys,
+// identical candidate semantics, finalize_kernel unchanged.
+#pragma once
+#include "scan_impl.cuh"
+
+namespace szg {
+
+constexpr int kSmallWarps = 16;
+
+template <int QT, int ND>
+struct SmallOps;
+template <int ND>
+struct SmallOps<Q8, ND> {
+    using Dig = uint4;
+    static constexpr int DPC = ND;
+    struct A { int a[ND]; };
+    static __device__ __forceinline__ void reset(A &s) {
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s.a[j] = 0;
+    }
+    static __device__ __forceinline__ void apply(const uint4 &v, const Dig *d, A &s) { Scorer<Q8, ND>::step(v, d, s.a); }
+    static __device__ __forceinline__ float finish(const A &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
+        typename Scorer<Q8, ND>::Acc t;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) t.a[j] = s.a[j];
+        return Scorer<Q8, ND>::finish(t, a, h, x);
+    }
+};
+template <int ND>
+struct SmallOps<Q4, ND> {
+    using Dig = uint4;
+    static constexpr int DPC = 2 * ND;
+    using A = typename Scorer<Q4, ND>::Acc;
+    static __device__ __forceinline__ void reset(A &s) { Scorer<Q4, ND>::reset(s); }
+    static __device__ __forceinline__ void apply(const uint4 &v, const Dig *d, A &s) { Scorer<Q4, ND>::step(v, d, s.hi, s.lo); }
+    static __device__ __forceinline__ float finish(const A &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
+        return Scorer<Q4, ND>::finish(s, a, h, x);
+    }
+};
+template <int ND>
+struct SmallOps<Q16, ND> {
+    using Dig = uint2;
+    static constexpr int DPC = ND;
+    struct A { int a[ND]; }; // |s16 * s8| <= 2^22 and at most 384 dims (C <= 48): int32 partials hold a whole row
+    static __device__ __forceinline__ void reset(A &s) {
+#pragma unroll
+        for (int j = 0; j < ND; ++j) s.a[j] = 0;
+    }
+    static __device__ __forceinline__ void apply(const uint4 &v, const Dig *d, A &s) { Scorer<Q16, ND>::step(v, d, s.a); }
+    static __device__ __forceinline__ float finish(const A &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
+        typename Scorer<Q16, ND>::Acc t;
+        t.I = digits_total<ND>(s.a); // the general kernel flushes per tile: one tile here
+        return Scorer<Q16, ND>::finish(t, a, h, x);
+    }
+};
+
+template <int QT, int ND, int C>
+__global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const ScanArgs a) {
+    // a lane holds 16 uint4 of row data at a time: U = 16 / C whole rows (of U different blocks) when C <= 8, else one
+    // row in pieces of up to 16 chunks (C = 24: 16 + 8)
+    constexpr int PC = C < 16 ? C : 16; // chunks per piece
+    constexpr int U = 16 / PC;          // blocks per step
+    constexpr int NP = (C + PC - 1) / PC;
+    using Ops = SmallOps<QT, ND>;
+    using Dig = typename Ops::Dig;
+    constexpr int DPC = Ops::DPC;
+    extern __shared__ __align__(16) unsigned char s_pq[]; // the item's prepared query: header + digits
+    __shared__ uint32_t s_pub[kSmallWarps];               // key of each warp's mth-best row so far (0xFFFFFFFF: none yet)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const uint32_t P = a.parts, nitems = a.nq * P, nlists = P * (uint32_t)nw;
+    const uint32_t mth = (32u + (uint32_t)nw - 1) / (uint32_t)nw;
+    const uint32_t stride = P * (uint32_t)nw;
+    const uint32_t n16 = (uint32_t)(a.pq_stride / 16);
+    for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const uint32_t q = item / P, p = item - q * P;
+        __syncthreads(); // the previous item's readers of s_pq / s_pub are done
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.pq + (size_t)q * a.pq_stride);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_pq);
+            for (uint32_t i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+            if (tid < nw) s_pub[tid] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        const PQHeader &h = *reinterpret_cast<const PQHeader *>(s_pq);
+        const Dig *dig = reinterpret_cast<const Dig *>(s_pq + sizeof(PQHeader));
+        WarpList<1> list;
+        list.init();
+        for (uint32_t b0 = p * (uint32_t)nw + (uint32_t)warp; b0 < a.nblk; b0 += stride * U) {
+            float2 ax[U];
+            uint32_t lv[U];
+            const uint4 *src[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t blk = b0 + (uint32_t)u * stride;
+                const bool in = blk < a.nblk;                    // warp-uniform
+                const uint32_t bc = in ? blk : a.nblk - 1;       // clamped: loads stay unconditional and in flight together
+                uint32_t w = __ldg(a.live + bc);
+                if (a.mask) w &= __ldg(a.mask + bc);
+                lv[u] = in ? w : 0u;
+                src[u] = a.codes + (size_t)bc * C * 32 + lane;
+                ax[u] = load_aux(a, bc * 32 + lane);
+            }
+            typename Ops::A acc[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) Ops::reset(acc[u]);
+#pragma unroll
+            for (int pz = 0; pz < NP; ++pz) {
+                uint4 data[U][PC];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int c = 0; c < PC; ++c)
+                        if (pz * PC + c < C) data[u][c] = __ldg(src[u] + (pz * PC + c) * 32);
+#pragma unroll
+                for (int c = 0; c < PC; ++c) {
+                    if (pz * PC + c < C) {
+                        Dig d[DPC]; // this chunk's digits: warp-uniform shared loads, used for the U rows of the lane
+#pragma unroll
+                        for (int j = 0; j < DPC; ++j) d[j] = dig[(pz * PC + c) * DPC + j];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) Ops::apply(data[u][c], d, acc[u]);
+                    }
+                }
+            }
+            unsigned long long keys[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float key = Ops::finish(acc[u], a, h, ax[u]);
+                const uint32_t blk = b0 + (uint32_t)u * stride;
+                keys[u] = ((lv[u] >> lane) & 1u) ? make_key64(key, blk * 32 + lane) : kNoKey;
+            }
+            { // the CTA's shared bound: once every warp has published, nothing above the largest published key matters
+                const uint32_t e = lane < nw ? *reinterpret_cast<volatile uint32_t *>(&s_pub[lane]) : 0u;
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, e);
+                if (mx != 0xFFFFFFFFu) {
+                    const unsigned long long b = ((unsigned long long)mx << 32) | 0xFFFFFFFFull;
+                    if (b < list.thr) list.thr = b; // keys equal to the bound still pass
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (lv[u]) list.offer(keys[u], lane);
+            if ((uint32_t)lane == mth - 1 && list.v[0] != kNoKey) {
+                const uint32_t pk = (uint32_t)(list.v[0] >> 32);
+                if (pk < s_pub[warp]) *reinterpret_cast<volatile uint32_t *>(&s_pub[warp]) = pk;
+            }
+        }
+        // this warp's list of (query q, part p) -> finalize_kernel
+        a.cand[((size_t)q * nlists + (size_t)p * nw + warp) * 32 + lane] = list.v[0];
+    }
+}
+
+// parts per query that minimise the makespan of nq x P items dealt round-robin to `grid` CTAs (ties: fewer parts =
+// fewer, longer lists); P <= 32 unless a single round needs more
+inline uint32_t small_parts(uint32_t nq, uint32_t grid) {
+    if (nq == 0) return 1;
+    if (nq * 32u <= grid) return grid / nq; // few queries: one round, every CTA busy
+    uint32_t best = 1;
+    double best_t = 1e30;
+    for (uint32_t P = 1; P <= 32; ++P) {
+        const uint32_t rounds = (nq * P + grid - 1) / grid;
+        const double t = (double)rounds / P + 0.002 * rounds; // + a small per-item cost
+        if (t < best_t - 1e-12) { best_t = t; best = P; }
+    }
+    return best;
+}
+
+template <int QT, int ND>
+cudaError_t launch_scan_small_nd(uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
+    switch (C) {
+    case 2: scan_small_kernel<QT, ND, 2><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    case 4: scan_small_kernel<QT, ND, 4><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    case 8: scan_small_kernel<QT, ND, 8><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    case 12: scan_small_kernel<QT, ND, 12><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    case 16: scan_small_kernel<QT, ND, 16><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    case 24: scan_small_kernel<QT, ND, 24><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    case 32: scan_small_kernel<QT, ND, 32><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    case 48: scan_small_kernel<QT, ND, 48><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+template <int QT>
+cudaError_t launch_scan_small_t(int nd, uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
+    if (nd == 2) return launch_scan_small_nd<QT, 2>(C, grid, smem, st, a);
+    return launch_scan_small_nd<QT, 3>(C, grid, smem, st, a);
+}
+
+inline bool scan_small_supported(int qt, uint32_t C) {
+    return qt <= Q16 && (C == 2 || C == 4 || C == 8 || C == 12 || C == 16 || C == 24 || C == 32 || C == 48);
+}
+
+} // namespace szg
