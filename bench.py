@@ -418,20 +418,59 @@ def run_b200(a):
         }
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    alg_bytes = my_rows * rb * a.nq  # one scan launch streams the shard once per query of the step
-    # DRAM traffic of that launch from the committed ncu --set full capture of the same kernel and row shape
-    # (dram__bytes_read.sum + dram__bytes_write.sum per row and query), scaled to this launch
+    # algorithmic bytes of one scan launch: every query of the launch scans the shard's payload once
+    nl = max(len(scan_ms), 1)
+    alg_bytes = my_rows * rb * a.nq * a.steps / nl
+    chunks = -(-rb // 16)
+    small = (a.quant <= 16 and a.k <= 24 and chunks in (2, 4, 8, 12, 16, 24, 32, 48) and os.environ.get("SZG_SCAN_SMALL", "1") != "0")
+    kernel = (f"scan_small_kernel<Q{a.quant}, 2 digits, {chunks} chunks> (queries dealt to CTA groups; {a.nq * a.steps // nl} queries x shard per launch)"
+              if small else f"scan_kernel<Q{a.quant}, top-k> ({a.nq * a.steps // nl} queries x shard per launch)")
+    # DRAM traffic of that launch from the committed ncu --set full capture of the same kernel, row shape and queries per
+    # launch (dram__bytes_read.sum + dram__bytes_write.sum), scaled by rows
     traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
             tr = json.load(f)
-        key = f"q{a.quant}_d{a.dims}"
-        if key in tr:
+        key = f"q{a.quant}_d{a.dims}_nq{a.nq}" if small else f"q{a.quant}_d{a.dims}"
+        if key in tr and "dram_bytes_per_row_per_launch" in tr[key]:
+            traffic = tr[key]["dram_bytes_per_row_per_launch"] * my_rows
+            traffic_src = tr[key]["source"]
+        elif key in tr:
             traffic = tr[key]["dram_bytes_per_row_per_query"] * my_rows * a.nq
             traffic_src = tr[key]["source"]
     except Exception:
         pass
     achieved = alg_bytes / (mean_scan_ms / 1e3) / 1e9 if mean_scan_ms == mean_scan_ms else None
+    dram_gbs = traffic / (mean_scan_ms / 1e3) / 1e9 if (traffic and mean_scan_ms == mean_scan_ms) else None
+    note = None
+    if small and a.nq > 1:
+        note = ("achieved counts every query's scan of the shard (algorithmic bytes); the queries of a launch run on different "
+                "CTA groups at the same time and find each other's rows in L2, so the DRAM traffic of the launch (traffic, "
+                "dram_achieved) is a fraction of it and frac can exceed 1.  The launch is bound by the L1 data pipe, not by HBM "
+                "(profiles/r01b_scan_small_q8_ncu_full.csv); single_query below is the HBM-bound case")
+
+    # ---- the same scan one query per launch: the memory-bound single-query case of the north star
+    single_query = None
+    if a.nq > 1:
+        for s in range(min(3, total_steps)):
+            sh.search_topk_dev(dq[s][:1].contiguous(), a.k)
+        sync_all()
+        ix.last_scan_times_ms(65536)
+        e0.record()
+        for s in range(a.warmup, total_steps):
+            sh.search_topk_dev(dq[s][:1].contiguous(), a.k)
+        e1.record()
+        sync_all()
+        t1q = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t1q, op=dist.ReduceOp.MAX)
+        sq_scan = ix.last_scan_times_ms(65536)
+        sq_ms = float(np.mean(sq_scan)) if len(sq_scan) else float("nan")
+        sq_ach = my_rows * rb / (sq_ms / 1e3) / 1e9 if sq_ms == sq_ms else None
+        single_query = {"value": a.steps / (float(t1q.item()) / 1e3), "unit": UNIT, "queries_per_launch": 1,
+                        "ms_per_query": float(t1q.item()) / a.steps, "scan_launch_ms": sq_ms,
+                        "roofline": {"bound": "hbm", "achieved": sq_ach, "peak": peak, "unit": "GB/s",
+                                     "frac": (sq_ach / peak) if sq_ach else None}}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -453,9 +492,11 @@ def run_b200(a):
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": f"scan_kernel<Q{a.quant}, top-k> (one launch per step = {a.nq} queries x shard)",
-                         "alg_bytes_per_launch": alg_bytes,
-                         "mean_launch_ms": mean_scan_ms, "launches_timed": int(len(scan_ms)), "peak_source": peak_src},
+                         "dram_achieved": dram_gbs, "dram_frac": (dram_gbs / peak) if dram_gbs else None,
+                         "kernel": kernel, "alg_bytes_per_launch": alg_bytes,
+                         "mean_launch_ms": mean_scan_ms, "launches_timed": int(len(scan_ms)), "peak_source": peak_src,
+                         "note": note},
+            "single_query": single_query,
             "cpu_baseline": cpu, "clocks": clocks, "batched": batched,
             "library": {"escalations": stats["escalations"], "uncertain_results": stats["uncertain_results"],
                         "scan_grid": stats["scan_grid"], "scan_block": stats["scan_block"]},

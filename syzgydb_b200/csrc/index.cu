@@ -396,6 +396,8 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
         a.pq = ws->d_pq.p + stride * q0;
         a.nq = m;
         a.parts = parts;
+        static const int adj_env = getenv("SZG_SMALL_ADJ") ? atoi(getenv("SZG_SMALL_ADJ")) : -1;
+        a.adjacent = adj_env >= 0 ? (uint32_t)adj_env : (h->C < 48 ? 1u : 0u);
         a.cand = ws->d_cand.p;
         if (timing) CK(cudaEventRecord(ws->t0[tbase + l], main));
         CK(launch_scan_small(h->qt, nd, h->C, grid, stride, main, a));

@@ -49,6 +49,7 @@ struct ScanArgs {
     uint32_t pq_smem_off;       // != 0: every warp keeps a private copy of its current prepared query at this
                                 // offset of dynamic shared memory (+ warp * pq_stride); 0: read it through L1
     uint32_t parts;             // scan_small_kernel only: work items (row parts) per query
+    uint32_t adjacent;          // scan_small_kernel only: the blocks of a step are adjacent (else a warp stride apart)
     // top-k output: per-warp candidate lists, consumed by finalize_kernel
     unsigned long long *cand;   // [nq][grid warps][32*E]
     // radius outputs

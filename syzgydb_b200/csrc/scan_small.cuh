@@ -75,10 +75,12 @@ struct SmallOps<Q16, ND> {
 
 template <int QT, int ND, int C>
 __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const ScanArgs a) {
-    // a lane holds 16 uint4 of row data at a time: U = 16 / C whole rows (of U different blocks) when C <= 8, else one
-    // row in pieces of up to 16 chunks (C = 24: 16 + 8)
-    constexpr int PC = C < 16 ? C : 16; // chunks per piece
-    constexpr int U = 16 / PC;          // blocks per step
+    // a lane holds 16 uint4 of row data at a time: U = 16 / C whole rows (of U different blocks) when C <= 8, else
+    // pieces of 8 chunks of two rows (C = 12: 4 chunks of four rows).  The digits of a chunk are read once for the U
+    // rows: the L1 data pipe, which carries the row loads and the digit broadcasts, is what limits this kernel (89 %
+    // with one row per lane, profiles/r01b_scan_small_q8_ncu_full.csv; cfg4: 2084 -> 2575 QPS with two)
+    constexpr int PC = C <= 8 ? C : (C % 8 == 0 ? 8 : 4); // chunks per piece (measured: 8 beats 4 and 16 at C = 24 .. 48)
+    constexpr int U = 16 / PC;                             // blocks per step
     constexpr int NP = (C + PC - 1) / PC;
     using Ops = SmallOps<QT, ND>;
     using Dig = typename Ops::Dig;
@@ -104,13 +106,16 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
         const Dig *dig = reinterpret_cast<const Dig *>(s_pq + sizeof(PQHeader));
         WarpList<1> list;
         list.init();
-        for (uint32_t b0 = p * (uint32_t)nw + (uint32_t)warp; b0 < a.nblk; b0 += stride * U) {
+        // a step takes U blocks: adjacent ones (contiguous in the mirror; a.adjacent) or `stride` apart
+        const uint32_t ustep = a.adjacent ? 1u : stride;
+        for (uint32_t g = p * (uint32_t)nw + (uint32_t)warp; (a.adjacent ? g * U : g) < a.nblk; g += a.adjacent ? stride : stride * U) {
+            const uint32_t b0 = a.adjacent ? g * U : g;
             float2 ax[U];
             uint32_t lv[U];
             const uint4 *src[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const uint32_t blk = b0 + (uint32_t)u * stride;
+                const uint32_t blk = b0 + (uint32_t)u * ustep;
                 const bool in = blk < a.nblk;                    // warp-uniform
                 const uint32_t bc = in ? blk : a.nblk - 1;       // clamped: loads stay unconditional and in flight together
                 uint32_t w = __ldg(a.live + bc);
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const float key = Ops::finish(acc[u], a, h, ax[u]);
-                const uint32_t blk = b0 + (uint32_t)u * stride;
+                const uint32_t blk = b0 + (uint32_t)u * ustep;
                 keys[u] = ((lv[u] >> lane) & 1u) ? make_key64(key, blk * 32 + lane) : kNoKey;
             }
             { // the CTA's shared bound: once every warp has published, nothing above the largest published key matters
