@@ -388,10 +388,13 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
     for (uint32_t l = 0, q0 = 0; q0 < nq; q0 += chunk, ++l) {
         const uint32_t m = std::min(chunk, nq - q0);
         // parts per query: as many as keep every CTA busy, but no part shorter than one block per warp
-        uint32_t parts = small_parts(m, sms);
+        const uint32_t qper = 1; // queries per item (pairs were measured slower: see scan_small.cuh)
+        const uint32_t groups = (m + qper - 1) / qper;
+        uint32_t parts = small_parts(groups, sms);
         parts = std::max<uint32_t>(1, std::min<uint32_t>(parts, (nblk + kSmallWarps - 1) / kSmallWarps));
         const uint32_t nlists = parts * kSmallWarps;
-        const int grid = (int)std::min<uint64_t>((uint64_t)m * parts, sms);
+        const int grid = (int)std::min<uint64_t>((uint64_t)groups * parts, sms);
+        a.qper = qper;
         if ((rc = ws->d_cand.ensure((size_t)m * nlists * 32))) return rc;
         a.pq = ws->d_pq.p + stride * q0;
         a.nq = m;
@@ -400,7 +403,7 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
         a.adjacent = adj_env >= 0 ? (uint32_t)adj_env : (h->C < 48 ? 1u : 0u);
         a.cand = ws->d_cand.p;
         if (timing) CK(cudaEventRecord(ws->t0[tbase + l], main));
-        CK(launch_scan_small(h->qt, nd, h->C, grid, stride, main, a));
+        CK(launch_scan_small(h->qt, nd, h->C, grid, stride * qper, main, a));
         if (timing) CK(cudaEventRecord(ws->t1[tbase + l], main));
         f.cand = ws->d_cand.p;
         f.nlists = nlists;

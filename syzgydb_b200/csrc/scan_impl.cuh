@@ -50,6 +50,7 @@ struct ScanArgs {
                                 // offset of dynamic shared memory (+ warp * pq_stride); 0: read it through L1
     uint32_t parts;             // scan_small_kernel only: work items (row parts) per query
     uint32_t adjacent;          // scan_small_kernel only: the blocks of a step are adjacent (else a warp stride apart)
+    uint32_t qper;              // scan_small_kernel only: queries per work item (1 or 2)
     // top-k output: per-warp candidate lists, consumed by finalize_kernel
     unsigned long long *cand;   // [nq][grid warps][32*E]
     // radius outputs

@@ -73,39 +73,44 @@ struct SmallOps<Q16, ND> {
     }
 };
 
-template <int QT, int ND, int C>
+template <int QT, int ND, int C, int Q>
 __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const ScanArgs a) {
     // a lane holds 16 uint4 of row data at a time: U = 16 / C whole rows (of U different blocks) when C <= 8, else
     // pieces of 8 chunks of two rows (C = 12: 4 chunks of four rows).  The digits of a chunk are read once for the U
     // rows: the L1 data pipe, which carries the row loads and the digit broadcasts, is what limits this kernel (89 %
-    // with one row per lane, profiles/r01b_scan_small_q8_ncu_full.csv; cfg4: 2084 -> 2575 QPS with two)
+    // with one row per lane, profiles/r01b_scan_small_q8_ncu_full.csv; cfg4: 2084 -> 2575 QPS with two).
+    // Q = 2: an item is a PAIR of queries -- every loaded row chunk is scored against both, which halves the row
+    // loads per query through that pipe.
     constexpr int PC = C <= 8 ? C : (C % 8 == 0 ? 8 : 4); // chunks per piece (measured: 8 beats 4 and 16 at C = 24 .. 48)
     constexpr int U = 16 / PC;                             // blocks per step
     constexpr int NP = (C + PC - 1) / PC;
     using Ops = SmallOps<QT, ND>;
     using Dig = typename Ops::Dig;
     constexpr int DPC = Ops::DPC;
-    extern __shared__ __align__(16) unsigned char s_pq[]; // the item's prepared query: header + digits
-    __shared__ uint32_t s_pub[kSmallWarps];               // key of each warp's mth-best row so far (0xFFFFFFFF: none yet)
+    extern __shared__ __align__(16) unsigned char s_pq[]; // the item's prepared queries: Q x (header + digits)
+    __shared__ uint32_t s_pub[Q][kSmallWarps];            // key of each warp's mth-best row so far (0xFFFFFFFF: none yet)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const uint32_t P = a.parts, nitems = a.nq * P, nlists = P * (uint32_t)nw;
+    const uint32_t P = a.parts, ngroups = (a.nq + Q - 1) / Q, nitems = ngroups * P, nlists = P * (uint32_t)nw;
     const uint32_t mth = (32u + (uint32_t)nw - 1) / (uint32_t)nw;
     const uint32_t stride = P * (uint32_t)nw;
     const uint32_t n16 = (uint32_t)(a.pq_stride / 16);
     for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const uint32_t q = item / P, p = item - q * P;
+        const uint32_t qg = item / P, p = item - qg * P;
+        const uint32_t q0 = qg * Q;
+        const uint32_t nqv = min((uint32_t)Q, a.nq - q0); // queries of this item (the last group may be short)
         __syncthreads(); // the previous item's readers of s_pq / s_pub are done
         {
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.pq + (size_t)q * a.pq_stride);
-            uint4 *dst = reinterpret_cast<uint4 *>(s_pq);
-            for (uint32_t i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-            if (tid < nw) s_pub[tid] = 0xFFFFFFFFu;
+            for (uint32_t i = tid; i < n16 * nqv; i += blockDim.x) {
+                const uint32_t qq = i / n16, k = i - qq * n16;
+                reinterpret_cast<uint4 *>(s_pq + (size_t)qq * a.pq_stride)[k] =
+                    __ldg(reinterpret_cast<const uint4 *>(a.pq + (size_t)(q0 + qq) * a.pq_stride) + k);
+            }
+            if (tid < nw * Q) s_pub[tid / nw][tid % nw] = 0xFFFFFFFFu;
         }
         __syncthreads();
-        const PQHeader &h = *reinterpret_cast<const PQHeader *>(s_pq);
-        const Dig *dig = reinterpret_cast<const Dig *>(s_pq + sizeof(PQHeader));
-        WarpList<1> list;
-        list.init();
+        WarpList<1> list[Q];
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq) list[qq].init();
         // a step takes U blocks: adjacent ones (contiguous in the mirror; a.adjacent) or `stride` apart
         const uint32_t ustep = a.adjacent ? 1u : stride;
         for (uint32_t g = p * (uint32_t)nw + (uint32_t)warp; (a.adjacent ? g * U : g) < a.nblk; g += a.adjacent ? stride : stride * U) {
@@ -124,9 +129,11 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
                 src[u] = a.codes + (size_t)bc * C * 32 + lane;
                 ax[u] = load_aux(a, bc * 32 + lane);
             }
-            typename Ops::A acc[U];
+            typename Ops::A acc[Q][U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) Ops::reset(acc[u]);
+            for (int qq = 0; qq < Q; ++qq)
+#pragma unroll
+                for (int u = 0; u < U; ++u) Ops::reset(acc[qq][u]);
 #pragma unroll
             for (int pz = 0; pz < NP; ++pz) {
                 uint4 data[U][PC];
@@ -138,39 +145,53 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
                     if (pz * PC + c < C) {
-                        Dig d[DPC]; // this chunk's digits: warp-uniform shared loads, used for the U rows of the lane
 #pragma unroll
-                        for (int j = 0; j < DPC; ++j) d[j] = dig[(pz * PC + c) * DPC + j];
+                        for (int qq = 0; qq < Q; ++qq) {
+                            if (Q == 1 || (uint32_t)qq < nqv) { // CTA-uniform
+                                // this chunk's digits of query qq: warp-uniform shared loads, used for the U rows of the lane
+                                const Dig *dig = reinterpret_cast<const Dig *>(s_pq + (size_t)qq * a.pq_stride + sizeof(PQHeader));
+                                Dig d[DPC];
 #pragma unroll
-                        for (int u = 0; u < U; ++u) Ops::apply(data[u][c], d, acc[u]);
+                                for (int j = 0; j < DPC; ++j) d[j] = dig[(pz * PC + c) * DPC + j];
+#pragma unroll
+                                for (int u = 0; u < U; ++u) Ops::apply(data[u][c], d, acc[qq][u]);
+                            }
+                        }
                     }
                 }
             }
-            unsigned long long keys[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float key = Ops::finish(acc[u], a, h, ax[u]);
-                const uint32_t blk = b0 + (uint32_t)u * ustep;
-                keys[u] = ((lv[u] >> lane) & 1u) ? make_key64(key, blk * 32 + lane) : kNoKey;
-            }
-            { // the CTA's shared bound: once every warp has published, nothing above the largest published key matters
-                const uint32_t e = lane < nw ? *reinterpret_cast<volatile uint32_t *>(&s_pub[lane]) : 0u;
-                const uint32_t mx = __reduce_max_sync(0xffffffffu, e);
-                if (mx != 0xFFFFFFFFu) {
-                    const unsigned long long b = ((unsigned long long)mx << 32) | 0xFFFFFFFFull;
-                    if (b < list.thr) list.thr = b; // keys equal to the bound still pass
+            for (int qq = 0; qq < Q; ++qq) {
+                if (Q > 1 && (uint32_t)qq >= nqv) continue;
+                const PQHeader &h = *reinterpret_cast<const PQHeader *>(s_pq + (size_t)qq * a.pq_stride);
+                unsigned long long keys[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float key = Ops::finish(acc[qq][u], a, h, ax[u]);
+                    const uint32_t blk = b0 + (uint32_t)u * ustep;
+                    keys[u] = ((lv[u] >> lane) & 1u) ? make_key64(key, blk * 32 + lane) : kNoKey;
+                }
+                { // the CTA's shared bound: once every warp has published, nothing above the largest published key matters
+                    const uint32_t e = lane < nw ? *reinterpret_cast<volatile uint32_t *>(&s_pub[qq][lane]) : 0u;
+                    const uint32_t mx = __reduce_max_sync(0xffffffffu, e);
+                    if (mx != 0xFFFFFFFFu) {
+                        const unsigned long long b = ((unsigned long long)mx << 32) | 0xFFFFFFFFull;
+                        if (b < list[qq].thr) list[qq].thr = b; // keys equal to the bound still pass
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (lv[u]) list[qq].offer(keys[u], lane);
+                if ((uint32_t)lane == mth - 1 && list[qq].v[0] != kNoKey) {
+                    const uint32_t pk = (uint32_t)(list[qq].v[0] >> 32);
+                    if (pk < s_pub[qq][warp]) *reinterpret_cast<volatile uint32_t *>(&s_pub[qq][warp]) = pk;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (lv[u]) list.offer(keys[u], lane);
-            if ((uint32_t)lane == mth - 1 && list.v[0] != kNoKey) {
-                const uint32_t pk = (uint32_t)(list.v[0] >> 32);
-                if (pk < s_pub[warp]) *reinterpret_cast<volatile uint32_t *>(&s_pub[warp]) = pk;
-            }
         }
-        // this warp's list of (query q, part p) -> finalize_kernel
-        a.cand[((size_t)q * nlists + (size_t)p * nw + warp) * 32 + lane] = list.v[0];
+        // this warp's lists of (query, part p) -> finalize_kernel
+#pragma unroll
+        for (int qq = 0; qq < Q; ++qq)
+            if ((uint32_t)qq < nqv) a.cand[((size_t)(q0 + qq) * nlists + (size_t)p * nw + warp) * 32 + lane] = list[qq].v[0];
     }
 }
 
@@ -189,25 +210,25 @@ inline uint32_t small_parts(uint32_t nq, uint32_t grid) {
     return best;
 }
 
-template <int QT, int ND>
+template <int QT, int ND, int Q>
 cudaError_t launch_scan_small_nd(uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
     switch (C) {
-    case 2: scan_small_kernel<QT, ND, 2><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
-    case 4: scan_small_kernel<QT, ND, 4><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
-    case 8: scan_small_kernel<QT, ND, 8><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
-    case 12: scan_small_kernel<QT, ND, 12><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
-    case 16: scan_small_kernel<QT, ND, 16><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
-    case 24: scan_small_kernel<QT, ND, 24><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
-    case 32: scan_small_kernel<QT, ND, 32><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
-    case 48: scan_small_kernel<QT, ND, 48><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+#define SZG_SMALL_CASE(CC) case CC: scan_small_kernel<QT, ND, CC, Q><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+    SZG_SMALL_CASE(2) SZG_SMALL_CASE(4) SZG_SMALL_CASE(8) SZG_SMALL_CASE(12) SZG_SMALL_CASE(16) SZG_SMALL_CASE(24)
+    SZG_SMALL_CASE(32) SZG_SMALL_CASE(48)
+#undef SZG_SMALL_CASE
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
+// Q (queries per item) = 2 was measured and is not instantiated: scoring every loaded chunk against a pair of queries halves the
+// row loads per query, but the pair's accumulators, lists and digits cost the registers that keep 16 loads in flight per lane --
+// cfg4 2374 -> 1217 QPS, 24-chunk rows 20 -> 37 us/query; only rows of <= 4 chunks gained (~10 %): profiles/r01b_scan_small_vs_general.log
 template <int QT>
 cudaError_t launch_scan_small_t(int nd, uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
-    if (nd == 2) return launch_scan_small_nd<QT, 2>(C, grid, smem, st, a);
-    return launch_scan_small_nd<QT, 3>(C, grid, smem, st, a);
+    if (a.qper != 1) return cudaErrorInvalidValue;
+    if (nd == 2) return launch_scan_small_nd<QT, 2, 1>(C, grid, smem, st, a);
+    return launch_scan_small_nd<QT, 3, 1>(C, grid, smem, st, a);
 }
 
 inline bool scan_small_supported(int qt, uint32_t C) {

@@ -844,3 +844,36 @@ def test_batch_tiny_and_emptied_collections(bits):
     with szg.Index(dims, bits, szg.COSINE) as ix:   # never filled
         gi, gd, gn, scanned = ix.search_batch(queries, 3)
         assert scanned == 0 and np.all(gn == 0)
+
+
+# ------------------------------------------------------------------ scan_small.cuh (rows up to 48 chunks, k <= 24)
+@pytest.mark.parametrize("bits,dims", [(4, 64), (4, 128), (8, 64), (8, 128), (4, 384), (16, 96), (8, 256), (16, 128), (8, 384),
+                                       (4, 768), (16, 256), (8, 512), (8, 768), (16, 384), (4, 1536)])
+def test_short_row_kernel_matches_general_kernel_and_oracle(bits, dims):
+    # chunk counts 2, 4, 8, 12, 16, 24, 32, 48; query counts that give one part per SM (1 query), several parts per query and
+    # several queries per CTA; a filter mask, tombstones and a ragged last block.  The general kernel is forced by setting a
+    # scan geometry option (the short-row kernel only runs with the automatic geometry).
+    metric = szg.COSINE if (bits + dims) % 3 else szg.EUCLIDEAN
+    n = 4000 + dims % 37
+    codes = o.synth_rows(300 + bits + dims, 0, n, dims, bits)
+    ids = np.arange(n, dtype=np.uint64) * 3
+    keep = np.ones(n, dtype=bool)
+    keep[5:n:11] = False
+    passmask = (np.arange(n) % 4 != 1).astype(np.uint8)
+    with szg.Index(dims, bits, metric) as ix, szg.Index(dims, bits, metric) as gx:
+        for x in (ix, gx):
+            x.upsert(ids, codes)
+            x.remove(ids[~keep])
+        gx.set_option(_capi.OPT_SCAN_WARPS, 16)  # general kernel
+        m1, m2 = ix.mask_create(ids, passmask), gx.mask_create(ids, passmask)
+        for nq, k, masked in ((1, 10, False), (3, 24, True), (37, 10, False), (150, 5, True), (300, 1, False)):
+            qs = o.synth_queries(900 + nq, 0, nq, dims)
+            a = ix.search_topk(qs, k, mask_id=m1 if masked else -1)
+            b = gx.search_topk(qs, k, mask_id=m2 if masked else -1)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+            live = keep & (passmask.astype(bool) if masked else True)
+            for qi in (0, nq - 1):
+                ri, rd, _ = o.search_exact(codes[keep], ids[keep], dims, bits, metric, qs[qi], k=k,
+                                           passmask=passmask[keep] if masked else None)
+                assert_results_match(a[0][qi, :a[2][qi]], a[1][qi, :a[2][qi]], ri, rd, what=f"short rows b{bits} d{dims} nq{nq}")
+                assert a[2][qi] == min(k, int(live.sum()))
