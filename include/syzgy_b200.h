@@ -340,6 +340,8 @@ typedef struct szg_stats {
     uint32_t scan_stages;       /* shared-memory ring stages per warp */
     uint32_t scan_tile_bytes;   /* bytes of one bulk-copied tile */
     uint32_t scan_smem_bytes;   /* dynamic shared memory per CTA */
+    uint32_t reserved0;
+    uint64_t combined_queries;  /* queries of concurrent szg_search_topk calls that were answered by a shared launch */
 } szg_stats;
 int szg_get_stats(szg_index *h, szg_stats *out);
 
@@ -354,6 +356,9 @@ int szg_get_stats(szg_index *h, szg_stats *out);
 #define SZG_OPT_DIGITS 7             /* fixed-point digits of the query: 0 automatic (2, re-run with 3 when the
                                         result cannot be certified), 2 or 3 forced */
 #define SZG_OPT_BATCH_TENSOR 8       /* 0: szg_search_batch uses the streaming scan; 1 (default): tensor cores */
+#define SZG_OPT_COMBINE 9            /* 1 (default): concurrent szg_search_topk calls on one handle (Search holds only the
+                                        RLock, collection.go:570) with the same k / mask / flags share one launch: whoever
+                                        arrives while a launch is running is answered together by the next one; 0: off */
 int szg_set_option(szg_index *h, int option, int64_t value);
 
 /* Time of the most recent scan launches on this handle, measured with CUDA events on the

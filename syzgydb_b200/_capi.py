@@ -28,6 +28,7 @@ OPT_SCAN_STAGES = 5
 OPT_SCAN_TILE_CHUNKS = 6
 OPT_DIGITS = 7
 OPT_BATCH_TENSOR = 8
+OPT_COMBINE = 9
 
 # szg_filter_op opcodes (include/syzgy_b200.h SZG_FOP_*)
 (FOP_COL, FOP_NUM, FOP_STR, FOP_BOOL, FOP_NULL, FOP_EQ, FOP_NE, FOP_LT, FOP_LE, FOP_GT, FOP_GE, FOP_AND, FOP_OR, FOP_NOT,
@@ -75,7 +76,7 @@ class Stats(C.Structure):
         ("device_bytes", C.c_uint64), ("live_rows", C.c_uint64), ("slots", C.c_uint64),
         ("rowbytes", C.c_uint32), ("pitch", C.c_uint32), ("sm_count", C.c_uint32), ("scan_grid", C.c_uint32),
         ("scan_block", C.c_uint32), ("scan_stages", C.c_uint32), ("scan_tile_bytes", C.c_uint32),
-        ("scan_smem_bytes", C.c_uint32),
+        ("scan_smem_bytes", C.c_uint32), ("reserved0", C.c_uint32), ("combined_queries", C.c_uint64),
     ]
 
 

@@ -3,6 +3,7 @@
 // streams, launches.  There is deliberately no CPU implementation of any search step.
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -193,6 +194,14 @@ struct szg_index {
     DevBuf<unsigned char> col_kind[kFilterMaxCols];
     DevBuf<unsigned long long> col_val[kFilterMaxCols];
     bool meta_used = false;
+    // combining of concurrent single-query calls (szg_search_topk)
+    struct PendingSearch;
+    std::mutex comb_mu;
+    std::condition_variable comb_cv;
+    std::vector<PendingSearch *> comb_queue;
+    bool comb_leader = false;
+    int combine = 1;
+    uint64_t combined_queries = 0;
     DevBuf<unsigned char> d_filter_blob; // program + tables + ranks of the filter being evaluated (kept between calls)
     std::unordered_map<std::string, uint32_t> dict;
     std::vector<std::string> dict_strs;
@@ -672,6 +681,7 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
         h->scan_geometry_set = true;
         return SZG_OK;
     case SZG_OPT_BATCH_TENSOR: h->batch_disabled = value == 0; return SZG_OK;
+    case SZG_OPT_COMBINE: h->combine = value != 0; return SZG_OK;
     case SZG_OPT_DIGITS:
         if (value != 0 && value != 2 && value != 3) return fail(SZG_EINVAL, "digits must be 0 (auto), 2 or 3");
         h->digits = (int)value;
@@ -1148,8 +1158,92 @@ int szg_mask_destroy(szg_index *h, int mask_id) {
     return SZG_OK;
 }
 
+static int search_topk_impl(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
+                            uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned);
+
+// Concurrent callers.  The reference answers one query per Search call and lets calls overlap (RLock only,
+// collection.go:570); a scan launch, however, owns the whole GPU, so overlapping calls would queue up one launch each and
+// every one of them would stream the collection from HBM alone.  Instead the calls combine: a caller that finds no launch in
+// flight becomes the leader and runs whatever is queued with its own k / mask / flags as ONE call (scan_small_kernel then
+// deals the queries to CTA groups and they share rows in L2); callers arriving meanwhile wait and are answered together by
+// the next leader.  Nobody waits for company: a lone caller runs at once, exactly as before.
+struct szg_index::PendingSearch {
+    const double *q; uint32_t nq, k; int mask_id; uint32_t flags;
+    uint64_t *out_ids; double *out_dist; uint32_t *out_n;
+    int rc = 0; std::string err; bool done = false;
+};
+constexpr uint32_t kCombineMaxCall = 16;   // calls with more queries than this are not combined
+constexpr uint32_t kCombineMaxBatch = 128; // queries of one combined launch
+
+static int search_topk_combined(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
+                                uint64_t *out_ids, double *out_dist, uint32_t *out_n) {
+    using P = szg_index::PendingSearch;
+    P me;
+    me.q = queries; me.nq = nq; me.k = k; me.mask_id = mask_id; me.flags = flags;
+    me.out_ids = out_ids; me.out_dist = out_dist; me.out_n = out_n;
+    std::unique_lock<std::mutex> lk(h->comb_mu);
+    h->comb_queue.push_back(&me);
+    while (!me.done) {
+        if (h->comb_leader) { h->comb_cv.wait(lk); continue; }
+        h->comb_leader = true;
+        // the batch: the oldest request and every queued one with the same parameters, in arrival order
+        std::vector<P *> batch;
+        P *first = h->comb_queue.front();
+        uint32_t total = 0;
+        for (auto it = h->comb_queue.begin(); it != h->comb_queue.end();) {
+            P *p = *it;
+            if (p->k == first->k && p->mask_id == first->mask_id && p->flags == first->flags &&
+                (batch.empty() || total + p->nq <= kCombineMaxBatch)) {
+                batch.push_back(p);
+                total += p->nq;
+                it = h->comb_queue.erase(it);
+            } else ++it;
+        }
+        lk.unlock();
+        int rc;
+        if (batch.size() == 1) {
+            P *p = batch[0];
+            rc = search_topk_impl(h, p->q, p->nq, p->k, p->mask_id, p->flags, p->out_ids, p->out_dist, p->out_n, nullptr);
+        } else {
+            const size_t d = (size_t)h->dim, kk = first->k;
+            std::vector<double> q(total * d);
+            std::vector<uint64_t> ids(total * kk);
+            std::vector<double> dist(total * kk);
+            std::vector<uint32_t> n(total);
+            size_t off = 0;
+            for (P *p : batch) { memcpy(q.data() + off * d, p->q, (size_t)p->nq * d * sizeof(double)); off += p->nq; }
+            rc = search_topk_impl(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
+            off = 0;
+            if (!rc)
+                for (P *p : batch) {
+                    memcpy(p->out_ids, ids.data() + off * kk, (size_t)p->nq * kk * 8);
+                    memcpy(p->out_dist, dist.data() + off * kk, (size_t)p->nq * kk * 8);
+                    memcpy(p->out_n, n.data() + off, (size_t)p->nq * 4);
+                    off += p->nq;
+                }
+        }
+        const std::string err = rc ? g_err : std::string();
+        lk.lock();
+        if (batch.size() > 1) h->combined_queries += total;
+        for (P *p : batch) { p->rc = rc; p->err = err; p->done = true; }
+        h->comb_leader = false;
+        h->comb_cv.notify_all();
+    }
+    if (me.rc) g_err = me.err;
+    return me.rc;
+}
+
 int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
                     uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
+    if (h && h->combine && queries && nq >= 1 && nq <= kCombineMaxCall && out_ids && out_dist && out_n && k >= 1 && k <= SZG_MAX_K) {
+        if (scanned) *scanned = h->live_rows;
+        return search_topk_combined(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n);
+    }
+    return search_topk_impl(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n, scanned);
+}
+
+static int search_topk_impl(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
+                            uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
     GUARD(h);
     int rc;
     if ((rc = check_search(h, queries, nq))) return rc;
@@ -1555,6 +1649,8 @@ int szg_get_stats(szg_index *h, szg_stats *out) {
     out->escalations = h->escalations;
     out->uncertain_results = h->uncertain;
     out->batch_queries = h->batch_queries;
+    out->reserved0 = 0;
+    out->combined_queries = h->combined_queries;
     out->device_bytes = h->codes.n * sizeof(uint4) + h->planar.n * sizeof(uint4) + h->ids.n * 8 + h->aux.n * 8 + h->live.n * 4 +
                         h->lut.n * 8 + h->masks.size() * (h->capacity / 32) * 4;
     out->live_rows = h->live_rows;

@@ -526,6 +526,42 @@ def test_concurrent_searches_on_one_handle():
         assert not errs, errs[0]
 
 
+def test_concurrent_single_query_calls_are_combined_and_identical():
+    # SZG_OPT_COMBINE: calls that arrive while a launch is running share the next launch; every caller still gets
+    # exactly what a call of its own returns (ids, fp64 distances, counts), also with different k / masks in the mix
+    import threading
+    d, bits, n = 128, 8, 600000
+    with szg.Index(d, bits, szg.COSINE) as ix:
+        ix.fill_synthetic(91, 0, n)
+        ids = np.arange(n, dtype=np.uint64)
+        m = ix.mask_create(ids, (ids % 3 == 0).astype(np.uint8))
+        qs = o.synth_queries(92, 0, 48, d)
+        ix.set_option(_capi.OPT_COMBINE, 0)
+        alone = {(qi, k, mk): ix.search_topk(qs[qi], k, mask_id=mk) for qi in range(48) for k, mk in ((10, -1), (3, m))}
+        assert ix.stats()["combined_queries"] == 0
+        ix.set_option(_capi.OPT_COMBINE, 1)
+        errs = []
+
+        def work(t):
+            try:
+                for rep in range(40):
+                    qi = (t * 7 + rep) % 48
+                    k, mk = ((10, -1), (3, m))[(t + rep) % 3 == 0]
+                    got = ix.search_topk(qs[qi], k, mask_id=mk)
+                    want = alone[(qi, k, mk)]
+                    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+                    assert got[3] == n
+                with pytest.raises(_capi.SzgError):  # an error reaches the caller that caused it
+                    ix.search_topk(qs[0], 10, mask_id=12345)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(t,)) for t in range(12)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs[0]
+        assert ix.stats()["combined_queries"] > 0, "no two calls ever shared a launch"
+
+
 def test_dimension_mismatch_is_a_status():
     # appendix B-12: Search does not validate len(query); the binding must reject it
     with szg.Index(8, 8, szg.COSINE) as ix:
