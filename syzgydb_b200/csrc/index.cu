@@ -372,7 +372,13 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
     CK(launch_prep(nq, main, pa));
     h->launches++;
     // queries per launch: bounded by the candidate buffer (parts <= SM count lists of 16 warps x 32 keys per query)
-    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / ((size_t)sms * kSmallWarps * 32 * 8)}));
+    // ... and by the constant window the prepared queries of a launch go through (SZG_SMALL_CONST=0: shared memory instead)
+    // measured (profiles/r01b_scan_small_vs_general.log): +5..7 % at 48 chunks, -5..10 % on rows of <= 8 chunks, nothing at 24
+    static const int const_env = getenv("SZG_SMALL_CONST") ? atoi(getenv("SZG_SMALL_CONST")) : -1;
+    const bool const_ok = const_env >= 0 ? const_env != 0 : h->C >= 32;
+    const size_t window_q = std::max<size_t>(1, (size_t)kConstSlots * 16 / stride);
+    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / ((size_t)sms * kSmallWarps * 32 * 8),
+                                                                             const_ok ? window_q : (size_t)4096}));
     const bool timing = h->timing != 0;
     const uint32_t nlaunch = (nq + chunk - 1) / chunk;
     uint32_t tbase = 0;
@@ -404,6 +410,7 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
         const uint32_t nlists = parts * kSmallWarps;
         const int grid = (int)std::min<uint64_t>((uint64_t)groups * parts, sms);
         a.qper = qper;
+        a.const_queries = const_ok ? 1u : 0u;
         if ((rc = ws->d_cand.ensure((size_t)m * nlists * 32))) return rc;
         a.pq = ws->d_pq.p + stride * q0;
         a.nq = m;

@@ -51,6 +51,7 @@ struct ScanArgs {
     uint32_t parts;             // scan_small_kernel only: work items (row parts) per query
     uint32_t adjacent;          // scan_small_kernel only: the blocks of a step are adjacent (else a warp stride apart)
     uint32_t qper;              // scan_small_kernel only: queries per work item (1 or 2)
+    uint32_t const_queries;     // scan_small_kernel only: the launch's prepared queries go through constant memory
     // top-k output: per-warp candidate lists, consumed by finalize_kernel
     unsigned long long *cand;   // [nq][grid warps][32*E]
     // radius outputs

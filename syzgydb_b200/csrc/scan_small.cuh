@@ -20,11 +20,19 @@
 // Keys are computed by the same Scorer<QT, ND>::step / finish as the general kernel: identical surrogate keys,
 // identical candidate semantics, finalize_kernel unchanged.
 #pragma once
+#include <mutex>
+
 #include "scan_impl.cuh"
 
 namespace szg {
 
 constexpr int kSmallWarps = 16;
+// Prepared queries of one launch in constant memory (bank 3): the digits are warp-uniform, so read from there they arrive
+// in uniform registers through the constant cache (SASS: LDCU.64 + IDP.4A with a UR operand) and leave the L1 data pipe --
+// the limiter of this kernel -- to the row loads.  One window per translation unit (quantization) and device; launches
+// that use it are chained by an event (scan_small launches fill the GPU and would not overlap anyway).
+constexpr uint32_t kConstSlots = 3840; // uint4 slots: 60 KB
+__constant__ uint4 c_pq[kConstSlots];
 
 template <int QT, int ND>
 struct SmallOps;
@@ -73,7 +81,7 @@ struct SmallOps<Q16, ND> {
     }
 };
 
-template <int QT, int ND, int C, int Q>
+template <int QT, int ND, int C, int Q, bool CQ>
 __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const ScanArgs a) {
     // a lane holds 16 uint4 of row data at a time: U = 16 / C whole rows (of U different blocks) when C <= 8, else
     // pieces of 8 chunks of two rows (C = 12: 4 chunks of four rows).  The digits of a chunk are read once for the U
@@ -100,14 +108,16 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
         const uint32_t nqv = min((uint32_t)Q, a.nq - q0); // queries of this item (the last group may be short)
         __syncthreads(); // the previous item's readers of s_pq / s_pub are done
         {
-            for (uint32_t i = tid; i < n16 * nqv; i += blockDim.x) {
-                const uint32_t qq = i / n16, k = i - qq * n16;
-                reinterpret_cast<uint4 *>(s_pq + (size_t)qq * a.pq_stride)[k] =
-                    __ldg(reinterpret_cast<const uint4 *>(a.pq + (size_t)(q0 + qq) * a.pq_stride) + k);
-            }
+            if (!CQ)
+                for (uint32_t i = tid; i < n16 * nqv; i += blockDim.x) {
+                    const uint32_t qq = i / n16, k = i - qq * n16;
+                    reinterpret_cast<uint4 *>(s_pq + (size_t)qq * a.pq_stride)[k] =
+                        __ldg(reinterpret_cast<const uint4 *>(a.pq + (size_t)(q0 + qq) * a.pq_stride) + k);
+                }
             if (tid < nw * Q) s_pub[tid / nw][tid % nw] = 0xFFFFFFFFu;
         }
         __syncthreads();
+        const uint32_t cbase = q0 * n16; // CQ: the item's first query in the constant window (uint4 slots; CTA-uniform)
         WarpList<1> list[Q];
 #pragma unroll
         for (int qq = 0; qq < Q; ++qq) list[qq].init();
@@ -149,10 +159,18 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
                         for (int qq = 0; qq < Q; ++qq) {
                             if (Q == 1 || (uint32_t)qq < nqv) { // CTA-uniform
                                 // this chunk's digits of query qq: warp-uniform shared loads, used for the U rows of the lane
-                                const Dig *dig = reinterpret_cast<const Dig *>(s_pq + (size_t)qq * a.pq_stride + sizeof(PQHeader));
                                 Dig d[DPC];
+                                if (CQ) {
+                                    constexpr uint32_t per16 = 16 / sizeof(Dig); // digit vectors per uint4 slot
+                                    const Dig *cd = reinterpret_cast<const Dig *>(c_pq);
+                                    const uint32_t at = (cbase + (uint32_t)qq * n16) * per16 + (uint32_t)(sizeof(PQHeader) / sizeof(Dig));
 #pragma unroll
-                                for (int j = 0; j < DPC; ++j) d[j] = dig[(pz * PC + c) * DPC + j];
+                                    for (int j = 0; j < DPC; ++j) d[j] = cd[at + (pz * PC + c) * DPC + j];
+                                } else {
+                                    const Dig *dig = reinterpret_cast<const Dig *>(s_pq + (size_t)qq * a.pq_stride + sizeof(PQHeader));
+#pragma unroll
+                                    for (int j = 0; j < DPC; ++j) d[j] = dig[(pz * PC + c) * DPC + j];
+                                }
 #pragma unroll
                                 for (int u = 0; u < U; ++u) Ops::apply(data[u][c], d, acc[qq][u]);
                             }
@@ -163,7 +181,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
 #pragma unroll
             for (int qq = 0; qq < Q; ++qq) {
                 if (Q > 1 && (uint32_t)qq >= nqv) continue;
-                const PQHeader &h = *reinterpret_cast<const PQHeader *>(s_pq + (size_t)qq * a.pq_stride);
+                const PQHeader &h = CQ ? *reinterpret_cast<const PQHeader *>(&c_pq[cbase + (uint32_t)qq * n16])
+                                       : *reinterpret_cast<const PQHeader *>(s_pq + (size_t)qq * a.pq_stride);
                 unsigned long long keys[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -210,10 +229,10 @@ inline uint32_t small_parts(uint32_t nq, uint32_t grid) {
     return best;
 }
 
-template <int QT, int ND, int Q>
+template <int QT, int ND, int Q, bool CQ>
 cudaError_t launch_scan_small_nd(uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
     switch (C) {
-#define SZG_SMALL_CASE(CC) case CC: scan_small_kernel<QT, ND, CC, Q><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
+#define SZG_SMALL_CASE(CC) case CC: scan_small_kernel<QT, ND, CC, Q, CQ><<<grid, kSmallWarps * 32, smem, st>>>(a); break;
     SZG_SMALL_CASE(2) SZG_SMALL_CASE(4) SZG_SMALL_CASE(8) SZG_SMALL_CASE(12) SZG_SMALL_CASE(16) SZG_SMALL_CASE(24)
     SZG_SMALL_CASE(32) SZG_SMALL_CASE(48)
 #undef SZG_SMALL_CASE
@@ -227,8 +246,26 @@ cudaError_t launch_scan_small_nd(uint32_t C, int grid, size_t smem, cudaStream_t
 template <int QT>
 cudaError_t launch_scan_small_t(int nd, uint32_t C, int grid, size_t smem, cudaStream_t st, const ScanArgs &a) {
     if (a.qper != 1) return cudaErrorInvalidValue;
-    if (nd == 2) return launch_scan_small_nd<QT, 2, 1>(C, grid, smem, st, a);
-    return launch_scan_small_nd<QT, 3, 1>(C, grid, smem, st, a);
+    const size_t bytes = (size_t)a.nq * a.pq_stride;
+    if (a.const_queries && bytes <= (size_t)kConstSlots * 16) {
+        // the launch's prepared queries -> this translation unit's constant window; users of the window are chained
+        static std::mutex mu;
+        static cudaEvent_t ev[64] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ev[dev]) {
+            if ((e = cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming)) != cudaSuccess) return e;
+        } else if ((e = cudaStreamWaitEvent(st, ev[dev], 0)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyToSymbolAsync(c_pq, a.pq, bytes, 0, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+        e = nd == 2 ? launch_scan_small_nd<QT, 2, 1, true>(C, grid, 16, st, a) : launch_scan_small_nd<QT, 3, 1, true>(C, grid, 16, st, a);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(ev[dev], st);
+    }
+    if (nd == 2) return launch_scan_small_nd<QT, 2, 1, false>(C, grid, smem, st, a);
+    return launch_scan_small_nd<QT, 3, 1, false>(C, grid, smem, st, a);
 }
 
 inline bool scan_small_supported(int qt, uint32_t C) {
