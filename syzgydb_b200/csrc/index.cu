@@ -1181,6 +1181,7 @@ struct szg_index::PendingSearch {
 };
 constexpr uint32_t kCombineMaxCall = 16;   // calls with more queries than this are not combined
 constexpr uint32_t kCombineMaxBatch = 128; // queries of one combined launch
+constexpr uint32_t kCombineTensorMin = 4;  // combined batches from this size on go to szg_search_batch
 
 static int search_topk_combined(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
                                 uint64_t *out_ids, double *out_dist, uint32_t *out_n) {
@@ -1219,7 +1220,12 @@ static int search_topk_combined(szg_index *h, const double *queries, uint32_t nq
             std::vector<uint32_t> n(total);
             size_t off = 0;
             for (P *p : batch) { memcpy(q.data() + off * d, p->q, (size_t)p->nq * d * sizeof(double)); off += p->nq; }
-            rc = search_topk_impl(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
+            // a combined batch is a batch: from a few queries on, the tensor-core contraction (identical results, it falls
+            // back to the scan by itself where it does not apply) answers it in about the time of one or two scans
+            if (total >= kCombineTensorMin && !h->batch_disabled)
+                rc = szg_search_batch(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
+            else
+                rc = search_topk_impl(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
             off = 0;
             if (!rc)
                 for (P *p : batch) {
@@ -1585,19 +1591,27 @@ int szg_search_radius(szg_index *h, const double *query, double radius, int mask
         CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         // exact inclusive test (collection.go:598) on the fp64 distances, then ascending order
-        std::vector<uint32_t> keep;
-        keep.reserve(count);
-        for (uint32_t i = 0; i < count; ++i)
-            if (ws->h_out_dist.p[i] <= radius) keep.push_back(i);
+        // distances are >= 0 (or NaN, which fails the test): their bit patterns order like the values, so the sort runs
+        // on packed integers and only equal distances fall back to the lexicographic id comparison
         const double *hd = ws->h_out_dist.p;
         const unsigned long long *hi = ws->h_out_ids.p;
-        std::sort(keep.begin(), keep.end(), [&](uint32_t x, uint32_t y) {
-            if (hd[x] != hd[y]) return hd[x] < hd[y];
-            return lex_less_u64(hi[x], hi[y]);
+        struct Hit { unsigned long long bits; uint32_t i; };
+        std::vector<Hit> keep;
+        keep.reserve(count);
+        for (uint32_t i = 0; i < count; ++i)
+            if (hd[i] <= radius) {
+                const double dv = hd[i] == 0.0 ? 0.0 : hd[i]; // -0.0 orders with +0.0
+                unsigned long long b;
+                memcpy(&b, &dv, 8);
+                keep.push_back(Hit{b, i});
+            }
+        std::sort(keep.begin(), keep.end(), [&](const Hit &x, const Hit &y) {
+            if (x.bits != y.bits) return x.bits < y.bits;
+            return lex_less_u64(hi[x.i], hi[y.i]);
         });
         res->ids.resize(keep.size());
         res->dist.resize(keep.size());
-        for (size_t i = 0; i < keep.size(); ++i) { res->ids[i] = hi[keep[i]]; res->dist[i] = hd[keep[i]]; }
+        for (size_t i = 0; i < keep.size(); ++i) { res->ids[i] = hi[keep[i].i]; res->dist[i] = hd[keep[i].i]; }
     }
     (void)flags;
     *out = res.release();
