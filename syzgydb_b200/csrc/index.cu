@@ -403,13 +403,21 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
     for (uint32_t l = 0, q0 = 0; q0 < nq; q0 += chunk, ++l) {
         const uint32_t m = std::min(chunk, nq - q0);
         // parts per query: as many as keep every CTA busy, but no part shorter than one block per warp
-        const uint32_t qper = 1; // queries per item (pairs were measured slower: see scan_small.cuh)
-        const uint32_t groups = (m + qper - 1) / qper;
+        const uint32_t qper = 1; // queries per warp (pairs were measured slower: see scan_small.cuh)
+        // warp groups per CTA, each on another query of the same row part (they share the rows in L1)
+        static const int wg_env = getenv("SZG_SMALL_WG") ? atoi(getenv("SZG_SMALL_WG")) : 0;
+        // measured (profiles/r01b_scan_small_vs_general.log): two groups win at 48 chunks (cfg4 2390 -> 2795 QPS, and 340 W
+        // instead of 460 W: the board no longer throttles) and on collections of a few MB; one group wins in between
+        uint32_t wgroups = wg_env == 1 || wg_env == 2 || wg_env == 4 ? (uint32_t)wg_env : ((h->C >= 32 || nblk < 8192) ? 2u : 1u);
+        while (wgroups > 1 && m < 2 * wgroups) wgroups >>= 1; // too few queries to fill the groups of several CTAs
+        const uint32_t gw = kSmallWarps / wgroups;
+        const uint32_t groups = (m + wgroups - 1) / wgroups;
         uint32_t parts = small_parts(groups, sms);
-        parts = std::max<uint32_t>(1, std::min<uint32_t>(parts, (nblk + kSmallWarps - 1) / kSmallWarps));
-        const uint32_t nlists = parts * kSmallWarps;
+        parts = std::max<uint32_t>(1, std::min<uint32_t>(parts, (nblk + gw - 1) / gw));
+        const uint32_t nlists = parts * gw;
         const int grid = (int)std::min<uint64_t>((uint64_t)groups * parts, sms);
         a.qper = qper;
+        a.wgroups = wgroups;
         a.const_queries = const_ok ? 1u : 0u;
         if ((rc = ws->d_cand.ensure((size_t)m * nlists * 32))) return rc;
         a.pq = ws->d_pq.p + stride * q0;
@@ -419,7 +427,7 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
         a.adjacent = adj_env >= 0 ? (uint32_t)adj_env : (h->C < 48 ? 1u : 0u);
         a.cand = ws->d_cand.p;
         if (timing) CK(cudaEventRecord(ws->t0[tbase + l], main));
-        CK(launch_scan_small(h->qt, nd, h->C, grid, stride * qper, main, a));
+        CK(launch_scan_small(h->qt, nd, h->C, grid, stride * wgroups, main, a));
         if (timing) CK(cudaEventRecord(ws->t1[tbase + l], main));
         f.cand = ws->d_cand.p;
         f.nlists = nlists;

@@ -52,6 +52,7 @@ struct ScanArgs {
     uint32_t adjacent;          // scan_small_kernel only: the blocks of a step are adjacent (else a warp stride apart)
     uint32_t qper;              // scan_small_kernel only: queries per work item (1 or 2)
     uint32_t const_queries;     // scan_small_kernel only: the launch's prepared queries go through constant memory
+    uint32_t wgroups;           // scan_small_kernel only: warp groups per CTA, each on another query of the same row part (1, 2, 4)
     // top-k output: per-warp candidate lists, consumed by finalize_kernel
     unsigned long long *cand;   // [nq][grid warps][32*E]
     // radius outputs

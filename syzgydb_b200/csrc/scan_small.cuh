@@ -95,35 +95,42 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
     using Ops = SmallOps<QT, ND>;
     using Dig = typename Ops::Dig;
     constexpr int DPC = Ops::DPC;
-    extern __shared__ __align__(16) unsigned char s_pq[]; // the item's prepared queries: Q x (header + digits)
-    __shared__ uint32_t s_pub[Q][kSmallWarps];            // key of each warp's mth-best row so far (0xFFFFFFFF: none yet)
+    extern __shared__ __align__(16) unsigned char s_pq[]; // the item's prepared queries: G x (header + digits)
+    __shared__ uint32_t s_pub[kSmallWarps];               // key of each warp's mth-best row so far (0xFFFFFFFF: none yet)
+    static_assert(Q == 1, "queries per warp: only 1 is instantiated");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const uint32_t P = a.parts, ngroups = (a.nq + Q - 1) / Q, nitems = ngroups * P, nlists = P * (uint32_t)nw;
-    const uint32_t mth = (32u + (uint32_t)nw - 1) / (uint32_t)nw;
-    const uint32_t stride = P * (uint32_t)nw;
+    // a.wgroups = G: the CTA's warps form G groups, each answering ANOTHER query over the SAME row part: the groups walk the
+    // part's blocks in the same order at the same pace, so a row brought into L1 for one group is a hit for the others
+    const uint32_t G = a.wgroups, gw = (uint32_t)nw / G;  // warps per group
+    const uint32_t wg = (uint32_t)warp / gw, wl = (uint32_t)warp - wg * gw;
+    const uint32_t P = a.parts, ngroups = (a.nq + G - 1) / G, nitems = ngroups * P, nlists = P * gw;
+    const uint32_t mth = (32u + gw - 1) / gw;
+    const uint32_t stride = P * gw;
     const uint32_t n16 = (uint32_t)(a.pq_stride / 16);
     for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
         const uint32_t qg = item / P, p = item - qg * P;
-        const uint32_t q0 = qg * Q;
-        const uint32_t nqv = min((uint32_t)Q, a.nq - q0); // queries of this item (the last group may be short)
+        const uint32_t q0 = qg * G;
+        const uint32_t nqv = min(G, a.nq - q0); // queries of this item (the last one may be short: its extra groups idle)
+        const uint32_t q = q0 + wg;
         __syncthreads(); // the previous item's readers of s_pq / s_pub are done
         {
             if (!CQ)
                 for (uint32_t i = tid; i < n16 * nqv; i += blockDim.x) {
-                    const uint32_t qq = i / n16, k = i - qq * n16;
-                    reinterpret_cast<uint4 *>(s_pq + (size_t)qq * a.pq_stride)[k] =
-                        __ldg(reinterpret_cast<const uint4 *>(a.pq + (size_t)(q0 + qq) * a.pq_stride) + k);
+                    const uint32_t qq = i / n16, kk = i - qq * n16;
+                    reinterpret_cast<uint4 *>(s_pq + (size_t)qq * a.pq_stride)[kk] =
+                        __ldg(reinterpret_cast<const uint4 *>(a.pq + (size_t)(q0 + qq) * a.pq_stride) + kk);
                 }
-            if (tid < nw * Q) s_pub[tid / nw][tid % nw] = 0xFFFFFFFFu;
+            if (tid < nw) s_pub[tid] = 0xFFFFFFFFu;
         }
         __syncthreads();
-        const uint32_t cbase = q0 * n16; // CQ: the item's first query in the constant window (uint4 slots; CTA-uniform)
-        WarpList<1> list[Q];
-#pragma unroll
-        for (int qq = 0; qq < Q; ++qq) list[qq].init();
+        if (wg >= nqv) continue; // warp-uniform; the barriers above are the only CTA-wide ones
+        const uint32_t cbase = q * n16; // CQ: this group's query in the constant window (uint4 slots; warp-uniform)
+        const unsigned char *my_pq = s_pq + (size_t)wg * a.pq_stride;
+        WarpList<1> list;
+        list.init();
         // a step takes U blocks: adjacent ones (contiguous in the mirror; a.adjacent) or `stride` apart
         const uint32_t ustep = a.adjacent ? 1u : stride;
-        for (uint32_t g = p * (uint32_t)nw + (uint32_t)warp; (a.adjacent ? g * U : g) < a.nblk; g += a.adjacent ? stride : stride * U) {
+        for (uint32_t g = p * gw + wl; (a.adjacent ? g * U : g) < a.nblk; g += a.adjacent ? stride : stride * U) {
             const uint32_t b0 = a.adjacent ? g * U : g;
             float2 ax[U];
             uint32_t lv[U];
@@ -139,11 +146,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
                 src[u] = a.codes + (size_t)bc * C * 32 + lane;
                 ax[u] = load_aux(a, bc * 32 + lane);
             }
-            typename Ops::A acc[Q][U];
+            typename Ops::A acc[U];
 #pragma unroll
-            for (int qq = 0; qq < Q; ++qq)
-#pragma unroll
-                for (int u = 0; u < U; ++u) Ops::reset(acc[qq][u]);
+            for (int u = 0; u < U; ++u) Ops::reset(acc[u]);
 #pragma unroll
             for (int pz = 0; pz < NP; ++pz) {
                 uint4 data[U][PC];
@@ -155,62 +160,50 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
 #pragma unroll
                 for (int c = 0; c < PC; ++c) {
                     if (pz * PC + c < C) {
+                        // this chunk's digits: warp-uniform loads (constant cache or shared memory), used for the U rows of the lane
+                        Dig d[DPC];
+                        if (CQ) {
+                            constexpr uint32_t per16 = 16 / sizeof(Dig); // digit vectors per uint4 slot
+                            const Dig *cd = reinterpret_cast<const Dig *>(c_pq);
+                            const uint32_t at = cbase * per16 + (uint32_t)(sizeof(PQHeader) / sizeof(Dig));
 #pragma unroll
-                        for (int qq = 0; qq < Q; ++qq) {
-                            if (Q == 1 || (uint32_t)qq < nqv) { // CTA-uniform
-                                // this chunk's digits of query qq: warp-uniform shared loads, used for the U rows of the lane
-                                Dig d[DPC];
-                                if (CQ) {
-                                    constexpr uint32_t per16 = 16 / sizeof(Dig); // digit vectors per uint4 slot
-                                    const Dig *cd = reinterpret_cast<const Dig *>(c_pq);
-                                    const uint32_t at = (cbase + (uint32_t)qq * n16) * per16 + (uint32_t)(sizeof(PQHeader) / sizeof(Dig));
+                            for (int j = 0; j < DPC; ++j) d[j] = cd[at + (pz * PC + c) * DPC + j];
+                        } else {
+                            const Dig *dig = reinterpret_cast<const Dig *>(my_pq + sizeof(PQHeader));
 #pragma unroll
-                                    for (int j = 0; j < DPC; ++j) d[j] = cd[at + (pz * PC + c) * DPC + j];
-                                } else {
-                                    const Dig *dig = reinterpret_cast<const Dig *>(s_pq + (size_t)qq * a.pq_stride + sizeof(PQHeader));
-#pragma unroll
-                                    for (int j = 0; j < DPC; ++j) d[j] = dig[(pz * PC + c) * DPC + j];
-                                }
-#pragma unroll
-                                for (int u = 0; u < U; ++u) Ops::apply(data[u][c], d, acc[qq][u]);
-                            }
+                            for (int j = 0; j < DPC; ++j) d[j] = dig[(pz * PC + c) * DPC + j];
                         }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) Ops::apply(data[u][c], d, acc[u]);
                     }
                 }
             }
+            const PQHeader &h = CQ ? *reinterpret_cast<const PQHeader *>(&c_pq[cbase]) : *reinterpret_cast<const PQHeader *>(my_pq);
+            unsigned long long keys[U];
 #pragma unroll
-            for (int qq = 0; qq < Q; ++qq) {
-                if (Q > 1 && (uint32_t)qq >= nqv) continue;
-                const PQHeader &h = CQ ? *reinterpret_cast<const PQHeader *>(&c_pq[cbase + (uint32_t)qq * n16])
-                                       : *reinterpret_cast<const PQHeader *>(s_pq + (size_t)qq * a.pq_stride);
-                unsigned long long keys[U];
+            for (int u = 0; u < U; ++u) {
+                const float key = Ops::finish(acc[u], a, h, ax[u]);
+                const uint32_t blk = b0 + (uint32_t)u * ustep;
+                keys[u] = ((lv[u] >> lane) & 1u) ? make_key64(key, blk * 32 + lane) : kNoKey;
+            }
+            { // the group's shared bound: once every warp of it has published, nothing above the largest published key matters
+                const uint32_t e = (uint32_t)lane < gw ? *reinterpret_cast<volatile uint32_t *>(&s_pub[wg * gw + lane]) : 0u;
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, e);
+                if (mx != 0xFFFFFFFFu) {
+                    const unsigned long long b = ((unsigned long long)mx << 32) | 0xFFFFFFFFull;
+                    if (b < list.thr) list.thr = b; // keys equal to the bound still pass
+                }
+            }
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float key = Ops::finish(acc[qq][u], a, h, ax[u]);
-                    const uint32_t blk = b0 + (uint32_t)u * ustep;
-                    keys[u] = ((lv[u] >> lane) & 1u) ? make_key64(key, blk * 32 + lane) : kNoKey;
-                }
-                { // the CTA's shared bound: once every warp has published, nothing above the largest published key matters
-                    const uint32_t e = lane < nw ? *reinterpret_cast<volatile uint32_t *>(&s_pub[qq][lane]) : 0u;
-                    const uint32_t mx = __reduce_max_sync(0xffffffffu, e);
-                    if (mx != 0xFFFFFFFFu) {
-                        const unsigned long long b = ((unsigned long long)mx << 32) | 0xFFFFFFFFull;
-                        if (b < list[qq].thr) list[qq].thr = b; // keys equal to the bound still pass
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (lv[u]) list[qq].offer(keys[u], lane);
-                if ((uint32_t)lane == mth - 1 && list[qq].v[0] != kNoKey) {
-                    const uint32_t pk = (uint32_t)(list[qq].v[0] >> 32);
-                    if (pk < s_pub[qq][warp]) *reinterpret_cast<volatile uint32_t *>(&s_pub[qq][warp]) = pk;
-                }
+            for (int u = 0; u < U; ++u)
+                if (lv[u]) list.offer(keys[u], lane);
+            if ((uint32_t)lane == mth - 1 && list.v[0] != kNoKey) {
+                const uint32_t pk = (uint32_t)(list.v[0] >> 32);
+                if (pk < s_pub[warp]) *reinterpret_cast<volatile uint32_t *>(&s_pub[warp]) = pk;
             }
         }
-        // this warp's lists of (query, part p) -> finalize_kernel
-#pragma unroll
-        for (int qq = 0; qq < Q; ++qq)
-            if ((uint32_t)qq < nqv) a.cand[((size_t)(q0 + qq) * nlists + (size_t)p * nw + warp) * 32 + lane] = list[qq].v[0];
+        // this warp's list of (query q, part p) -> finalize_kernel
+        a.cand[((size_t)q * nlists + (size_t)p * gw + wl) * 32 + lane] = list.v[0];
     }
 }
 
