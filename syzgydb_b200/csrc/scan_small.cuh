@@ -1,24 +1,27 @@
-// scan_small.cuh -- the top-k scan for SHORT quantized rows (C = 2 .. 24 chunks of 16 bytes per row: at most
-// 384 bytes; BASELINE configs[1]: 1M x 128 4-bit = 64-byte rows, configs[0]: 100k x 384 8-bit) and k <= 24.
+// scan_small.cuh -- the top-k scan (k <= 24) for quantized rows of 2 .. 48 chunks of 16 bytes (at most 768 bytes): BASELINE
+// configs[0] 100k x 384 8-bit, configs[1] 1M x 128 4-bit (64-byte rows), configs[3] 10M x 768 8-bit.
 //
-// Why a second kernel: a 32-row block of such rows is only C * 512 bytes.  The general kernel (scan_impl.cuh)
-// spends ~420 instructions per block on them, of which the arithmetic is ~150 -- ring stages, barriers, per-tile
-// bookkeeping, run-time chunk loops and per-chunk digit loads are sized for rows of kilobytes -- and with every warp
-// of the grid walking every query it ends a query after a dozen blocks (2368 candidate lists per query, each warmed
-// up from empty).  Measured (profiles/r01_small_rows_*): 20 us per query for 64 MB that sit in L2, issue-bound.
+// Why a second kernel: the general kernel (scan_impl.cuh) was built for one query streaming gigabytes.  On short rows a
+// 32-row block is only C * 512 bytes and it spends ~420 instructions per block of which the arithmetic is ~150 (ring
+// stages, barriers, per-tile bookkeeping, run-time chunk loops, per-chunk digit loads); with every warp of the grid walking
+// every query a query ends after a dozen blocks per warp (2368 candidate lists per query, each warmed up from empty); and
+// when a call brings several queries each of them streams the collection from HBM alone.
 //
 // What is different here:
-//  * chunk count, digit count and blocks per step are compile-time: everything is unrolled, no ring, no barriers --
-//    a lane loads its row's chunks with plain coalesced 128-bit loads (the collection fits L2 at these row sizes or
-//    streams with a dozen warps' worth of 8 KB steps in flight per SM), 16 uint4 (U = 16 / C blocks) per step;
-//  * the query's digits are read from shared memory once per chunk and applied to the U rows a lane holds;
-//  * queries are dealt to CTAs: a launch of nq queries is cut in nq x P work items (query, part), an item is
-//    processed by ONE CTA whose warps stride over the part's blocks, so a query ends in P x warps lists (16 when
-//    nq >= SM count) and a warp sees hundreds of blocks per query; all warps of the CTA share one bound (the same
-//    argument as the general kernel's short-scan variant).  P = SM count for a single query: the decomposition the
-//    general kernel has.
+//  * chunk count, digit count and rows per lane are compile-time: everything is unrolled, no ring, no barriers in the
+//    loop -- a lane loads its row's chunks with plain coalesced 128-bit loads, 16 uint4 in flight per lane;
+//  * the query's digits are read once per chunk and applied to the U rows a lane holds; from 32 chunks per row on they
+//    come from constant memory (warp-uniform LDC through the constant cache instead of the L1 data pipe);
+//  * queries are dealt to CTAs: a launch of nq queries is cut in work items (query, row part), an item is processed by
+//    ONE CTA whose warps stride over the part's blocks, so a query ends in P x warps lists (16 when nq >= SM count)
+//    and a warp sees hundreds of blocks per query; the warps on a query share one bound (the argument of the general
+//    kernel's short-scan variant).  P = SM count for a single query: the decomposition the general kernel has;
+//  * CTAs of different queries sweep the collection in the same order at the same pace: a row fetched from HBM for one
+//    query is an L2 hit for the others; with two warp groups per CTA (a.wgroups), each on another query of the same
+//    part, also an L1 hit (cfg4, 32 queries per launch: 7.76 GB of DRAM traffic for 245.8 GB of scans).
 // Keys are computed by the same Scorer<QT, ND>::step / finish as the general kernel: identical surrogate keys,
-// identical candidate semantics, finalize_kernel unchanged.
+// identical candidate semantics, finalize_kernel unchanged.  Measurements and the variants that were tried and dropped:
+// DESIGN.md section 5a, profiles/r01b_scan_small_vs_general.log.
 #pragma once
 #include <mutex>
 
@@ -85,10 +88,9 @@ template <int QT, int ND, int C, int Q, bool CQ>
 __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const ScanArgs a) {
     // a lane holds 16 uint4 of row data at a time: U = 16 / C whole rows (of U different blocks) when C <= 8, else
     // pieces of 8 chunks of two rows (C = 12: 4 chunks of four rows).  The digits of a chunk are read once for the U
-    // rows: the L1 data pipe, which carries the row loads and the digit broadcasts, is what limits this kernel (89 %
-    // with one row per lane, profiles/r01b_scan_small_q8_ncu_full.csv; cfg4: 2084 -> 2575 QPS with two).
-    // Q = 2: an item is a PAIR of queries -- every loaded row chunk is scored against both, which halves the row
-    // loads per query through that pipe.
+    // rows: the L1 data pipe, which carries the row loads and (through shared memory) the digit broadcasts, limited the
+    // first version of this kernel (89 % with one row per lane; cfg4: 2084 -> 2575 QPS with two).
+    // Q (queries per WARP) stays 1: see launch_scan_small_t.
     constexpr int PC = C <= 8 ? C : (C % 8 == 0 ? 8 : 4); // chunks per piece (measured: 8 beats 4 and 16 at C = 24 .. 48)
     constexpr int U = 16 / PC;                             // blocks per step
     constexpr int NP = (C + PC - 1) / PC;
