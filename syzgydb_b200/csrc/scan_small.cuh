@@ -29,7 +29,13 @@
 
 namespace szg {
 
-constexpr int kSmallWarps = 16;
+#ifndef SZG_SMALL_WARPS
+#define SZG_SMALL_WARPS 16 // warps per CTA (tuning builds: make EXTRA=-DSZG_SMALL_WARPS=24)
+#endif
+#ifndef SZG_SMALL_PCBIG
+#define SZG_SMALL_PCBIG 8  // chunks per piece for rows above 8 chunks
+#endif
+constexpr int kSmallWarps = SZG_SMALL_WARPS;
 // Prepared queries of one launch in constant memory (bank 3): the digits are warp-uniform, so read from there they arrive
 // in uniform registers through the constant cache (SASS: LDCU.64 + IDP.4A with a UR operand) and leave the L1 data pipe --
 // the limiter of this kernel -- to the row loads.  One window per translation unit (quantization) and device; launches
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
     // rows: the L1 data pipe, which carries the row loads and (through shared memory) the digit broadcasts, limited the
     // first version of this kernel (89 % with one row per lane; cfg4: 2084 -> 2575 QPS with two).
     // Q (queries per WARP) stays 1: see launch_scan_small_t.
-    constexpr int PC = C <= 8 ? C : (C % 8 == 0 ? 8 : 4); // chunks per piece (measured: 8 beats 4 and 16 at C = 24 .. 48)
+    constexpr int PC = C <= 8 ? C : (C % SZG_SMALL_PCBIG == 0 ? SZG_SMALL_PCBIG : 4); // chunks per piece (measured: 8 beats 4 and 16 at C = 24 .. 48)
     constexpr int U = 16 / PC;                             // blocks per step
     constexpr int NP = (C + PC - 1) / PC;
     using Ops = SmallOps<QT, ND>;
