@@ -414,7 +414,7 @@ int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, 
         const uint32_t groups = (m + wgroups - 1) / wgroups;
         uint32_t parts = small_parts(groups, sms);
         parts = std::max<uint32_t>(1, std::min<uint32_t>(parts, (nblk + gw - 1) / gw));
-        const uint32_t nlists = parts * gw;
+        const uint32_t nlists = parts; // the warps of a group merge their lists before writing
         const int grid = (int)std::min<uint64_t>((uint64_t)groups * parts, sms);
         a.qper = qper;
         a.wgroups = wgroups;

@@ -159,6 +159,19 @@ struct WarpList {
         v[0] = m;
         thr = __shfl_sync(0xffffffffu, m, 31);
     }
+    // E == 1 only: `other` is another SORTED list (lane i = rank i); keeps the 32 smallest of the union, sorted
+    __device__ __forceinline__ void merge_sorted(unsigned long long other, int lane) {
+        unsigned long long rev = __shfl_sync(0xffffffffu, other, 31 - lane);
+        unsigned long long m = v[0] < rev ? v[0] : rev; // bitonic
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            unsigned long long o = __shfl_xor_sync(0xffffffffu, m, j);
+            bool keep_min = (lane & j) == 0;
+            m = keep_min ? (m < o ? m : o) : (m > o ? m : o);
+        }
+        v[0] = m;
+        thr = __shfl_sync(0xffffffffu, m, 31);
+    }
     // every lane offers one key (kNoKey = nothing)
     __device__ __forceinline__ void offer(unsigned long long ck, int lane) {
         unsigned m = __ballot_sync(0xffffffffu, ck < thr);
@@ -193,10 +206,22 @@ __device__ __forceinline__ void block_bitonic_sort(unsigned long long *s, int n,
 }
 
 template <int E>
-__device__ __forceinline__ void block_merge(const WarpList<E> &L, unsigned long long *pool, int tid, int lane,
+__device__ __forceinline__ void block_merge(WarpList<E> &L, unsigned long long *pool, int tid, int lane,
                                             int warp, int nwarps) {
 #pragma unroll
     for (int e = 0; e < E; ++e) pool[(warp * 32 + lane) * E + e] = L.v[e];
+    if (E == 1 && (nwarps & (nwarps - 1)) == 0) {
+        // 32-key lists: a tree of pairwise merges of sorted lists (log2(warps) barriers) instead of sorting warps * 32 keys
+        for (int half = nwarps >> 1; half >= 1; half >>= 1) {
+            __syncthreads();
+            if (warp < half) {
+                L.merge_sorted(pool[(warp + half) * 32 + lane], lane);
+                pool[warp * 32 + lane] = L.v[0];
+            }
+        }
+        __syncthreads();
+        return;
+    }
     __syncthreads();
     block_bitonic_sort(pool, nwarps * 32 * E, tid, nwarps * 32);
 }

@@ -105,13 +105,14 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
     constexpr int DPC = Ops::DPC;
     extern __shared__ __align__(16) unsigned char s_pq[]; // the item's prepared queries: G x (header + digits)
     __shared__ uint32_t s_pub[kSmallWarps];               // key of each warp's mth-best row so far (0xFFFFFFFF: none yet)
+    __shared__ unsigned long long s_merge[kSmallWarps * 32]; // the warps' lists at the end of an item, merged per group
     static_assert(Q == 1, "queries per warp: only 1 is instantiated");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     // a.wgroups = G: the CTA's warps form G groups, each answering ANOTHER query over the SAME row part: the groups walk the
     // part's blocks in the same order at the same pace, so a row brought into L1 for one group is a hit for the others
     const uint32_t G = a.wgroups, gw = (uint32_t)nw / G;  // warps per group
     const uint32_t wg = (uint32_t)warp / gw, wl = (uint32_t)warp - wg * gw;
-    const uint32_t P = a.parts, ngroups = (a.nq + G - 1) / G, nitems = ngroups * P, nlists = P * gw;
+    const uint32_t P = a.parts, ngroups = (a.nq + G - 1) / G, nitems = ngroups * P, nlists = P; // one list per (query, part)
     const uint32_t mth = (32u + gw - 1) / gw;
     const uint32_t stride = P * gw;
     const uint32_t n16 = (uint32_t)(a.pq_stride / 16);
@@ -131,14 +132,14 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
             if (tid < nw) s_pub[tid] = 0xFFFFFFFFu;
         }
         __syncthreads();
-        if (wg >= nqv) continue; // warp-uniform; the barriers above are the only CTA-wide ones
+        const bool active = wg < nqv; // warp-uniform: the groups beyond the item's queries only keep the barriers company
         const uint32_t cbase = q * n16; // CQ: this group's query in the constant window (uint4 slots; warp-uniform)
         const unsigned char *my_pq = s_pq + (size_t)wg * a.pq_stride;
         WarpList<1> list;
         list.init();
         // a step takes U blocks: adjacent ones (contiguous in the mirror; a.adjacent) or `stride` apart
         const uint32_t ustep = a.adjacent ? 1u : stride;
-        for (uint32_t g = p * gw + wl; (a.adjacent ? g * U : g) < a.nblk; g += a.adjacent ? stride : stride * U) {
+        for (uint32_t g = p * gw + wl; active && (a.adjacent ? g * U : g) < a.nblk; g += a.adjacent ? stride : stride * U) {
             const uint32_t b0 = a.adjacent ? g * U : g;
             float2 ax[U];
             uint32_t lv[U];
@@ -210,8 +211,16 @@ __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const S
                 if (pk < s_pub[warp]) *reinterpret_cast<volatile uint32_t *>(&s_pub[warp]) = pk;
             }
         }
-        // this warp's list of (query q, part p) -> finalize_kernel
-        a.cand[((size_t)q * nlists + (size_t)p * gw + wl) * 32 + lane] = list.v[0];
+        // the group's lists -> one list of (query q, part p) for finalize_kernel: a tree of pairwise merges of sorted lists
+        s_merge[warp * 32 + lane] = list.v[0];
+        for (uint32_t half = gw >> 1; half >= 1; half >>= 1) {
+            __syncthreads();
+            if (active && wl < half) {
+                list.merge_sorted(s_merge[(warp + half) * 32 + lane], lane);
+                s_merge[warp * 32 + lane] = list.v[0];
+            }
+        }
+        if (active && wl == 0) a.cand[((size_t)q * nlists + p) * 32 + lane] = list.v[0];
     }
 }
 
