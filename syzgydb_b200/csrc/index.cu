@@ -102,6 +102,8 @@ struct Workspace {
     DevBuf<unsigned long long> d_out_ids;
     DevBuf<double> d_out_dist;
     DevBuf<uint32_t> d_out_n, d_out_flags;
+    DevBuf<unsigned char> d_out_pack; // first-pass outputs of a host-buffer top-k call, packed
+    PinBuf<unsigned char> h_out_pack;
     DevBuf<uint32_t> d_slots;
     PinBuf<double> h_q;
     PinBuf<unsigned long long> h_out_ids;
@@ -120,7 +122,7 @@ struct Workspace {
     }
     void destroy() {
         d_q.release(); d_q2.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
-        d_out_n.release(); d_out_flags.release(); d_slots.release();
+        d_out_n.release(); d_out_flags.release(); d_slots.release(); d_out_pack.release(); h_out_pack.release();
         d_cand.release(); d_gmth.release();
         h_q.release(); h_out_ids.release(); h_out_dist.release(); h_out_n.release(); h_out_flags.release();
         h_slots.release();
@@ -533,19 +535,39 @@ int check_search(szg_index *h, const void *q, uint32_t nq) {
 // Copies the results of the first pass (already enqueued on ws->main into ws->d_out_*) to the host and
 // re-runs, together, the queries whose candidate set could not be certified: first with the 3-digit
 // (precise) surrogate, then with larger candidate sets.
+// layout of the packed first-pass outputs of a host-buffer call: [ids on*8 | dist on*8 | n nq*4 | flags nq*4]: one D2H copy
+struct OutPack {
+    unsigned char *d = nullptr, *h = nullptr;
+    size_t on = 0, nq = 0;
+    size_t bytes() const { return on * 16 + nq * 8; }
+    unsigned long long *d_ids() const { return reinterpret_cast<unsigned long long *>(d); }
+    double *d_dist() const { return reinterpret_cast<double *>(d + on * 8); }
+    uint32_t *d_n() const { return reinterpret_cast<uint32_t *>(d + on * 16); }
+    uint32_t *d_flags() const { return reinterpret_cast<uint32_t *>(d + on * 16 + nq * 4); }
+};
+
 int collect_and_escalate(szg_index *h, Workspace *ws, uint32_t nq, uint32_t k, const uint32_t *mask, uint32_t flags,
-                         int nd0, int mode0, uint64_t *out_ids, double *out_dist, uint32_t *out_n) {
+                         int nd0, int mode0, uint64_t *out_ids, double *out_dist, uint32_t *out_n, const OutPack *pack = nullptr) {
     int rc;
     cudaStream_t st = ws->main;
     const size_t on = (size_t)nq * k;
-    CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, on * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, on * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, nq * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    memcpy(out_ids, ws->h_out_ids.p, on * 8);
-    memcpy(out_dist, ws->h_out_dist.p, on * 8);
-    memcpy(out_n, ws->h_out_n.p, nq * 4);
+    if (pack) {
+        CK(cudaMemcpyAsync(pack->h, pack->d, pack->bytes(), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(out_ids, pack->h, on * 8);
+        memcpy(out_dist, pack->h + on * 8, on * 8);
+        memcpy(out_n, pack->h + on * 16, nq * 4);
+        memcpy(ws->h_out_flags.p, pack->h + on * 16 + nq * 4, nq * 4);
+    } else {
+        CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, on * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, on * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, nq * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(out_ids, ws->h_out_ids.p, on * 8);
+        memcpy(out_dist, ws->h_out_dist.p, on * 8);
+        memcpy(out_n, ws->h_out_n.p, nq * 4);
+    }
     // Queries whose candidate set could not be certified are re-run together, first with the
     // 3-digit (precise) surrogate, then with larger candidate sets.
     if (!(flags & SZG_F_NO_FP64_VERIFY)) {
@@ -1291,10 +1313,14 @@ static int search_topk_impl(szg_index *h, const double *queries, uint32_t nq, ui
     cudaStream_t st = ws->main;
     CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st));
     const int mode0 = mode_for_k(h, k), nd0 = first_digits(h);
-    if ((rc = run_topk(h, ws, ws->d_q.p, nq, k, mask, flags, mode0, nd0, ws->d_out_ids.p, ws->d_out_dist.p,
-                       ws->d_out_n.p, ws->d_out_flags.p)))
+    // the first pass writes its four outputs into one buffer: one copy back instead of four
+    OutPack pack;
+    pack.on = on; pack.nq = nq;
+    if ((rc = ws->d_out_pack.ensure(pack.bytes())) || (rc = ws->h_out_pack.ensure(pack.bytes()))) return rc;
+    pack.d = ws->d_out_pack.p; pack.h = ws->h_out_pack.p;
+    if ((rc = run_topk(h, ws, ws->d_q.p, nq, k, mask, flags, mode0, nd0, pack.d_ids(), pack.d_dist(), pack.d_n(), pack.d_flags())))
         return rc;
-    return collect_and_escalate(h, ws, nq, k, mask, flags, nd0, mode0, out_ids, out_dist, out_n);
+    return collect_and_escalate(h, ws, nq, k, mask, flags, nd0, mode0, out_ids, out_dist, out_n, &pack);
 }
 
 // ---- batched queries on the tensor cores (batch_q8.cu)
