@@ -3,6 +3,8 @@ include/syzgy_b200.h declares; without a GPU it fails loudly instead of falling 
 import ctypes
 import os
 import re
+import subprocess
+import tempfile
 
 import pytest
 
@@ -71,3 +73,46 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "pyoracle" not in text and "libsyzgy_oracle" not in text and "import oracle" not in text, f
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path=None):
+    # the binding mirrors four structs by hand: compile the header with gcc and compare sizes, field offsets and constants
+    probe = r"""
+#include <stddef.h>
+#include <stdio.h>
+#include "syzgy_b200.h"
+#define F(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+    printf("sizeof.szg_stats %zu\n", sizeof(szg_stats));
+    printf("sizeof.szg_meta_value %zu\n", sizeof(szg_meta_value));
+    printf("sizeof.szg_filter_op %zu\n", sizeof(szg_filter_op));
+    printf("sizeof.szg_spanfile_info %zu\n", sizeof(szg_spanfile_info));
+    F(szg_stats, batch_queries); F(szg_stats, rowbytes); F(szg_stats, scan_smem_bytes); F(szg_stats, combined_queries);
+    F(szg_meta_value, kind); F(szg_meta_value, str_len); F(szg_meta_value, num); F(szg_meta_value, str);
+    F(szg_filter_op, op); F(szg_filter_op, arg); F(szg_filter_op, num); F(szg_filter_op, str); F(szg_filter_op, str_len);
+    F(szg_filter_op, table_len); F(szg_filter_op, table);
+    printf("const.SZG_FOP_NOT_EXISTS %u\n", SZG_FOP_NOT_EXISTS);
+    printf("const.SZG_FOP_STR_TABLE %u\n", SZG_FOP_STR_TABLE);
+    printf("const.SZG_OPT_COMBINE %d\n", SZG_OPT_COMBINE);
+    printf("const.SZG_MV_ERROR %u\n", SZG_MV_ERROR);
+    return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "probe.c"), os.path.join(d, "probe")
+        open(src, "w").write(probe)
+        subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+        out = dict(line.split() for line in subprocess.check_output([exe], text=True).splitlines())
+    structs = {"szg_stats": _capi.Stats, "szg_meta_value": _capi.MetaValue, "szg_filter_op": _capi.FilterOp,
+               "szg_spanfile_info": _capi.SpanFileInfo}
+    for name, cls in structs.items():
+        assert ctypes.sizeof(cls) == int(out[f"sizeof.{name}"]), name
+    for key, val in out.items():
+        if key.startswith(("sizeof.", "const.")):
+            continue
+        sname, field = key.split(".")
+        assert getattr(structs[sname], field).offset == int(val), key
+    assert _capi.FOP_NOT_EXISTS == int(out["const.SZG_FOP_NOT_EXISTS"]) and _capi.FOP_STR_TABLE == int(out["const.SZG_FOP_STR_TABLE"])
+    assert _capi.OPT_COMBINE == int(out["const.SZG_OPT_COMBINE"])
+    from syzgydb_b200 import filter as hf
+    assert hf.MV_ERROR == int(out["const.SZG_MV_ERROR"])
