@@ -1220,54 +1220,62 @@ static int search_topk_combined(szg_index *h, const double *queries, uint32_t nq
     me.q = queries; me.nq = nq; me.k = k; me.mask_id = mask_id; me.flags = flags;
     me.out_ids = out_ids; me.out_dist = out_dist; me.out_n = out_n;
     std::unique_lock<std::mutex> lk(h->comb_mu);
-    h->comb_queue.push_back(&me);
+    try { h->comb_queue.push_back(&me); } catch (...) { return fail(SZG_ENOMEM, "out of host memory"); }
     while (!me.done) {
         if (h->comb_leader) { h->comb_cv.wait(lk); continue; }
         h->comb_leader = true;
         // the batch: the oldest request and every queued one with the same parameters, in arrival order
         std::vector<P *> batch;
-        P *first = h->comb_queue.front();
         uint32_t total = 0;
-        for (auto it = h->comb_queue.begin(); it != h->comb_queue.end();) {
-            P *p = *it;
-            if (p->k == first->k && p->mask_id == first->mask_id && p->flags == first->flags &&
-                (batch.empty() || total + p->nq <= kCombineMaxBatch)) {
-                batch.push_back(p);
-                total += p->nq;
-                it = h->comb_queue.erase(it);
-            } else ++it;
+        int rc = SZG_OK;
+        try { // nothing may leave this block by exception: the other callers wait for the leader (and the ABI never throws)
+            P *first = h->comb_queue.front();
+            batch.reserve(h->comb_queue.size());
+            for (auto it = h->comb_queue.begin(); it != h->comb_queue.end();) {
+                P *p = *it;
+                if (p->k == first->k && p->mask_id == first->mask_id && p->flags == first->flags &&
+                    (batch.empty() || total + p->nq <= kCombineMaxBatch)) {
+                    batch.push_back(p);
+                    total += p->nq;
+                    it = h->comb_queue.erase(it);
+                } else ++it;
+            }
+            lk.unlock();
+            if (batch.size() == 1) {
+                P *p = batch[0];
+                rc = search_topk_impl(h, p->q, p->nq, p->k, p->mask_id, p->flags, p->out_ids, p->out_dist, p->out_n, nullptr);
+            } else {
+                const size_t d = (size_t)h->dim, kk = first->k;
+                std::vector<double> q(total * d);
+                std::vector<uint64_t> ids(total * kk);
+                std::vector<double> dist(total * kk);
+                std::vector<uint32_t> n(total);
+                size_t off = 0;
+                for (P *p : batch) { memcpy(q.data() + off * d, p->q, (size_t)p->nq * d * sizeof(double)); off += p->nq; }
+                // a combined batch is a batch: from a few queries on, the tensor-core contraction (identical results, it falls
+                // back to the scan by itself where it does not apply) answers it in about the time of one or two scans
+                if (total >= kCombineTensorMin && !h->batch_disabled)
+                    rc = szg_search_batch(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
+                else
+                    rc = search_topk_impl(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
+                off = 0;
+                if (!rc)
+                    for (P *p : batch) {
+                        memcpy(p->out_ids, ids.data() + off * kk, (size_t)p->nq * kk * 8);
+                        memcpy(p->out_dist, dist.data() + off * kk, (size_t)p->nq * kk * 8);
+                        memcpy(p->out_n, n.data() + off, (size_t)p->nq * 4);
+                        off += p->nq;
+                    }
+            }
+        } catch (const std::bad_alloc &) {
+            rc = fail(SZG_ENOMEM, "out of host memory while combining %zu concurrent searches", batch.size());
+        } catch (...) {
+            rc = fail(SZG_EINTERNAL, "unexpected exception while combining concurrent searches");
         }
-        lk.unlock();
-        int rc;
-        if (batch.size() == 1) {
-            P *p = batch[0];
-            rc = search_topk_impl(h, p->q, p->nq, p->k, p->mask_id, p->flags, p->out_ids, p->out_dist, p->out_n, nullptr);
-        } else {
-            const size_t d = (size_t)h->dim, kk = first->k;
-            std::vector<double> q(total * d);
-            std::vector<uint64_t> ids(total * kk);
-            std::vector<double> dist(total * kk);
-            std::vector<uint32_t> n(total);
-            size_t off = 0;
-            for (P *p : batch) { memcpy(q.data() + off * d, p->q, (size_t)p->nq * d * sizeof(double)); off += p->nq; }
-            // a combined batch is a batch: from a few queries on, the tensor-core contraction (identical results, it falls
-            // back to the scan by itself where it does not apply) answers it in about the time of one or two scans
-            if (total >= kCombineTensorMin && !h->batch_disabled)
-                rc = szg_search_batch(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
-            else
-                rc = search_topk_impl(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
-            off = 0;
-            if (!rc)
-                for (P *p : batch) {
-                    memcpy(p->out_ids, ids.data() + off * kk, (size_t)p->nq * kk * 8);
-                    memcpy(p->out_dist, dist.data() + off * kk, (size_t)p->nq * kk * 8);
-                    memcpy(p->out_n, n.data() + off, (size_t)p->nq * 4);
-                    off += p->nq;
-                }
-        }
-        const std::string err = rc ? g_err : std::string();
-        lk.lock();
-        if (batch.size() > 1) h->combined_queries += total;
+        std::string err;
+        try { if (rc) err = g_err; } catch (...) {}
+        if (!lk.owns_lock()) lk.lock();
+        if (batch.size() > 1 && !rc) h->combined_queries += total;
         for (P *p : batch) { p->rc = rc; p->err = err; p->done = true; }
         h->comb_leader = false;
         h->comb_cv.notify_all();
