@@ -199,7 +199,6 @@ struct szg_index {
     // combining of concurrent single-query calls (szg_search_topk)
     struct PendingSearch;
     std::mutex comb_mu;
-    std::condition_variable comb_cv;
     std::vector<PendingSearch *> comb_queue;
     bool comb_leader = false;
     int combine = 1;
@@ -1208,6 +1207,7 @@ struct szg_index::PendingSearch {
     const double *q; uint32_t nq, k; int mask_id; uint32_t flags;
     uint64_t *out_ids; double *out_dist; uint32_t *out_n;
     int rc = 0; std::string err; bool done = false;
+    std::condition_variable cv; // the caller sleeps on its own variable: a finished launch wakes its callers and one new leader only
 };
 constexpr uint32_t kCombineMaxCall = 16;   // calls with more queries than this are not combined
 constexpr uint32_t kCombineMaxBatch = 128; // queries of one combined launch
@@ -1222,7 +1222,7 @@ static int search_topk_combined(szg_index *h, const double *queries, uint32_t nq
     std::unique_lock<std::mutex> lk(h->comb_mu);
     try { h->comb_queue.push_back(&me); } catch (...) { return fail(SZG_ENOMEM, "out of host memory"); }
     while (!me.done) {
-        if (h->comb_leader) { h->comb_cv.wait(lk); continue; }
+        if (h->comb_leader) { me.cv.wait(lk); continue; }
         h->comb_leader = true;
         // the batch: the oldest request and every queued one with the same parameters, in arrival order
         std::vector<P *> batch;
@@ -1276,9 +1276,12 @@ static int search_topk_combined(szg_index *h, const double *queries, uint32_t nq
         try { if (rc) err = g_err; } catch (...) {}
         if (!lk.owns_lock()) lk.lock();
         if (batch.size() > 1 && !rc) h->combined_queries += total;
-        for (P *p : batch) { p->rc = rc; p->err = err; p->done = true; }
+        for (P *p : batch) {
+            p->rc = rc; p->err = err; p->done = true;
+            if (p != &me) p->cv.notify_one();
+        }
         h->comb_leader = false;
-        h->comb_cv.notify_all();
+        if (!h->comb_queue.empty() && h->comb_queue.front() != &me) h->comb_queue.front()->cv.notify_one(); // the next leader
     }
     if (me.rc) g_err = me.err;
     return me.rc;
