@@ -107,6 +107,41 @@ def test_lowering_and_column_extraction():
     assert hf.column_values(b"{", ["age"])[0] == hf.DOC_INVALID and hf.column_values(b"3", ["age"])[0] == hf.DOC_OTHER
 
 
+def _stack_effect(prog):
+    """The value-stack discipline szg_filter_mask checks before it runs a program."""
+    sp = 0
+    for o in prog:
+        op = o["op"]
+        if op in (_capi.FOP_COL, _capi.FOP_NUM, _capi.FOP_STR, _capi.FOP_BOOL, _capi.FOP_NULL, _capi.FOP_EXISTS, _capi.FOP_NOT_EXISTS):
+            pops = 0
+        elif op in (_capi.FOP_NOT, _capi.FOP_CONTAINS, _capi.FOP_STARTS_WITH, _capi.FOP_ENDS_WITH, _capi.FOP_STR_TABLE):
+            pops = 1
+        elif op in (_capi.FOP_IN, _capi.FOP_NOT_IN):
+            pops = o["arg"] + 1
+        else:
+            pops = 2
+        assert sp >= pops, (o, sp)
+        sp += 1 - pops
+        assert sp <= 16
+    return sp
+
+
+def test_every_covered_reference_case_lowers_to_a_well_formed_program():
+    lowered = 0
+    for name, tree, doc, want in REFERENCE_TREE_CASES + REFERENCE_QUERY_CASES:
+        fields = sorted(set(_paths(tree)))
+        cols = {f: i for i, f in enumerate(fields)}
+        try:
+            prog = hf.lower(tree, cols, dictionary=lambda: ["john_doe123", "x"])
+        except hf.Unsupported:
+            assert "LENGTH" in name, name  # the only reference case outside the covered subset
+            continue
+        assert _stack_effect(prog) == 1, name
+        assert all(o.get("arg", 0) < 32 for o in prog if o["op"] in (_capi.FOP_COL, _capi.FOP_EXISTS, _capi.FOP_NOT_EXISTS))
+        lowered += 1
+    assert lowered == len(REFERENCE_TREE_CASES) + len(REFERENCE_QUERY_CASES) - 1
+
+
 # ------------------------------------------------------------------------------------------------ device path
 FIELDS = ["age", "status", "flag", "tags", "user.email", "name", "score", "tags.length"]
 COLS = {f: i for i, f in enumerate(FIELDS)}
