@@ -555,10 +555,13 @@ def test_concurrent_single_query_calls_are_combined_and_identical():
                     ix.search_topk(qs[0], 10, mask_id=12345)
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
-        th = [threading.Thread(target=work, args=(t,)) for t in range(12)]
-        [t.start() for t in th]
-        [t.join() for t in th]
-        assert not errs, errs[0]
+        for attempt in range(4):  # whether two calls overlap is up to the scheduler: give it a few rounds
+            th = [threading.Thread(target=work, args=(t,)) for t in range(12)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+            assert not errs, errs[0]
+            if ix.stats()["combined_queries"] > 0:
+                break
         assert ix.stats()["combined_queries"] > 0, "no two calls ever shared a launch"
 
 
