@@ -17,7 +17,10 @@
  *    4-bit high-nibble-first, 16/32/64-bit big-endian.  rowbytes = getVectorSize
  *    (collection.go:796-811).
  *  - threading: concurrent searches on one handle are safe (Search holds only the RLock,
- *    collection.go:570); mutations (upsert/remove/mask/reserve/fill/destroy) must not
+ *    collection.go:570), and so is building or destroying a filter mask next to them
+ *    (szg_mask_create / szg_filter_mask / szg_mask_destroy: Search applies its filter under
+ *    the RLock, collection.go:592-594) -- a mask must only outlive the searches that name it.
+ *    Mutations (upsert/encode/remove/meta_upsert/reserve/fill/set_option/destroy) must not
  *    overlap anything else on the same handle (they run under the write lock,
  *    collection.go:428, 491, 512).  Different handles are independent.
  *  - there is no CPU fallback: without a CUDA device every call fails with SZG_ECUDA.
@@ -69,6 +72,19 @@ const char *szg_last_error(void);
  * (collection.go:224-314: DimensionCount, Quantization (0 => 64, 254-256), DistanceMethod).
  */
 int szg_create(int dim, int quantization, int metric, int device, szg_index **out);
+
+/*
+ * One handle over ndev CUDA devices of this box (the reference serves a collection from ONE process,
+ * rest.go:20-23, so multi-GPU has to sit behind the same handle the shim already holds).  The rows are dealt to the devices
+ * (record id % ndev; a synthetic range is cut in ndev contiguous pieces), every entry point of this header works on the
+ * handle as on a single-device one, and results do not depend on ndev: a search runs on every device at once, the devices
+ * store their k x 16-byte lists straight into devices[0]'s memory over NVLink (peer stores, then a system-scope release of
+ * a per-query arrival counter) and the merge kernel on devices[0] waits on those counters -- no collective library, no
+ * host hop.  devices[0] needs peer access from the others (any NVLink / NVSwitch box); a device may be listed more than
+ * once (several shards on one GPU: used by the tests on single-GPU machines).  Device-resident calls (*_dev) take their
+ * pointers on devices[0].
+ */
+int szg_create_sharded(int dim, int quantization, int metric, const int *devices, int ndev, szg_index **out);
 
 /* Replaces: Collection.Close for the mirror (collection.go:408-421). */
 int szg_destroy(szg_index *h);
@@ -196,8 +212,10 @@ int szg_meta_dictionary_get(szg_index *h, uint32_t code, const char **str, uint3
 
 
 /*
- * Exact top-k for nq queries (each scans the whole mirror on its own: single-query GEMV
- * semantics, not the batched contraction).  Replaces: Search with Precision=="exact",
+ * Exact top-k for nq queries.  One to three queries are memory-bound scans (each streams the whole
+ * mirror: single-query GEMV semantics); from SZG_OPT_BATCH_MIN_QUERIES queries on the call is a
+ * batch and takes the tensor-core contraction of szg_search_batch when the geometry fits -- same
+ * results, bit for bit.  Replaces: Search with Precision=="exact",
  * Radius==0, K>0 (collection.go:672-684 driving consider 583-629 and the drain 693-697).
  *   queries  nq*dim float64, never quantized (collection.go:596)
  *   mask_id  -1 = no filter
@@ -231,6 +249,10 @@ int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t 
  */
 int szg_search_radius(szg_index *h, const double *query, double radius, int mask_id, uint32_t flags,
                       szg_result **out, uint64_t *scanned);
+/* nq radius searches in one call (many Search requests arriving together, rest.go:371-487): out[q] receives the result of
+ * query q with radius radii[q]; they share the launches and the copies.  Every result is freed with szg_result_free. */
+int szg_search_radius_batch(szg_index *h, const double *queries, uint32_t nq, const double *radii, int mask_id,
+                            uint32_t flags, szg_result **out, uint64_t *scanned);
 int szg_result_count(const szg_result *r, uint64_t *n);
 int szg_result_fetch(const szg_result *r, uint64_t offset, uint64_t n, uint64_t *out_ids,
                      double *out_dist);
@@ -245,6 +267,11 @@ void szg_result_free(szg_result *r);
  * SZG_MISSING_DISTANCE.  Filter and tombstones are NOT applied here (the replay does it).
  */
 int szg_rescore(szg_index *h, const double *query, const uint64_t *ids, uint64_t m, double *out_dist);
+/* The candidate lists of nlists queries in one call (one copy each way, one launch): list l = ids[list_offsets[l] ..
+ * list_offsets[l + 1]) is scored against queries[l * dim ..]; out_dist is indexed like ids.  What a shim serving several
+ * medium-precision searches at once (or one search's speculative batches of several trees) calls. */
+int szg_rescore_batch(szg_index *h, const double *queries, uint32_t nlists, const uint64_t *ids,
+                      const uint64_t *list_offsets, double *out_dist);
 
 /* ---- span file -> mirror -------------------------------------------------------
  * Direct reader of a collection's .dat file (grammar spanfile.go:1-22).  Replaces, for loading, OpenFile's
@@ -340,15 +367,17 @@ typedef struct szg_stats {
     uint32_t scan_stages;       /* shared-memory ring stages per warp */
     uint32_t scan_tile_bytes;   /* bytes of one bulk-copied tile */
     uint32_t scan_smem_bytes;   /* dynamic shared memory per CTA */
-    uint32_t reserved0;
+    uint32_t shards;            /* devices of a sharded handle (1 otherwise) */
     uint64_t combined_queries;  /* queries of concurrent szg_search_topk calls that were answered by a shared launch */
+    uint64_t graph_launches;    /* host-buffer top-k calls replayed as one captured launch sequence (CUDA graph) */
 } szg_stats;
 int szg_get_stats(szg_index *h, szg_stats *out);
 
 /* tuning / test knobs */
 #define SZG_OPT_STREAMS 1            /* streams a multi-query call is spread over (1..4, default 2) */
-#define SZG_OPT_TIMING 2             /* CUDA events around every scan launch: 0 off, 1 keep the last call's
-                                        (default), 2 accumulate over calls until szg_last_scan_times_ms reads them */
+#define SZG_OPT_TIMING 2             /* CUDA events around every scan launch: 0 off (default), 1 keep the last call's,
+                                        2 accumulate over calls until szg_last_scan_times_ms reads them.  While it is on,
+                                        calls are not replayed as captured launch sequences */
 #define SZG_OPT_MIN_CANDIDATE_MODE 3 /* force candidate set >= 32<<v (v in 0..3; -1 = automatic) */
 #define SZG_OPT_SCAN_WARPS 4         /* warps per scan CTA: 8 or 16 (default 16) */
 #define SZG_OPT_SCAN_STAGES 5        /* ring stages per warp, 2..8 (default 2) */
@@ -359,6 +388,11 @@ int szg_get_stats(szg_index *h, szg_stats *out);
 #define SZG_OPT_COMBINE 9            /* 1 (default): concurrent szg_search_topk calls on one handle (Search holds only the
                                         RLock, collection.go:570) with the same k / mask / flags share one launch: whoever
                                         arrives while a launch is running is answered together by the next one; 0: off */
+#define SZG_OPT_BATCH_MIN_QUERIES 10 /* szg_search_topk(_dev) calls with at least this many queries are batches: they take
+                                        the tensor-core contraction when its geometry fits (default 4, the measured
+                                        crossover: one or two queries are HBM-bound scans, four cost one batched pass) */
+#define SZG_OPT_GRAPHS 11            /* 1 (default): repeated host-buffer top-k call shapes are replayed as one captured
+                                        launch sequence (CUDA graph) instead of launch by launch; 0: off */
 int szg_set_option(szg_index *h, int option, int64_t value);
 
 /* Time of the most recent scan launches on this handle, measured with CUDA events on the

@@ -29,6 +29,8 @@ OPT_SCAN_TILE_CHUNKS = 6
 OPT_DIGITS = 7
 OPT_BATCH_TENSOR = 8
 OPT_COMBINE = 9
+OPT_BATCH_MIN_QUERIES = 10
+OPT_GRAPHS = 11
 
 # szg_filter_op opcodes (include/syzgy_b200.h SZG_FOP_*)
 (FOP_COL, FOP_NUM, FOP_STR, FOP_BOOL, FOP_NULL, FOP_EQ, FOP_NE, FOP_LT, FOP_LE, FOP_GT, FOP_GE, FOP_AND, FOP_OR, FOP_NOT,
@@ -42,6 +44,7 @@ EXPORTS = [
     "szg_fill_synthetic", "szg_fetch_codes", "szg_get_stats", "szg_set_option", "szg_last_scan_times_ms",
     "szg_spanfile_open", "szg_spanfile_close", "szg_spanfile_get_info", "szg_spanfile_ids", "szg_spanfile_record",
     "szg_spanfile_load", "szg_meta_upsert", "szg_filter_mask", "szg_meta_dictionary_size", "szg_meta_dictionary_get",
+    "szg_create_sharded", "szg_search_radius_batch", "szg_rescore_batch",
 ]
 
 
@@ -76,7 +79,8 @@ class Stats(C.Structure):
         ("device_bytes", C.c_uint64), ("live_rows", C.c_uint64), ("slots", C.c_uint64),
         ("rowbytes", C.c_uint32), ("pitch", C.c_uint32), ("sm_count", C.c_uint32), ("scan_grid", C.c_uint32),
         ("scan_block", C.c_uint32), ("scan_stages", C.c_uint32), ("scan_tile_bytes", C.c_uint32),
-        ("scan_smem_bytes", C.c_uint32), ("reserved0", C.c_uint32), ("combined_queries", C.c_uint64),
+        ("scan_smem_bytes", C.c_uint32), ("shards", C.c_uint32), ("combined_queries", C.c_uint64),
+        ("graph_launches", C.c_uint64),
     ]
 
 
@@ -97,6 +101,7 @@ def load():
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_float))
     L.szg_last_error.restype = C.c_char_p
     L.szg_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.szg_create_sharded.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.szg_destroy.argtypes = [vp]
     L.szg_reserve.argtypes = [vp, C.c_uint64]
     L.szg_upsert.argtypes = [vp, u64p, u8p, C.c_uint64]
@@ -112,6 +117,8 @@ def load():
     L.szg_search_topk.argtypes = [vp, f64p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, u64p, f64p, u32p, u64p]
     L.szg_search_batch.argtypes = L.szg_search_topk.argtypes
     L.szg_search_radius.argtypes = [vp, f64p, C.c_double, C.c_int, C.c_uint32, C.POINTER(vp), u64p]
+    L.szg_search_radius_batch.argtypes = [vp, f64p, C.c_uint32, f64p, C.c_int, C.c_uint32, C.POINTER(vp), u64p]
+    L.szg_rescore_batch.argtypes = [vp, f64p, C.c_uint32, u64p, u64p, f64p]
     L.szg_result_count.argtypes = [vp, u64p]
     L.szg_result_fetch.argtypes = [vp, C.c_uint64, C.c_uint64, u64p, f64p]
     L.szg_result_free.argtypes = [vp]
@@ -156,11 +163,18 @@ def vector_size(quant: int, dims: int) -> int:
 class Index:
     """GPU mirror of one collection (or of one row shard).  Thin, 1:1 over the C ABI."""
 
-    def __init__(self, dim: int, quant: int, metric: int, device: int = 0):
+    def __init__(self, dim: int, quant: int, metric: int, device: int = 0, devices=None):
+        """devices=[d0, d1, ...]: one handle over several GPUs (szg_create_sharded); results do not depend on the list."""
         self._L = load()
         self._h = C.c_void_p()
-        _check(self._L.szg_create(dim, quant, metric, device, C.byref(self._h)))
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(self._L.szg_create_sharded(dim, quant, metric, devs, len(devices), C.byref(self._h)))
+            device = int(devices[0]) if len(devices) else 0
+        else:
+            _check(self._L.szg_create(dim, quant, metric, device, C.byref(self._h)))
         self.dim, self.quant, self.metric, self.device = dim, (quant or 64), metric, device
+        self.devices = list(devices) if devices is not None else [device]
         self.rowbytes = vector_size(self.quant, dim)
 
     # -- lifecycle
@@ -351,6 +365,48 @@ class Index:
         finally:
             self._L.szg_result_free(res)
         return ids, dist, scanned.value
+
+    def search_radius_batch(self, queries, radii, mask_id: int = -1, flags: int = 0):
+        """nq radius searches in one call; returns a list of (ids, dist) per query and `scanned`."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)
+        r = np.ascontiguousarray(radii, dtype=np.float64).reshape(-1)
+        if r.size != q.shape[0]:
+            raise ValueError("one radius per query")
+        nq = q.shape[0]
+        res = (C.c_void_p * max(nq, 1))()
+        scanned = C.c_uint64(0)
+        _check(self._L.szg_search_radius_batch(self._h, _p(q, C.c_double), nq, _p(r, C.c_double), mask_id, flags, res,
+                                               C.byref(scanned)))
+        out = []
+        try:
+            for i in range(nq):
+                n = C.c_uint64(0)
+                _check(self._L.szg_result_count(res[i], C.byref(n)))
+                ids = np.zeros(n.value, dtype=np.uint64)
+                dist = np.zeros(n.value, dtype=np.float64)
+                if n.value:
+                    _check(self._L.szg_result_fetch(res[i], 0, n.value, _p(ids, C.c_uint64), _p(dist, C.c_double)))
+                out.append((ids, dist))
+        finally:
+            for i in range(nq):
+                if res[i]:
+                    self._L.szg_result_free(res[i])
+        return out, scanned.value
+
+    def rescore_batch(self, queries, id_lists):
+        """Candidate lists of several queries in one call (szg_rescore_batch); returns one distance array per list."""
+        q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, self.dim)
+        if len(id_lists) != q.shape[0]:
+            raise ValueError("one candidate list per query")
+        off = np.zeros(len(id_lists) + 1, dtype=np.uint64)
+        for i, l in enumerate(id_lists):
+            off[i + 1] = off[i] + len(l)
+        ids = (np.concatenate([np.asarray(l, dtype=np.uint64) for l in id_lists]) if len(id_lists) else np.zeros(0, np.uint64))
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = np.zeros(ids.size, dtype=np.float64)
+        _check(self._L.szg_rescore_batch(self._h, _p(q, C.c_double), q.shape[0], _p(ids, C.c_uint64), _p(off, C.c_uint64),
+                                         _p(out, C.c_double)))
+        return [out[int(off[i]):int(off[i + 1])] for i in range(len(id_lists))]
 
     def rescore(self, query, ids) -> np.ndarray:
         q = np.ascontiguousarray(query, dtype=np.float64).reshape(-1)

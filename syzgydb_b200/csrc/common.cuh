@@ -7,7 +7,8 @@
 //       codes[((b * C + c) * 32 + lane)]   (uint4 units, C = chunks per row)
 //   so a warp-wide LDG.128 of "chunk c of my row" reads one contiguous 512-byte span,
 //   and 8 rows x 16 B is exactly one UMMA K-major core matrix (used by the batched
-//   tensor-core path).
+//   tensor-core path).  Quantized rows (4/8/16-bit) use exactly this; float rows group
+//   their chunks by 8 (chunk_index_grouped below).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -186,6 +187,27 @@ __host__ __device__ inline void chunk_to_disk(int qt, unsigned char *b) {
 
 __device__ __forceinline__ size_t chunk_index(uint32_t slot, uint32_t C, uint32_t c) {
     return ((size_t)(slot >> 5) * C + c) * 32 + (slot & 31);
+}
+// Float rows (32/64-bit collections) are never an MMA operand, but they are what candidate lists of the LSH index gather
+// (BASELINE configs[2]: 3072-byte fp64 rows), and in the layout above a row's 16-byte chunks lie 512 bytes apart: every
+// chunk of a gathered row costs a 32-byte sector of its own (measured 7.2x the row bytes from DRAM).  So float rows keep
+// their chunks in GROUPS of 8 -- 128 contiguous bytes per row, i.e. whole lines for a gather:
+//     codes[(((b * C/8 + c/8) * 32 + lane) * 8 + ((c % 8) ^ (lane % 8)))]          (C is rounded up to a multiple of 8)
+// A block is still one contiguous span of C * 512 bytes and a tile of 8 n chunks one of 4096 n bytes, so the streaming scan
+// moves it with the same bulk copies; the XOR swizzle spreads the 8 lanes of a quarter warp over all 32 banks when they
+// read "chunk j of my row" from the staged tile with LDS.128.
+constexpr int kGroupChunks = 8;
+__host__ __device__ inline bool grouped_layout(int qt) { return qt >= F32; }
+__device__ __forceinline__ size_t chunk_index_grouped(uint32_t slot, uint32_t C, uint32_t c) {
+    const uint32_t lane = slot & 31;
+    return ((((size_t)(slot >> 5) * (C >> 3) + (c >> 3)) * 32 + lane) << 3) + ((c & 7u) ^ (lane & 7u));
+}
+template <int QT>
+__device__ __forceinline__ size_t chunk_at(uint32_t slot, uint32_t C, uint32_t c) {
+    return QT >= F32 ? chunk_index_grouped(slot, C, c) : chunk_index(slot, C, c);
+}
+__device__ __forceinline__ size_t chunk_at_rt(int qt, uint32_t slot, uint32_t C, uint32_t c) {
+    return qt >= F32 ? chunk_index_grouped(slot, C, c) : chunk_index(slot, C, c);
 }
 
 } // namespace szg

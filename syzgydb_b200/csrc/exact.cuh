@@ -76,11 +76,10 @@ template <int QT, int METRIC>
 __device__ double exact_distance_impl(const uint4 *__restrict__ codes, uint32_t C, uint32_t dims,
                                       const double *__restrict__ lut, const double *__restrict__ q,
                                       uint32_t slot) {
-    const uint4 *p = codes + chunk_index(slot, C, 0);
     ExactAcc s = {0.0, 0.0, 0.0, 0.0};
     uint32_t i = 0;
     for (uint32_t c = 0; c < C && i < dims; ++c) {
-        uint4 v = p[(size_t)c * 32];
+        uint4 v = codes[chunk_at<QT>(slot, C, c)];
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
         if (QT == Q4) {
 #pragma unroll

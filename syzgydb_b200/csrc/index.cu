@@ -1,30 +1,16 @@
 // index.cu -- the GPU mirror of one collection (or one row shard) and the C ABI of
 // include/syzgy_b200.h.  Host logic only: slot allocation, id -> slot map, workspaces,
 // streams, launches.  There is deliberately no CPU implementation of any search step.
-#include <algorithm>
 #include <cmath>
-#include <condition_variable>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <memory>
-#include <mutex>
-#include <string>
-#include <unordered_map>
-#include <unordered_set>
-#include <vector>
 
-#include "../../include/syzgy_b200.h"
-#include "kernels.h"
-#include "scan_small.cuh"
+#include "index_internal.h"
+#include "sharded.h"
 
 using namespace szg;
 
-namespace {
+namespace szg {
 
-thread_local std::string g_err;
+static thread_local std::string g_err;
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -35,214 +21,15 @@ int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+const std::string &last_error_string() { return g_err; }
+void set_last_error_string(const std::string &s) { g_err = s; }
 
-} // namespace
-
-// error channel and geometry for the other translation units of the library (spanfile.cu)
-namespace szg {
+// error channel for the other translation units of the library (spanfile.cu)
 int set_error(int code, const char *msg) { return fail(code, "%s", msg); }
+
 } // namespace szg
 
-namespace {
-
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(e_ == cudaErrorMemoryAllocation ? SZG_ENOMEM : SZG_ECUDA, "%s failed: %s (%s:%d)", \
-                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
-    } while (0)
-
-constexpr int kMaxStreams = 4;
-constexpr size_t kStageBytes = 64u << 20;
-
-template <typename T>
-struct DevBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    int ensure(size_t want, bool keep = false, cudaStream_t st = 0) {
-        if (want <= n) return SZG_OK;
-        T *np = nullptr;
-        CK(cudaMalloc(&np, want * sizeof(T)));
-        if (keep && p && n) {
-            cudaError_t e = cudaMemcpyAsync(np, p, n * sizeof(T), cudaMemcpyDeviceToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { cudaFree(np); return fail(SZG_ECUDA, "device copy failed: %s", cudaGetErrorString(e)); }
-        }
-        if (p) cudaFree(p);
-        p = np;
-        n = want;
-        return SZG_OK;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-};
-template <typename T>
-struct PinBuf {
-    T *p = nullptr;
-    size_t n = 0;
-    int ensure(size_t want) {
-        if (want <= n) return SZG_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr; n = 0;
-        CK(cudaMallocHost(&p, want * sizeof(T)));
-        n = want;
-        return SZG_OK;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; n = 0; }
-};
-
-struct Workspace {
-    cudaStream_t main = nullptr; // owned for host calls; the caller's stream for *_dev calls
-    bool owns_main = false;
-    DevBuf<double> d_q, d_q2;
-    DevBuf<unsigned char> d_pq;
-    DevBuf<unsigned long long> d_cand; // [nq][scan CTAs][32*E] candidate keys, scan -> finalize
-    DevBuf<unsigned int> d_gmth;       // batched path: per (query, row range) shared bound keys
-    DevBuf<unsigned int> d_ticket;     // radius hit counter
-    DevBuf<unsigned long long> d_out_ids;
-    DevBuf<double> d_out_dist;
-    DevBuf<uint32_t> d_out_n, d_out_flags;
-    DevBuf<unsigned char> d_out_pack; // first-pass outputs of a host-buffer top-k call, packed
-    PinBuf<unsigned char> h_out_pack;
-    DevBuf<uint32_t> d_slots;
-    PinBuf<double> h_q;
-    PinBuf<unsigned long long> h_out_ids;
-    PinBuf<double> h_out_dist;
-    PinBuf<uint32_t> h_out_n, h_out_flags, h_slots;
-    std::vector<cudaEvent_t> t0, t1; // per-scan timing events
-    uint32_t timed = 0;
-
-    int init(bool own) {
-        owns_main = own;
-        if (own) CK(cudaStreamCreateWithFlags(&main, cudaStreamNonBlocking));
-        int rc = d_ticket.ensure(4);
-        if (rc) return rc;
-        CK(cudaMemset(d_ticket.p, 0, 4 * sizeof(unsigned int)));
-        return SZG_OK;
-    }
-    void destroy() {
-        d_q.release(); d_q2.release(); d_pq.release(); d_ticket.release(); d_out_ids.release(); d_out_dist.release();
-        d_out_n.release(); d_out_flags.release(); d_slots.release(); d_out_pack.release(); h_out_pack.release();
-        d_cand.release(); d_gmth.release();
-        h_q.release(); h_out_ids.release(); h_out_dist.release(); h_out_n.release(); h_out_flags.release();
-        h_slots.release();
-        for (auto e : t0) cudaEventDestroy(e);
-        for (auto e : t1) cudaEventDestroy(e);
-        if (owns_main && main) cudaStreamDestroy(main);
-    }
-};
-
-struct IdRange {
-    uint64_t id0;
-    uint32_t slot0, n;
-};
-
-} // namespace
-
-struct szg_result {
-    std::vector<uint64_t> ids;
-    std::vector<double> dist;
-};
-
-struct szg_index {
-    int dim = 0, quant = 0, metric = 0, device = 0, qt = 0;
-    uint32_t rowbytes = 0, C = 0, maxint = 0;
-    int sm_count = 0;
-    // storage
-    DevBuf<uint4> codes;
-    DevBuf<unsigned long long> ids;
-    DevBuf<unsigned long long> aux; // 8 bytes per slot reserved; typed per (quant, metric)
-    DevBuf<uint32_t> live;
-    DevBuf<double> lut;
-    uint32_t capacity = 0; // slots allocated (multiple of 64)
-    uint32_t nslots = 0;   // high-water mark
-    uint64_t live_rows = 0;
-    std::unordered_map<uint64_t, uint32_t> map;
-    std::vector<IdRange> ranges;
-    std::unordered_set<uint64_t> range_dead;
-    std::vector<uint32_t> free_slots;
-    std::map<int, uint32_t *> masks;
-    int next_mask = 1;
-    // staging for mutations
-    PinBuf<unsigned char> h_stage;
-    DevBuf<unsigned char> d_stage;
-    DevBuf<double> d_vec; // float64 vectors of an szg_encode batch
-    PinBuf<uint32_t> h_slots;
-    DevBuf<uint32_t> d_slots;
-    PinBuf<unsigned long long> h_ids;
-    DevBuf<unsigned long long> d_ids_in;
-    cudaStream_t mut_stream = nullptr;
-    // workspaces
-    std::mutex mu;
-    std::vector<Workspace *> free_ws;
-    std::map<void *, Workspace *> dev_ws;
-    // options / stats
-    int nstreams = 2;
-    int timing = 1;
-    int force_mode = -1;
-    uint64_t launches = 0, escalations = 0, uncertain = 0;
-    std::vector<float> last_times;
-    Workspace *last_timed_ws = nullptr;
-    int scan_warps = 16, scan_stages = 2, scan_tile_chunks = 8;
-    bool scan_geometry_set = false; // SZG_OPT_SCAN_* given: no automatic choice
-    int batch_disabled = 0; // SZG_OPT_BATCH_TENSOR = 0 routes szg_search_batch to the streaming scan
-    // 16-bit collections: byte-planar copy of the codes, the operand of the batched path (rebuilt lazily after mutations)
-    DevBuf<uint4> planar;
-    bool planar_dirty = true;
-    uint32_t planar_nblk = 0;
-    uint64_t batch_queries = 0;
-    // metadata columns (filter.cu): allocated on first use, sized to `capacity`
-    DevBuf<unsigned char> doc_kind;
-    DevBuf<unsigned char> col_kind[kFilterMaxCols];
-    DevBuf<unsigned long long> col_val[kFilterMaxCols];
-    bool meta_used = false;
-    // combining of concurrent single-query calls (szg_search_topk)
-    struct PendingSearch;
-    std::mutex comb_mu;
-    std::vector<PendingSearch *> comb_queue;
-    bool comb_leader = false;
-    int combine = 1;
-    uint64_t combined_queries = 0;
-    DevBuf<unsigned char> d_filter_blob; // program + tables + ranks of the filter being evaluated (kept between calls)
-    std::unordered_map<std::string, uint32_t> dict;
-    std::vector<std::string> dict_strs;
-    int digits = 0; // 0 = automatic (2-digit fast pass, 3-digit re-run when uncertain), 2 or 3 = forced // streaming geometry (SZG_OPT_SCAN_*)
-
-    bool lookup(uint64_t id, uint32_t *slot) const {
-        auto it = map.find(id);
-        if (it != map.end()) { *slot = it->second; return true; }
-        for (const auto &r : ranges)
-            if (id >= r.id0 && id - r.id0 < r.n) {
-                if (!range_dead.empty() && range_dead.count(id)) return false;
-                *slot = r.slot0 + (uint32_t)(id - r.id0);
-                return true;
-            }
-        return false;
-    }
-    RowsArgs rows_args() {
-        RowsArgs a;
-        a.codes = codes.p; a.aux = aux.p; a.live = live.p; a.ids = ids.p;
-        a.C = C; a.dims = (uint32_t)dim; a.metric = (uint32_t)metric; a.maxint = maxint; a.rowbytes = rowbytes;
-        a.qt = qt;
-        return a;
-    }
-};
-
-namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = true;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-#define GUARD(h)                                                                 \
-    if (!(h)) return fail(SZG_EINVAL, "null handle");                            \
-    DeviceGuard guard_((h)->device);                                             \
-    if (!guard_.ok) return fail(SZG_ECUDA, "cannot select CUDA device %d", (h)->device)
+namespace szg {
 
 int grow(szg_index *h, uint64_t want_slots) {
     if (want_slots <= h->capacity) return SZG_OK;
@@ -314,314 +101,22 @@ int mode_for_k(const szg_index *h, uint32_t k) {
     return mode;
 }
 
-size_t pq_stride(const szg_index *h, int nd) {
-    size_t payload = ((size_t)h->C * pq_bytes_per_chunk(h->qt, nd) + 15) / 16 * 16;
-    return sizeof(PQHeader) + payload;
-}
-// digits of the first pass: 2 (fast) for quantized rows unless SZG_OPT_DIGITS forces 3
-int first_digits(const szg_index *h) { return (h->qt <= Q16 && h->digits != 3) ? 2 : 3; }
-
-constexpr size_t kCandBytes = 64u << 20;       // candidate lists of one scan launch (bounds queries per launch)
-constexpr size_t kScanSmemLimit = 224 * 1024; // dynamic; + ~3 KB static stays under the 227 KB CTA limit
-
-// Persistent launch: one CTA per SM (fewer when the collection has fewer row blocks than warps).
-int plan_scan(szg_index *h, int nd, ScanPlan *p, int *grid) {
-    // measured on B200 (profiles/r01_tune_scan_*): 16 warps x 4 KB tiles win on multi-GB shards (7.29 vs 7.04 TB/s at
-    // 7.7 GB), 8 warps x 8 KB tiles on ~1 GB shards (7.41 vs 7.04 TB/s at 0.96 GB: half as many per-warp lists per query)
-    uint32_t warps = (uint32_t)h->scan_warps, tile_chunks = (uint32_t)h->scan_tile_chunks;
-    if (!h->scan_geometry_set && h->qt == Q8 && (uint64_t)h->nslots * h->rowbytes < 1500000000ull && h->C >= 16) {
-        warps = 8;
-        tile_chunks = 16;
-    }
-    if (!scan_plan(h->C, warps, (uint32_t)h->scan_stages, tile_chunks, pq_stride(h, nd), kScanSmemLimit, p))
-        return fail(SZG_EINTERNAL, "scan geometry does not fit shared memory");
-    const uint32_t nblk = (h->nslots + 31) / 32;
-    uint32_t g = (nblk + p->warps - 1) / p->warps;
-    g = std::max<uint32_t>(1, std::min<uint32_t>(g, (uint32_t)h->sm_count));
-    *grid = (int)g;
-    return SZG_OK;
-}
-
-
-void fill_scan_args(szg_index *h, ScanArgs &a, const uint32_t *mask) {
-    memset(&a, 0, sizeof a);
-    a.codes = h->codes.p;
-    a.aux = h->aux.p;
-    a.live = h->live.p;
-    a.mask = mask;
-    a.ids = h->ids.p;
-    a.lut = h->lut.p;
-    a.C = h->C;
-    a.nblk = (h->nslots + 31) / 32;
-    a.dims = (uint32_t)h->dim;
-    a.metric = (uint32_t)h->metric;
-}
-
-// run_topk for short rows: the launch is cut in (query, part) items handled by one CTA each (scan_small.cuh)
-int run_topk_small(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32_t k, const uint32_t *mask, uint32_t flags,
-                   int nd, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags) {
-    const size_t stride = pq_stride(h, nd);
-    int rc;
-    if ((rc = ws->d_pq.ensure(stride * nq))) return rc;
-    const uint32_t nblk = (h->nslots + 31) / 32;
-    const uint32_t sms = (uint32_t)h->sm_count;
-    cudaStream_t main = ws->main;
-    PrepArgs pa;
-    pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
-    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
-    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
-    CK(launch_prep(nq, main, pa));
-    h->launches++;
-    // queries per launch: bounded by the candidate buffer (parts <= SM count lists of 16 warps x 32 keys per query)
-    // ... and by the constant window the prepared queries of a launch go through (SZG_SMALL_CONST=0: shared memory instead)
-    // measured (profiles/r01b_scan_small_vs_general.log): +5..7 % at 48 chunks, -5..10 % on rows of <= 8 chunks, nothing at 24
-    static const int const_env = getenv("SZG_SMALL_CONST") ? atoi(getenv("SZG_SMALL_CONST")) : -1;
-    const bool const_ok = const_env >= 0 ? const_env != 0 : h->C >= 32;
-    const size_t window_q = std::max<size_t>(1, (size_t)kConstSlots * 16 / stride);
-    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / ((size_t)sms * kSmallWarps * 32 * 8),
-                                                                             const_ok ? window_q : (size_t)4096}));
-    const bool timing = h->timing != 0;
-    const uint32_t nlaunch = (nq + chunk - 1) / chunk;
-    uint32_t tbase = 0;
-    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nlaunch <= 65536) tbase = ws->timed;
-    if (timing) {
-        while (ws->t0.size() < tbase + nlaunch) {
-            cudaEvent_t a, b;
-            CK(cudaEventCreate(&a));
-            CK(cudaEventCreate(&b));
-            ws->t0.push_back(a);
-            ws->t1.push_back(b);
-        }
-    }
-    ScanArgs a;
-    fill_scan_args(h, a, mask);
-    a.pq_stride = stride;
-    FinalizeArgs f;
-    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p;
-    f.pq_stride = stride;
-    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
-    f.flags = flags & SZG_F_NO_FP64_VERIFY;
-    for (uint32_t l = 0, q0 = 0; q0 < nq; q0 += chunk, ++l) {
-        const uint32_t m = std::min(chunk, nq - q0);
-        // parts per query: as many as keep every CTA busy, but no part shorter than one block per warp
-        const uint32_t qper = 1; // queries per warp (pairs were measured slower: see scan_small.cuh)
-        // warp groups per CTA, each on another query of the same row part (they share the rows in L1)
-        static const int wg_env = getenv("SZG_SMALL_WG") ? atoi(getenv("SZG_SMALL_WG")) : 0;
-        // measured (profiles/r01b_scan_small_vs_general.log): two groups win at 48 chunks (cfg4 2390 -> 2795 QPS, and 340 W
-        // instead of 460 W: the board no longer throttles) and on collections of a few MB; one group wins in between
-        uint32_t wgroups = wg_env == 1 || wg_env == 2 || wg_env == 4 ? (uint32_t)wg_env : ((h->C >= 32 || nblk < 8192) ? 2u : 1u);
-        while (wgroups > 1 && m < 2 * wgroups) wgroups >>= 1; // too few queries to fill the groups of several CTAs
-        const uint32_t gw = kSmallWarps / wgroups;
-        const uint32_t groups = (m + wgroups - 1) / wgroups;
-        uint32_t parts = small_parts(groups, sms);
-        parts = std::max<uint32_t>(1, std::min<uint32_t>(parts, (nblk + gw - 1) / gw));
-        const uint32_t nlists = parts; // the warps of a group merge their lists before writing
-        const int grid = (int)std::min<uint64_t>((uint64_t)groups * parts, sms);
-        a.qper = qper;
-        a.wgroups = wgroups;
-        a.const_queries = const_ok ? 1u : 0u;
-        if ((rc = ws->d_cand.ensure((size_t)m * nlists * 32))) return rc;
-        a.pq = ws->d_pq.p + stride * q0;
-        a.nq = m;
-        a.parts = parts;
-        static const int adj_env = getenv("SZG_SMALL_ADJ") ? atoi(getenv("SZG_SMALL_ADJ")) : -1;
-        a.adjacent = adj_env >= 0 ? (uint32_t)adj_env : (h->C < 48 ? 1u : 0u);
-        a.cand = ws->d_cand.p;
-        if (timing) CK(cudaEventRecord(ws->t0[tbase + l], main));
-        CK(launch_scan_small(h->qt, nd, h->C, grid, stride * wgroups, main, a));
-        if (timing) CK(cudaEventRecord(ws->t1[tbase + l], main));
-        f.cand = ws->d_cand.p;
-        f.nlists = nlists;
-        f.queries = d_q + (size_t)q0 * h->dim;
-        f.pq = a.pq;
-        f.out_ids = d_out_ids + (size_t)q0 * k; f.out_dist = d_out_dist + (size_t)q0 * k;
-        f.out_n = d_out_n + q0; f.out_flags = d_out_flags + q0;
-        CK(launch_finalize(h->qt, 0, m, main, f));
-        h->launches += 2;
-    }
-    if (timing) { ws->timed = tbase + nlaunch; h->last_timed_ws = ws; }
-    return SZG_OK;
-}
-
-// Enqueues prep + scan + finalize for nq queries on ws->main.  One scan launch serves a whole chunk of
-// queries (persistent warps walk query after query); the chunk size is bounded by the candidate
-// buffer.  Inputs/outputs are device pointers; `ws` supplies scratch.
-int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32_t k, const uint32_t *mask,
-             uint32_t flags, int mode, int nd, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
-             uint32_t *d_out_flags) {
-    const size_t stride = pq_stride(h, nd);
-    int rc;
-    if ((rc = ws->d_pq.ensure(stride * nq))) return rc;
-    ScanPlan plan;
-    int grid = 0;
-    if ((rc = plan_scan(h, nd, &plan, &grid))) return rc;
-    const size_t Kp = 32u << mode;
-    // short rows, k <= 24: the kernel of scan_small.cuh (SZG_SCAN_SMALL=0 keeps the general kernel, for comparisons)
-    static const bool small_ok = !(getenv("SZG_SCAN_SMALL") && atoi(getenv("SZG_SCAN_SMALL")) == 0);
-    static const uint32_t small_maxc = getenv("SZG_SCAN_SMALL_MAXC") ? (uint32_t)atoi(getenv("SZG_SCAN_SMALL_MAXC")) : 48u;
-    const bool small = small_ok && mode == 0 && !h->scan_geometry_set && scan_small_supported(h->qt, h->C) && h->C <= small_maxc &&
-                       h->nslots >= 32;
-    if (small) return run_topk_small(h, ws, d_q, nq, k, mask, flags, nd, d_out_ids, d_out_dist, d_out_n, d_out_flags);
-    const size_t nlists = (size_t)grid * plan.warps;
-    const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / (nlists * Kp * 8)}));
-    if ((rc = ws->d_cand.ensure((size_t)chunk * nlists * Kp))) return rc;
-
-    cudaStream_t main = ws->main;
-    PrepArgs pa;
-    pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
-    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
-    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
-    CK(launch_prep(nq, main, pa));
-    h->launches++;
-    const bool timing = h->timing != 0;
-    const uint32_t nlaunch = (nq + chunk - 1) / chunk;
-    // timing == 2 accumulates events over calls (bounded) until szg_last_scan_times_ms drains them
-    uint32_t tbase = 0;
-    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nlaunch <= 65536) tbase = ws->timed;
-    if (timing) {
-        while (ws->t0.size() < tbase + nlaunch) {
-            cudaEvent_t a, b;
-            CK(cudaEventCreate(&a));
-            CK(cudaEventCreate(&b));
-            ws->t0.push_back(a);
-            ws->t1.push_back(b);
-        }
-    }
-    ScanArgs a;
-    fill_scan_args(h, a, mask);
-    a.Ct = plan.Ct; a.stages = plan.stages; a.pq_smem_off = plan.pq_smem_off;
-    a.pq_stride = stride;
-    a.cand = ws->d_cand.p;
-    FinalizeArgs f;
-    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.cand = ws->d_cand.p;
-    f.pq_stride = stride;
-    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
-    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.nlists = (uint32_t)nlists;
-    for (uint32_t l = 0, q0 = 0; q0 < nq; q0 += chunk, ++l) {
-        const uint32_t m = std::min(chunk, nq - q0);
-        a.pq = ws->d_pq.p + stride * q0;
-        a.nq = m;
-        if (timing) CK(cudaEventRecord(ws->t0[tbase + l], main));
-        CK(launch_scan(h->qt, mode, nd, grid, (int)plan.warps * 32, plan.smem, main, a));
-        if (timing) CK(cudaEventRecord(ws->t1[tbase + l], main));
-        // merge of the per-warp lists, fp64 re-score, ordered output: one CTA per query
-        f.queries = d_q + (size_t)q0 * h->dim;
-        f.pq = a.pq;
-        f.out_ids = d_out_ids + (size_t)q0 * k; f.out_dist = d_out_dist + (size_t)q0 * k;
-        f.out_n = d_out_n + q0; f.out_flags = d_out_flags + q0;
-        CK(launch_finalize(h->qt, mode, m, main, f));
-        h->launches += 2;
-    }
-    if (timing) { ws->timed = tbase + nlaunch; h->last_timed_ws = ws; }
-    return SZG_OK;
-}
-
 int get_mask(szg_index *h, int mask_id, const uint32_t **out) {
     *out = nullptr;
     if (mask_id < 0) return SZG_OK;
+    std::lock_guard<std::mutex> lk(h->mask_mu);
     auto it = h->masks.find(mask_id);
     if (it == h->masks.end()) return fail(SZG_ENOTFOUND, "unknown mask id %d", mask_id);
     *out = it->second;
     return SZG_OK;
 }
 
-int check_search(szg_index *h, const void *q, uint32_t nq) {
-    if (!q && nq) return fail(SZG_EINVAL, "null query");
-    (void)h;
-    return SZG_OK;
-}
-
-// Copies the results of the first pass (already enqueued on ws->main into ws->d_out_*) to the host and
-// re-runs, together, the queries whose candidate set could not be certified: first with the 3-digit
-// (precise) surrogate, then with larger candidate sets.
-// layout of the packed first-pass outputs of a host-buffer call: [ids on*8 | dist on*8 | n nq*4 | flags nq*4]: one D2H copy
-struct OutPack {
-    unsigned char *d = nullptr, *h = nullptr;
-    size_t on = 0, nq = 0;
-    size_t bytes() const { return on * 16 + nq * 8; }
-    unsigned long long *d_ids() const { return reinterpret_cast<unsigned long long *>(d); }
-    double *d_dist() const { return reinterpret_cast<double *>(d + on * 8); }
-    uint32_t *d_n() const { return reinterpret_cast<uint32_t *>(d + on * 16); }
-    uint32_t *d_flags() const { return reinterpret_cast<uint32_t *>(d + on * 16 + nq * 4); }
-};
-
-int collect_and_escalate(szg_index *h, Workspace *ws, uint32_t nq, uint32_t k, const uint32_t *mask, uint32_t flags,
-                         int nd0, int mode0, uint64_t *out_ids, double *out_dist, uint32_t *out_n, const OutPack *pack = nullptr) {
-    int rc;
-    cudaStream_t st = ws->main;
-    const size_t on = (size_t)nq * k;
-    if (pack) {
-        CK(cudaMemcpyAsync(pack->h, pack->d, pack->bytes(), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        memcpy(out_ids, pack->h, on * 8);
-        memcpy(out_dist, pack->h + on * 8, on * 8);
-        memcpy(out_n, pack->h + on * 16, nq * 4);
-        memcpy(ws->h_out_flags.p, pack->h + on * 16 + nq * 4, nq * 4);
-    } else {
-        CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, on * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, on * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, nq * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, nq * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        memcpy(out_ids, ws->h_out_ids.p, on * 8);
-        memcpy(out_dist, ws->h_out_dist.p, on * 8);
-        memcpy(out_n, ws->h_out_n.p, nq * 4);
-    }
-    // Queries whose candidate set could not be certified are re-run together, first with the
-    // 3-digit (precise) surrogate, then with larger candidate sets.
-    if (!(flags & SZG_F_NO_FP64_VERIFY)) {
-        std::vector<uint32_t> pending;
-        for (uint32_t i = 0; i < nq; ++i)
-            if (ws->h_out_flags.p[i] & 1u) pending.push_back(i);
-        int nd = nd0, mode = mode0;
-        while (!pending.empty()) {
-            if (nd == 2) nd = 3;
-            else if (mode < 3) ++mode;
-            else break;
-            const uint32_t m = (uint32_t)pending.size();
-            h->escalations += m;
-            if ((rc = ws->d_q2.ensure((size_t)m * h->dim))) return rc;
-            for (uint32_t j = 0; j < m; ++j)
-                CK(cudaMemcpyAsync(ws->d_q2.p + (size_t)j * h->dim, ws->d_q.p + (size_t)pending[j] * h->dim,
-                                   (size_t)h->dim * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            if ((rc = run_topk(h, ws, ws->d_q2.p, m, k, mask, flags, mode, nd, ws->d_out_ids.p, ws->d_out_dist.p,
-                               ws->d_out_n.p, ws->d_out_flags.p)))
-                return rc;
-            CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ws->h_out_n.p, ws->d_out_n.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ws->h_out_flags.p, ws->d_out_flags.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            std::vector<uint32_t> still;
-            for (uint32_t j = 0; j < m; ++j) {
-                const uint32_t i = pending[j];
-                memcpy(out_ids + (size_t)i * k, ws->h_out_ids.p + (size_t)j * k, (size_t)k * 8);
-                memcpy(out_dist + (size_t)i * k, ws->h_out_dist.p + (size_t)j * k, (size_t)k * 8);
-                out_n[i] = ws->h_out_n.p[j];
-                if (ws->h_out_flags.p[j] & 1u) still.push_back(i);
-            }
-            pending.swap(still);
-        }
-        h->uncertain += pending.size();
-    }
-    return SZG_OK;
-}
-
-} // namespace
-
 // geometry of a handle, for spanfile.cu
-namespace szg {
 void index_geometry(const szg_index *h, int *dim, int *quant, int *metric, uint32_t *rowbytes) {
     *dim = h->dim; *quant = h->quant; *metric = h->metric; *rowbytes = h->rowbytes;
 }
-} // namespace szg
 
-// ====================================================================== C ABI
-extern "C" {
-
-const char *szg_last_error(void) { return g_err.c_str(); }
-
-int szg_create(int dim, int quantization, int metric, int device, szg_index **out) {
+int create_single(int dim, int quantization, int metric, int device, std::shared_ptr<MetaDict> dict, szg_index **out) {
     if (!out) return fail(SZG_EINVAL, "null out pointer");
     *out = nullptr;
     if (quantization == 0) quantization = 64; // collection.go:254-256
@@ -655,9 +150,12 @@ int szg_create(int dim, int quantization, int metric, int device, szg_index **ou
     h->maxint = quantization <= 16 ? (1u << quantization) - 1u : 0u;
     h->rowbytes = quantization == 4 ? (uint32_t)(dim + 1) / 2 : (uint32_t)dim * (quantization / 8);
     h->C = (h->rowbytes + 15) / 16;
+    if (grouped_layout(qt)) h->C = (h->C + kGroupChunks - 1) / kGroupChunks * kGroupChunks; // float rows: chunk groups of 8 (common.cuh)
     h->sm_count = prop.multiProcessorCount;
+    h->dict = dict ? dict : std::make_shared<MetaDict>();
     CK(cudaStreamCreateWithFlags(&h->mut_stream, cudaStreamNonBlocking));
-    CK(scan_configure(qt, kScanSmemLimit));
+    CK(scan_configure(qt, 224 * 1024));
+    if (qt <= Q16) CK(batch_configure(batch_dynamic_limit()));
     if (quantization <= 16) {
         const size_t n = (size_t)1 << quantization;
         std::vector<double> lut(n);
@@ -673,7 +171,7 @@ int szg_create(int dim, int quantization, int metric, int device, szg_index **ou
     return SZG_OK;
 }
 
-int szg_destroy(szg_index *h) {
+int destroy_single(szg_index *h) {
     if (!h) return SZG_OK;
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
@@ -690,8 +188,26 @@ int szg_destroy(szg_index *h) {
     return SZG_OK;
 }
 
+} // namespace szg
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *szg_last_error(void) { return szg::last_error_string().c_str(); }
+
+int szg_create(int dim, int quantization, int metric, int device, szg_index **out) {
+    return create_single(dim, quantization, metric, device, nullptr, out);
+}
+
+int szg_destroy(szg_index *h) {
+    if (h && h->sh) return sharded_destroy(h);
+    return destroy_single(h);
+}
+
 int szg_set_option(szg_index *h, int option, int64_t value) {
     if (!h) return fail(SZG_EINVAL, "null handle");
+    if (h->sh) return sharded_set_option(h, option, value);
+    h->generation++; // captured launch sequences were recorded under the old options
     switch (option) {
     case SZG_OPT_STREAMS:
         if (value < 1 || value > kMaxStreams) return fail(SZG_EINVAL, "streams must be in [1, %d]", kMaxStreams);
@@ -717,6 +233,11 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
         h->scan_geometry_set = true;
         return SZG_OK;
     case SZG_OPT_BATCH_TENSOR: h->batch_disabled = value == 0; return SZG_OK;
+    case SZG_OPT_BATCH_MIN_QUERIES:
+        if (value < 1 || value > 4096) return fail(SZG_EINVAL, "batch threshold must be in [1, 4096]");
+        h->batch_min = (int)value;
+        return SZG_OK;
+    case SZG_OPT_GRAPHS: h->use_graphs = value != 0; return SZG_OK;
     case SZG_OPT_COMBINE: h->combine = value != 0; return SZG_OK;
     case SZG_OPT_DIGITS:
         if (value != 0 && value != 2 && value != 3) return fail(SZG_EINVAL, "digits must be 0 (auto), 2 or 3");
@@ -731,22 +252,27 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
 }
 
 int szg_reserve(szg_index *h, uint64_t nrows) {
+    if (h && h->sh) return sharded_reserve(h, nrows);
     GUARD(h);
     return grow(h, nrows);
 }
 
 int szg_count(szg_index *h, uint64_t *n) {
     if (!h || !n) return fail(SZG_EINVAL, "null argument");
-    *n = h->live_rows;
+    *n = h->sh ? sharded_count(h) : h->live_rows;
     return SZG_OK;
 }
+
+} // extern "C"
+
+namespace szg {
 
 // One staged batch of rows into the mirror: slot assignment on the host, then scatter + aux on the device.  The
 // stream-1 bytes come either from the caller (codes) or from encode_kernel over the caller's float64 vectors, in
 // which case they are also handed back (out_codes) for the span file.
-static int upsert_rows(szg_index *h, const uint64_t *ids, const uint8_t *codes, const double *vectors, uint8_t *out_codes,
-                       uint64_t n, bool into_mirror) {
-    if (into_mirror) h->planar_dirty = true;
+int upsert_rows(szg_index *h, const uint64_t *ids, const uint8_t *codes, const double *vectors, uint8_t *out_codes,
+                uint64_t n, bool into_mirror) {
+    if (into_mirror) { h->planar_dirty = true; h->generation++; }
     uint64_t per = std::max<uint64_t>(1, kStageBytes / h->rowbytes);
     if (vectors) per = std::max<uint64_t>(1, std::min<uint64_t>(per, kStageBytes / ((uint64_t)h->dim * sizeof(double))));
     int rc;
@@ -805,23 +331,33 @@ static int upsert_rows(szg_index *h, const uint64_t *ids, const uint8_t *codes, 
     return SZG_OK;
 }
 
+} // namespace szg
+
+extern "C" {
+
 int szg_upsert(szg_index *h, const uint64_t *ids, const uint8_t *codes, uint64_t n) {
-    GUARD(h);
+    if (!h) return fail(SZG_EINVAL, "null handle");
     if (n && (!ids || !codes)) return fail(SZG_EINVAL, "null ids/codes");
+    if (h->sh) return sharded_upsert(h, ids, codes, nullptr, nullptr, n, true);
+    GUARD(h);
     return upsert_rows(h, ids, codes, nullptr, nullptr, n, true);
 }
 
 int szg_encode(szg_index *h, const uint64_t *ids, const double *vectors, uint64_t n, uint8_t *out_codes, int upsert) {
-    GUARD(h);
+    if (!h) return fail(SZG_EINVAL, "null handle");
     if (n && !vectors) return fail(SZG_EINVAL, "null vectors");
     if (n && upsert && !ids) return fail(SZG_EINVAL, "null ids");
     if (!upsert && !out_codes) return fail(SZG_EINVAL, "nothing to do: no output buffer and no upsert");
+    if (h->sh) return sharded_upsert(h, upsert ? ids : nullptr, nullptr, vectors, out_codes, n, upsert != 0);
+    GUARD(h);
     return upsert_rows(h, ids, nullptr, vectors, out_codes, n, upsert != 0);
 }
 
 int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_removed) {
+    if (h && h->sh) return n && !ids ? fail(SZG_EINVAL, "null ids") : sharded_remove(h, ids, n, n_removed);
     GUARD(h);
     if (n && !ids) return fail(SZG_EINVAL, "null ids");
+    h->generation++;
     std::vector<uint32_t> slots;
     for (uint64_t i = 0; i < n; ++i) {
         uint32_t slot;
@@ -853,9 +389,11 @@ int szg_remove(szg_index *h, const uint64_t *ids, uint64_t n, uint64_t *n_remove
 }
 
 int szg_fill_synthetic(szg_index *h, uint64_t seed, uint64_t row0, uint64_t nrows) {
+    if (h && h->sh) return nrows ? sharded_fill_synthetic(h, seed, row0, nrows) : SZG_OK;
     GUARD(h);
     if (!nrows) return SZG_OK;
     h->planar_dirty = true;
+    h->generation++;
     if ((uint64_t)h->nslots + nrows > 0xFFFFFF00ull) return fail(SZG_EINVAL, "too many rows");
     for (const auto &r : h->ranges)
         if (row0 < r.id0 + r.n && r.id0 < row0 + nrows) return fail(SZG_EINVAL, "synthetic range overlaps an existing one");
@@ -889,6 +427,7 @@ static int map_ids(szg_index *h, const uint64_t *ids, uint64_t n, uint32_t *slot
 }
 
 int szg_fetch_codes(szg_index *h, const uint64_t *ids, uint64_t n, uint8_t *out_codes) {
+    if (h && h->sh) return n && (!ids || !out_codes) ? fail(SZG_EINVAL, "null argument") : sharded_fetch_codes(h, ids, n, out_codes);
     GUARD(h);
     if (n && (!ids || !out_codes)) return fail(SZG_EINVAL, "null argument");
     const uint64_t per = std::max<uint64_t>(1, kStageBytes / h->rowbytes);
@@ -911,9 +450,13 @@ int szg_fetch_codes(szg_index *h, const uint64_t *ids, uint64_t n, uint8_t *out_
 }
 
 int szg_mask_create(szg_index *h, const uint64_t *ids, const uint8_t *pass, uint64_t n, int *mask_id) {
+    if (h && h->sh) return !mask_id || (n && (!ids || !pass)) ? fail(SZG_EINVAL, "null argument") : sharded_mask_create(h, ids, pass, n, mask_id);
     GUARD(h);
     if (!mask_id || (n && (!ids || !pass))) return fail(SZG_EINVAL, "null argument");
     if (n > 0xFFFFFFFFull) return fail(SZG_EINVAL, "too many ids");
+    // Search builds masks while it holds only the RLock (collection.go:570, 592-594): builders take turns on the staging
+    // buffers, running searches are not disturbed (they only look masks up)
+    std::lock_guard<std::mutex> build(h->mask_build_mu);
     const size_t words = h->capacity / 32;
     uint32_t *mask = nullptr;
     CK(cudaMalloc(&mask, words * 4));
@@ -939,6 +482,7 @@ int szg_mask_create(szg_index *h, const uint64_t *ids, const uint8_t *pass, uint
         if (e != cudaSuccess) rc = fail(SZG_ECUDA, "sync failed: %s", cudaGetErrorString(e));
     }
     if (rc) { cudaFree(mask); return rc; }
+    std::lock_guard<std::mutex> lk(h->mask_mu);
     *mask_id = h->next_mask++;
     h->masks[*mask_id] = mask;
     return SZG_OK;
@@ -961,17 +505,23 @@ static int meta_column_ready(szg_index *h, DevBuf<unsigned char> &kind, DevBuf<u
 
 static uint32_t dict_code(szg_index *h, const char *sp, uint32_t len, bool insert) {
     std::string key(sp ? sp : "", sp ? len : 0);
-    auto it = h->dict.find(key);
-    if (it != h->dict.end()) return it->second;
+    auto it = h->dict->codes.find(key);
+    if (it != h->dict->codes.end()) return it->second;
     if (!insert) return 0xFFFFFFFFu;
-    const uint32_t code = (uint32_t)h->dict_strs.size();
-    h->dict_strs.push_back(key);
-    h->dict.emplace(std::move(key), code);
+    const uint32_t code = (uint32_t)h->dict->strs.size();
+    h->dict->strs.push_back(key);
+    h->dict->codes.emplace(std::move(key), code);
     return code;
 }
 
 int szg_meta_upsert(szg_index *h, const uint64_t *ids, uint64_t n, const uint8_t *doc_kind, const uint32_t *cols,
                     uint32_t ncols, const szg_meta_value *values) {
+    if (h && h->sh) {
+        if (n && (!ids || !doc_kind || (ncols && (!cols || !values)))) return fail(SZG_EINVAL, "null argument");
+        for (uint32_t j = 0; j < ncols; ++j)
+            if (cols[j] >= kFilterMaxCols) return fail(SZG_EINVAL, "metadata column %u out of range (max %u)", cols[j], kFilterMaxCols - 1);
+        return sharded_meta_upsert(h, ids, n, doc_kind, cols, ncols, values);
+    }
     GUARD(h);
     if (n && (!ids || !doc_kind || (ncols && (!cols || !values)))) return fail(SZG_EINVAL, "null argument");
     if (n > 0xFFFFFFFFull) return fail(SZG_EINVAL, "too many ids");
@@ -1027,29 +577,31 @@ int szg_meta_upsert(szg_index *h, const uint64_t *ids, uint64_t n, const uint8_t
 }
 
 int szg_meta_dictionary_size(szg_index *h, uint32_t *size) {
-    GUARD(h);
+    if (!h) return fail(SZG_EINVAL, "null handle");
     if (!size) return fail(SZG_EINVAL, "null argument");
-    *size = (uint32_t)h->dict_strs.size();
+    *size = (uint32_t)h->dict->strs.size();
     return SZG_OK;
 }
 
 int szg_meta_dictionary_get(szg_index *h, uint32_t code, const char **str, uint32_t *len) {
-    GUARD(h);
+    if (!h) return fail(SZG_EINVAL, "null handle");
     if (!str || !len) return fail(SZG_EINVAL, "null argument");
-    if (code >= h->dict_strs.size()) return fail(SZG_ENOTFOUND, "no string with code %u", code);
-    *str = h->dict_strs[code].data();
-    *len = (uint32_t)h->dict_strs[code].size();
+    if (code >= h->dict->strs.size()) return fail(SZG_ENOTFOUND, "no string with code %u", code);
+    *str = h->dict->strs[code].data();
+    *len = (uint32_t)h->dict->strs[code].size();
     return SZG_OK;
 }
 
 int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *mask_id) {
+    if (h && h->sh) return !ops || !nops || !mask_id ? fail(SZG_EINVAL, "null argument") : sharded_filter_mask(h, ops, nops, mask_id);
     GUARD(h);
     if (!ops || !nops || !mask_id) return fail(SZG_EINVAL, "null argument");
     if (nops > 4096) return fail(SZG_EINVAL, "filter program too long");
+    std::lock_guard<std::mutex> build(h->mask_build_mu);
     int rc;
     cudaStream_t st = h->mut_stream;
     // ---- validate the stack discipline and lower the literals
-    const uint32_t D = (uint32_t)h->dict_strs.size();
+    const uint32_t D = (uint32_t)h->dict->strs.size();
     std::vector<std::string> lits; // literal strings that are not in the dictionary get virtual codes D, D + 1, ...
     auto literal_code = [&](const szg_filter_op &o) -> uint32_t {
         uint32_t c = dict_code(h, o.str, o.str_len, false);
@@ -1106,7 +658,7 @@ int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *
             std::vector<unsigned char> &t = tables[i];
             t.resize(std::max<uint32_t>(D, 1));
             for (uint32_t c = 0; c < D; ++c) {
-                const std::string &x = h->dict_strs[c];
+                const std::string &x = h->dict->strs[c];
                 bool r;
                 if (o.op == SZG_FOP_CONTAINS) r = x.find(lit) != std::string::npos;
                 else if (o.op == SZG_FOP_STARTS_WITH) r = x.size() >= lit.size() && x.compare(0, lit.size(), lit) == 0;
@@ -1135,7 +687,7 @@ int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *
         const uint32_t total = D + (uint32_t)lits.size();
         std::vector<uint32_t> order(total);
         for (uint32_t i = 0; i < total; ++i) order[i] = i;
-        auto str_of = [&](uint32_t c) -> const std::string & { return c < D ? h->dict_strs[c] : lits[c - D]; };
+        auto str_of = [&](uint32_t c) -> const std::string & { return c < D ? h->dict->strs[c] : lits[c - D]; };
         std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return str_of(x) < str_of(y); });
         rank.resize(total);
         for (uint32_t i = 0; i < total; ++i) rank[order[i]] = i;
@@ -1180,534 +732,30 @@ int szg_filter_mask(szg_index *h, const szg_filter_op *ops, uint32_t nops, int *
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     h->launches++;
     if (e != cudaSuccess) { cudaFree(mask); return fail(SZG_ECUDA, "filter evaluation failed: %s", cudaGetErrorString(e)); }
+    std::lock_guard<std::mutex> lk(h->mask_mu);
     *mask_id = h->next_mask++;
     h->masks[*mask_id] = mask;
     return SZG_OK;
 }
 
 int szg_mask_destroy(szg_index *h, int mask_id) {
+    if (h && h->sh) return sharded_mask_destroy(h, mask_id);
     GUARD(h);
-    auto it = h->masks.find(mask_id);
-    if (it == h->masks.end()) return fail(SZG_ENOTFOUND, "unknown mask id %d", mask_id);
-    cudaFree(it->second);
-    h->masks.erase(it);
-    return SZG_OK;
-}
-
-static int search_topk_impl(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                            uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned);
-
-// Concurrent callers.  The reference answers one query per Search call and lets calls overlap (RLock only,
-// collection.go:570); a scan launch, however, owns the whole GPU, so overlapping calls would queue up one launch each and
-// every one of them would stream the collection from HBM alone.  Instead the calls combine: a caller that finds no launch in
-// flight becomes the leader and runs whatever is queued with its own k / mask / flags as ONE call (scan_small_kernel then
-// deals the queries to CTA groups and they share rows in L2); callers arriving meanwhile wait and are answered together by
-// the next leader.  Nobody waits for company: a lone caller runs at once, exactly as before.
-struct szg_index::PendingSearch {
-    const double *q; uint32_t nq, k; int mask_id; uint32_t flags;
-    uint64_t *out_ids; double *out_dist; uint32_t *out_n;
-    int rc = 0; std::string err; bool done = false;
-    std::condition_variable cv; // the caller sleeps on its own variable: a finished launch wakes its callers and one new leader only
-};
-constexpr uint32_t kCombineMaxCall = 16;   // calls with more queries than this are not combined
-constexpr uint32_t kCombineMaxBatch = 128; // queries of one combined launch
-constexpr uint32_t kCombineTensorMin = 4;  // combined batches from this size on go to szg_search_batch
-
-static int search_topk_combined(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                                uint64_t *out_ids, double *out_dist, uint32_t *out_n) {
-    using P = szg_index::PendingSearch;
-    P me;
-    me.q = queries; me.nq = nq; me.k = k; me.mask_id = mask_id; me.flags = flags;
-    me.out_ids = out_ids; me.out_dist = out_dist; me.out_n = out_n;
-    std::unique_lock<std::mutex> lk(h->comb_mu);
-    try { h->comb_queue.push_back(&me); } catch (...) { return fail(SZG_ENOMEM, "out of host memory"); }
-    while (!me.done) {
-        if (h->comb_leader) { me.cv.wait(lk); continue; }
-        h->comb_leader = true;
-        // the batch: the oldest request and every queued one with the same parameters, in arrival order
-        std::vector<P *> batch;
-        uint32_t total = 0;
-        int rc = SZG_OK;
-        try { // nothing may leave this block by exception: the other callers wait for the leader (and the ABI never throws)
-            P *first = h->comb_queue.front();
-            batch.reserve(h->comb_queue.size());
-            for (auto it = h->comb_queue.begin(); it != h->comb_queue.end();) {
-                P *p = *it;
-                if (p->k == first->k && p->mask_id == first->mask_id && p->flags == first->flags &&
-                    (batch.empty() || total + p->nq <= kCombineMaxBatch)) {
-                    batch.push_back(p);
-                    total += p->nq;
-                    it = h->comb_queue.erase(it);
-                } else ++it;
-            }
-            lk.unlock();
-            if (batch.size() == 1) {
-                P *p = batch[0];
-                rc = search_topk_impl(h, p->q, p->nq, p->k, p->mask_id, p->flags, p->out_ids, p->out_dist, p->out_n, nullptr);
-            } else {
-                const size_t d = (size_t)h->dim, kk = first->k;
-                std::vector<double> q(total * d);
-                std::vector<uint64_t> ids(total * kk);
-                std::vector<double> dist(total * kk);
-                std::vector<uint32_t> n(total);
-                size_t off = 0;
-                for (P *p : batch) { memcpy(q.data() + off * d, p->q, (size_t)p->nq * d * sizeof(double)); off += p->nq; }
-                // a combined batch is a batch: from a few queries on, the tensor-core contraction (identical results, it falls
-                // back to the scan by itself where it does not apply) answers it in about the time of one or two scans
-                if (total >= kCombineTensorMin && !h->batch_disabled)
-                    rc = szg_search_batch(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
-                else
-                    rc = search_topk_impl(h, q.data(), total, first->k, first->mask_id, first->flags, ids.data(), dist.data(), n.data(), nullptr);
-                off = 0;
-                if (!rc)
-                    for (P *p : batch) {
-                        memcpy(p->out_ids, ids.data() + off * kk, (size_t)p->nq * kk * 8);
-                        memcpy(p->out_dist, dist.data() + off * kk, (size_t)p->nq * kk * 8);
-                        memcpy(p->out_n, n.data() + off, (size_t)p->nq * 4);
-                        off += p->nq;
-                    }
-            }
-        } catch (const std::bad_alloc &) {
-            rc = fail(SZG_ENOMEM, "out of host memory while combining %zu concurrent searches", batch.size());
-        } catch (...) {
-            rc = fail(SZG_EINTERNAL, "unexpected exception while combining concurrent searches");
-        }
-        std::string err;
-        try { if (rc) err = g_err; } catch (...) {}
-        if (!lk.owns_lock()) lk.lock();
-        if (batch.size() > 1 && !rc) h->combined_queries += total;
-        for (P *p : batch) {
-            p->rc = rc; p->err = err; p->done = true;
-            if (p != &me) p->cv.notify_one();
-        }
-        h->comb_leader = false;
-        if (!h->comb_queue.empty() && h->comb_queue.front() != &me) h->comb_queue.front()->cv.notify_one(); // the next leader
-    }
-    if (me.rc) g_err = me.err;
-    return me.rc;
-}
-
-int szg_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                    uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
-    if (h && h->combine && queries && nq >= 1 && nq <= kCombineMaxCall && out_ids && out_dist && out_n && k >= 1 && k <= SZG_MAX_K) {
-        if (scanned) *scanned = h->live_rows;
-        return search_topk_combined(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n);
-    }
-    return search_topk_impl(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n, scanned);
-}
-
-static int search_topk_impl(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                            uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
-    GUARD(h);
-    int rc;
-    if ((rc = check_search(h, queries, nq))) return rc;
-    if (k < 1 || k > SZG_MAX_K) return fail(SZG_EINVAL, "k=%u outside [1, %u]", k, SZG_MAX_K);
-    if (nq && (!out_ids || !out_dist || !out_n)) return fail(SZG_EINVAL, "null output");
-    if (scanned) *scanned = h->live_rows;
-    if (!nq) return SZG_OK;
-    const uint32_t *mask;
-    if ((rc = get_mask(h, mask_id, &mask))) return rc;
-    if (h->live_rows == 0) { // empty collection: zero results, nothing to launch (collection.go:706-709)
-        for (uint32_t i = 0; i < nq; ++i) out_n[i] = 0;
-        return SZG_OK;
-    }
-    Workspace *ws;
-    if ((rc = acquire_ws(h, &ws))) return rc;
-    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
-    const size_t qn = (size_t)nq * h->dim, on = (size_t)nq * k;
-    if ((rc = ws->h_q.ensure(qn)) || (rc = ws->d_q.ensure(qn)) || (rc = ws->d_out_ids.ensure(on)) ||
-        (rc = ws->d_out_dist.ensure(on)) || (rc = ws->d_out_n.ensure(nq)) || (rc = ws->d_out_flags.ensure(nq)) ||
-        (rc = ws->h_out_ids.ensure(on)) || (rc = ws->h_out_dist.ensure(on)) || (rc = ws->h_out_n.ensure(nq)) ||
-        (rc = ws->h_out_flags.ensure(nq)))
-        return rc;
-    memcpy(ws->h_q.p, queries, qn * sizeof(double));
-    cudaStream_t st = ws->main;
-    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st));
-    const int mode0 = mode_for_k(h, k), nd0 = first_digits(h);
-    // the first pass writes its four outputs into one buffer: one copy back instead of four
-    OutPack pack;
-    pack.on = on; pack.nq = nq;
-    if ((rc = ws->d_out_pack.ensure(pack.bytes())) || (rc = ws->h_out_pack.ensure(pack.bytes()))) return rc;
-    pack.d = ws->d_out_pack.p; pack.h = ws->h_out_pack.p;
-    if ((rc = run_topk(h, ws, ws->d_q.p, nq, k, mask, flags, mode0, nd0, pack.d_ids(), pack.d_dist(), pack.d_n(), pack.d_flags())))
-        return rc;
-    return collect_and_escalate(h, ws, nq, k, mask, flags, nd0, mode0, out_ids, out_dist, out_n, &pack);
-}
-
-// ---- batched queries on the tensor cores (batch_q8.cu)
-struct BatchPlan { uint32_t slice, stages, keep, nranges, gpl, ngroups, Cb; int mode; bool p16, p4; };
-
-// true when the tensor-core path can serve (collection, k): 8-bit rows, an even number of 16-byte chunks that
-// fits the TMEM columns reserved for the query digits, candidate lists of at most 128 keys, 2-digit queries
-static bool plan_batch(const szg_index *h, uint32_t nq, uint32_t k, BatchPlan *p) {
-    if (h->qt > Q16 || h->digits == 3 || k < 1 || nq < 1 || h->batch_disabled || h->live_rows == 0) return false;
-    // chunks of the contraction operand (16 dimensions each): the 8-bit row itself, one byte plane of a 16-bit row,
-    // or the one-byte-per-code copy of a 4-bit row
-    p->p16 = h->qt == Q16;
-    p->p4 = h->qt == Q4;
-    p->Cb = h->qt == Q8 ? h->C : (uint32_t)(h->dim + 15) / 16;
-    if ((p->Cb % 2) != 0 || p->Cb > batch_max_chunks()) return false;
-    p->mode = mode_for_k(h, k); // candidates per list = 32 << mode, as in the streaming scan
-    if (p->mode > 2) return false;
-    p->keep = 32u << p->mode;
-    const size_t ring_limit = batch_dynamic_limit();
-    if (ring_limit <= batch_list_bytes(p->keep)) return false;
-    const size_t stage_limit = ring_limit - batch_list_bytes(p->keep);
-    uint32_t want_slice = 0;
-    if (const char *e = getenv("SZG_BATCH_SLICE")) want_slice = (uint32_t)atoi(e);
-    p->slice = batch_slice_chunks(p->Cb, want_slice, stage_limit);
-    p->stages = batch_stages(p->slice, stage_limit);
-    if (p->stages < 2) return false;
-    p->ngroups = (nq + 63) / 64;
-    p->gpl = std::min<uint32_t>(p->ngroups, 16); // query groups per launch (they share the L2 copy of a row range)
-    const uint32_t nblk = (h->nslots + 31) / 32;
-    p->nranges = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)h->sm_count / p->gpl, (nblk + 3) / 4));
-    return true;
-}
-
-// prep -> batch_kernel (one launch per 16 query groups) -> finalize, all on ws->main; outputs on the device
-static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const double *d_q, uint32_t nq, uint32_t k,
-                     const uint32_t *mask, uint32_t flags, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
-                     uint32_t *d_out_flags) {
-    int rc;
-    cudaStream_t st = ws->main;
-    const int nd = 2; // 2 digit planes x 64 queries = the M dimension
-    // the query digits are laid out like an 8-bit row of Cb chunks in both cases
-    const size_t stride = sizeof(PQHeader) + (size_t)p.Cb * nd * 16;
-    if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * p.nranges * p.keep)) ||
-        (rc = ws->d_gmth.ensure((size_t)nq * p.nranges)))
-        return rc;
-    const uint32_t nblk_now = (h->nslots + 31) / 32;
-    if (p.p16 || p.p4) {
-        // (re)build the byte copy after a mutation.  16-bit: [high-byte plane | low-byte plane], each nblk x Cb x 32 uint4;
-        // 4-bit: one plane, one byte per code.  Searches may run concurrently (RLock): the first one in rebuilds and
-        // waits, the others wait on the mutex.
-        std::lock_guard<std::mutex> lk(h->mu);
-        if (h->planar_dirty || h->planar_nblk != nblk_now) {
-            const size_t plane = (size_t)nblk_now * p.Cb * 32;
-            if ((rc = h->planar.ensure((p.p16 ? 2 : 1) * plane))) return rc;
-            CK(cudaStreamSynchronize(h->mut_stream));
-            if (p.p16) CK(launch_planar16(h->codes.p, h->C, h->planar.p, h->planar.p + plane, p.Cb, nblk_now, st));
-            else CK(launch_expand4(h->codes.p, h->C, h->planar.p, p.Cb, nblk_now, st));
-            CK(cudaStreamSynchronize(st));
-            h->launches++;
-            h->planar_dirty = false;
-            h->planar_nblk = nblk_now;
-        }
-    }
-    PrepArgs pa;
-    pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
-    pa.dims = (uint32_t)h->dim; pa.C = p.Cb; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
-    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 0; pa.radius = 0.0;
-    pa.planar16 = (p.p16 || p.p4) ? 1 : 0; // digits laid out like an 8-bit row of Cb chunks
-    CK(launch_prep(nq, st, pa));
-    h->launches++;
-    CK(batch_configure(batch_dynamic_limit()));
-    BatchArgs b;
-    memset(&b, 0, sizeof b);
-    b.codes = (p.p16 || p.p4) ? h->planar.p : h->codes.p;
-    b.codes_lo = p.p16 ? h->planar.p + (size_t)nblk_now * p.Cb * 32 : nullptr;
-    b.aux = h->aux.p; b.live = h->live.p; b.mask = mask;
-    b.pq = ws->d_pq.p; b.pq_stride = stride; b.cand = ws->d_cand.p; b.keep = p.keep;
-    b.C = p.Cb; b.nblk = nblk_now; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
-    b.nranges = p.nranges; b.nlists = p.nranges; b.stages = p.stages; b.slice = p.slice;
-    b.gmth = ws->d_gmth.p; b.mth = (p.keep + p.nranges - 1) / p.nranges;
-    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, (size_t)nq * p.nranges * sizeof(unsigned int), st));
-    if (const char *dbg = getenv("SZG_BATCH_DEBUG")) b.debug = (uint32_t)atoi(dbg);
-    const bool timing = h->timing != 0;
-    const uint32_t nlaunch = (p.ngroups + p.gpl - 1) / p.gpl;
-    uint32_t tbase = 0;
-    if (timing && h->timing == 2 && h->last_timed_ws == ws && ws->timed + nlaunch <= 65536) tbase = ws->timed;
-    if (timing) {
-        while (ws->t0.size() < tbase + nlaunch) {
-            cudaEvent_t e0, e1;
-            CK(cudaEventCreate(&e0));
-            CK(cudaEventCreate(&e1));
-            ws->t0.push_back(e0);
-            ws->t1.push_back(e1);
-        }
-    }
-    for (uint32_t l = 0, g0 = 0; g0 < p.ngroups; g0 += p.gpl, ++l) {
-        b.group0 = g0;
-        b.ngroups = std::min(p.gpl, p.ngroups - g0);
-        if (timing) CK(cudaEventRecord(ws->t0[tbase + l], st));
-        CK(launch_batch(b, st));
-        if (timing) CK(cudaEventRecord(ws->t1[tbase + l], st));
-        h->launches++;
-    }
-    if (timing) { ws->timed = tbase + nlaunch; h->last_timed_ws = ws; }
-    FinalizeArgs f;
-    f.codes = h->codes.p; f.ids = h->ids.p; f.lut = h->lut.p; f.cand = ws->d_cand.p;
-    f.pq = ws->d_pq.p; f.pq_stride = stride; f.queries = d_q;
-    f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
-    f.flags = flags & SZG_F_NO_FP64_VERIFY; f.nlists = p.nranges; // one sorted list of `keep` keys per row range
-    f.out_ids = d_out_ids; f.out_dist = d_out_dist; f.out_n = d_out_n; f.out_flags = d_out_flags;
-    CK(launch_finalize(h->qt, p.mode, nq, st, f));
-    h->launches++;
-    h->batch_queries += nq;
-    return SZG_OK;
-}
-
-// Batched search: same results as szg_search_topk for every query, computed by the tensor-core
-// contraction kernel (batch_q8.cu) when the collection is 8-bit and the geometry fits; every other
-// case is routed to the streaming scan (still on the GPU).
-int szg_search_batch(szg_index *h, const double *queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                     uint64_t *out_ids, double *out_dist, uint32_t *out_n, uint64_t *scanned) {
-    GUARD(h);
-    int rc;
-    BatchPlan p;
-    if (!plan_batch(h, nq, k, &p)) return szg_search_topk(h, queries, nq, k, mask_id, flags, out_ids, out_dist, out_n, scanned);
-    if ((rc = check_search(h, queries, nq))) return rc;
-    if (!out_ids || !out_dist || !out_n) return fail(SZG_EINVAL, "null output");
-    if (scanned) *scanned = h->live_rows;
-    const uint32_t *mask;
-    if ((rc = get_mask(h, mask_id, &mask))) return rc;
-    Workspace *ws;
-    if ((rc = acquire_ws(h, &ws))) return rc;
-    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
-    const size_t qn = (size_t)nq * h->dim, on = (size_t)nq * k;
-    if ((rc = ws->h_q.ensure(qn)) || (rc = ws->d_q.ensure(qn)) || (rc = ws->d_out_ids.ensure(on)) ||
-        (rc = ws->d_out_dist.ensure(on)) || (rc = ws->d_out_n.ensure(nq)) || (rc = ws->d_out_flags.ensure(nq)) ||
-        (rc = ws->h_out_ids.ensure(on)) || (rc = ws->h_out_dist.ensure(on)) || (rc = ws->h_out_n.ensure(nq)) ||
-        (rc = ws->h_out_flags.ensure(nq)))
-        return rc;
-    memcpy(ws->h_q.p, queries, qn * sizeof(double));
-    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, ws->main));
-    if ((rc = run_batch(h, ws, p, ws->d_q.p, nq, k, mask, flags, ws->d_out_ids.p, ws->d_out_dist.p, ws->d_out_n.p,
-                        ws->d_out_flags.p)))
-        return rc;
-    return collect_and_escalate(h, ws, nq, k, mask, flags, 2, p.mode, out_ids, out_dist, out_n);
-}
-
-// Device-resident form of szg_search_batch (queries and outputs in HBM, everything enqueued on `stream`, no host
-// synchronisation): what a row-sharded deployment calls before its all-gather + szg_merge_topk_dev.
-int szg_search_batch_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                         uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags, void *stream) {
-    GUARD(h);
-    BatchPlan p;
-    if (!plan_batch(h, nq, k, &p))
-        return szg_search_topk_dev(h, d_queries, nq, k, mask_id, flags, d_out_ids, d_out_dist, d_out_n, d_out_flags, stream);
-    int rc;
-    if ((rc = check_search(h, d_queries, nq))) return rc;
-    if (k > SZG_MAX_K) return fail(SZG_EINVAL, "k=%u outside [1, %u]", k, SZG_MAX_K);
-    if (!d_out_ids || !d_out_dist || !d_out_n) return fail(SZG_EINVAL, "null output");
-    const uint32_t *mask;
-    if ((rc = get_mask(h, mask_id, &mask))) return rc;
-    Workspace *ws;
+    uint32_t *p = nullptr;
     {
-        std::lock_guard<std::mutex> lk(h->mu);
-        auto it = h->dev_ws.find(stream);
-        if (it == h->dev_ws.end()) {
-            ws = new Workspace();
-            if ((rc = ws->init(false))) { ws->destroy(); delete ws; return rc; }
-            ws->main = (cudaStream_t)stream;
-            h->dev_ws[stream] = ws;
-        } else ws = it->second;
+        std::lock_guard<std::mutex> lk(h->mask_mu);
+        auto it = h->masks.find(mask_id);
+        if (it == h->masks.end()) return fail(SZG_ENOTFOUND, "unknown mask id %d", mask_id);
+        p = it->second;
+        h->masks.erase(it);
     }
-    if (!d_out_flags) {
-        if ((rc = ws->d_out_flags.ensure(nq))) return rc;
-        d_out_flags = ws->d_out_flags.p;
-    }
-    return run_batch(h, ws, p, d_queries, nq, k, mask, flags, (unsigned long long *)d_out_ids, d_out_dist, d_out_n, d_out_flags);
-}
-
-int szg_search_topk_dev(szg_index *h, const double *d_queries, uint32_t nq, uint32_t k, int mask_id, uint32_t flags,
-                        uint64_t *d_out_ids, double *d_out_dist, uint32_t *d_out_n, uint32_t *d_out_flags,
-                        void *stream) {
-    GUARD(h);
-    int rc;
-    if ((rc = check_search(h, d_queries, nq))) return rc;
-    if (k < 1 || k > SZG_MAX_K) return fail(SZG_EINVAL, "k=%u outside [1, %u]", k, SZG_MAX_K);
-    if (!nq) return SZG_OK;
-    if (!d_out_ids || !d_out_dist || !d_out_n) return fail(SZG_EINVAL, "null output");
-    const uint32_t *mask;
-    if ((rc = get_mask(h, mask_id, &mask))) return rc;
-    Workspace *ws;
-    {
-        std::lock_guard<std::mutex> lk(h->mu);
-        auto it = h->dev_ws.find(stream);
-        if (it == h->dev_ws.end()) {
-            ws = new Workspace();
-            if ((rc = ws->init(false))) { ws->destroy(); delete ws; return rc; }
-            ws->main = (cudaStream_t)stream;
-            h->dev_ws[stream] = ws;
-        } else ws = it->second;
-    }
-    if (!d_out_flags) {
-        if ((rc = ws->d_out_flags.ensure(nq))) return rc;
-        d_out_flags = ws->d_out_flags.p;
-    }
-    if (h->live_rows == 0) {
-        CK(cudaMemsetAsync(d_out_n, 0, nq * 4, ws->main));
-        CK(cudaMemsetAsync(d_out_flags, 0, nq * 4, ws->main));
-        return SZG_OK;
-    }
-    // no host synchronisation here, hence no escalation: SZG_OPT_DIGITS = 2 (or automatic) runs the fast
-    // surrogate and reports uncertified queries in d_out_flags; the caller re-runs those with szg_search_topk
-    return run_topk(h, ws, d_queries, nq, k, mask, flags, mode_for_k(h, k), first_digits(h),
-                    (unsigned long long *)d_out_ids, d_out_dist, d_out_n, d_out_flags);
-}
-
-int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const double *d_gathered_dist,
-                       const uint32_t *d_gathered_n, const uint32_t *d_gathered_flags, uint64_t rank_stride_bytes,
-                       uint32_t nranks, uint32_t nq, uint32_t k, uint64_t *d_out_ids, double *d_out_dist,
-                       uint32_t *d_out_n, uint32_t *d_out_flags, void *stream) {
-    GUARD(h);
-    if (!nq) return SZG_OK;
-    if (!d_gathered_ids || !d_gathered_dist || !d_gathered_n || !d_out_ids || !d_out_dist || !d_out_n)
-        return fail(SZG_EINVAL, "null argument");
-    if (k < 1 || k > SZG_MAX_K || nranks < 1 || (size_t)nranks * k * 16 > 200 * 1024)
-        return fail(SZG_EINVAL, "merge of %u lists of k=%u is not supported", nranks, k);
-    MergeArgs a;
-    a.g_ids = (const unsigned long long *)d_gathered_ids; a.g_dist = d_gathered_dist; a.g_n = d_gathered_n;
-    a.g_flags = d_gathered_flags; a.out_flags = d_out_flags;
-    a.rank_stride = (size_t)rank_stride_bytes;
-    a.G = nranks; a.nq = nq; a.k = k;
-    a.out_ids = (unsigned long long *)d_out_ids; a.out_dist = d_out_dist; a.out_n = d_out_n;
-    CK(launch_merge(a, (cudaStream_t)stream));
-    h->launches++;
-    return SZG_OK;
-}
-
-int szg_search_radius(szg_index *h, const double *query, double radius, int mask_id, uint32_t flags,
-                      szg_result **out, uint64_t *scanned) {
-    GUARD(h);
-    int rc;
-    if (!out) return fail(SZG_EINVAL, "null out pointer");
-    *out = nullptr;
-    if ((rc = check_search(h, query, 1))) return rc;
-    if (!(radius > 0)) return fail(SZG_EINVAL, "radius must be > 0 (collection.go:598)");
-    if (scanned) *scanned = h->live_rows;
-    const uint32_t *mask;
-    if ((rc = get_mask(h, mask_id, &mask))) return rc;
-    std::unique_ptr<szg_result> res(new szg_result());
-    if (h->live_rows == 0) { *out = res.release(); return SZG_OK; }
-    Workspace *ws;
-    if ((rc = acquire_ws(h, &ws))) return rc;
-    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
-    const int nd = first_digits(h); // the radius threshold carries the surrogate error bound: no re-run needed
-    const size_t stride = pq_stride(h, nd);
-    if ((rc = ws->h_q.ensure(h->dim)) || (rc = ws->d_q.ensure(h->dim)) || (rc = ws->d_pq.ensure(stride)) ||
-        (rc = ws->h_out_n.ensure(1)))
-        return rc;
-    memcpy(ws->h_q.p, query, (size_t)h->dim * sizeof(double));
-    cudaStream_t st = ws->main;
-    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, (size_t)h->dim * sizeof(double), cudaMemcpyHostToDevice, st));
-    PrepArgs pa;
-    pa.queries = ws->d_q.p; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
-    pa.dims = (uint32_t)h->dim; pa.C = h->C; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
-    pa.qt = h->qt; pa.nd = nd; pa.radius_mode = 1; pa.radius = radius;
-    CK(launch_prep(1, st, pa));
-    h->launches++;
-    ScanPlan plan;
-    int grid = 0;
-    if ((rc = plan_scan(h, nd, &plan, &grid))) return rc;
-    unsigned int *d_count = ws->d_ticket.p;
-    uint32_t count = 0;
-    size_t cap = std::max<size_t>(4096, h->nslots / 64);
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        if ((rc = ws->d_slots.ensure(cap))) return rc;
-        CK(cudaMemsetAsync(d_count, 0, 4, st));
-        ScanArgs a;
-        fill_scan_args(h, a, mask);
-        a.pq = ws->d_pq.p; a.pq_stride = stride; a.nq = 1;
-        a.rad_count = d_count; a.rad_slots = ws->d_slots.p; a.rad_cap = (uint32_t)ws->d_slots.n;
-        a.Ct = plan.Ct; a.stages = plan.stages; a.pq_smem_off = plan.pq_smem_off;
-        CK(launch_scan(h->qt, MODE_RADIUS, nd, grid, (int)plan.warps * 32, plan.smem, st, a));
-        h->launches++;
-        CK(cudaMemcpyAsync(ws->h_out_n.p, d_count, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        count = ws->h_out_n.p[0];
-        if (count <= ws->d_slots.n) break;
-        cap = count; // the compaction buffer was too small: size it exactly and rescan
-    }
-    if (count > ws->d_slots.n) return fail(SZG_EINTERNAL, "radius compaction buffer could not be sized");
-    if (count) {
-        if ((rc = ws->d_out_ids.ensure(count)) || (rc = ws->d_out_dist.ensure(count)) ||
-            (rc = ws->h_out_ids.ensure(count)) || (rc = ws->h_out_dist.ensure(count)))
-            return rc;
-        RescoreArgs ra;
-        ra.codes = h->codes.p; ra.ids = h->ids.p; ra.lut = h->lut.p; ra.q = ws->d_q.p; ra.slots = ws->d_slots.p;
-        ra.count_ptr = nullptr; ra.out_dist = ws->d_out_dist.p; ra.out_ids = ws->d_out_ids.p;
-        ra.C = h->C; ra.dims = (uint32_t)h->dim; ra.metric = (uint32_t)h->metric; ra.m = count; ra.qt = h->qt;
-        CK(launch_rescore(ra, st));
-        h->launches++;
-        CK(cudaMemcpyAsync(ws->h_out_ids.p, ws->d_out_ids.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        // exact inclusive test (collection.go:598) on the fp64 distances, then ascending order
-        // distances are >= 0 (or NaN, which fails the test): their bit patterns order like the values, so the sort runs
-        // on packed integers and only equal distances fall back to the lexicographic id comparison
-        const double *hd = ws->h_out_dist.p;
-        const unsigned long long *hi = ws->h_out_ids.p;
-        struct Hit { unsigned long long bits; uint32_t i; };
-        std::vector<Hit> keep;
-        keep.reserve(count);
-        for (uint32_t i = 0; i < count; ++i)
-            if (hd[i] <= radius) {
-                const double dv = hd[i] == 0.0 ? 0.0 : hd[i]; // -0.0 orders with +0.0
-                unsigned long long b;
-                memcpy(&b, &dv, 8);
-                keep.push_back(Hit{b, i});
-            }
-        std::sort(keep.begin(), keep.end(), [&](const Hit &x, const Hit &y) {
-            if (x.bits != y.bits) return x.bits < y.bits;
-            return lex_less_u64(hi[x.i], hi[y.i]);
-        });
-        res->ids.resize(keep.size());
-        res->dist.resize(keep.size());
-        for (size_t i = 0; i < keep.size(); ++i) { res->ids[i] = hi[keep[i].i]; res->dist[i] = hd[keep[i].i]; }
-    }
-    (void)flags;
-    *out = res.release();
-    return SZG_OK;
-}
-
-int szg_result_count(const szg_result *r, uint64_t *n) {
-    if (!r || !n) return fail(SZG_EINVAL, "null argument");
-    *n = r->ids.size();
-    return SZG_OK;
-}
-int szg_result_fetch(const szg_result *r, uint64_t offset, uint64_t n, uint64_t *out_ids, double *out_dist) {
-    if (!r) return fail(SZG_EINVAL, "null result");
-    if (offset > r->ids.size() || n > r->ids.size() - offset) return fail(SZG_EINVAL, "range outside the result");
-    if (out_ids) memcpy(out_ids, r->ids.data() + offset, n * 8);
-    if (out_dist) memcpy(out_dist, r->dist.data() + offset, n * 8);
-    return SZG_OK;
-}
-void szg_result_free(szg_result *r) { delete r; }
-
-int szg_rescore(szg_index *h, const double *query, const uint64_t *ids, uint64_t m, double *out_dist) {
-    GUARD(h);
-    int rc;
-    if ((rc = check_search(h, query, 1))) return rc;
-    if (!m) return SZG_OK;
-    if (!ids || !out_dist) return fail(SZG_EINVAL, "null argument");
-    if (m > 0xFFFFFFF0ull) return fail(SZG_EINVAL, "too many ids");
-    Workspace *ws;
-    if ((rc = acquire_ws(h, &ws))) return rc;
-    struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
-    if ((rc = ws->h_q.ensure(h->dim)) || (rc = ws->d_q.ensure(h->dim)) || (rc = ws->h_slots.ensure(m)) ||
-        (rc = ws->d_slots.ensure(m)) || (rc = ws->d_out_dist.ensure(m)) || (rc = ws->h_out_dist.ensure(m)))
-        return rc;
-    memcpy(ws->h_q.p, query, (size_t)h->dim * sizeof(double));
-    map_ids(h, ids, m, ws->h_slots.p, false);
-    cudaStream_t st = ws->main;
-    CK(cudaMemcpyAsync(ws->d_q.p, ws->h_q.p, (size_t)h->dim * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ws->d_slots.p, ws->h_slots.p, m * 4, cudaMemcpyHostToDevice, st));
-    RescoreArgs ra;
-    ra.codes = h->codes.p; ra.ids = h->ids.p; ra.lut = h->lut.p; ra.q = ws->d_q.p; ra.slots = ws->d_slots.p;
-    ra.count_ptr = nullptr; ra.out_dist = ws->d_out_dist.p; ra.out_ids = nullptr;
-    ra.C = h->C; ra.dims = (uint32_t)h->dim; ra.metric = (uint32_t)h->metric; ra.m = (uint32_t)m; ra.qt = h->qt;
-    CK(launch_rescore(ra, st));
-    h->launches++;
-    CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, m * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    memcpy(out_dist, ws->h_out_dist.p, m * 8);
+    h->generation++; // a captured launch sequence may hold this mask's address
+    cudaFree(p);
     return SZG_OK;
 }
 
 int szg_get_stats(szg_index *h, szg_stats *out) {
+    if (h && h->sh) return out ? sharded_get_stats(h, out) : fail(SZG_EINVAL, "null out");
     GUARD(h);
     if (!out) return fail(SZG_EINVAL, "null out");
     memset(out, 0, sizeof *out);
@@ -1715,8 +763,9 @@ int szg_get_stats(szg_index *h, szg_stats *out) {
     out->escalations = h->escalations;
     out->uncertain_results = h->uncertain;
     out->batch_queries = h->batch_queries;
-    out->reserved0 = 0;
+    out->shards = 1;
     out->combined_queries = h->combined_queries;
+    out->graph_launches = h->graph_launches;
     out->device_bytes = h->codes.n * sizeof(uint4) + h->planar.n * sizeof(uint4) + h->ids.n * 8 + h->aux.n * 8 + h->live.n * 4 +
                         h->lut.n * 8 + h->masks.size() * (h->capacity / 32) * 4;
     out->live_rows = h->live_rows;
@@ -1736,22 +785,5 @@ int szg_get_stats(szg_index *h, szg_stats *out) {
     return SZG_OK;
 }
 
-int szg_last_scan_times_ms(szg_index *h, float *out_ms, uint32_t cap, uint32_t *n) {
-    GUARD(h);
-    if (!n) return fail(SZG_EINVAL, "null n");
-    *n = 0;
-    Workspace *ws = h->last_timed_ws;
-    if (!ws || !ws->timed) return SZG_OK;
-    const uint32_t m = std::min(cap, ws->timed);
-    for (uint32_t i = 0; i < m; ++i) {
-        CK(cudaEventSynchronize(ws->t1[i]));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, ws->t0[i], ws->t1[i]));
-        if (out_ms) out_ms[i] = ms;
-    }
-    *n = m;
-    ws->timed = 0; // drained (matters for the accumulating mode)
-    return SZG_OK;
-}
 
 } // extern "C"

@@ -141,18 +141,18 @@ cudaError_t launch_prep(uint32_t nq, cudaStream_t st, const PrepArgs &a) {
 }
 
 // =================================================================== upload / layout
-__device__ __forceinline__ void store_chunk(uint4 *codes, uint32_t slot, uint32_t C, uint32_t c,
+__device__ __forceinline__ void store_chunk(int qt, uint4 *codes, uint32_t slot, uint32_t C, uint32_t c,
                                             const unsigned char *b) {
     uint4 v;
     v.x = b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24);
     v.y = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
     v.z = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
     v.w = b[12] | (b[13] << 8) | (b[14] << 16) | ((uint32_t)b[15] << 24);
-    codes[chunk_index(slot, C, c)] = v;
+    codes[chunk_at_rt(qt, slot, C, c)] = v;
 }
-__device__ __forceinline__ void load_chunk(const uint4 *codes, uint32_t slot, uint32_t C, uint32_t c,
+__device__ __forceinline__ void load_chunk(int qt, const uint4 *codes, uint32_t slot, uint32_t C, uint32_t c,
                                            unsigned char *b) {
-    uint4 v = codes[chunk_index(slot, C, c)];
+    uint4 v = codes[chunk_at_rt(qt, slot, C, c)];
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     for (int k = 0; k < 4; ++k)
         for (int i = 0; i < 4; ++i) b[4 * k + i] = (unsigned char)(w[k] >> (8 * i));
@@ -169,10 +169,10 @@ __global__ void scatter_kernel(const RowsArgs a, const unsigned char *__restrict
     if (slot == 0xFFFFFFFFu) return; // superseded duplicate of the same batch
     unsigned char b[16];
     const unsigned char *src = staged + (size_t)row * a.rowbytes + (size_t)c * 16;
-    const uint32_t remain = a.rowbytes - c * 16;
+    const uint32_t remain = c * 16 < a.rowbytes ? a.rowbytes - c * 16 : 0u; // float rows: C is padded to a multiple of 8 chunks
     for (int i = 0; i < 16; ++i) b[i] = (uint32_t)i < remain ? src[i] : 0;
     chunk_to_device(a.qt, b);
-    store_chunk(a.codes, slot, a.C, c, b);
+    store_chunk(a.qt, a.codes, slot, a.C, c, b);
     if (c == 0) {
         a.ids[slot] = ids_in[row];
         atomicOr(a.live + (slot >> 5), 1u << (slot & 31));
@@ -224,7 +224,7 @@ __global__ void synth_kernel(const RowsArgs a, unsigned long long seed, unsigned
         }
     }
     chunk_to_device(a.qt, b);
-    store_chunk(a.codes, slot, a.C, c, b);
+    store_chunk(a.qt, a.codes, slot, a.C, c, b);
     if (c == 0) {
         a.ids[slot] = row;
         atomicOr(a.live + (slot >> 5), 1u << (slot & 31));
@@ -252,7 +252,7 @@ __global__ void aux_kernel(const RowsArgs a, const uint32_t *__restrict__ slots,
     double fs = 0.0;
     uint32_t dim = 0;
     for (uint32_t c = 0; c < a.C && dim < a.dims; ++c) {
-        uint4 v = a.codes[chunk_index(slot, a.C, c)];
+        uint4 v = a.codes[chunk_at_rt(a.qt, slot, a.C, c)];
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         for (int k = 0; k < 4; ++k) {
             if (a.qt == Q4) {
@@ -332,9 +332,9 @@ __global__ void fetch_kernel(const RowsArgs a, const uint32_t *__restrict__ slot
     const uint32_t row = (uint32_t)(t / a.C), c = (uint32_t)(t % a.C);
     if (row >= n) return;
     unsigned char b[16];
-    load_chunk(a.codes, slots[row], a.C, c, b);
+    load_chunk(a.qt, a.codes, slots[row], a.C, c, b);
     chunk_to_disk(a.qt, b);
-    const uint32_t remain = a.rowbytes - c * 16;
+    const uint32_t remain = c * 16 < a.rowbytes ? a.rowbytes - c * 16 : 0u;
     unsigned char *dst = out + (size_t)row * a.rowbytes + (size_t)c * 16;
     for (int i = 0; i < 16; ++i)
         if ((uint32_t)i < remain) dst[i] = b[i];
@@ -408,7 +408,7 @@ __global__ void encode_kernel(const RowsArgs a, const double *__restrict__ vec, 
         }
     }
     unsigned char *dst = staged + (size_t)row * a.rowbytes + (size_t)c * 16;
-    const uint32_t remain = a.rowbytes - c * 16;
+    const uint32_t remain = c * 16 < a.rowbytes ? a.rowbytes - c * 16 : 0u;
     if (remain >= 16 && (((size_t)row * a.rowbytes) & 15u) == 0) {
         *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(b);
     } else {
@@ -423,39 +423,6 @@ cudaError_t launch_encode(const RowsArgs &a, const double *vec, unsigned char *s
     return cudaGetLastError();
 }
 
-// ============================================================ K3: gather + fp64 re-score
-// thread per candidate, visit order preserved; replaces decodeVector + distance inside
-// `consider` (collection.go:584-596) for the ids an index (lshtree.go:316-335) or the
-// radius compaction produced.
-template <int QT>
-__global__ void __launch_bounds__(128) rescore_kernel(const RescoreArgs a) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t m = a.m;
-    if (a.count_ptr) { uint32_t c = *a.count_ptr; m = c < m ? c : m; }
-    if (i >= m) return;
-    const uint32_t slot = a.slots[i];
-    if (slot == 0xFFFFFFFFu) {
-        a.out_dist[i] = -1.0; // SZG_MISSING_DISTANCE
-        if (a.out_ids) a.out_ids[i] = 0;
-        return;
-    }
-    a.out_dist[i] = exact_distance<QT>(a.codes, a.C, a.dims, (int)a.metric, a.lut, a.q, slot);
-    if (a.out_ids) a.out_ids[i] = a.ids[slot];
-}
-
-cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st) {
-    if (!a.m) return cudaSuccess;
-    const unsigned grid = (a.m + 127) / 128;
-    switch (a.qt) {
-    case Q4: rescore_kernel<Q4><<<grid, 128, 0, st>>>(a); break;
-    case Q8: rescore_kernel<Q8><<<grid, 128, 0, st>>>(a); break;
-    case Q16: rescore_kernel<Q16><<<grid, 128, 0, st>>>(a); break;
-    case F32: rescore_kernel<F32><<<grid, 128, 0, st>>>(a); break;
-    default: rescore_kernel<F64><<<grid, 128, 0, st>>>(a); break;
-    }
-    return cudaGetLastError();
-}
-
 // ===================================================== K5: merge of row-sharded top-k lists
 // One CTA per query: the G*k gathered (distance, id) pairs are ranked by
 // (distance, lexicographic decimal id) and the first k written out.
@@ -466,7 +433,26 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
     double *s_d = reinterpret_cast<double *>(sm);
     unsigned long long *s_i = reinterpret_cast<unsigned long long *>(s_d + cap);
     __shared__ uint32_t s_total;
-    if (tid == 0) s_total = 0;
+    if (tid == 0) {
+        s_total = 0;
+        if (a.wait_cnt) {
+            // sharded search inside one process (sharded.cu): the shards' finalize kernels store their lists straight into this
+            // device's gather buffer over NVLink and then bump wait_cnt[q] (system-scope release).  Wait for all of them
+            // (acquire); bounded, so that a failed launch on another device surfaces as an error instead of a hang.
+            const volatile uint32_t *cnt = a.wait_cnt + q;
+            unsigned long long t0 = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            uint32_t seen;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                if (seen >= a.wait_target) break;
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > a.wait_timeout_ns) { if (a.err) atomicOr(a.err, 1u); break; }
+                __nanosleep(64);
+            }
+        }
+    }
     __syncthreads();
     for (uint32_t e = tid; e < cap; e += 256) {
         const uint32_t g = e / a.k, j = e % a.k;
@@ -482,11 +468,11 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
             dist_g = a.g_dist + (size_t)g * a.nq * a.k;
             n_g = a.g_n + (size_t)g * a.nq;
         }
-        const uint32_t n = n_g[q];
+        const uint32_t n = __ldcg(n_g + q); // L2: the lists may have been written by peer devices during this launch
         const size_t src = (size_t)q * a.k + j;
         const bool ok = j < n;
-        s_d[e] = ok ? dist_g[src] : __longlong_as_double(0x7ff8000000000000ll);
-        s_i[e] = ok ? ids_g[src] : 0ull;
+        s_d[e] = ok ? __ldcg(dist_g + src) : __longlong_as_double(0x7ff8000000000000ll);
+        s_i[e] = ok ? __ldcg(ids_g + src) : 0ull;
         if (ok) atomicAdd(&s_total, 1u);
     }
     __syncthreads();
@@ -513,11 +499,25 @@ __global__ void __launch_bounds__(256) merge_kernel(const MergeArgs a) {
                     const uint32_t *f_g = a.rank_stride
                         ? reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(a.g_flags) + g * a.rank_stride)
                         : a.g_flags + (size_t)g * a.nq;
-                    fl |= f_g[q];
+                    fl |= __ldcg(f_g + q);
                 }
             a.out_flags[q] = fl;
         }
     }
+}
+
+// an empty shard has nothing to finalize: it still reports in (sharded search)
+__global__ void bump_kernel(uint32_t *cnt, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        __threadfence_system();
+        atomicAdd_system(cnt + i, 1u);
+    }
+}
+cudaError_t launch_bump(uint32_t *cnt, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    bump_kernel<<<(n + 127) / 128, 128, 0, st>>>(cnt, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_merge(const MergeArgs &a, cudaStream_t st) {

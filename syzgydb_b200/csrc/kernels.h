@@ -54,19 +54,45 @@ cudaError_t launch_fetch(const RowsArgs &a, const uint32_t *slots, uint32_t n, u
 // ingest: n float64 vectors -> stream-1 bytes (encodeDocument, collection.go:713-744 + quantize, quantization.go:5-23)
 cudaError_t launch_encode(const RowsArgs &a, const double *vec, unsigned char *staged, uint32_t n, cudaStream_t st);
 
+// K3: fp64 distances of gathered rows in the reference's operation order (gather.cu)
 struct RescoreArgs {
     const uint4 *codes;
     const unsigned long long *ids;
     const double *lut;
-    const double *q;
+    const double *q;            // nlists x dims
+    const uint32_t *list_off;   // nlists + 1 offsets into slots: list l is scored against query l (NULL: one list, one query)
+    uint32_t nlists;
     const uint32_t *slots;      // 0xFFFFFFFF = missing
-    const uint32_t *count_ptr;  // optional device count (min with m)
     double *out_dist;
     unsigned long long *out_ids; // optional
     uint32_t C, dims, metric, m;
     int qt;
 };
 cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st);
+
+// K2, second half: exact distances of the rows the radius scan compacted, inclusive test (collection.go:598), ascending
+// (distance, lexicographic id) order -- all on the device
+constexpr uint32_t kRadiusSortSmall = 2048; // results up to this size are sorted by the launch that scores them
+struct RadiusFinishArgs {
+    const uint4 *codes;
+    const unsigned long long *ids;
+    const double *lut;
+    const double *q;
+    const uint32_t *slots;       // compacted by the scan
+    const uint32_t *count_ptr;   // how many (device); at most cap are present
+    uint32_t cap;
+    double radius;
+    unsigned long long *keys;    // scratch: pairs (distance bits, id); capacity = the power of two >= cap
+    uint32_t *out_count;         // exact hits
+    double *out_dist;            // [<= cap] ascending
+    unsigned long long *out_ids;
+    uint32_t C, dims, metric;
+    int qt;
+};
+// scores + filters every compacted row and, when at most kRadiusSortSmall pass, orders them (out_dist / out_ids final)
+cudaError_t launch_radius_finish(const RadiusFinishArgs &a, cudaStream_t st);
+// larger results: global bitonic sort of the m hits left in a.keys by launch_radius_finish, then out_dist / out_ids
+cudaError_t launch_radius_sort_large(const RadiusFinishArgs &a, uint32_t m, cudaStream_t st);
 
 // byte-planar copy of a 16-bit collection's codes (operand of the batched path)
 // one-byte-per-code copy of a 4-bit collection's codes (operand of the batched path)
@@ -147,7 +173,13 @@ struct MergeArgs {
     double *out_dist;
     uint32_t *out_n;
     uint32_t *out_flags; // optional [nq]: OR of the ranks' flags
+    // sharded search in one process: wait until wait_cnt[q] >= wait_target (peer shards report in), at most wait_timeout_ns
+    const uint32_t *wait_cnt;
+    uint32_t wait_target;
+    unsigned long long wait_timeout_ns;
+    uint32_t *err;       // bit0 set when the wait timed out
 };
 cudaError_t launch_merge(const MergeArgs &a, cudaStream_t st);
+cudaError_t launch_bump(uint32_t *cnt, uint32_t n, cudaStream_t st);
 
 } // namespace szg

@@ -76,6 +76,9 @@ struct FinalizeArgs {
     double *out_dist;                 // [nq][k]
     uint32_t *out_n;                  // [nq]
     uint32_t *out_flags;              // [nq] bit0: candidate margin below tolerance ("uncertain")
+    uint32_t *done_cnt;               // optional [nq], possibly in a PEER device's memory (sharded search): bumped, system
+                                      // scope, once query q's results are written -- the merge kernel on the root device
+                                      // waits for it (sharded.cu)
 };
 
 // ------------------------------------------------------------------ mbarrier / bulk copy
@@ -273,7 +276,8 @@ struct Scorer<Q8, ND> {
             acc[j] = dp4a_us(v.w, (int)d.w, acc[j]);
         }
     }
-    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *stage, int lane, uint32_t n, const unsigned char *spq, int) {
+        const uint4 *sd = stage + lane;
         const uint4 *dg = reinterpret_cast<const uint4 *>(spq);
         int b[ND]; // second accumulator set: shortens the dependent IDP chains
 #pragma unroll
@@ -317,7 +321,8 @@ struct Scorer<Q4, ND> {
             }
         }
     }
-    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *stage, int lane, uint32_t n, const unsigned char *spq, int) {
+        const uint4 *sd = stage + lane;
         const uint4 *dg = reinterpret_cast<const uint4 *>(spq);
         uint32_t c = 0;
         for (; c + 2 <= n; c += 2) {
@@ -350,7 +355,8 @@ struct Scorer<Q16, ND> {
             acc[j] = dp2a_hi_ss((int)v.w, (int)d.y, acc[j]);
         }
     }
-    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *stage, int lane, uint32_t n, const unsigned char *spq, int) {
+        const uint4 *sd = stage + lane;
         const uint2 *dg = reinterpret_cast<const uint2 *>(spq);
         int acc[ND];
 #pragma unroll
@@ -386,22 +392,23 @@ struct Scorer<F32, ND> {
             else { float d = qq[k] - x[k]; acc[k] = fmaf(d, d, acc[k]); }
         }
     }
+    // the staged tile holds whole chunk groups: [group][lane][8 chunks, XOR-swizzled by lane % 8] (common.cuh); n % 8 == 0
     template <int METRIC>
-    static __device__ __forceinline__ void loop(Acc &s, const uint4 *sd, uint32_t n, const float4 *sq) {
-        uint32_t c = 0;
-        for (; c + 4 <= n; c += 4) {
-            uint4 v0 = sd[(c + 0) * 32], v1 = sd[(c + 1) * 32], v2 = sd[(c + 2) * 32], v3 = sd[(c + 3) * 32];
-            step<METRIC>(v0, sq[c + 0], s.a);
-            step<METRIC>(v1, sq[c + 1], s.a);
-            step<METRIC>(v2, sq[c + 2], s.a);
-            step<METRIC>(v3, sq[c + 3], s.a);
+    static __device__ __forceinline__ void loop(Acc &s, const uint4 *stage, int lane, uint32_t n, const float4 *sq) {
+        const uint32_t sw = (uint32_t)lane & 7u;
+        for (uint32_t c = 0; c < n; c += 8) {
+            const uint4 *g = stage + ((size_t)(c >> 3) * 32 + lane) * 8;
+            uint4 v[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) v[j] = g[j ^ sw];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) step<METRIC>(v[j], sq[c + j], s.a);
         }
-        for (; c < n; ++c) step<METRIC>(sd[c * 32], sq[c], s.a);
     }
-    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int metric) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *stage, int lane, uint32_t n, const unsigned char *spq, int metric) {
         const float4 *sq = reinterpret_cast<const float4 *>(spq);
-        if (metric == COSINE) loop<COSINE>(s, sd, n, sq);
-        else loop<EUCLID>(s, sd, n, sq);
+        if (metric == COSINE) loop<COSINE>(s, stage, lane, n, sq);
+        else loop<EUCLID>(s, stage, lane, n, sq);
     }
     static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
         const float r = (s.a[0] + s.a[1]) + (s.a[2] + s.a[3]);
@@ -428,21 +435,21 @@ struct Scorer<F64, ND> {
         }
     }
     template <int METRIC>
-    static __device__ __forceinline__ void loop(Acc &s, const uint4 *sd, uint32_t n, const double2 *sq) {
-        uint32_t c = 0;
-        for (; c + 4 <= n; c += 4) {
-            uint4 v0 = sd[(c + 0) * 32], v1 = sd[(c + 1) * 32], v2 = sd[(c + 2) * 32], v3 = sd[(c + 3) * 32];
-            step<METRIC>(v0, sq[c + 0], s.a);
-            step<METRIC>(v1, sq[c + 1], s.a);
-            step<METRIC>(v2, sq[c + 2], s.a);
-            step<METRIC>(v3, sq[c + 3], s.a);
+    static __device__ __forceinline__ void loop(Acc &s, const uint4 *stage, int lane, uint32_t n, const double2 *sq) {
+        const uint32_t sw = (uint32_t)lane & 7u;
+        for (uint32_t c = 0; c < n; c += 8) {
+            const uint4 *g = stage + ((size_t)(c >> 3) * 32 + lane) * 8;
+            uint4 v[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) v[j] = g[j ^ sw];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) step<METRIC>(v[j], sq[c + j], s.a);
         }
-        for (; c < n; ++c) step<METRIC>(sd[c * 32], sq[c], s.a);
     }
-    static __device__ __forceinline__ void tile(Acc &s, const uint4 *sd, uint32_t n, const unsigned char *spq, int metric) {
+    static __device__ __forceinline__ void tile(Acc &s, const uint4 *stage, int lane, uint32_t n, const unsigned char *spq, int metric) {
         const double2 *sq = reinterpret_cast<const double2 *>(spq);
-        if (metric == COSINE) loop<COSINE>(s, sd, n, sq);
-        else loop<EUCLID>(s, sd, n, sq);
+        if (metric == COSINE) loop<COSINE>(s, stage, lane, n, sq);
+        else loop<EUCLID>(s, stage, lane, n, sq);
     }
     static __device__ __forceinline__ float finish(const Acc &s, const ScanArgs &a, const PQHeader &h, const float2 &x) {
         const double r = s.a[0] + s.a[1];
@@ -455,47 +462,52 @@ struct Scorer<F64, ND> {
 constexpr int kFinalizeThreads = 512;
 constexpr size_t kFinalizeStageBytes = 64 * 1024; // staging area of the fp64 re-score
 
-// fp64 distances of the Kp candidates in pool[], in the reference's operation order (same element
-// order and the same un-fused multiply/add sequence as exact_distance_impl), but with the
-// operands staged through shared memory slab by slab: the whole CTA fetches the candidates'
-// chunks (one memory round trip per slab instead of one per chunk and candidate), then thread r
-// runs the sequential chain of candidate r out of shared memory.  dequantize: 4/8-bit through a
-// shared copy of the host-built table, 16-bit with the same three IEEE operations
-// ((v / maxInt) * 2 - 1, quantization.go:34-35).
-template <int QT, int METRIC>
-__device__ void exact_staged(const FinalizeArgs &a, const double *__restrict__ q, const unsigned long long *pool,
-                             int Kp, unsigned char *stage, double *s_out, int tid) {
+// fp64 distances of up to NT candidates (s_slot[0 .. Kp), 0xFFFFFFFF = none) to the query q, in the reference's operation
+// order (decodeVector + dequantize collection.go:768-794 / quantization.go:25-36, euclideanDistance 812-819, angularDistance
+// 821-832: sequential over the dimensions, un-fused multiply and add), with the operands staged through shared memory slab
+// by slab: the NT threads fetch the candidates' chunks together (one memory round trip per slab, and -- float rows, whose
+// chunks are grouped by 8 -- whole 128-byte lines per row), then thread r runs the sequential chain of candidate r out of
+// shared memory.  dequantize: 4/8-bit through a shared copy of the host-built table, 16-bit with the same three IEEE
+// operations ((v / maxInt) * 2 - 1, quantization.go:34-35).  Used by finalize_kernel (the survivors of a top-k scan),
+// rescore_kernel (candidate lists of the LSH index) and radius_exact_kernel.  s_out[r] = distance (NaN possible: Acos).
+template <int QT, int METRIC, int NT>
+__device__ void exact_staged(const uint4 *__restrict__ codes, const double *__restrict__ lut, uint32_t C, uint32_t dims,
+                             const double *__restrict__ q, const uint32_t *s_slot, int Kp, unsigned char *stage,
+                             size_t stage_bytes, double *s_out, int tid) {
     constexpr int EPC = QT == Q4 ? 32 : QT == Q8 ? 16 : QT == Q16 ? 8 : QT == F32 ? 4 : 2;
     constexpr int LUTN = QT == Q4 ? 16 : QT == Q8 ? 256 : 0;
+    constexpr uint32_t GR = QT >= F32 ? (uint32_t)kGroupChunks : 1u; // slabs of float rows hold whole chunk groups
     double *s_lut = reinterpret_cast<double *>(stage);
     unsigned char *body = stage + LUTN * sizeof(double);
-    const size_t budget = kFinalizeStageBytes - LUTN * sizeof(double);
+    const size_t budget = stage_bytes - LUTN * sizeof(double);
     // per chunk: Kp uint4 of codes + EPC doubles of the query; rows padded by one uint4 against bank conflicts
     uint32_t SC = (uint32_t)((budget - (size_t)Kp * 16) / ((size_t)Kp * 16 + EPC * 8));
-    if (SC > a.C) SC = a.C;
+    if (SC > C) SC = C;
+    SC = SC / GR * GR;
+    if (SC < GR) SC = GR; // callers size the stage so that one group of Kp rows fits
     uint4 *s_codes = reinterpret_cast<uint4 *>(body);
     double *s_q = reinterpret_cast<double *>(body + (size_t)Kp * (SC + 1) * 16);
-    for (int i = tid; i < LUTN; i += kFinalizeThreads) s_lut[i] = a.lut[i];
+    for (int i = tid; i < LUTN; i += NT) s_lut[i] = lut[i];
 
-    const bool mine = tid < Kp && pool[tid < Kp ? tid : 0] != kNoKey;
+    const bool mine = tid < Kp && s_slot[tid < Kp ? tid : 0] != 0xFFFFFFFFu;
     ExactAcc acc = {0.0, 0.0, 0.0, 0.0};
-    for (uint32_t c0 = 0; c0 < a.C; c0 += SC) {
-        const uint32_t nc = min(SC, a.C - c0);
+    for (uint32_t c0 = 0; c0 < C; c0 += SC) {
+        const uint32_t nc = min(SC, C - c0);
         __syncthreads(); // previous slab fully consumed (and the table written)
-        for (uint32_t idx = tid; idx < (uint32_t)Kp * nc; idx += kFinalizeThreads) {
+        for (uint32_t idx = tid; idx < (uint32_t)Kp * nc; idx += NT) {
             const uint32_t r = idx / nc, c = idx % nc;
-            const unsigned long long key = pool[r];
-            if (key != kNoKey) s_codes[(size_t)r * (SC + 1) + c] = __ldg(a.codes + chunk_index((uint32_t)key, a.C, c0 + c));
+            const uint32_t slot = s_slot[r];
+            if (slot != 0xFFFFFFFFu) s_codes[(size_t)r * (SC + 1) + c] = __ldg(codes + chunk_at<QT>(slot, C, c0 + c));
         }
-        for (uint32_t e = tid; e < nc * EPC; e += kFinalizeThreads) {
+        for (uint32_t e = tid; e < nc * EPC; e += NT) {
             const uint32_t i = c0 * EPC + e;
-            s_q[e] = i < a.dims ? q[i] : 0.0;
+            s_q[e] = i < dims ? q[i] : 0.0;
         }
         __syncthreads();
         if (mine) {
             const uint4 *row = s_codes + (size_t)tid * (SC + 1);
             uint32_t i = c0 * EPC;
-            for (uint32_t c = 0; c < nc && i < a.dims; ++c) {
+            for (uint32_t c = 0; c < nc && i < dims; ++c) {
                 const uint4 v = row[c];
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
                 const double *qq = s_q + (size_t)c * EPC;
@@ -506,9 +518,9 @@ __device__ void exact_staged(const FinalizeArgs &a, const double *__restrict__ q
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             const uint32_t byte = (w[k] >> (8 * b)) & 0xFF;
-                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], s_lut[byte >> 4]);
+                            if (i < dims) exact_step<METRIC>(acc, qq[e], s_lut[byte >> 4]);
                             ++i; ++e;
-                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], s_lut[byte & 0x0F]);
+                            if (i < dims) exact_step<METRIC>(acc, qq[e], s_lut[byte & 0x0F]);
                             ++i; ++e;
                         }
                 } else if (QT == Q8) {
@@ -516,7 +528,7 @@ __device__ void exact_staged(const FinalizeArgs &a, const double *__restrict__ q
                     for (int k = 0; k < 4; ++k)
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
-                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], s_lut[(w[k] >> (8 * b)) & 0xFF]);
+                            if (i < dims) exact_step<METRIC>(acc, qq[e], s_lut[(w[k] >> (8 * b)) & 0xFF]);
                             ++i; ++e;
                         }
                 } else if (QT == Q16) {
@@ -526,19 +538,19 @@ __device__ void exact_staged(const FinalizeArgs &a, const double *__restrict__ q
                         for (int hlf = 0; hlf < 2; ++hlf) {
                             const uint32_t u = ((w[k] >> (16 * hlf)) & 0xFFFF) ^ 0x8000u; // stored centred
                             const double x = __dsub_rn(__dmul_rn(__ddiv_rn((double)u, 65535.0), 2.0), 1.0);
-                            if (i < a.dims) exact_step<METRIC>(acc, qq[e], x);
+                            if (i < dims) exact_step<METRIC>(acc, qq[e], x);
                             ++i; ++e;
                         }
                 } else if (QT == F32) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (i < a.dims) exact_step<METRIC>(acc, qq[e], (double)__uint_as_float(w[k]));
+                        if (i < dims) exact_step<METRIC>(acc, qq[e], (double)__uint_as_float(w[k]));
                         ++i; ++e;
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        if (i < a.dims) exact_step<METRIC>(acc, qq[e], __hiloint2double((int)w[2 * k + 1], (int)w[2 * k]));
+                        if (i < dims) exact_step<METRIC>(acc, qq[e], __hiloint2double((int)w[2 * k + 1], (int)w[2 * k]));
                         ++i; ++e;
                     }
                 }
@@ -565,13 +577,19 @@ __device__ void exact_staged(const FinalizeArgs &a, const double *__restrict__ q
 // fp64, orders by (distance, lexicographic id), writes min(k, #) results and certifies.
 template <int QT>
 __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHeader *hdr, unsigned long long *out_ids,
-                              double *out_dist, uint32_t *out_n, uint32_t *out_flags, const unsigned long long *pool,
-                              int Kp, double *s_ex, unsigned long long *s_id, unsigned char *stage, int tid) {
+                              double *out_dist, uint32_t *out_n, uint32_t *out_flags, uint32_t *done_cnt,
+                              const unsigned long long *pool, int Kp, double *s_ex, unsigned long long *s_id,
+                              unsigned char *stage, int tid) {
     __shared__ double s_dk;
+    __shared__ uint32_t s_slot[32 * kMaxListE];
     if (tid == 0) s_dk = 0.0;
     if (!(a.flags & 1u)) {
-        if (a.metric == COSINE) exact_staged<QT, COSINE>(a, q, pool, Kp, stage, s_ex, tid);
-        else exact_staged<QT, EUCLID>(a, q, pool, Kp, stage, s_ex, tid);
+        if (tid < Kp) s_slot[tid] = pool[tid] == kNoKey ? 0xFFFFFFFFu : (uint32_t)pool[tid];
+        __syncthreads();
+        if (a.metric == COSINE)
+            exact_staged<QT, COSINE, kFinalizeThreads>(a.codes, a.lut, a.C, a.dims, q, s_slot, Kp, stage, kFinalizeStageBytes, s_ex, tid);
+        else
+            exact_staged<QT, EUCLID, kFinalizeThreads>(a.codes, a.lut, a.C, a.dims, q, s_slot, Kp, stage, kFinalizeStageBytes, s_ex, tid);
     }
     bool valid = false;
     double d = 0.0;
@@ -626,6 +644,13 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHe
         }
         *out_flags = uncertain ? 1u : 0u;
     }
+    if (done_cnt) {
+        // sharded search: the outputs above went to the root device's gather buffer; publish them (every writer fences, the
+        // barrier orders the fences before thread 0's release) and tell the root's merge kernel
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) atomicAdd_system(done_cnt, 1u);
+    }
 }
 
 template <int QT, int MODE>
@@ -658,7 +683,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
     unsigned char *stage = reinterpret_cast<unsigned char *>(s_id + Kp);
     finalize_topk<QT>(a, a.queries + (size_t)qi * a.dims,
                       reinterpret_cast<const PQHeader *>(a.pq + (size_t)qi * a.pq_stride), a.out_ids + (size_t)qi * a.k,
-                      a.out_dist + (size_t)qi * a.k, a.out_n + qi, a.out_flags + qi, pool, Kp, s_ex, s_id, stage, tid);
+                      a.out_dist + (size_t)qi * a.k, a.out_n + qi, a.out_flags + qi, a.done_cnt ? a.done_cnt + qi : nullptr,
+                      pool, Kp, s_ex, s_id, stage, tid);
 }
 inline size_t finalize_smem_bytes(int mode) {
     const size_t Kp = 32u << mode;
@@ -798,7 +824,7 @@ __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanA
         mbar_wait(&bars[cs], (phases >> cs) & 1u);
         phases ^= 1u << cs;
         const uint32_t c0 = tile * Ct, n = min(Ct, C - c0);
-        Sc::tile(acc, reinterpret_cast<const uint4 *>(ring + (size_t)cs * stage_bytes) + lane, n,
+        Sc::tile(acc, reinterpret_cast<const uint4 *>(ring + (size_t)cs * stage_bytes), lane, n,
                          pq + sizeof(PQHeader) + (size_t)c0 * bpc, (int)a.metric);
         if (tile == T - 1) {
             const PQHeader &h = *reinterpret_cast<const PQHeader *>(pq);
@@ -848,22 +874,28 @@ struct ScanPlan {
     size_t smem;
 };
 inline bool scan_plan(uint32_t C, uint32_t warps, uint32_t stages, uint32_t max_tile_chunks, size_t pq_stride,
-                      size_t smem_limit, ScanPlan *p) {
-    if ((size_t)warps * stages * 512 > smem_limit) return false;
+                      size_t smem_limit, ScanPlan *p, uint32_t granule = 1) {
+    // granule: tiles hold whole multiples of it (8 for float rows, whose chunks are grouped by 8; C is a multiple of it)
+    if ((size_t)warps * stages * 512 * granule > smem_limit) return false;
     // per-warp private copies of the prepared query, unless they would squeeze the rings below 2 KB tiles
     const size_t pq_all = (size_t)warps * pq_stride;
     const uint32_t want = max_tile_chunks < C ? max_tile_chunks : C;
-    const uint32_t floor_ct = want < 4 ? want : 4;
+    uint32_t floor_ct = want < 4 ? want : 4;
+    if (floor_ct < granule) floor_ct = granule;
     const bool pq_in_smem = pq_all + (size_t)warps * stages * 512 * floor_ct <= smem_limit;
     const size_t ring_budget = smem_limit - (pq_in_smem ? pq_all : 0);
     size_t per_stage = ring_budget / ((size_t)warps * stages) / 512;
     uint32_t Ct = (uint32_t)(per_stage < max_tile_chunks ? per_stage : max_tile_chunks);
     if (Ct > C) Ct = C;
     if (Ct > (uint32_t)kMaxTileChunks) Ct = kMaxTileChunks;
-    if (Ct < 1) return false;
+    Ct = Ct / granule * granule;
+    if (Ct < granule) {
+        if (per_stage < granule) return false;
+        Ct = granule;
+    }
     // equalise tiles: the smallest Ct that keeps the same number of tiles per block
     const uint32_t T = (C + Ct - 1) / Ct;
-    Ct = (C + T - 1) / T;
+    Ct = ((C + T - 1) / T + granule - 1) / granule * granule;
     p->Ct = Ct; p->stages = stages; p->warps = warps;
     const size_t rings = (size_t)warps * stages * Ct * 512;
     p->pq_smem_off = pq_in_smem ? (uint32_t)rings : 0; // rings start at 0, so a non-zero offset doubles as the flag

@@ -11,6 +11,7 @@
 #include <random>
 #include <shared_mutex>
 #include <stdexcept>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -238,11 +239,18 @@ struct Collection::Impl {
     // lsh tree (newLSHTree(c, 100, 5), collection.go:292)
     std::vector<std::unique_ptr<LshNode>> roots;
     int threshold = 100;
-    std::mt19937_64 rng;
-    std::normal_distribution<double> gauss{0.0, 1.0};
+    // one random source per tree: the reference inserts into its 5 trees on 5 goroutines (lshtree.go:101-114) -- sharing one
+    // rand.Rand without a lock, which is why its trees are not reproducible; here every tree owns its stream, so the bulk
+    // path can build the trees on 5 threads and still be deterministic for a given Seed
+    struct TreeRng {
+        std::mt19937_64 rng;
+        std::normal_distribution<double> gauss{0.0, 1.0};
+    };
+    std::vector<TreeRng> trng;
     // test hooks
-    std::vector<uint64_t> last_visit;
-    int last_batches = 0;
+    // test hooks (LastVisitSequence / LastRescoreBatches): Search holds only the shared lock, so they are per calling thread
+    static thread_local std::vector<uint64_t> last_visit;
+    static thread_local int last_batches;
 
     std::vector<double> docVector(uint64_t id) const { // getDocument's decode (collection.go:470-484)
         auto it = store.find(id);
@@ -250,21 +258,21 @@ struct Collection::Impl {
         return decodeVector(it->second.codes.data(), opt.DimensionCount, opt.Quantization);
     }
 
-    std::vector<double> randomNormalizedVector(int dim) { // lshtree.go:38-44, 10-28
+    std::vector<double> randomNormalizedVector(int dim, TreeRng &tr) { // lshtree.go:38-44, 10-28
         std::vector<double> v((size_t)dim);
         double norm = 0;
-        for (auto &x : v) { x = gauss(rng); norm += x * x; }
+        for (auto &x : v) { x = tr.gauss(tr.rng); norm += x * x; }
         if (norm == 0) return v;
         norm = std::sqrt(norm);
         for (auto &x : v) x /= norm;
         return v;
     }
 
-    std::unique_ptr<LshNode> split(std::unique_ptr<LshNode> node) { // lshtree.go:172-248
+    std::unique_ptr<LshNode> split(std::unique_ptr<LshNode> node, TreeRng &tr) { // lshtree.go:172-248
         const size_t n = node->ids.size();
-        const size_t i1 = (size_t)(rng() % n);
+        const size_t i1 = (size_t)(tr.rng() % n);
         size_t i2;
-        do { i2 = (size_t)(rng() % n); } while (i2 == i1);
+        do { i2 = (size_t)(tr.rng() % n); } while (i2 == i1);
         const std::vector<double> v1 = docVector(node->ids[i1]), v2 = docVector(node->ids[i2]);
         bool same = true; // aboutEqual, tolerance 1e-9 (lshtree.go:158-170)
         for (size_t i = 0; i < v1.size(); ++i)
@@ -272,7 +280,7 @@ struct Collection::Impl {
         if (same) return node;
         std::vector<double> mid(v1.size());
         for (size_t i = 0; i < v1.size(); ++i) mid[i] = (v1[i] + v2[i]) / 2;
-        std::vector<double> normal = randomNormalizedVector((int)mid.size());
+        std::vector<double> normal = randomNormalizedVector((int)mid.size(), tr);
         double b = 0;
         if (opt.DistanceMethod == Euclidean) b = std::sqrt(dotProduct(mid, mid));
         std::vector<uint64_t> leftIDs, rightIDs;
@@ -295,17 +303,17 @@ struct Collection::Impl {
     }
 
     std::unique_ptr<LshNode> insert(std::unique_ptr<LshNode> node, uint64_t id, const std::vector<double> &v,
-                                    double length) { // lshtree.go:116-134
+                                    double length, TreeRng &tr) { // lshtree.go:116-134
         if (node->isLeaf()) {
             node->ids.push_back(id);
-            if ((int)node->ids.size() > threshold) node = split(std::move(node));
+            if ((int)node->ids.size() > threshold) node = split(std::move(node), tr);
             return node;
         }
         double dist;
         bool right;
         distanceToHyperplane(opt.DistanceMethod, v, length, node->normal, node->b, &dist, &right);
-        if (!right) node->left = insert(std::move(node->left), id, v, length);
-        else node->right = insert(std::move(node->right), id, v, length);
+        if (!right) node->left = insert(std::move(node->left), id, v, length, tr);
+        else node->right = insert(std::move(node->right), id, v, length, tr);
         return node;
     }
 
@@ -328,7 +336,23 @@ struct Collection::Impl {
 
     void addPoint(uint64_t id, const std::vector<double> &v) { // lshtree.go:101-114 (sequential here)
         const double length = vectorLength(v);
-        for (auto &root : roots) root = insert(std::move(root), id, v, length);
+        for (size_t t = 0; t < roots.size(); ++t) roots[t] = insert(std::move(roots[t]), id, v, length, trng[t]);
+    }
+    // the reload loop of NewCollection (collection.go:298-311) for many documents: one thread per tree, like the
+    // reference's goroutine per tree; the store is only read
+    void addPoints(const std::vector<uint64_t> &ids, const std::vector<std::vector<double>> &vectors) {
+        if (ids.size() < 4096) {
+            for (size_t i = 0; i < ids.size(); ++i) addPoint(ids[i], vectors[i]);
+            return;
+        }
+        std::vector<double> length(ids.size());
+        for (size_t i = 0; i < ids.size(); ++i) length[i] = vectorLength(vectors[i]);
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < roots.size(); ++t)
+            th.emplace_back([&, t]() {
+                for (size_t i = 0; i < ids.size(); ++i) roots[t] = insert(std::move(roots[t]), ids[i], vectors[i], length[i], trng[t]);
+            });
+        for (auto &x : th) x.join();
     }
     void removePoint(uint64_t id, const std::vector<double> &v) { // lshtree.go:250-255
         const double length = vectorLength(v);
@@ -364,8 +388,11 @@ Collection::Collection(const CollectionOptions &options) : p_(new Impl) {
         throw std::invalid_argument("Unsupported distance method"); // collection.go:281-282 panics
     if (szg_create(p_->opt.DimensionCount, p_->opt.Quantization, p_->opt.DistanceMethod, p_->opt.Device, &p_->gpu) != SZG_OK)
         throw std::runtime_error(std::string("syzgy_b200 create: ") + szg_last_error());
-    p_->rng.seed(options.Seed);
-    for (int i = 0; i < 5; ++i) p_->roots.push_back(std::make_unique<LshNode>());
+    p_->trng.resize(5);
+    for (int i = 0; i < 5; ++i) {
+        p_->trng[i].rng.seed(options.Seed * 0x9E3779B97F4A7C15ull + (uint64_t)i);
+        p_->roots.push_back(std::make_unique<LshNode>());
+    }
 }
 
 std::unique_ptr<Collection> Collection::Open(const std::string &path, int device, uint64_t seed) {
@@ -449,8 +476,10 @@ void Collection::Close() {
 }
 
 const CollectionOptions &Collection::Options() const { return p_->opt; }
-const std::vector<uint64_t> &Collection::LastVisitSequence() const { return p_->last_visit; }
-int Collection::LastRescoreBatches() const { return p_->last_batches; }
+thread_local std::vector<uint64_t> Collection::Impl::last_visit;
+thread_local int Collection::Impl::last_batches = 0;
+const std::vector<uint64_t> &Collection::LastVisitSequence() const { return Impl::last_visit; }
+int Collection::LastRescoreBatches() const { return Impl::last_batches; }
 
 void Collection::AddDocument(uint64_t id, const std::vector<double> &vector, const std::string &metadata) {
     std::unique_lock<std::shared_mutex> lk(p_->mu);
@@ -481,7 +510,7 @@ void Collection::AddDocuments(const std::vector<uint64_t> &ids, const std::vecto
         const uint8_t *row = all.data() + i * (size_t)p_->rowbytes;
         p_->store[ids[i]] = Impl::Rec{metadata.empty() ? std::string() : metadata[i], std::vector<uint8_t>(row, row + p_->rowbytes)};
     }
-    for (size_t i = 0; i < ids.size(); ++i) p_->addPoint(ids[i], vectors[i]);
+    p_->addPoints(ids, vectors);
 }
 
 bool Collection::GetDocument(uint64_t id, Document *out) const {

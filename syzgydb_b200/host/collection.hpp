@@ -104,7 +104,7 @@ public:
     std::vector<SearchResults> SearchBatch(const std::vector<SearchArgs> &args);
     void Close();                                                  // collection.go:408-421
 
-    // test hooks: the ids the last index-driven Search fed to `consider`, in order, and how many GPU
+    // test hooks: the ids the calling thread's last index-driven Search fed to `consider`, in order, and how many GPU
     // rescoring batches it took
     const std::vector<uint64_t> &LastVisitSequence() const;
     int LastRescoreBatches() const;

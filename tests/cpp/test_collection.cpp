@@ -210,13 +210,29 @@ static Corpus make_corpus(int n, int dims, int bits, uint64_t seed, bool gaussia
     return c;
 }
 
-static void lsh_case(const char *name, int n, int dims, int bits, int metric, int k, double radius, bool filter) {
+struct LshVariant { int k; double radius; bool filter; };
+static void lsh_queries(const char *name, Collection &c, const Corpus &cp, int n, int dims, int bits, int metric, int k, double radius,
+                        bool filter);
+// one collection, one or more (k, radius, filter) variants of the same three queries
+static void lsh_cases(const char *name, int n, int dims, int bits, int metric, const std::vector<LshVariant> &variants) {
     Corpus cp = make_corpus(n, dims, bits, 1234 + n + dims, metric == Cosine);
     CollectionOptions o; o.Name = name; o.DistanceMethod = metric; o.DimensionCount = dims; o.Quantization = bits; o.Seed = 99;
     Collection c(o);
     std::vector<std::string> meta;
     for (uint64_t id : cp.ids) meta.push_back("{\"bucket\": " + std::to_string(id % 10) + "}");
     c.AddDocuments(cp.ids, cp.vecs, meta);
+    std::vector<std::vector<double>>().swap(cp.vecs); // the collection keeps the encoded rows; the oracle needs cp.codes only
+    for (const LshVariant &v : variants) {
+        const int before = g_fail;
+        lsh_queries(name, c, cp, n, dims, bits, metric, v.k, v.radius, v.filter);
+        if (variants.size() > 1) std::printf("%s %s k=%d radius=%g filter=%d\n", g_fail == before ? "PASS" : "FAILED", name, v.k, v.radius, (int)v.filter);
+    }
+}
+static void lsh_case(const char *name, int n, int dims, int bits, int metric, int k, double radius, bool filter) {
+    lsh_cases(name, n, dims, bits, metric, {LshVariant{k, radius, filter}});
+}
+static void lsh_queries(const char *name, Collection &c, const Corpus &cp, int n, int dims, int bits, int metric, int k, double radius,
+                        bool filter) {
     std::mt19937_64 rng(5);
     std::uniform_real_distribution<double> u(-1, 1);
     std::vector<uint8_t> pass;
@@ -320,6 +336,19 @@ static int open_mode(int argc, char **argv) {
 }
 
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "--cfg3") {
+        // BASELINE.json configs[2] at its stated size (default 1 M x 384 float64, cosine): LSH-tree candidate walk on the
+        // host, candidates re-scored on the GPU, radius 0.46 with the `bucket < 3` filter, then top-k -- both against the
+        // oracle's replay of `consider` over the same visit sequence and against its exact scan (lsh_case above)
+        const int n = argc > 2 ? std::atoi(argv[2]) : 1000000;
+        try {
+            lsh_cases("cfg3", n, 384, 64, Cosine, {LshVariant{0, 0.46, true}, LshVariant{10, 0, false}});
+        } catch (const std::exception &e) {
+            std::printf("ERROR %s\n", e.what());
+            return 2;
+        }
+        return g_fail ? 1 : 0;
+    }
     if (argc > 4 && std::string(argv[1]) == "--open") {
         try {
             return open_mode(argc, argv);

@@ -35,6 +35,18 @@ def test_host_mirror_collection_tests_on_gpu():
 
 
 @pytest.mark.gpu
+def test_host_mirror_cfg3_at_size_lsh_radius_filter_against_oracle():
+    """BASELINE.json configs[2] at its stated size: 1 M x 384 float64 cosine documents in the C++ host mirror (5 LSH trees built
+    on 5 threads), medium-precision Search with radius 0.46 + the bucket < 3 filter and with K = 10: the GPU-rescored
+    result must equal the oracle's replay of `consider` over the same visit sequence (lshtree.go:283-351,
+    collection.go:598-619), and the exact search the oracle's scan of all rows."""
+    _build()
+    out = subprocess.run([BIN, "--cfg3", "1000000"], capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
+    assert "PASS cfg3 k=0 radius=0.46 filter=1" in out.stdout and "PASS cfg3 k=10 radius=0 filter=0" in out.stdout, out.stdout[-4000:]
+
+
+@pytest.mark.gpu
 def test_host_mirror_opens_a_collection_file_and_batches(tmp_path):
     """Collection::Open over a span file written by the restated reference writer (updates and removals included),
     then SearchBatch: the C++ mirror must return what the oracle returns, with the metadata of the file."""

@@ -171,3 +171,72 @@ def test_load_span_file_into_the_mirror_and_search(tmp_path, bits, metric, dims,
         with szg.Index(dims + 1, bits, metric) as other:
             with pytest.raises(szg.SzgError):
                 sf.load_into(other)
+
+
+# ------------------------------------------------------------------ the reference's own span-file tests, restated end to end
+def test_reference_checksum_verification(tmp_path):
+    """spanfile_test.go:66-97 (TestChecksumVerification): WriteRecord("record1", {1: "Hello"}), flip byte offset+9 of the span,
+    reading the record must fail on the checksum.  The library's reader meets such a span when it opens the file
+    (scanFile, spanfile.go:313-329: the span is skipped and counted); the same file with a document id shows the
+    record gone from szg_spanfile_record / szg_spanfile_ids, like ReadRecord's error."""
+    for rid in (b"record1", b"1"):
+        w = sfo.SpanFileWriter()
+        w.write_record(rid, [(1, b"Hello")])
+        clean = w.tobytes()
+        path = os.path.join(tmp_path, "ok_%s.dat" % rid.decode())
+        with open(path, "wb") as f:
+            f.write(clean)
+        with szg.SpanFile(path) as sf:
+            assert sf.info()["spans_corrupt"] == 0 and sf.info()["spans_active"] == 2   # the "" span OpenFile writes + the record
+            if rid == b"1":
+                assert sf.record(1) == (b"Hello", None) and sf.ids().tolist() == [1]
+        data = bytearray(clean)
+        offset = w.index[rid]
+        data[offset + 9] ^= 0xFF                                       # spanfile_test.go:84
+        ref_index, ref_stats = sfo.scan_file(bytes(data))              # the restated verifyChecksum (spanfile.go:841-849) rejects it
+        assert rid not in ref_index and ref_stats["corrupt"] == 1
+        path = os.path.join(tmp_path, "bad_%s.dat" % rid.decode())
+        with open(path, "wb") as f:
+            f.write(data)
+        with szg.SpanFile(path) as sf:
+            info = sf.info()
+            assert info["spans_corrupt"] == 1 and info["spans_active"] == 1 and info["records"] == 0
+            if rid == b"1":
+                assert sf.ids().size == 0
+                with pytest.raises(KeyError):                          # ReadRecord: error (spanfile.go:513-519)
+                    sf.record(1)
+
+
+def test_reference_sequence_number_wraparound(tmp_path):
+    """spanfile_test.go:117-134 (TestSequenceNumberWraparound): with sequenceNumber = 0xFFFFFFFF a WriteRecord succeeds and
+    the counter wraps to 0.  On disk that record carries sequence 0xFFFFFFFF (a 5-byte 7-code); the reader must parse it,
+    report next_sequence = 0 like scanFile's highest + 1 in uint32 (spanfile.go:355), and -- the reference's rule, kept bug
+    for bug -- let it win over any later write of the same record, whose sequence number (0, 1, ...) is lower (337-341)."""
+    w = sfo.SpanFileWriter()
+    w.write_header("wrap", 0, 2, 8)
+    w.seq = 0xFFFFFFFF
+    w.add_document(5, b"\x01\x02", b'{"v": 1}')
+    assert w.seq == 0                                                  # the reference's assertion
+    path = os.path.join(tmp_path, "wrap.dat")
+    with open(path, "wb") as f:
+        f.write(w.tobytes())
+    with szg.SpanFile(path) as sf:
+        info = sf.info()
+        assert info["next_sequence"] == 0 and info["records"] == 1 and info["spans_corrupt"] == 0
+        assert sf.record(5) == (b"\x01\x02", b'{"v": 1}')
+    # a second version written after the wrap (sequence 0) next to the first one (e.g. after a crash before the old span was
+    # freed): both are valid spans; scanFile keeps the HIGHER sequence number, i.e. the older write
+    tail = sfo.serialize_span(0, b"5", [(0, b'{"v": 2}'), (1, b"\x09\x09")])
+    tail += sfo.crc32_ieee(bytes(tail)).to_bytes(4, "big")
+    data = bytearray(w.tobytes())
+    off = 0
+    while off + 8 <= len(data) and int.from_bytes(data[off:off + 4], "big") != 0:
+        off += int.from_bytes(data[off + 4:off + 8], "big")
+    data[off:off + len(tail)] = tail
+    ref_index, _ = sfo.scan_file(bytes(data))
+    assert ref_index[b"5"].stream(1) == b"\x01\x02"
+    path2 = os.path.join(tmp_path, "wrap2.dat")
+    with open(path2, "wb") as f:
+        f.write(data)
+    with szg.SpanFile(path2) as sf:
+        assert sf.record(5) == (b"\x01\x02", b'{"v": 1}') and sf.info()["spans_active"] >= 3
