@@ -57,6 +57,14 @@ def lib():
         L.orc_search_exact.restype = C.c_int64
         L.orc_search_exact.argtypes = [u8p, u64p, C.c_int64, C.c_int64, C.c_int, C.c_int, f64p, C.c_int64,
                                        C.c_double, u8p, i64p, C.c_int, u64p, f64p, C.c_int64, f64p]
+        L.orc_spans_build.restype = C.c_void_p
+        L.orc_spans_build.argtypes = [u8p, u64p, C.c_int64, C.c_int64, C.c_int64]
+        L.orc_spans_free.argtypes = [C.c_void_p]
+        L.orc_crc32.restype = C.c_uint32
+        L.orc_crc32.argtypes = [u8p, C.c_int64]
+        L.orc_search_exact_spans.restype = C.c_int64
+        L.orc_search_exact_spans.argtypes = [C.c_void_p, u8p, u64p, C.c_int64, C.c_int64, C.c_int, C.c_int, f64p, C.c_int64,
+                                             C.c_double, u8p, i64p, u64p, f64p, C.c_int64, f64p]
         L.orc_replay.restype = C.c_int64
         L.orc_replay.argtypes = [u8p, u64p, C.c_int64, C.c_int64, C.c_int, C.c_int, f64p, C.c_int64,
                                  C.c_double, u8p, i64p, C.c_int64, u64p, f64p, C.c_int64, i64p]
@@ -131,9 +139,37 @@ def lex_order(ids) -> np.ndarray:
     return perm
 
 
+class Spans:
+    """In-memory span-file image of a row-major code matrix (orc_spans_build): what the faithful CPU variant of the scan
+    reads every record from -- decimal-string key, index lookup, parseSpan, CRC-32 over the whole span."""
+
+    def __init__(self, codes, ids, meta_len=24):
+        self.codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self.ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        rb = self.codes.size // max(self.ids.size, 1)
+        self._h = lib().orc_spans_build(_p(self.codes, C.c_uint8), _p(self.ids, C.c_uint64), self.ids.size, rb, meta_len)
+
+    def close(self):
+        if self._h:
+            lib().orc_spans_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def crc32(data: bytes) -> int:
+    d = np.frombuffer(data, dtype=np.uint8)
+    return int(lib().orc_crc32(_p(np.ascontiguousarray(d), C.c_uint8), d.size))
+
+
 def search_exact(codes, ids, dims, bits, metric, query, k=0, radius=0.0, passmask=None, order="lex",
-                 faithful=False, out_cap=None):
-    """Search(Precision="exact").  Returns (ids, dists, percent_searched)."""
+                 faithful=False, out_cap=None, spans=None):
+    """Search(Precision="exact").  Returns (ids, dists, percent_searched).  spans: a Spans image of the same rows -> every
+    record goes through the restated getDocument (the faithful CPU variant)."""
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     ids = np.ascontiguousarray(ids, dtype=np.uint64)
     n = ids.size
@@ -148,10 +184,15 @@ def search_exact(codes, ids, dims, bits, metric, query, k=0, radius=0.0, passmas
     oi = np.zeros(cap, dtype=np.uint64)
     od = np.zeros(cap, dtype=np.float64)
     pct = C.c_double(0)
-    m = lib().orc_search_exact(_p(codes, C.c_uint8), _p(ids, C.c_uint64), n, dims, bits, metric,
-                               _p(q, C.c_double), int(k), float(radius), _p(pm, C.c_uint8),
-                               _p(order, C.c_int64), int(faithful), _p(oi, C.c_uint64), _p(od, C.c_double),
-                               cap, C.byref(pct))
+    if spans is not None:
+        m = lib().orc_search_exact_spans(spans._h, _p(codes, C.c_uint8), _p(ids, C.c_uint64), n, dims, bits, metric,
+                                         _p(q, C.c_double), int(k), float(radius), _p(pm, C.c_uint8), _p(order, C.c_int64),
+                                         _p(oi, C.c_uint64), _p(od, C.c_double), cap, C.byref(pct))
+    else:
+        m = lib().orc_search_exact(_p(codes, C.c_uint8), _p(ids, C.c_uint64), n, dims, bits, metric,
+                                   _p(q, C.c_double), int(k), float(radius), _p(pm, C.c_uint8),
+                                   _p(order, C.c_int64), int(faithful), _p(oi, C.c_uint64), _p(od, C.c_double),
+                                   cap, C.byref(pct))
     m = min(int(m), cap)
     return oi[:m].copy(), od[:m].copy(), pct.value
 

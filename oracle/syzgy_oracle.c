@@ -294,16 +294,178 @@ typedef struct {
     orc_heap heap;
     int64_t points_searched;
     double *scratch; /* decoded row: decodeVector's make([]float64) */
-    int faithful;    /* 1: malloc per record like decodeVector does */
+    int faithful;    /* 1: every record goes through getDocument's whole path (orc_get_document below) */
+    const struct orc_spans *spans; /* faithful: the span-file image of the rows */
 } orc_search;
+
+/* --------------------------------------------------- getDocument, the faithful CPU variant
+ * What the reference does per record BEFORE the arithmetic: collection.go:470-484 formats the id (fmt.Sprintf "%d"),
+ * SpanFile.ReadRecord (spanfile.go:513-519) looks the string up in map[string]uint64, parseSpan (730-818) walks magic,
+ * length, the 7-code sequence number, the record id and the streams, and verifyChecksum (841-849) runs CRC-32/IEEE over
+ * the WHOLE span on every read; decodeVector (768-794) then allocates the []float64.  orc_spans is an in-memory image of
+ * those spans for a row-major code matrix (built once, outside any timed region), with a string-keyed hash index.
+ * CRC: slicing-by-8 here; Go's hash/crc32 uses PCLMULQDQ on amd64 and is faster -- the figure this variant produces is a
+ * restatement's, reported beside the lean one, never instead of it. */
+static uint32_t g_crc_tab[8][256];
+static int g_crc_ready = 0;
+static void crc_init(void) {
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        g_crc_tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; i++)
+        for (int t = 1; t < 8; t++) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xFF];
+    g_crc_ready = 1;
+}
+static uint32_t crc32_ieee(const uint8_t *p, size_t n) {
+    uint32_t c = 0xFFFFFFFFu;
+    while (n >= 8) {
+        uint32_t a, b;
+        memcpy(&a, p, 4);
+        memcpy(&b, p + 4, 4);
+        a ^= c;
+        c = g_crc_tab[7][a & 0xFF] ^ g_crc_tab[6][(a >> 8) & 0xFF] ^ g_crc_tab[5][(a >> 16) & 0xFF] ^ g_crc_tab[4][a >> 24] ^
+            g_crc_tab[3][b & 0xFF] ^ g_crc_tab[2][(b >> 8) & 0xFF] ^ g_crc_tab[1][(b >> 16) & 0xFF] ^ g_crc_tab[0][b >> 24];
+        p += 8;
+        n -= 8;
+    }
+    while (n--) c = g_crc_tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+    return ~c;
+}
+uint32_t orc_crc32(const uint8_t *p, int64_t n) { /* check value: "123456789" -> 0xCBF43926 */
+    if (!g_crc_ready) crc_init();
+    return crc32_ieee(p, (size_t)n);
+}
+
+/* write7Code, spanfile.go:568-625 (thresholds off by one: n < 0x7f takes 1 byte, so 127 takes 2) */
+static size_t write7(uint8_t *out, uint64_t v) {
+    int len = v < 0x7f ? 1 : v < 0x3fff ? 2 : v < 0x1fffff ? 3 : v < 0xfffffff ? 4 : 5;
+    for (int i = 0; i < len; i++) out[i] = (uint8_t)(((v >> (7 * (len - 1 - i))) & 0x7f) | (i + 1 < len ? 0x80 : 0));
+    return (size_t)len;
+}
+/* read7Code, spanfile.go:627-636 */
+static uint64_t read7(const uint8_t *p, size_t *at) {
+    uint64_t v = 0;
+    for (;;) {
+        uint8_t b = p[(*at)++];
+        v = (v << 7) | (b & 0x7f);
+        if (!(b & 0x80)) return v;
+    }
+}
+
+typedef struct orc_spans {
+    uint8_t *buf;
+    size_t len;
+    int64_t nrows;
+    uint64_t *slot_off;  /* open addressing: offset + 1 of the span whose record id hashes here (0 = empty) */
+    size_t nslots;       /* power of two */
+} orc_spans;
+
+static uint64_t str_hash(const char *s, size_t n) { /* FNV-1a: a string hash like the one Go's map runs on the key */
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t i = 0; i < n; i++) h = (h ^ (uint8_t)s[i]) * 1099511628211ULL;
+    return h;
+}
+
+/* serializeSpan + WriteRecord (spanfile.go:679-728, 398-475) for every row: streams {0: metadata, 1: vector bytes}
+ * (collection.go:446-449), sequence numbers 1.., the CRC at the end.  meta_len bytes of metadata per record. */
+orc_spans *orc_spans_build(const uint8_t *codes, const uint64_t *ids, int64_t nrows, int64_t rowbytes, int64_t meta_len) {
+    if (!g_crc_ready) crc_init();
+    orc_spans *sp = (orc_spans *)calloc(1, sizeof *sp);
+    sp->nrows = nrows;
+    size_t cap = (size_t)nrows * ((size_t)rowbytes + (size_t)meta_len + 48) + 64;
+    sp->buf = (uint8_t *)malloc(cap);
+    sp->nslots = 16;
+    while (sp->nslots < (size_t)nrows * 2) sp->nslots <<= 1;
+    sp->slot_off = (uint64_t *)calloc(sp->nslots, sizeof(uint64_t));
+    size_t at = 0;
+    for (int64_t r = 0; r < nrows; r++) {
+        char key[24];
+        int klen = snprintf(key, sizeof key, "%llu", (unsigned long long)ids[r]);
+        const size_t start = at;
+        uint8_t *b = sp->buf;
+        memcpy(b + at, "SPAN", 4);
+        at += 8; /* length patched below */
+        at += write7(b + at, (uint64_t)r + 1);
+        at += write7(b + at, (uint64_t)klen);
+        memcpy(b + at, key, (size_t)klen);
+        at += (size_t)klen;
+        b[at++] = 2;
+        b[at++] = 0;
+        at += write7(b + at, (uint64_t)meta_len);
+        memset(b + at, '{', (size_t)meta_len);
+        at += (size_t)meta_len;
+        b[at++] = 1;
+        at += write7(b + at, (uint64_t)rowbytes);
+        memcpy(b + at, codes + r * rowbytes, (size_t)rowbytes);
+        at += (size_t)rowbytes;
+        const uint32_t total = (uint32_t)(at - start + 4);
+        b[start + 4] = (uint8_t)(total >> 24); b[start + 5] = (uint8_t)(total >> 16);
+        b[start + 6] = (uint8_t)(total >> 8); b[start + 7] = (uint8_t)total;
+        const uint32_t crc = crc32_ieee(b + start, at - start);
+        b[at++] = (uint8_t)(crc >> 24); b[at++] = (uint8_t)(crc >> 16); b[at++] = (uint8_t)(crc >> 8); b[at++] = (uint8_t)crc;
+        size_t h = (size_t)str_hash(key, (size_t)klen) & (sp->nslots - 1);
+        while (sp->slot_off[h]) h = (h + 1) & (sp->nslots - 1);
+        sp->slot_off[h] = (uint64_t)start + 1;
+    }
+    sp->len = at;
+    return sp;
+}
+void orc_spans_free(orc_spans *sp) {
+    if (!sp) return;
+    free(sp->buf);
+    free(sp->slot_off);
+    free(sp);
+}
+
+/* getDocument (collection.go:470-484): id -> decimal string -> index lookup -> parseSpan + verifyChecksum -> stream 1.
+ * Returns the vector bytes inside the image (NULL: record not found or checksum mismatch). */
+static const uint8_t *orc_get_document(const orc_spans *sp, uint64_t id, int64_t *veclen) {
+    char key[24];
+    const int klen = snprintf(key, sizeof key, "%llu", (unsigned long long)id); /* fmt.Sprintf("%d", id) */
+    size_t h = (size_t)str_hash(key, (size_t)klen) & (sp->nslots - 1);
+    for (;; h = (h + 1) & (sp->nslots - 1)) {
+        if (!sp->slot_off[h]) return NULL;
+        const uint8_t *b = sp->buf + (sp->slot_off[h] - 1);
+        /* parseSpan, spanfile.go:730-818 */
+        if (memcmp(b, "SPAN", 4) != 0) return NULL;
+        const uint32_t length = ((uint32_t)b[4] << 24) | ((uint32_t)b[5] << 16) | ((uint32_t)b[6] << 8) | b[7];
+        size_t at = 8;
+        (void)read7(b, &at); /* sequence number */
+        const uint64_t idlen = read7(b, &at);
+        if (idlen != (uint64_t)klen || memcmp(b + at, key, (size_t)klen) != 0) continue; /* another key in this bucket chain */
+        at += (size_t)idlen;
+        const int nstreams = b[at++];
+        const uint8_t *vec = NULL;
+        for (int s = 0; s < nstreams; s++) {
+            const int sid = b[at++];
+            const uint64_t slen = read7(b, &at);
+            if (sid == 1) { vec = b + at; *veclen = (int64_t)slen; }
+            at += (size_t)slen;
+        }
+        /* verifyChecksum, spanfile.go:841-849: over everything but the last 4 bytes, on every read */
+        const uint32_t want = ((uint32_t)b[length - 4] << 24) | ((uint32_t)b[length - 3] << 16) | ((uint32_t)b[length - 2] << 8) | b[length - 1];
+        if (crc32_ieee(b, length - 4) != want) return NULL;
+        return vec;
+    }
+}
 
 /* collection.go:583-629.  `row` is the record already resolved (getDocument found it);
  * row < 0 stands for "record not found" (StopSearch, 585-587). */
 static int orc_consider(orc_search *s, int64_t row, double *radius) {
     if (row < 0) return ORC_STOP_SEARCH;
     double *vec = s->scratch;
-    if (s->faithful) vec = (double *)malloc((size_t)s->dims * sizeof(double));
-    orc_decode(s->codes + row * s->rowbytes, s->dims, s->bits, vec); /* 470-484 */
+    const uint8_t *bytes = s->codes + row * s->rowbytes;
+    if (s->faithful) {
+        if (s->spans) { /* the record as getDocument reaches it: string key, index, parseSpan, CRC over the span */
+            int64_t vl = 0;
+            bytes = orc_get_document(s->spans, s->ids[row], &vl);
+            if (!bytes || vl != s->rowbytes) return ORC_STOP_SEARCH; /* 585-587 */
+        }
+        vec = (double *)malloc((size_t)s->dims * sizeof(double)); /* decodeVector's make([]float64, dims) */
+    }
+    orc_decode(bytes, s->dims, s->bits, vec); /* 470-484 */
     s->points_searched++;                                             /* 589 */
     int signal = ORC_POINT_CHECKED;
     if (s->pass && !s->pass[row]) { /* 592-594 */
@@ -382,13 +544,35 @@ void orc_lex_order(const uint64_t *ids, int64_t n, int64_t *perm) {
  * results (may exceed out_cap in radius mode; only out_cap are written).
  * *percent_searched follows 700-710 (nrows == numRecords).
  */
+static int64_t search_exact_impl(const uint8_t *codes, const uint64_t *ids, int64_t nrows, int64_t dims,
+                         int bits, int metric, const double *query, int64_t k, double radius,
+                         const uint8_t *pass, const int64_t *order, int faithful, const orc_spans *spans,
+                         uint64_t *out_ids, double *out_dist, int64_t out_cap,
+                         double *percent_searched);
 int64_t orc_search_exact(const uint8_t *codes, const uint64_t *ids, int64_t nrows, int64_t dims,
                          int bits, int metric, const double *query, int64_t k, double radius,
                          const uint8_t *pass, const int64_t *order, int faithful,
                          uint64_t *out_ids, double *out_dist, int64_t out_cap,
                          double *percent_searched) {
+    return search_exact_impl(codes, ids, nrows, dims, bits, metric, query, k, radius, pass, order, faithful, NULL, out_ids, out_dist,
+                             out_cap, percent_searched);
+}
+/* the faithful variant: every record through orc_get_document over the span image `spans` of the same rows */
+int64_t orc_search_exact_spans(const orc_spans *spans, const uint8_t *codes, const uint64_t *ids, int64_t nrows, int64_t dims,
+                               int bits, int metric, const double *query, int64_t k, double radius, const uint8_t *pass,
+                               const int64_t *order, uint64_t *out_ids, double *out_dist, int64_t out_cap,
+                               double *percent_searched) {
+    return search_exact_impl(codes, ids, nrows, dims, bits, metric, query, k, radius, pass, order, 1, spans, out_ids, out_dist, out_cap,
+                             percent_searched);
+}
+static int64_t search_exact_impl(const uint8_t *codes, const uint64_t *ids, int64_t nrows, int64_t dims,
+                         int bits, int metric, const double *query, int64_t k, double radius,
+                         const uint8_t *pass, const int64_t *order, int faithful, const orc_spans *spans,
+                         uint64_t *out_ids, double *out_dist, int64_t out_cap,
+                         double *percent_searched) {
     orc_search s;
     memset(&s, 0, sizeof s);
+    s.spans = spans;
     s.codes = codes; s.ids = ids; s.nrows = nrows; s.dims = dims; s.bits = bits;
     s.metric = metric; s.rowbytes = orc_vector_size(bits, dims);
     s.query = query; s.k = k; s.radius = radius; s.pass = pass; s.faithful = faithful;

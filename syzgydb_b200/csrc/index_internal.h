@@ -80,6 +80,7 @@ struct GraphEntry {
     bool failed = false;     // capture did not work for this shape: plain launches
     int mode0 = 0, nd0 = 0;  // what the captured first pass runs with (the escalation ladder continues from there)
     uint32_t kernels = 0;    // kernel nodes (statistics)
+    const void *buffers[7] = {}; // addresses of the workspace buffers the nodes refer to
 };
 
 struct Workspace {

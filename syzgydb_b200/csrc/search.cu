@@ -497,6 +497,19 @@ int search_host(szg_index *h, const double *queries, uint32_t nq, uint32_t k, in
                              (prefer_batch ? 1u : 0u);
         GraphEntry &ge = ws->graphs[key];
         const uint64_t gen = h->generation;
+        // the captured nodes hold the addresses of this workspace's buffers: another call shape that made one of them grow
+        // (and move) since the capture makes the sequence stale
+        auto fingerprint = [&](const void *(&fp)[7]) {
+            fp[0] = ws->d_q.p; fp[1] = ws->h_q.p; fp[2] = ws->d_pq.p; fp[3] = ws->d_cand.p; fp[4] = ws->d_gmth.p;
+            fp[5] = ws->d_out_pack.p; fp[6] = ws->h_out_pack.p;
+        };
+        const void *now[7];
+        fingerprint(now);
+        if (ge.exec && (ge.generation != gen || memcmp(now, ge.buffers, sizeof now) != 0)) {
+            cudaGraphExecDestroy(ge.exec);
+            ge.exec = nullptr;
+            if (ge.generation == gen) ge.generation = 0; // moved buffers: this call runs launch by launch, the next one captures
+        }
         if (ge.exec && ge.generation == gen) {
             mode0 = ge.mode0; nd0 = ge.nd0;
             CK(cudaGraphLaunch(ge.exec, st));
@@ -524,12 +537,12 @@ int search_host(szg_index *h, const double *queries, uint32_t nq, uint32_t k, in
             } else {
                 ge.mode0 = mode0; ge.nd0 = nd0;
                 ge.kernels = (uint32_t)(h->launches.load() - l0);
+                fingerprint(ge.buffers);
                 CK(cudaGraphLaunch(ge.exec, st));
                 h->graph_launches++;
                 done = true;
             }
         } else if (ge.generation != gen) {
-            if (ge.exec) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; }
             ge.generation = gen;
             ge.failed = false;
             if (ws->graphs.size() > 64) { // a caller that varies its shapes: keep the table small
@@ -761,10 +774,13 @@ int radius_device(szg_index *h, const double *queries, uint32_t nq, const double
     // seen, with headroom) so that a steady workload never rescans; an overflow sizes the buffer exactly and rescans once.
     unsigned int *d_count = ws->d_ticket.p; // [nq] surrogate hits, [nq .. 2nq) exact hits
     size_t cap = std::max<size_t>({(size_t)4096, (size_t)h->nslots / 64, (size_t)ws->radius_cap_hint});
-    std::vector<uint32_t> count(nq, 0);
     uint32_t tbase = 0;
     bool timing = false;
+    std::vector<RadiusFinishArgs> fin(nq);
     for (int attempt = 0; attempt < 3; ++attempt) {
+        // the hits are ordered by bitonic networks over a power of two of (distance, id) pairs per query
+        size_t kcap = 2 * kRadiusSortSmall;
+        while (kcap < cap) kcap <<= 1;
         if ((rc = ws->d_slots.ensure(cap * nq))) return rc;
         CK(cudaMemsetAsync(d_count, 0, 2 * (size_t)nq * 4, st));
         if ((rc = timing_reserve(h, ws, nq, &tbase, &timing))) return rc;
@@ -781,15 +797,15 @@ int radius_device(szg_index *h, const double *queries, uint32_t nq, const double
         }
         if (timing) ws->timed = tbase + nq;
         // exact pass over whatever fitted (an overflowing query is redone anyway): distances + sortable keys
-        if ((rc = ws->d_out_ids.ensure(cap * nq)) || (rc = ws->d_out_dist.ensure(cap * nq)) || (rc = ws->d_keys.ensure(2 * cap * nq)))
+        if ((rc = ws->d_out_ids.ensure(cap * nq)) || (rc = ws->d_out_dist.ensure(cap * nq)) || (rc = ws->d_keys.ensure(2 * kcap * nq)))
             return rc;
         for (uint32_t q = 0; q < nq; ++q) {
-            RadiusFinishArgs fa;
+            RadiusFinishArgs &fa = fin[q];
             fa.codes = h->codes.p; fa.ids = h->ids.p; fa.lut = h->lut.p; fa.q = ws->d_q.p + (size_t)q * h->dim;
             fa.slots = ws->d_slots.p + cap * q; fa.count_ptr = d_count + q; fa.cap = (uint32_t)cap;
             fa.radius = radii[q];
             fa.out_dist = ws->d_out_dist.p + cap * q; fa.out_ids = ws->d_out_ids.p + cap * q;
-            fa.keys = ws->d_keys.p + 2 * cap * q; fa.out_count = d_count + nq + q;
+            fa.keys = ws->d_keys.p + 2 * kcap * q; fa.out_count = d_count + nq + q;
             fa.C = h->C; fa.dims = (uint32_t)h->dim; fa.metric = (uint32_t)h->metric; fa.qt = h->qt;
             CK(launch_radius_finish(fa, st));
             h->launches += 2;
@@ -804,9 +820,17 @@ int radius_device(szg_index *h, const double *queries, uint32_t nq, const double
         if (attempt == 2) return fail(SZG_EINTERNAL, "radius compaction buffer could not be sized");
         cap = worst; // too small: size it exactly and rescan
     }
-    // the exact hits of every query, already filtered and ordered: one copy each
+    // results above kRadiusSortSmall hits were left unordered by launch_radius_finish: order them now
     size_t total = 0;
-    for (uint32_t q = 0; q < nq; ++q) total += ws->h_out_n.p[nq + q];
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t m = ws->h_out_n.p[nq + q];
+        total += m;
+        if (m > kRadiusSortSmall) {
+            CK(launch_radius_sort_large(fin[q], m, st));
+            h->launches++;
+        }
+    }
+    // the exact hits of every query, filtered and ordered: one copy each
     if (total) {
         if ((rc = ws->h_out_ids.ensure(total)) || (rc = ws->h_out_dist.ensure(total))) return rc;
         size_t off = 0;

@@ -80,6 +80,14 @@ class ShardedIndex:
         self.device = self.shard.device
         self._bufs = {}
         self.total_rows = 0
+        self.uncertain_total = 0   # queries returned uncertified after the whole escalation ladder (this rank's count)
+        self.digits_option = 0     # the caller's SZG_OPT_DIGITS / SZG_OPT_MIN_CANDIDATE_MODE (set them through set_options)
+        self.min_mode_option = -1
+
+    def set_options(self, digits: int = 0, min_candidate_mode: int = -1):
+        self.digits_option, self.min_mode_option = digits, min_candidate_mode
+        self.shard.index.set_option(_capi.OPT_DIGITS, digits)
+        self.shard.index.set_option(_capi.OPT_MIN_CANDIDATE_MODE, min_candidate_mode)
 
     # -- ingest -------------------------------------------------------------------------------
     def fill_synthetic(self, seed: int, nrows: int):
@@ -155,20 +163,32 @@ class ShardedIndex:
             torch.cuda.current_stream(self.device).synchronize()
         ids, dd, n = unpack_record(h_out.numpy(), nq, k)
         unc = unpack_flags(h_out.numpy(), nq, k) & 1
-        if unc.any() and isinstance(self.shard, CudaShard):
-            # a rank could not certify its local candidate set with the fast surrogate: those queries are
-            # re-run through the escalating host call on every rank and merged again (rare; collective)
-            self.shard.index.set_option(_capi.OPT_DIGITS, 3)
+        self.uncertain_total = getattr(self, "uncertain_total", 0)
+        if unc.any() and isinstance(self.shard, CudaShard) and not (flags & _capi.F_NO_FP64_VERIFY):
+            # Some rank could not certify its local candidate set with the fast surrogate.  The merged flags are the OR over
+            # the ranks, so every rank sees the same set and walks the same ladder as the single-device host call
+            # (collect_and_escalate): the precise 3-digit surrogate first, then candidate sets of 64, 128, 256 rows; what is
+            # still uncertified after that is counted and returned as it is.  The handle's options are restored afterwards.
+            ix = self.shard.index
+            sel = np.nonzero(unc)[0]
+            ladder = [(3, -1), (3, 1), (3, 2), (3, 3)]  # (digits, minimum candidate mode)
             try:
-                sel = np.nonzero(unc)[0]
-                out2 = self.search_topk_dev(tq[torch.from_numpy(sel).to(self.device)].contiguous(), k, mask_id, flags)
-                h2 = self._buffers(len(sel), k)[3]
-                h2.copy_(out2, non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
-                i2, d2, n2 = unpack_record(h2.numpy(), len(sel), k)
-                ids[sel], dd[sel], n[sel] = i2, d2, n2
+                for digits, mode in ladder:
+                    if sel.size == 0:
+                        break
+                    ix.set_option(_capi.OPT_DIGITS, digits)
+                    ix.set_option(_capi.OPT_MIN_CANDIDATE_MODE, mode)
+                    out2 = self.search_topk_dev(tq[torch.from_numpy(sel).to(self.device)].contiguous(), k, mask_id, flags)
+                    h2 = self._buffers(len(sel), k)[3]
+                    h2.copy_(out2, non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    i2, d2, n2 = unpack_record(h2.numpy(), len(sel), k)
+                    ids[sel], dd[sel], n[sel] = i2, d2, n2
+                    sel = sel[(unpack_flags(h2.numpy(), len(sel), k) & 1).astype(bool)]
             finally:
-                self.shard.index.set_option(_capi.OPT_DIGITS, 0)
+                ix.set_option(_capi.OPT_DIGITS, self.digits_option)
+                ix.set_option(_capi.OPT_MIN_CANDIDATE_MODE, self.min_mode_option)
+            self.uncertain_total += int(sel.size)
         return ids, dd, n
 
     def close(self):

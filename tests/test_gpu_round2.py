@@ -223,8 +223,8 @@ def test_radius_ties_are_ordered_by_lexicographic_id():
     q = o.synth_queries(4, 0, 1, d)[0]
     with szg.Index(d, 8, szg.EUCLIDEAN) as ix:
         ix.upsert(ids, codes)
-        ri, rd, _ = o.search_exact(codes, ids, d, 8, szg.EUCLIDEAN, q, radius=1.2)
-        gi, gd, _ = ix.search_radius(q, 1.2)
+        ri, rd, _ = o.search_exact(codes, ids, d, 8, szg.EUCLIDEAN, q, radius=2.3)
+        gi, gd, _ = ix.search_radius(q, 2.3)
         assert gi.size == ri.size and gi.size > 200
         assert np.array_equal(gd, rd)
         # within a tie group the oracle's heap drain is not the scan order; the device orders ties by lexicographic id

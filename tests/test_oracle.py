@@ -219,3 +219,24 @@ def test_go_math_restatement_against_libm():
     finally:
         o.libm_acos_mode(False)
     assert abs(d_go - d_libm) <= 4 * math.ulp(d_go)
+
+
+def test_faithful_getdocument_variant_reads_the_same_records():
+    """The faithful CPU variant (decimal-string key -> index -> parseSpan -> CRC-32 over the span -> decode with
+    an allocation per record, collection.go:470-484 / spanfile.go:730-849) must find every record the lean variant reads."""
+    import zlib
+    assert o.crc32(b"123456789") == 0xCBF43926
+    blob = bytes(range(256)) * 37 + b"tail"
+    assert o.crc32(blob) == zlib.crc32(blob)
+    for bits, dims in ((8, 96), (4, 33), (64, 5)):
+        n = 3000
+        codes = o.synth_rows(9, 0, n, dims, bits)
+        ids = np.arange(n, dtype=np.uint64) * 7 + 3
+        sp = o.Spans(codes, ids)
+        q = o.synth_queries(10, 0, 1, dims)[0]
+        for kw in (dict(k=10), dict(radius=0.49 if bits != 4 else 4.0)):
+            metric = o.COSINE if bits != 4 else o.EUCLIDEAN
+            a = o.search_exact(codes, ids, dims, bits, metric, q, **kw)
+            b = o.search_exact(codes, ids, dims, bits, metric, q, spans=sp, **kw)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1], equal_nan=True) and a[2] == b[2] == 100.0
+        sp.close()
