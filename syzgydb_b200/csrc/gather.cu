@@ -19,23 +19,25 @@ namespace {
 
 constexpr size_t kGatherStageBytes = 64 * 1024;
 
-template <int QT, int NT>
+constexpr int kGatherThreads = 256; // all of them fetch; thread r < KP runs candidate r's chain
+
+template <int QT, int KP>
 __device__ __forceinline__ void score_batch(const uint4 *codes, const double *lut, uint32_t C, uint32_t dims, uint32_t metric,
                                             const double *q, const uint32_t *s_slot, unsigned char *stage, double *s_out, int tid) {
-    if (metric == COSINE) exact_staged<QT, COSINE, NT>(codes, lut, C, dims, q, s_slot, NT, stage, kGatherStageBytes, s_out, tid);
-    else exact_staged<QT, EUCLID, NT>(codes, lut, C, dims, q, s_slot, NT, stage, kGatherStageBytes, s_out, tid);
+    if (metric == COSINE) exact_staged<QT, COSINE, kGatherThreads>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+    else exact_staged<QT, EUCLID, kGatherThreads>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
 }
 
-// CTA b scores candidates [b NT, b NT + NT) of the flat candidate array; where that range crosses a list boundary the
+// CTA b scores candidates [b KP, b KP + KP) of the flat candidate array; where that range crosses a list boundary the
 // pieces are scored one after the other, each against its own query.
-template <int QT, int NT>
-__global__ void __launch_bounds__(NT) rescore_kernel(const RescoreArgs a) {
+template <int QT, int KP>
+__global__ void __launch_bounds__(kGatherThreads) rescore_kernel(const RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char stage[];
-    __shared__ uint32_t s_slot[NT];
-    __shared__ double s_out[NT];
+    __shared__ uint32_t s_slot[KP];
+    __shared__ double s_out[KP];
     const int tid = threadIdx.x;
-    uint32_t base = blockIdx.x * NT;
-    const uint32_t end = min(base + (uint32_t)NT, a.m);
+    uint32_t base = blockIdx.x * KP;
+    const uint32_t end = min(base + (uint32_t)KP, a.m);
     // the list that holds candidate `base`: the last l with list_off[l] <= base
     uint32_t l = 0;
     if (a.list_off) {
@@ -52,9 +54,9 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const RescoreArgs a) {
             const uint32_t n = lend - base;
             const uint32_t slot = (uint32_t)tid < n ? a.slots[base + tid] : 0xFFFFFFFFu;
             __syncthreads(); // the previous piece's s_out / s_slot readers are done
-            s_slot[tid] = slot;
+            if (tid < KP) s_slot[tid] = slot;
             __syncthreads();
-            score_batch<QT, NT>(a.codes, a.lut, a.C, a.dims, a.metric, a.q + (size_t)l * a.dims, s_slot, stage, s_out, tid);
+            score_batch<QT, KP>(a.codes, a.lut, a.C, a.dims, a.metric, a.q + (size_t)l * a.dims, s_slot, stage, s_out, tid);
             if ((uint32_t)tid < n) {
                 a.out_dist[base + tid] = slot == 0xFFFFFFFFu ? -1.0 /* SZG_MISSING_DISTANCE */ : s_out[tid];
                 if (a.out_ids) a.out_ids[base + tid] = slot == 0xFFFFFFFFu ? 0ull : a.ids[slot];
@@ -65,19 +67,19 @@ __global__ void __launch_bounds__(NT) rescore_kernel(const RescoreArgs a) {
     }
 }
 
-template <int QT, int NT>
-__global__ void __launch_bounds__(NT) radius_exact_kernel(const RadiusFinishArgs a) {
+template <int QT, int KP>
+__global__ void __launch_bounds__(kGatherThreads) radius_exact_kernel(const RadiusFinishArgs a) {
     extern __shared__ __align__(16) unsigned char stage[];
-    __shared__ uint32_t s_slot[NT];
-    __shared__ double s_out[NT];
+    __shared__ uint32_t s_slot[KP];
+    __shared__ double s_out[KP];
     const int tid = threadIdx.x;
     const uint32_t m = min(*a.count_ptr, a.cap);
-    const uint32_t base = blockIdx.x * NT;
+    const uint32_t base = blockIdx.x * KP;
     if (base >= m) return;
-    const uint32_t n = min((uint32_t)NT, m - base);
-    s_slot[tid] = (uint32_t)tid < n ? a.slots[base + tid] : 0xFFFFFFFFu;
+    const uint32_t n = min((uint32_t)KP, m - base);
+    if (tid < KP) s_slot[tid] = (uint32_t)tid < n ? a.slots[base + tid] : 0xFFFFFFFFu;
     __syncthreads();
-    score_batch<QT, NT>(a.codes, a.lut, a.C, a.dims, a.metric, a.q, s_slot, stage, s_out, tid);
+    score_batch<QT, KP>(a.codes, a.lut, a.C, a.dims, a.metric, a.q, s_slot, stage, s_out, tid);
     if ((uint32_t)tid < n) {
         const double d = s_out[tid];
         if (d <= a.radius) { // inclusive (collection.go:598); NaN fails
@@ -170,13 +172,13 @@ __global__ void radius_pad_kernel(unsigned long long *keys, uint32_t m, uint32_t
 }
 
 template <int NT>
-cudaError_t rescore_nt(const RescoreArgs &a, cudaStream_t st) {
+cudaError_t rescore_nt(const RescoreArgs &a, cudaStream_t st) { // NT = candidates per CTA
     const unsigned grid = (a.m + NT - 1) / NT;
     cudaError_t e = cudaSuccess;
 #define SZG_RS(QT)                                                                                                          \
     do {                                                                                                                    \
         e = cudaFuncSetAttribute(rescore_kernel<QT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherStageBytes); \
-        if (e == cudaSuccess) rescore_kernel<QT, NT><<<grid, NT, kGatherStageBytes, st>>>(a);                               \
+        if (e == cudaSuccess) rescore_kernel<QT, NT><<<grid, kGatherThreads, kGatherStageBytes, st>>>(a);                               \
     } while (0)
     switch (a.qt) {
     case Q4: SZG_RS(Q4); break;
@@ -205,7 +207,7 @@ cudaError_t launch_radius_finish(const RadiusFinishArgs &a, cudaStream_t st) {
 #define SZG_RX(QT)                                                                                                           \
     do {                                                                                                                     \
         e = cudaFuncSetAttribute(radius_exact_kernel<QT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherStageBytes); \
-        if (e == cudaSuccess) radius_exact_kernel<QT, NT><<<grid, NT, kGatherStageBytes, st>>>(a);                           \
+        if (e == cudaSuccess) radius_exact_kernel<QT, NT><<<grid, kGatherThreads, kGatherStageBytes, st>>>(a);                           \
     } while (0)
     switch (a.qt) {
     case Q4: SZG_RX(Q4); break;

@@ -494,10 +494,28 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     for (uint32_t c0 = 0; c0 < C; c0 += SC) {
         const uint32_t nc = min(SC, C - c0);
         __syncthreads(); // previous slab fully consumed (and the table written)
-        for (uint32_t idx = tid; idx < (uint32_t)Kp * nc; idx += NT) {
-            const uint32_t r = idx / nc, c = idx % nc;
-            const uint32_t slot = s_slot[r];
-            if (slot != 0xFFFFFFFFu) s_codes[(size_t)r * (SC + 1) + c] = __ldg(codes + chunk_at<QT>(slot, C, c0 + c));
+        // gathered rows: every load is a DRAM round trip of its own, so a thread keeps 8 of them in flight
+        constexpr int PF = 8;
+        const uint32_t total = (uint32_t)Kp * nc;
+        for (uint32_t idx0 = tid; idx0 < total; idx0 += NT * PF) {
+            uint4 v[PF];
+            uint32_t at[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const uint32_t idx = idx0 + (uint32_t)u * NT;
+                at[u] = 0xFFFFFFFFu;
+                if (idx < total) {
+                    const uint32_t r = idx / nc, c = idx - r * nc;
+                    const uint32_t slot = s_slot[r];
+                    if (slot != 0xFFFFFFFFu) {
+                        v[u] = __ldg(codes + chunk_at<QT>(slot, C, c0 + c));
+                        at[u] = r * (SC + 1) + c;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (at[u] != 0xFFFFFFFFu) s_codes[at[u]] = v[u];
         }
         for (uint32_t e = tid; e < nc * EPC; e += NT) {
             const uint32_t i = c0 * EPC + e;

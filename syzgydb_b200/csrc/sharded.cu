@@ -530,7 +530,7 @@ int sharded_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32
     };
     int mode0 = 0, nd0 = 0;
     if ((rc = run(w0->d_q.p, nq, 0, 0, prefer_batch, &mode0, &nd0))) return rc;
-    for (auto sh : S->shards) drain_timing(sh, W->ws[&sh - &S->shards[0]]);
+    for (uint32_t g = 0; g < S->G(); ++g) drain_timing(S->shards[g], W->ws[g]);
     memcpy(out_ids, W->h_out.p, on * 8);
     memcpy(out_dist, W->h_out.p + on * 8, on * 8);
     memcpy(out_n, W->h_out.p + on * 16, (size_t)nq * 4);

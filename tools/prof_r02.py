@@ -1,0 +1,43 @@
+"""Small drivers for the round-2 ncu captures (one kernel each; see profiles/README.md):
+   python tools/prof_r02.py single   -- 1 query per call on 10M x 768 8-bit (scan_small + finalize)
+   python tools/prof_r02.py batch32  -- 32 queries per call (batch_kernel, the headline launch)
+   python tools/prof_r02.py rescore  -- 200 k gathered fp64 rows (rescore_kernel) and 200-candidate calls
+   python tools/prof_r02.py radius   -- cfg3 radius search"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import syzgydb_b200 as szg  # noqa: E402
+from syzgydb_b200 import _capi  # noqa: E402
+
+mode = sys.argv[1]
+rows = int(sys.argv[2]) if len(sys.argv) > 2 else None
+rng = np.random.default_rng(1)
+if mode in ("single", "batch32"):
+    n = rows or 10_000_000
+    with szg.Index(768, 8, szg.COSINE) as ix:
+        ix.fill_synthetic(0x5A590004, 0, n)
+        ix.set_option(_capi.OPT_GRAPHS, 0)
+        ix.set_option(_capi.OPT_COMBINE, 0)
+        nq = 1 if mode == "single" else 32
+        for _ in range(4):
+            ix.search_topk(rng.uniform(-1, 1, size=(nq, 768)), 10)
+elif mode == "rescore":
+    n = rows or 1_000_000
+    with szg.Index(384, 64, szg.COSINE) as ix:
+        ix.fill_synthetic(0x5A590003, 0, n)
+        q = rng.uniform(-1, 1, size=384)
+        ids = rng.integers(0, n, size=200_000).astype(np.uint64)
+        for _ in range(3):
+            ix.rescore(q, ids)
+        for _ in range(3):
+            ix.rescore(q, ids[:200])
+elif mode == "radius":
+    n = rows or 1_000_000
+    with szg.Index(384, 64, szg.COSINE) as ix:
+        ix.fill_synthetic(0x5A590003, 0, n)
+        for _ in range(3):
+            ix.search_radius(rng.uniform(-1, 1, size=384), 0.46)
+print("ok")
