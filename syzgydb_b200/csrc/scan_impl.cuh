@@ -462,14 +462,39 @@ struct Scorer<F64, ND> {
 constexpr int kFinalizeThreads = 512;
 constexpr size_t kFinalizeStageBytes = 64 * 1024; // staging area of the fp64 re-score
 
-// fp64 distances of up to NT candidates (s_slot[0 .. Kp), 0xFFFFFFFF = none) to the query q, in the reference's operation
-// order (decodeVector + dequantize collection.go:768-794 / quantization.go:25-36, euclideanDistance 812-819, angularDistance
-// 821-832: sequential over the dimensions, un-fused multiply and add), with the operands staged through shared memory slab
-// by slab: the NT threads fetch the candidates' chunks together (one memory round trip per slab, and -- float rows, whose
-// chunks are grouped by 8 -- whole 128-byte lines per row), then thread r runs the sequential chain of candidate r out of
-// shared memory.  dequantize: 4/8-bit through a shared copy of the host-built table, 16-bit with the same three IEEE
-// operations ((v / maxInt) * 2 - 1, quantization.go:34-35).  Used by finalize_kernel (the survivors of a top-k scan),
-// rescore_kernel (candidate lists of the LSH index) and radius_exact_kernel.  s_out[r] = distance (NaN possible: Acos).
+// fp64 distances of up to NT / 2 candidates (s_slot[0 .. Kp), 0xFFFFFFFF = none) to the query q, bit for bit what the
+// reference computes: decodeVector + dequantize (collection.go:768-794, quantization.go:25-36), then euclideanDistance
+// (812-819) or angularDistance (821-832) -- sequential over the dimensions, un-fused multiply and add.  Organised so that
+// only what MUST be sequential is:
+//   fetch     the NT threads gather the candidates' chunks slab by slab into shared memory, 8 loads in flight per thread
+//             (float rows keep their chunks in groups of 8: whole 128-byte lines per row);
+//   products  every rounded product of the reference's loop body -- q_i x_i and x_i x_i (cosine), (q_i - x_i)^2 (euclid),
+//             q_i q_i once per slab -- is independent of the running sums, so all threads compute them in parallel
+//             (__dmul_rn / __dsub_rn: the same IEEE operations, never contracted);
+//   chains    one thread per running sum (dot and m2 of a candidate; m1 = sum q_i^2 rides with candidate 0's) adds the
+//             products in dimension order with __dadd_rn: a pure dependent-add chain out of shared memory, which is the
+//             irreducible critical path (d adds).
+// dequantize: 4/8-bit through a shared copy of the host-built table, 16-bit with the same three IEEE operations
+// ((v / maxInt) * 2 - 1, quantization.go:34-35).  Used by finalize_kernel (the survivors of a top-k scan), rescore_kernel
+// (candidate lists of the LSH index) and radius_exact_kernel.  s_out[r] = distance (NaN possible: math.Acos of a ratio > 1).
+template <int QT>
+__device__ __forceinline__ double staged_element(const uint4 *row, uint32_t e, const double *s_lut) {
+    if (QT == Q4) {
+        const uint32_t byte = reinterpret_cast<const unsigned char *>(row)[e >> 1];
+        return s_lut[(e & 1u) ? (byte & 0x0Fu) : (byte >> 4)]; // even index: high nibble (collection.go:774-779)
+    } else if (QT == Q8) {
+        return s_lut[reinterpret_cast<const unsigned char *>(row)[e]];
+    } else if (QT == Q16) {
+        const uint32_t u = (uint32_t)reinterpret_cast<const unsigned short *>(row)[e] ^ 0x8000u; // stored centred
+        return __dsub_rn(__dmul_rn(__ddiv_rn((double)u, 65535.0), 2.0), 1.0);
+    } else if (QT == F32) {
+        return (double)reinterpret_cast<const float *>(row)[e]; // widened, quantization.go:27-28
+    } else {
+        return reinterpret_cast<const double *>(row)[e];
+    }
+}
+
+
 template <int QT, int METRIC, int NT>
 __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__restrict__ lut, uint32_t C, uint32_t dims,
                              const double *__restrict__ q, const uint32_t *s_slot, int Kp, unsigned char *stage,
@@ -477,20 +502,33 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     constexpr int EPC = QT == Q4 ? 32 : QT == Q8 ? 16 : QT == Q16 ? 8 : QT == F32 ? 4 : 2;
     constexpr int LUTN = QT == Q4 ? 16 : QT == Q8 ? 256 : 0;
     constexpr uint32_t GR = QT >= F32 ? (uint32_t)kGroupChunks : 1u; // slabs of float rows hold whole chunk groups
+    constexpr int NA = METRIC == COSINE ? 2 : 1;                       // running sums per candidate
     double *s_lut = reinterpret_cast<double *>(stage);
-    unsigned char *body = stage + LUTN * sizeof(double);
-    const size_t budget = stage_bytes - LUTN * sizeof(double);
+    // products: [Kp * NA][ESP] + (cosine) q_i^2 [ES]; ES dimensions per round, rows ESP = ES | 1 doubles apart so that the
+    // chain threads (one row each) spread over the banks.  Half of a 64 KB stage, a quarter for the largest candidate sets.
+    double *s_prod = reinterpret_cast<double *>(stage + LUTN * sizeof(double));
+    const size_t prod_bytes = Kp > 128 ? 16 * 1024 : 32 * 1024;
+    uint32_t ES = (uint32_t)(prod_bytes / 8 / ((size_t)Kp * NA + 1));
+    ES = ES > 49 ? 48 : (ES > 1 ? ES - 1 : 1); // 48: leaves a whole 768-byte row per candidate to the slab of a 32-candidate set
+    const uint32_t ESP = ES | 1u;
+    double *s_pq = s_prod + (size_t)Kp * NA * ESP;
+    unsigned char *body = reinterpret_cast<unsigned char *>(s_pq + ((ES + 1) & ~1u));
+    const size_t budget = stage_bytes - (size_t)(body - stage);
     // per chunk: Kp uint4 of codes + EPC doubles of the query; rows padded by one uint4 against bank conflicts
     uint32_t SC = (uint32_t)((budget - (size_t)Kp * 16) / ((size_t)Kp * 16 + EPC * 8));
     if (SC > C) SC = C;
     SC = SC / GR * GR;
-    if (SC < GR) SC = GR; // callers size the stage so that one group of Kp rows fits
+    if (SC < GR) SC = GR;
     uint4 *s_codes = reinterpret_cast<uint4 *>(body);
     double *s_q = reinterpret_cast<double *>(body + (size_t)Kp * (SC + 1) * 16);
     for (int i = tid; i < LUTN; i += NT) s_lut[i] = lut[i];
 
-    const bool mine = tid < Kp && s_slot[tid < Kp ? tid : 0] != 0xFFFFFFFFu;
-    ExactAcc acc = {0.0, 0.0, 0.0, 0.0};
+    // chain t < Kp * NA: candidate t / NA, running sum t % NA (cosine: 0 = dot, 1 = m2; chain 1 also carries m1)
+    const bool chain = tid < Kp * NA;
+    const int cr = tid / NA, ca = tid - cr * NA;
+    const bool live = chain && s_slot[chain ? cr : 0] != 0xFFFFFFFFu;
+    double acc = 0.0, m1 = 0.0;
+    const bool has_m1 = METRIC == COSINE && tid == 1;
     for (uint32_t c0 = 0; c0 < C; c0 += SC) {
         const uint32_t nc = min(SC, C - c0);
         __syncthreads(); // previous slab fully consumed (and the table written)
@@ -522,69 +560,63 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
             s_q[e] = i < dims ? q[i] : 0.0;
         }
         __syncthreads();
-        if (mine) {
-            const uint4 *row = s_codes + (size_t)tid * (SC + 1);
-            uint32_t i = c0 * EPC;
-            for (uint32_t c = 0; c < nc && i < dims; ++c) {
-                const uint4 v = row[c];
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                const double *qq = s_q + (size_t)c * EPC;
-                int e = 0;
-                if (QT == Q4) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const uint32_t byte = (w[k] >> (8 * b)) & 0xFF;
-                            if (i < dims) exact_step<METRIC>(acc, qq[e], s_lut[byte >> 4]);
-                            ++i; ++e;
-                            if (i < dims) exact_step<METRIC>(acc, qq[e], s_lut[byte & 0x0F]);
-                            ++i; ++e;
-                        }
-                } else if (QT == Q8) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            if (i < dims) exact_step<METRIC>(acc, qq[e], s_lut[(w[k] >> (8 * b)) & 0xFF]);
-                            ++i; ++e;
-                        }
-                } else if (QT == Q16) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int hlf = 0; hlf < 2; ++hlf) {
-                            const uint32_t u = ((w[k] >> (16 * hlf)) & 0xFFFF) ^ 0x8000u; // stored centred
-                            const double x = __dsub_rn(__dmul_rn(__ddiv_rn((double)u, 65535.0), 2.0), 1.0);
-                            if (i < dims) exact_step<METRIC>(acc, qq[e], x);
-                            ++i; ++e;
-                        }
-                } else if (QT == F32) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (i < dims) exact_step<METRIC>(acc, qq[e], (double)__uint_as_float(w[k]));
-                        ++i; ++e;
-                    }
+        const uint32_t i_slab = c0 * EPC;
+        if (i_slab >= dims) break; // padding chunks only (uniform)
+        const uint32_t ne_slab = min(nc * (uint32_t)EPC, dims - i_slab); // real dimensions in this slab
+        for (uint32_t e0 = 0; e0 < ne_slab; e0 += ES) {
+            const uint32_t ne = min(ES, ne_slab - e0);
+            // ---- products (all threads)
+            for (uint32_t idx = tid; idx < (uint32_t)Kp * ne; idx += NT) {
+                const uint32_t r = idx / ne, e = idx - r * ne;
+                if (s_slot[r] == 0xFFFFFFFFu) continue;
+                const double x = staged_element<QT>(s_codes + (size_t)r * (SC + 1), e0 + e, s_lut);
+                const double qi = s_q[e0 + e];
+                if (METRIC == COSINE) {
+                    s_prod[((size_t)r * 2 + 0) * ESP + e] = __dmul_rn(qi, x); // dot += query[i] * vec[i]   (collection.go:824)
+                    s_prod[((size_t)r * 2 + 1) * ESP + e] = __dmul_rn(x, x);  // m2 += vec[i] * vec[i]     (826)
                 } else {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (i < dims) exact_step<METRIC>(acc, qq[e], __hiloint2double((int)w[2 * k + 1], (int)w[2 * k]));
-                        ++i; ++e;
-                    }
+                    const double diff = __dsub_rn(qi, x);                     // diff := query[i] - vec[i]  (815)
+                    s_prod[(size_t)r * ESP + e] = __dmul_rn(diff, diff);      // sum += diff * diff         (816)
                 }
             }
+            if (METRIC == COSINE)
+                for (uint32_t e = tid; e < ne; e += NT) s_pq[e] = __dmul_rn(s_q[e0 + e], s_q[e0 + e]); // m1 += query[i] * query[i] (825)
+            __syncthreads();
+            // ---- chains (one thread per running sum), in dimension order
+            if (live) {
+                const double *p = s_prod + (size_t)tid * ESP;
+                if (has_m1) {
+#pragma unroll 8
+                    for (uint32_t e = 0; e < ne; ++e) {
+                        acc = __dadd_rn(acc, p[e]);
+                        m1 = __dadd_rn(m1, s_pq[e]);
+                    }
+                } else {
+#pragma unroll 8
+                    for (uint32_t e = 0; e < ne; ++e) acc = __dadd_rn(acc, p[e]);
+                }
+            } else if (has_m1) { // candidate 0 is missing: m1 is still needed by the others
+                for (uint32_t e = 0; e < ne; ++e) m1 = __dadd_rn(m1, s_pq[e]);
+            }
+            __syncthreads();
         }
     }
-    if (mine) {
+    // ---- the running sums meet: s_prod is free now
+    __syncthreads();
+    if (chain) s_prod[tid] = acc;
+    if (has_m1) s_pq[0] = m1;
+    __syncthreads();
+    if (tid < Kp && s_slot[tid] != 0xFFFFFFFFu) {
         double d;
         if (METRIC == COSINE) {
-            if (acc.m1 == 0.0 || acc.m2 == 0.0) d = 1.0; // collection.go:828-830
+            const double dot = s_prod[2 * tid], m2 = s_prod[2 * tid + 1], mm1 = s_pq[0];
+            if (mm1 == 0.0 || m2 == 0.0) d = 1.0; // collection.go:828-830
             else {
-                const double r = __ddiv_rn(acc.dot, __dmul_rn(__dsqrt_rn(acc.m1), __dsqrt_rn(acc.m2)));
+                const double r = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(mm1), __dsqrt_rn(m2)));
                 d = __ddiv_rn(go_acos(r), 3.141592653589793); // math.Acos(r > 1) = NaN
             }
         } else {
-            d = __dsqrt_rn(acc.sum);
+            d = __dsqrt_rn(s_prod[tid]);
         }
         s_out[tid] = d;
     }

@@ -29,6 +29,7 @@ struct ShardWs { // one in-flight sharded search
     PinBuf<unsigned char> h_out;
     DevBuf<double> d_q2;             // root: queries of an escalation pass
     cudaEvent_t ev_start = nullptr;
+    std::vector<cudaEvent_t> ev_done; // per shard: its lists are written (used when the merge must not spin, see sharded_pass)
     bool bound = false;              // ws[0] belongs to a caller's stream
 };
 
@@ -52,6 +53,11 @@ struct Sharded {
     std::map<int, std::vector<int>> masks;
     int next_mask = 1;
     unsigned long long wait_timeout_ns = 20ull * 1000 * 1000 * 1000;
+    // The merge kernel may wait in-kernel for the other shards' arrival counters only when every one of them runs on
+    // ANOTHER GPU: kernels that wait on one another as separate launches on ONE GPU are not guaranteed to run at the same
+    // time (B200_PROFILING.md).  With a device listed twice (tests on single-GPU boxes) the root stream waits for the
+    // shards' events instead and the merge launches afterwards.
+    bool spin_merge = true;
 
     uint32_t G() const { return (uint32_t)shards.size(); }
     uint32_t owner(uint64_t id) const {
@@ -107,6 +113,8 @@ void free_shard_ws(Sharded *S, ShardWs *W) {
         if (!W->ws[g] || (g == 0 && W->bound)) continue; // a bound root workspace belongs to the root's dev_ws table
         release_ws(S->shards[g], W->ws[g]);
     }
+    for (uint32_t g = 0; g < W->ev_done.size(); ++g)
+        if (W->ev_done[g]) { DeviceGuard gd(S->devices[g]); cudaEventDestroy(W->ev_done[g]); }
     {
         DeviceGuard gd(S->devices[0]);
         W->d_gather.release(); W->d_done.release(); W->d_out.release(); W->h_out.release(); W->d_q2.release();
@@ -126,6 +134,11 @@ int new_shard_ws(Sharded *S, void *bound_stream, ShardWs **out) {
             rc = ws_for_stream(S->shards[0], bound_stream, &W->ws[0]);
             W->bound = true;
         } else rc = acquire_ws(S->shards[g], &W->ws[g]);
+        if (!rc && !S->spin_merge) {
+            W->ev_done.resize(S->G(), nullptr);
+            cudaError_t e = cudaEventCreateWithFlags(&W->ev_done[g], cudaEventDisableTiming);
+            if (e != cudaSuccess) rc = fail(SZG_ECUDA, "event creation failed: %s", cudaGetErrorString(e));
+        }
     }
     if (!rc) {
         DeviceGuard gd(S->devices[0]);
@@ -168,7 +181,7 @@ int sharded_pass(szg_index *h, ShardWs *W, const double *d_q_root, uint32_t nq, 
         CK(cudaEventRecord(W->ev_start, st0));
     }
     PeerSink sink;
-    sink.done_cnt = W->d_done.p;
+    sink.done_cnt = S->spin_merge ? W->d_done.p : nullptr;
     for (uint32_t g = 0; g < G; ++g) {
         szg_index *sh = S->shards[g];
         DeviceGuard gd(sh->device);
@@ -185,8 +198,11 @@ int sharded_pass(szg_index *h, ShardWs *W, const double *d_q_root, uint32_t nq, 
                                reinterpret_cast<uint32_t *>(r + (size_t)nq * k * 16 + (size_t)nq * 4), &sink, &mode, &nd)))
             return rc;
         if (g == 0) { if (mode_out) *mode_out = mode; if (nd_out) *nd_out = nd; }
+        if (!S->spin_merge && g) CK(cudaEventRecord(W->ev_done[g], ws->main));
     }
     DeviceGuard gd(S->devices[0]);
+    if (!S->spin_merge)
+        for (uint32_t g = 1; g < G; ++g) CK(cudaStreamWaitEvent(st0, W->ev_done[g], 0));
     MergeArgs a;
     memset(&a, 0, sizeof a);
     unsigned char *r0 = W->d_gather.p;
@@ -197,7 +213,7 @@ int sharded_pass(szg_index *h, ShardWs *W, const double *d_q_root, uint32_t nq, 
     a.rank_stride = rec;
     a.G = G; a.nq = nq; a.k = k;
     a.out_ids = d_out_ids; a.out_dist = d_out_dist; a.out_n = d_out_n; a.out_flags = d_out_flags;
-    a.wait_cnt = W->d_done.p; a.wait_target = G; a.wait_timeout_ns = S->wait_timeout_ns; a.err = W->d_done.p + nq;
+    if (S->spin_merge) { a.wait_cnt = W->d_done.p; a.wait_target = G; a.wait_timeout_ns = S->wait_timeout_ns; a.err = W->d_done.p + nq; }
     CK(launch_merge(a, st0));
     h->launches++;
     return SZG_OK;
@@ -244,6 +260,10 @@ int sharded_create(int dim, int quantization, int metric, const int *devices, in
         for (auto sh : S->shards) destroy_single(sh);
         return rc;
     }
+    for (int g = 0; g < ndev; ++g)
+        for (int j = g + 1; j < ndev; ++j)
+            if (devices[g] == devices[j]) S->spin_merge = false;
+    if (const char *e = getenv("SZG_SHARD_SPIN")) S->spin_merge = S->spin_merge && atoi(e) != 0; // 0: event joins (A/B measurements)
     szg_index *s0 = S->shards[0];
     h->dim = s0->dim; h->quant = s0->quant; h->metric = s0->metric; h->device = s0->device; h->qt = s0->qt;
     h->rowbytes = s0->rowbytes; h->C = s0->C; h->maxint = s0->maxint; h->sm_count = s0->sm_count;
