@@ -393,6 +393,8 @@ int szg_get_stats(szg_index *h, szg_stats *out);
                                         crossover: one or two queries are HBM-bound scans, four cost one batched pass) */
 #define SZG_OPT_GRAPHS 11            /* 1 (default): repeated host-buffer top-k call shapes are replayed as one captured
                                         launch sequence (CUDA graph) instead of launch by launch; 0: off */
+#define SZG_OPT_TRACE_BUFFER 12      /* profiling: a device pointer to 8 int64 words that finalize_kernel's first CTA fills with
+                                        clock64() at its phase boundaries (0 = off) */
 int szg_set_option(szg_index *h, int option, int64_t value);
 
 /* Time of the most recent scan launches on this handle, measured with CUDA events on the

@@ -31,6 +31,7 @@ OPT_BATCH_TENSOR = 8
 OPT_COMBINE = 9
 OPT_BATCH_MIN_QUERIES = 10
 OPT_GRAPHS = 11
+OPT_TRACE_BUFFER = 12
 
 # szg_filter_op opcodes (include/syzgy_b200.h SZG_FOP_*)
 (FOP_COL, FOP_NUM, FOP_STR, FOP_BOOL, FOP_NULL, FOP_EQ, FOP_NE, FOP_LT, FOP_LE, FOP_GT, FOP_GE, FOP_AND, FOP_OR, FOP_NOT,

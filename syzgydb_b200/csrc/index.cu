@@ -238,6 +238,7 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
         h->batch_min = (int)value;
         return SZG_OK;
     case SZG_OPT_GRAPHS: h->use_graphs = value != 0; return SZG_OK;
+    case SZG_OPT_TRACE_BUFFER: h->trace = reinterpret_cast<long long *>((uintptr_t)value); return SZG_OK;
     case SZG_OPT_COMBINE: h->combine = value != 0; return SZG_OK;
     case SZG_OPT_DIGITS:
         if (value != 0 && value != 2 && value != 3) return fail(SZG_EINVAL, "digits must be 0 (auto), 2 or 3");

@@ -76,6 +76,7 @@ struct FinalizeArgs {
     double *out_dist;                 // [nq][k]
     uint32_t *out_n;                  // [nq]
     uint32_t *out_flags;              // [nq] bit0: candidate margin below tolerance ("uncertain")
+    long long *trace;                 // optional (SZG_OPT_TRACE_BUFFER): clock64 of CTA 0 at the phase boundaries, 8 words
     uint32_t *done_cnt;               // optional [nq], possibly in a PEER device's memory (sharded search): bumped, system
                                       // scope, once query q's results are written -- the merge kernel on the root device
                                       // waits for it (sharded.cu)
@@ -506,13 +507,18 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     double *s_lut = reinterpret_cast<double *>(stage);
     // products: [Kp * NA][ESP] + (cosine) q_i^2 [ES]; ES dimensions per round, rows ESP = ES | 1 doubles apart so that the
     // chain threads (one row each) spread over the banks.  Half of a 64 KB stage, a quarter for the largest candidate sets.
+    // When the chains occupy at most half of the threads (a 32-candidate set: 2 warps of 16), the other warps compute the
+    // products of round r + 1 into a second buffer WHILE the chain warps add round r: the dependent fp64 adds (~40 cycles
+    // each on this part) are then the only thing on the critical path.
+    const int chainT = (Kp * NA + 31) / 32 * 32; // threads of the warps that run chains
+    const bool overlap = chainT * 2 <= NT;
     double *s_prod = reinterpret_cast<double *>(stage + LUTN * sizeof(double));
     const size_t prod_bytes = Kp > 128 ? 16 * 1024 : 32 * 1024;
-    uint32_t ES = (uint32_t)(prod_bytes / 8 / ((size_t)Kp * NA + 1));
+    uint32_t ES = (uint32_t)(prod_bytes / (overlap ? 2 : 1) / 8 / ((size_t)Kp * NA + 1));
     ES = ES > 49 ? 48 : (ES > 1 ? ES - 1 : 1); // 48: leaves a whole 768-byte row per candidate to the slab of a 32-candidate set
     const uint32_t ESP = ES | 1u;
-    double *s_pq = s_prod + (size_t)Kp * NA * ESP;
-    unsigned char *body = reinterpret_cast<unsigned char *>(s_pq + ((ES + 1) & ~1u));
+    const size_t buf_doubles = (size_t)Kp * NA * ESP + ((ES + 1) & ~1u); // one buffer: the products, then q_i^2
+    unsigned char *body = reinterpret_cast<unsigned char *>(s_prod + buf_doubles * (overlap ? 2 : 1));
     const size_t budget = stage_bytes - (size_t)(body - stage);
     // per chunk: Kp uint4 of codes + EPC doubles of the query; rows padded by one uint4 against bank conflicts
     uint32_t SC = (uint32_t)((budget - (size_t)Kp * 16) / ((size_t)Kp * 16 + EPC * 8));
@@ -563,53 +569,75 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
         const uint32_t i_slab = c0 * EPC;
         if (i_slab >= dims) break; // padding chunks only (uniform)
         const uint32_t ne_slab = min(nc * (uint32_t)EPC, dims - i_slab); // real dimensions in this slab
-        for (uint32_t e0 = 0; e0 < ne_slab; e0 += ES) {
-            const uint32_t ne = min(ES, ne_slab - e0);
-            // ---- products (all threads)
-            for (uint32_t idx = tid; idx < (uint32_t)Kp * ne; idx += NT) {
+        // ---- rounds of ES dimensions: products (parallel), then the chains (one thread per running sum, dimension order)
+        auto produce = [&](uint32_t e0, uint32_t ne, double *buf, uint32_t pt, uint32_t pn) {
+            double *bq = buf + (size_t)Kp * NA * ESP;
+            for (uint32_t idx = pt; idx < (uint32_t)Kp * ne; idx += pn) {
                 const uint32_t r = idx / ne, e = idx - r * ne;
                 if (s_slot[r] == 0xFFFFFFFFu) continue;
                 const double x = staged_element<QT>(s_codes + (size_t)r * (SC + 1), e0 + e, s_lut);
                 const double qi = s_q[e0 + e];
                 if (METRIC == COSINE) {
-                    s_prod[((size_t)r * 2 + 0) * ESP + e] = __dmul_rn(qi, x); // dot += query[i] * vec[i]   (collection.go:824)
-                    s_prod[((size_t)r * 2 + 1) * ESP + e] = __dmul_rn(x, x);  // m2 += vec[i] * vec[i]     (826)
+                    buf[((size_t)r * 2 + 0) * ESP + e] = __dmul_rn(qi, x); // dot += query[i] * vec[i]   (collection.go:824)
+                    buf[((size_t)r * 2 + 1) * ESP + e] = __dmul_rn(x, x);  // m2 += vec[i] * vec[i]     (826)
                 } else {
-                    const double diff = __dsub_rn(qi, x);                     // diff := query[i] - vec[i]  (815)
-                    s_prod[(size_t)r * ESP + e] = __dmul_rn(diff, diff);      // sum += diff * diff         (816)
+                    const double diff = __dsub_rn(qi, x);                   // diff := query[i] - vec[i]  (815)
+                    buf[(size_t)r * ESP + e] = __dmul_rn(diff, diff);       // sum += diff * diff         (816)
                 }
             }
             if (METRIC == COSINE)
-                for (uint32_t e = tid; e < ne; e += NT) s_pq[e] = __dmul_rn(s_q[e0 + e], s_q[e0 + e]); // m1 += query[i] * query[i] (825)
-            __syncthreads();
-            // ---- chains (one thread per running sum), in dimension order
+                for (uint32_t e = pt; e < ne; e += pn) bq[e] = __dmul_rn(s_q[e0 + e], s_q[e0 + e]); // m1 += query[i] * query[i] (825)
+        };
+        auto consume = [&](uint32_t ne, const double *buf) {
+            const double *bq = buf + (size_t)Kp * NA * ESP;
             if (live) {
-                const double *p = s_prod + (size_t)tid * ESP;
+                const double *p = buf + (size_t)tid * ESP;
                 if (has_m1) {
 #pragma unroll 8
                     for (uint32_t e = 0; e < ne; ++e) {
                         acc = __dadd_rn(acc, p[e]);
-                        m1 = __dadd_rn(m1, s_pq[e]);
+                        m1 = __dadd_rn(m1, bq[e]);
                     }
                 } else {
 #pragma unroll 8
                     for (uint32_t e = 0; e < ne; ++e) acc = __dadd_rn(acc, p[e]);
                 }
             } else if (has_m1) { // candidate 0 is missing: m1 is still needed by the others
-                for (uint32_t e = 0; e < ne; ++e) m1 = __dadd_rn(m1, s_pq[e]);
+                for (uint32_t e = 0; e < ne; ++e) m1 = __dadd_rn(m1, bq[e]);
             }
+        };
+        if (!overlap) {
+            for (uint32_t e0 = 0; e0 < ne_slab; e0 += ES) {
+                const uint32_t ne = min(ES, ne_slab - e0);
+                produce(e0, ne, s_prod, (uint32_t)tid, (uint32_t)NT);
+                __syncthreads();
+                consume(ne, s_prod);
+                __syncthreads();
+            }
+        } else {
+            const bool producer = tid >= chainT;
+            const uint32_t pt = (uint32_t)(tid - chainT), pn = (uint32_t)(NT - chainT);
+            if (producer) produce(0, min(ES, ne_slab), s_prod, pt, pn);
             __syncthreads();
+            uint32_t b = 0;
+            for (uint32_t e0 = 0; e0 < ne_slab; e0 += ES, b ^= 1u) {
+                const uint32_t ne = min(ES, ne_slab - e0);
+                if (!producer) consume(ne, s_prod + buf_doubles * b);
+                else if (e0 + ES < ne_slab) produce(e0 + ES, min(ES, ne_slab - e0 - ES), s_prod + buf_doubles * (b ^ 1u), pt, pn);
+                __syncthreads();
+            }
         }
     }
     // ---- the running sums meet: s_prod is free now
     __syncthreads();
+    double *s_m1 = s_prod + buf_doubles - 1;
     if (chain) s_prod[tid] = acc;
-    if (has_m1) s_pq[0] = m1;
+    if (has_m1) *s_m1 = m1;
     __syncthreads();
     if (tid < Kp && s_slot[tid] != 0xFFFFFFFFu) {
         double d;
         if (METRIC == COSINE) {
-            const double dot = s_prod[2 * tid], m2 = s_prod[2 * tid + 1], mm1 = s_pq[0];
+            const double dot = s_prod[2 * tid], m2 = s_prod[2 * tid + 1], mm1 = *s_m1;
             if (mm1 == 0.0 || m2 == 0.0) d = 1.0; // collection.go:828-830
             else {
                 const double r = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(mm1), __dsqrt_rn(m2)));
@@ -633,6 +661,8 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHe
     __shared__ double s_dk;
     __shared__ uint32_t s_slot[32 * kMaxListE];
     if (tid == 0) s_dk = 0.0;
+    unsigned long long id = 0; // fetched now: the load's latency hides behind the exact pass
+    if (tid < Kp && pool[tid] != kNoKey) id = __ldg(a.ids + (uint32_t)pool[tid]);
     if (!(a.flags & 1u)) {
         if (tid < Kp) s_slot[tid] = pool[tid] == kNoKey ? 0xFFFFFFFFu : (uint32_t)pool[tid];
         __syncthreads();
@@ -641,14 +671,12 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHe
         else
             exact_staged<QT, EUCLID, kFinalizeThreads>(a.codes, a.lut, a.C, a.dims, q, s_slot, Kp, stage, kFinalizeStageBytes, s_ex, tid);
     }
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[3] = clock64();
     bool valid = false;
     double d = 0.0;
-    unsigned long long id = 0;
     if (tid < Kp) {
         unsigned long long key = pool[tid];
         if (key != kNoKey) {
-            uint32_t slot = (uint32_t)key;
-            id = a.ids[slot];
             if (a.flags & 1u) d = key_to_distance(a.metric, key_to_float((uint32_t)(key >> 32)));
             else d = s_ex[tid];
             valid = (d == d); // NaN is never returned
@@ -675,6 +703,7 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHe
         if ((uint32_t)rank + 1 == a.k) s_dk = d;
     }
     __syncthreads();
+    if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[4] = clock64();
     if (tid == 0) {
         uint32_t n = (uint32_t)cnt < a.k ? (uint32_t)cnt : a.k;
         *out_n = n;
@@ -714,6 +743,8 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t qi = blockIdx.x;
     const unsigned long long *cand = a.cand + (size_t)qi * a.nlists * Kp;
+    const bool tr = a.trace && qi == 0 && tid == 0;
+    if (tr) a.trace[0] = clock64();
     WarpList<E> list;
     list.init();
     const uint32_t total = a.nlists * Kp;
@@ -725,9 +756,17 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
             v[u] = i < total ? __ldg(cand + i) : kNoKey;
         }
 #pragma unroll
-        for (int u = 0; u < PF; ++u) list.offer(v[u], lane);
+        for (int u = 0; u < PF; ++u) {
+            if (E == 1) {
+                // every 32 keys are one SORTED list of a scan CTA / row range (lane = rank): six merge steps instead of a
+                // sort of the batch
+                if (__ballot_sync(0xffffffffu, v[u] < list.thr)) list.merge_sorted(v[u], lane);
+            } else list.offer(v[u], lane);
+        }
     }
+    if (tr) a.trace[1] = clock64();
     block_merge<E>(list, pool, tid, lane, warp, NW);
+    if (tr) a.trace[2] = clock64();
     double *s_ex = reinterpret_cast<double *>(pool + NW * Kp);
     unsigned long long *s_id = reinterpret_cast<unsigned long long *>(s_ex + Kp);
     unsigned char *stage = reinterpret_cast<unsigned char *>(s_id + Kp);
@@ -735,6 +774,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
                       reinterpret_cast<const PQHeader *>(a.pq + (size_t)qi * a.pq_stride), a.out_ids + (size_t)qi * a.k,
                       a.out_dist + (size_t)qi * a.k, a.out_n + qi, a.out_flags + qi, a.done_cnt ? a.done_cnt + qi : nullptr,
                       pool, Kp, s_ex, s_id, stage, tid);
+    if (tr) a.trace[5] = clock64();
 }
 inline size_t finalize_smem_bytes(int mode) {
     const size_t Kp = 32u << mode;

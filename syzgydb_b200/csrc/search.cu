@@ -92,6 +92,7 @@ static void fill_finalize_args(szg_index *h, FinalizeArgs &f, size_t stride, uin
     f.C = h->C; f.dims = (uint32_t)h->dim; f.metric = (uint32_t)h->metric; f.k = k;
     f.flags = flags & SZG_F_NO_FP64_VERIFY;
     f.done_cnt = sink ? sink->done_cnt : nullptr;
+    f.trace = h->trace;
 }
 
 // run_topk for short rows: the launch is cut in (query, part) items handled by one CTA each (scan_small.cuh)

@@ -82,6 +82,19 @@ __global__ void __launch_bounds__(1024, 1) idp_peak_kernel(int iters, unsigned s
     if (t == 0x12345) *sink = (unsigned)t;
 }
 
+// dependent fp64 add chain of one warp: cycles per DADD = the latency that bounds the exact (reference-order) distance of
+// the survivors of a search: d sequential adds per running sum
+__global__ void dadd_latency_kernel(int n, double x, double *out, long long *cycles) {
+    double acc = x;
+    const long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc = __dadd_rn(acc, x);
+    }
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) { *out = acc; *cycles = t1 - t0; }
+}
+
 template <typename F>
 static float time_ms(F launch, int rounds) {
     cudaEvent_t e0, e1;
@@ -132,6 +145,16 @@ int main() {
         const double lane_ops = (double)sms * 2 * 1024 * iters * 8;
         printf(", \"idp_status\": \"%s\", \"idp4a_lane_gops\": %.1f, \"idp4a_lane_ops_per_clk_per_sm\": %.1f", cudaGetErrorString(e),
                lane_ops / (ms * 1e-3) / 1e9, lane_ops / (ms * 1e-3) / sms / (p.clockRate * 1e3));
+    }
+    {
+        double *dout;
+        long long *dc, hc = 0;
+        cudaMalloc(&dout, 8);
+        cudaMalloc(&dc, 8);
+        dadd_latency_kernel<<<1, 32>>>(4096, 1e-9, dout, dc);
+        dadd_latency_kernel<<<1, 32>>>(4096, 1e-9, dout, dc);
+        cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+        printf(", \"dadd_dependent_latency_cycles\": %.2f", (double)hc / (4096.0 * 16));
     }
     printf("}\n");
     return 0;
