@@ -53,6 +53,8 @@ struct ScanArgs {
     uint32_t qper;              // scan_small_kernel only: queries per work item (1 or 2)
     uint32_t const_queries;     // scan_small_kernel only: the launch's prepared queries go through constant memory
     uint32_t wgroups;           // scan_small_kernel only: warp groups per CTA, each on another query of the same row part (1, 2, 4)
+    uint32_t cta_merge;         // scan_kernel, one query per launch: the warps of a CTA merge their lists before writing
+                                // (one list per CTA instead of one per warp: finalize_kernel reads 16x fewer keys)
     // top-k output: per-warp candidate lists, consumed by finalize_kernel
     unsigned long long *cand;   // [nq][grid warps][32*E]
     // radius outputs
@@ -514,8 +516,12 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     const bool overlap = chainT * 2 <= NT;
     double *s_prod = reinterpret_cast<double *>(stage + LUTN * sizeof(double));
     const size_t prod_bytes = Kp > 128 ? 16 * 1024 : 32 * 1024;
+    // ES = dimensions per round: a power of two <= 32, so that a warp's lanes map to (candidate, dimension) pairs with shifts
     uint32_t ES = (uint32_t)(prod_bytes / (overlap ? 2 : 1) / 8 / ((size_t)Kp * NA + 1));
-    ES = ES > 49 ? 48 : (ES > 1 ? ES - 1 : 1); // 48: leaves a whole 768-byte row per candidate to the slab of a 32-candidate set
+    ES = ES > 1 ? ES - 1 : 1;
+    uint32_t ES_log = 0;
+    while (ES_log < 5 && (2u << ES_log) <= ES) ++ES_log;
+    ES = 1u << ES_log;
     const uint32_t ESP = ES | 1u;
     const size_t buf_doubles = (size_t)Kp * NA * ESP + ((ES + 1) & ~1u); // one buffer: the products, then q_i^2
     unsigned char *body = reinterpret_cast<unsigned char *>(s_prod + buf_doubles * (overlap ? 2 : 1));
@@ -571,10 +577,13 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
         const uint32_t ne_slab = min(nc * (uint32_t)EPC, dims - i_slab); // real dimensions in this slab
         // ---- rounds of ES dimensions: products (parallel), then the chains (one thread per running sum, dimension order)
         auto produce = [&](uint32_t e0, uint32_t ne, double *buf, uint32_t pt, uint32_t pn) {
+            // pt / pn: this thread's index among the pn producing threads (whole warps).  A warp covers 32 / ES candidates
+            // per pass: lane = (candidate offset, dimension)
             double *bq = buf + (size_t)Kp * NA * ESP;
-            for (uint32_t idx = pt; idx < (uint32_t)Kp * ne; idx += pn) {
-                const uint32_t r = idx / ne, e = idx - r * ne;
-                if (s_slot[r] == 0xFFFFFFFFu) continue;
+            const uint32_t e = pt & (ES - 1);
+            const uint32_t cpp = pn >> ES_log; // candidates per pass of all producing threads
+            for (uint32_t r = pt >> ES_log; r < (uint32_t)Kp; r += cpp) {
+                if (e >= ne || s_slot[r] == 0xFFFFFFFFu) continue;
                 const double x = staged_element<QT>(s_codes + (size_t)r * (SC + 1), e0 + e, s_lut);
                 const double qi = s_q[e0 + e];
                 if (METRIC == COSINE) {
@@ -954,6 +963,15 @@ __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanA
         issue(cs);
         __syncwarp(); // meta written by lane 0 is visible to the warp
         cs = (cs + 1 == S) ? 0 : cs + 1;
+    }
+    if (MODE != MODE_RADIUS && a.cta_merge) {
+        // a.nq == 1: every warp of the CTA ends here.  The rings are idle now; their memory holds the merge pool.
+        __syncthreads();
+        unsigned long long *pool = reinterpret_cast<unsigned long long *>(smem);
+        block_merge<E>(list, pool, tid, lane, warp, nwarps);
+        unsigned long long *dst = a.cand + (size_t)blockIdx.x * Kp;
+        for (int i = tid; i < Kp; i += (int)blockDim.x) dst[i] = pool[i];
+        return;
     }
     while (cq < a.nq) { flush(); ++cq; } // remaining queries (also the ones this warp had no block for)
 }

@@ -193,7 +193,9 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
     const bool small = small_ok && mode == 0 && !h->scan_geometry_set && scan_small_supported(h->qt, h->C) && h->C <= small_maxc &&
                        h->nslots >= 32;
     if (small) return run_topk_small(h, ws, d_q, nq, k, mask, flags, nd, d_out_ids, d_out_dist, d_out_n, d_out_flags, sink);
-    const size_t nlists = (size_t)grid * plan.warps;
+    // one query per launch: the warps of a CTA merge their lists in the (idle) ring memory before writing them
+    const bool cta_merge = nq == 1 && plan.smem >= (size_t)plan.warps * Kp * 8 && (plan.warps & (plan.warps - 1)) == 0;
+    const size_t nlists = cta_merge ? (size_t)grid : (size_t)grid * plan.warps;
     const uint32_t chunk = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)nq, (size_t)4096, kCandBytes / (nlists * Kp * 8)}));
     if ((rc = ws->d_cand.ensure((size_t)chunk * nlists * Kp))) return rc;
 
@@ -213,6 +215,7 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
     a.Ct = plan.Ct; a.stages = plan.stages; a.pq_smem_off = plan.pq_smem_off;
     a.pq_stride = stride;
     a.cand = ws->d_cand.p;
+    a.cta_merge = cta_merge ? 1u : 0u;
     FinalizeArgs f;
     fill_finalize_args(h, f, stride, k, flags, sink);
     f.cand = ws->d_cand.p;
