@@ -105,6 +105,7 @@ struct __align__(16) QState {
     uint32_t zero;            // zero query
     uint32_t valid;
     uint32_t pub;             // smallest mth-best key this range has published for the query (0xFFFFFFFF = none)
+    uint32_t inserts;         // rows inserted into the list (profiling)
 };
 
 // threshold of the fast test "v > T" such that every key <= thr passes (see the file comment); fp32 arithmetic
@@ -196,6 +197,7 @@ __device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, c
         else key = (ax.y + s.qn2) - nf * s.c_dot2;
         const unsigned long long k64 = make_key64(key, slot0 + col);
         if (k64 < s.thr) {
+            if (lane == 0) ++s.inserts;
             const unsigned long long last = list_insert<E>(wl + j * (32 * E), k64, lane, capm1, mthm1, gmw + (size_t)j * R, &s.pub);
             __syncwarp();
             if (lane == 0) { s.thr = last < s.gbound ? last : s.gbound; s.T = fast_threshold<COS>(s); }
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         s.thr = s.valid ? kNoKey : 0ull;
         s.gbound = kNoKey;
         s.pub = 0xFFFFFFFFu;
+        s.inserts = 0;
         // 16-bit: the header's numc belongs to centred codes (+sum W); the byte planes hold uncentred ones: -65535 sum W
         s.numc = P16 ? -65535ll * (long long)hdr->numc : (long long)hdr->numc;
         s.c_key = (float)hdr->c_key; s.c_dot2 = (float)(2.0 * hdr->c_dot); s.qn2 = (float)hdr->qn2;
@@ -579,6 +582,9 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         };
         auto poll_bounds = [&]() -> bool { return R <= 16 ? poll_plain() : poll_grouped(); };
         bool seeding = R > 1;
+        const bool tr = a.trace && blockIdx.x == 0 && warp == 2 && lane == 0;
+        if (tr) a.trace[0] = clock64();
+        uint32_t npolls = 0;
         for (uint32_t tile = 0;; ++tile) {
             const uint32_t d = P16 ? 0u : (tile & 1u), x = tile % kAuxSlots;
             // side data of the tile (aux pairs, live words): read in place; removed / filtered rows are rejected only
@@ -588,6 +594,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             if (cur == kNoBlock) break;
             if (R > 1 && tile >= 2 && ((tile & (tile - 1)) == 0 || (tile & poll_mask) == 0)) {
                 poll_bounds();
+                ++npolls;
                 T = qs->T;
             }
             const uint32_t capm1 = seeding ? mthm1 : Kp - 1;
@@ -676,11 +683,21 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 __syncwarp();
                 // all ranges of the group are normally co-resident (grid <= SM count) and publish within a tile time; the
                 // bound is an optimisation only, so the wait is bounded (~4 ms) and the range simply goes on without it
-                for (int spin = 0; !poll_bounds() && spin < 20000; ++spin) __nanosleep(200);
+                if (tr) a.trace[1] = clock64();
+                int spin = 0;
+                for (; !poll_bounds() && spin < 20000; ++spin) __nanosleep(200);
+                if (tr) { a.trace[2] = clock64(); a.trace[5] = spin; }
                 T = qs->T;
             }
         }
         __syncwarp();
+        if (tr) {
+            a.trace[3] = clock64();
+            uint32_t ins = 0;
+            for (int j = 0; j < 8; ++j) ins += wq[j].inserts;
+            a.trace[4] = ins;
+            a.trace[6] = npolls;
+        }
         if (seeding && lane < 8 && wq[lane].valid) // a range without live rows: tell the others not to wait for it
             *reinterpret_cast<volatile uint32_t *>(gmw + (size_t)lane * R) = 0xFFFFFFFEu;
         // hand the lists to finalize_kernel: cand[query][row range][Kp]

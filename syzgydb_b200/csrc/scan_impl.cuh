@@ -501,7 +501,8 @@ __device__ __forceinline__ double staged_element(const uint4 *row, uint32_t e, c
 template <int QT, int METRIC, int NT>
 __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__restrict__ lut, uint32_t C, uint32_t dims,
                              const double *__restrict__ q, const uint32_t *s_slot, int Kp, unsigned char *stage,
-                             size_t stage_bytes, double *s_out, int tid) {
+                             size_t stage_bytes, double *s_out, int tid, long long *trace = nullptr) {
+    long long t_chain = 0, t_bar = 0;
     constexpr int EPC = QT == Q4 ? 32 : QT == Q8 ? 16 : QT == Q16 ? 8 : QT == F32 ? 4 : 2;
     constexpr int LUTN = QT == Q4 ? 16 : QT == Q8 ? 256 : 0;
     constexpr uint32_t GR = QT >= F32 ? (uint32_t)kGroupChunks : 1u; // slabs of float rows hold whole chunk groups
@@ -573,6 +574,7 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
         }
         __syncthreads();
         const uint32_t i_slab = c0 * EPC;
+        if (trace && tid == 0 && c0 == 0) trace[6] = clock64();
         if (i_slab >= dims) break; // padding chunks only (uniform)
         const uint32_t ne_slab = min(nc * (uint32_t)EPC, dims - i_slab); // real dimensions in this slab
         // ---- rounds of ES dimensions: products (parallel), then the chains (one thread per running sum, dimension order)
@@ -631,14 +633,18 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
             uint32_t b = 0;
             for (uint32_t e0 = 0; e0 < ne_slab; e0 += ES, b ^= 1u) {
                 const uint32_t ne = min(ES, ne_slab - e0);
+                const long long ta = trace ? clock64() : 0;
                 if (!producer) consume(ne, s_prod + buf_doubles * b);
                 else if (e0 + ES < ne_slab) produce(e0 + ES, min(ES, ne_slab - e0 - ES), s_prod + buf_doubles * (b ^ 1u), pt, pn);
+                const long long tb = trace ? clock64() : 0;
                 __syncthreads();
+                if (trace) { t_chain += tb - ta; t_bar += clock64() - tb; }
             }
         }
     }
     // ---- the running sums meet: s_prod is free now
     __syncthreads();
+    if (trace && tid == 0) trace[7] = (t_chain << 32) | (t_bar & 0xFFFFFFFFll);
     double *s_m1 = s_prod + buf_doubles - 1;
     if (chain) s_prod[tid] = acc;
     if (has_m1) *s_m1 = m1;
@@ -676,9 +682,11 @@ __device__ void finalize_topk(const FinalizeArgs &a, const double *q, const PQHe
         if (tid < Kp) s_slot[tid] = pool[tid] == kNoKey ? 0xFFFFFFFFu : (uint32_t)pool[tid];
         __syncthreads();
         if (a.metric == COSINE)
-            exact_staged<QT, COSINE, kFinalizeThreads>(a.codes, a.lut, a.C, a.dims, q, s_slot, Kp, stage, kFinalizeStageBytes, s_ex, tid);
+            exact_staged<QT, COSINE, kFinalizeThreads>(a.codes, a.lut, a.C, a.dims, q, s_slot, Kp, stage, kFinalizeStageBytes, s_ex, tid,
+                                                       blockIdx.x == 0 ? a.trace : nullptr);
         else
-            exact_staged<QT, EUCLID, kFinalizeThreads>(a.codes, a.lut, a.C, a.dims, q, s_slot, Kp, stage, kFinalizeStageBytes, s_ex, tid);
+            exact_staged<QT, EUCLID, kFinalizeThreads>(a.codes, a.lut, a.C, a.dims, q, s_slot, Kp, stage, kFinalizeStageBytes, s_ex, tid,
+                                                       blockIdx.x == 0 ? a.trace : nullptr);
     }
     if (a.trace && blockIdx.x == 0 && tid == 0) a.trace[3] = clock64();
     bool valid = false;

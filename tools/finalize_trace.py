@@ -24,5 +24,5 @@ for bits, dims, metric in ((8, 768, szg.COSINE), (4, 128, szg.EUCLIDEAN), (64, 3
             ix.search_topk(rng.uniform(-1, 1, size=(nq, dims)), 10)
             torch.cuda.synchronize()
             t = buf.cpu().numpy()
-            out.append([int(t[i + 1] - t[i]) for i in range(5)])
-        print(f"q{bits} d{dims} nq{nq}: cycles [merge lists, block merge, exact_staged, ranking, certify] =", out[-3:])
+            out.append([int(t[i + 1] - t[i]) for i in range(5)] + [int(t[6] - t[2]), int(t[7] >> 32), int(t[7] & 0xFFFFFFFF)])
+        print(f"q{bits} d{dims} nq{nq}: cycles [merge lists, block merge, exact_staged, ranking, certify | fetch+stage, thread0 in chains, thread0 at barriers] =", out[-3:])
