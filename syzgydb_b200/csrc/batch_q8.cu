@@ -213,7 +213,8 @@ template <bool COS, bool FITS, int E, bool P16 = false>
 __device__ __forceinline__ float score16(const uint32_t (&r)[32], const uint32_t (&rl)[32], const float4 (&ax)[8], int numc32, long long numc64,
                                          float T, float c2,
                                          uint32_t colp, const float2 *xaux, const uint32_t *xwords, QState *wq, unsigned long long *wl,
-                                         uint32_t slot0, const float *Tsrc, uint32_t *gmw, uint32_t R, uint32_t mthm1, uint32_t capm1) {
+                                         uint32_t slot0, const float *Tsrc, uint32_t *gmw, uint32_t R, uint32_t mthm1, uint32_t capm1,
+                                         bool seeding = false) {
     float numf[16], v[16];
 #pragma unroll
     for (int rep = 0; rep < 8; ++rep) {
@@ -238,6 +239,24 @@ __device__ __forceinline__ float score16(const uint32_t (&r)[32], const uint32_t
 #pragma unroll
     for (int g4 = 0; g4 < 4; ++g4) m4[g4] = fmaxf(fmaxf(v[4 * g4], v[4 * g4 + 1]), fmaxf(v[4 * g4 + 2], v[4 * g4 + 3]));
     const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])); // fmaxf ignores NaN (dead rows)
+    if (seeding && mthm1 < 8) {
+        // Seeding pass with no threshold yet: all that is wanted from this tile is the key of SOME mth-best row to publish (any
+        // mth rows of the range bound its mth-best key from above).  Without this, T = -inf sends every one of the 64 rows
+        // x 8 queries of the call down the one-pair-at-a-time path (measured: ~100 us per launch, the fixed cost that bent
+        // the multi-GPU curve).  Keep the best pair of each of the query's 4 lanes (the 4 lanes of a query hold 16 rows
+        // each): threshold = the mth-largest of the 4 lane maxima (the smallest when mth > 4).
+        const bool open = T == -INFINITY;
+        const float m0 = mx == mx ? mx : -INFINITY;
+        const float m1 = __shfl_xor_sync(0xffffffffu, m0, 1);
+        const float hi01 = fmaxf(m0, m1), lo01 = fminf(m0, m1);
+        const float hi23 = __shfl_xor_sync(0xffffffffu, hi01, 2), lo23 = __shfl_xor_sync(0xffffffffu, lo01, 2);
+        // the four values of the query, ordered: s0 >= s1 >= s2 >= s3
+        const float s0 = fmaxf(hi01, hi23), s3 = fminf(lo01, lo23);
+        const float mid_a = fminf(hi01, hi23), mid_b = fmaxf(lo01, lo23);
+        const float s1 = fmaxf(mid_a, mid_b), s2 = fminf(mid_a, mid_b);
+        const float pick = mthm1 == 0 ? s0 : mthm1 == 1 ? s1 : mthm1 == 2 ? s2 : s3;
+        if (open && pick > -INFINITY) T = pick - fabsf(pick) * 9.5367431640625e-7f - 1e-30f; // just below: the picked pair passes
+    }
     if (__any_sync(0xffffffffu, mx > T)) {
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) {
@@ -626,8 +645,8 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             };
             const uint32_t slot0 = cur * kTileRows;
             auto score = [&](const uint32_t (&rr)[32], uint32_t part) {
-                if (fits) T = score16<COS, true, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
-                else T = score16<COS, false, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                if (fits) T = score16<COS, true, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
+                else T = score16<COS, false, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
             };
             if (P16) {
                 // high-byte accumulators in buffer 0, low-byte ones in buffer 1: each is drained to registers and released
@@ -650,9 +669,9 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[1]); // low-byte accumulators too
-                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
                 load_ax(1);
-                T = score16<COS, false, E, true>(rc, rd, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1);
+                T = score16<COS, false, E, true>(rc, rd, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
             } else {
             // both halves of this warp's part of the accumulator go to registers first, so the buffer returns to the
             // MMA warp before any scoring (a warp that has rows to insert would otherwise hold it)

@@ -19,7 +19,7 @@ namespace {
 
 constexpr size_t kGatherStageBytes = 64 * 1024;
 
-constexpr int kGatherThreads = 256; // all of them fetch; thread r < KP runs candidate r's chain
+constexpr int kGatherThreads = 288; // all of them fetch; 2 x 128 + 1 of them run the sums of a 128-candidate batch (dot, m2; sum q^2)
 
 template <int QT, int KP>
 __device__ __forceinline__ void score_batch(const uint4 *codes, const double *lut, uint32_t C, uint32_t dims, uint32_t metric,

@@ -513,7 +513,11 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     // When the chains occupy at most half of the threads (a 32-candidate set: 2 warps of 16), the other warps compute the
     // products of round r + 1 into a second buffer WHILE the chain warps add round r: the dependent fp64 adds (~40 cycles
     // each on this part) are then the only thing on the critical path.
-    const int chainT = (Kp * NA + 31) / 32 * 32; // threads of the warps that run chains
+    // chains: thread t < Kp * NA -> candidate t / NA, running sum t % NA; cosine: thread Kp * NA carries m1 = sum q_i^2 (a
+    // thread of its own, in a warp of its own when Kp * NA fills whole warps: no divergence inside the chain warps)
+    const bool m1_own = METRIC == COSINE && Kp * NA < NT; // else (the largest candidate sets) thread 0 carries m1 as a second sum
+    const int nchains = Kp * NA + (m1_own ? 1 : 0);
+    const int chainT = (nchains + 31) / 32 * 32; // threads of the warps that run chains
     const bool overlap = chainT * 2 <= NT;
     double *s_prod = reinterpret_cast<double *>(stage + LUTN * sizeof(double));
     const size_t prod_bytes = Kp > 128 ? 16 * 1024 : 32 * 1024;
@@ -536,12 +540,11 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     double *s_q = reinterpret_cast<double *>(body + (size_t)Kp * (SC + 1) * 16);
     for (int i = tid; i < LUTN; i += NT) s_lut[i] = lut[i];
 
-    // chain t < Kp * NA: candidate t / NA, running sum t % NA (cosine: 0 = dot, 1 = m2; chain 1 also carries m1)
     const bool chain = tid < Kp * NA;
-    const int cr = tid / NA, ca = tid - cr * NA;
+    const int cr = tid / NA;
+    const bool has_m1 = METRIC == COSINE && tid == (m1_own ? Kp * NA : 0);
     const bool live = chain && s_slot[chain ? cr : 0] != 0xFFFFFFFFu;
     double acc = 0.0, m1 = 0.0;
-    const bool has_m1 = METRIC == COSINE && tid == 1;
     for (uint32_t c0 = 0; c0 < C; c0 += SC) {
         const uint32_t nc = min(SC, C - c0);
         __syncthreads(); // previous slab fully consumed (and the table written)
@@ -600,21 +603,27 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
                 for (uint32_t e = pt; e < ne; e += pn) bq[e] = __dmul_rn(s_q[e0 + e], s_q[e0 + e]); // m1 += query[i] * query[i] (825)
         };
         auto consume = [&](uint32_t ne, const double *buf) {
-            const double *bq = buf + (size_t)Kp * NA * ESP;
+            // all products of the round into registers first (independent loads), then the dependent adds: the critical
+            // path is one shared-memory latency plus ne fp64 add latencies
             if (live) {
                 const double *p = buf + (size_t)tid * ESP;
-                if (has_m1) {
-#pragma unroll 8
-                    for (uint32_t e = 0; e < ne; ++e) {
-                        acc = __dadd_rn(acc, p[e]);
-                        m1 = __dadd_rn(m1, bq[e]);
-                    }
-                } else {
-#pragma unroll 8
-                    for (uint32_t e = 0; e < ne; ++e) acc = __dadd_rn(acc, p[e]);
-                }
-            } else if (has_m1) { // candidate 0 is missing: m1 is still needed by the others
-                for (uint32_t e = 0; e < ne; ++e) m1 = __dadd_rn(m1, bq[e]);
+                double v[32];
+#pragma unroll
+                for (uint32_t e = 0; e < 32; ++e)
+                    if (e < ES) v[e] = e < ne ? p[e] : 0.0;
+#pragma unroll
+                for (uint32_t e = 0; e < 32; ++e)
+                    if (e < ne) acc = __dadd_rn(acc, v[e]);
+            }
+            if (has_m1) {
+                const double *p = buf + (size_t)Kp * NA * ESP;
+                double v[32];
+#pragma unroll
+                for (uint32_t e = 0; e < 32; ++e)
+                    if (e < ES) v[e] = e < ne ? p[e] : 0.0;
+#pragma unroll
+                for (uint32_t e = 0; e < 32; ++e)
+                    if (e < ne) m1 = __dadd_rn(m1, v[e]);
             }
         };
         if (!overlap) {
