@@ -281,38 +281,55 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- GPU arm
+IN_FLIGHT = 2  # device-resident steps in flight: consecutive steps go to alternating streams, like requests of concurrent callers
+
+
 class DevRunner:
-    """Device-resident calls of one handle on GPU 0's current torch stream, with reusable output buffers."""
+    """Device-resident calls of one handle on GPU 0, with reusable output buffers.  Steps are issued on IN_FLIGHT alternating
+    streams, so that the merge / exact re-score of one step overlaps the scan of the next (each step's own launches stay
+    ordered on its stream)."""
 
     def __init__(self, ix, torch, dev):
         self.ix, self.torch, self.dev = ix, torch, dev
         self.bufs = {}
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(IN_FLIGHT)]
 
-    def out(self, nq, k):
-        key = (nq, k)
+    def out(self, nq, k, slot=0):
+        key = (nq, k, slot)
         if key not in self.bufs:
             t = self.torch
             self.bufs[key] = (t.zeros((nq, k), dtype=t.int64, device=self.dev), t.zeros((nq, k), dtype=t.float64, device=self.dev),
                               t.zeros(nq, dtype=t.int32, device=self.dev), t.zeros(nq, dtype=t.int32, device=self.dev))
         return self.bufs[key]
 
-    def topk(self, tq, k, batched=False):
+    def topk(self, tq, k, batched=False, slot=0):
         nq = tq.shape[0]
-        oi, od, on, of = self.out(nq, k)
-        st = self.torch.cuda.current_stream(self.dev).cuda_stream
+        oi, od, on, of = self.out(nq, k, slot)
+        st = self.streams[slot].cuda_stream
         fn = self.ix.search_batch_dev if batched else self.ix.search_topk_dev
         fn(tq.data_ptr(), nq, k, oi.data_ptr(), od.data_ptr(), on.data_ptr(), st, d_out_flags=of.data_ptr())
         return oi, od, on, of
 
 
-def timed(torch, dev, fn, n):
+def timed(torch, dev, fn, n, run, in_flight=IN_FLIGHT):
+    """Times n steps fn(i, slot) with CUDA events; steps alternate over `in_flight` of the runner's streams (all of them start
+    after the start event and the end event waits for all of them)."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
     w0 = time.perf_counter()
-    e0.record()
+    cur = torch.cuda.current_stream(dev)
+    e0.record(cur)
+    streams = run.streams[:in_flight]
+    for s in streams:
+        s.wait_event(e0)
     for i in range(n):
-        fn(i)
-    e1.record()
+        fn(i, i % len(streams))
+    for s in streams:
+        if s is not cur:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            cur.wait_event(ev)
+    e1.record(cur)
     torch.cuda.synchronize(dev)
     return e0.elapsed_time(e1), w0, time.perf_counter()
 
@@ -436,20 +453,23 @@ def run_b200(a):
 
     # ---- value: queries resident in HBM; per-launch kernel times from CUDA events inside the library (SZG_OPT_TIMING = 2)
     ix.set_option(_capi.OPT_TIMING, 2)
-    for s in range(a.warmup):
-        run.topk(dq[s], a.k)
+    for s in range(max(a.warmup, IN_FLIGHT)):
+        run.topk(dq[s % total_steps], a.k, slot=s % IN_FLIGHT)
     torch.cuda.synchronize(dev)
     kernel_times()
     st0 = ix.stats()
-    ms, w0, w1 = timed(torch, dev, lambda i: run.topk(dq[a.warmup + i], a.k), a.steps)
+    ms, w0, w1 = timed(torch, dev, lambda i, slot: run.topk(dq[a.warmup + i], a.k, slot=slot), a.steps, run)
     clocks = sampler.window(w0, w1)
+    if clocks.get("sm_mhz") is None:  # the timed region is shorter than the 100 ms sampling interval: the nearest samples
+        clocks = sampler.window(w0 - 0.25, w1 + 0.25)
+        clocks["note"] = "timed region shorter than the sampling interval: samples within +-0.25 s of it; see sustained.clocks"
     scan_ms = kernel_times()
     st1 = ix.stats()
     launches = st1["kernel_launches"] - st0["kernel_launches"]
     tensor_served = st1["batch_queries"] - st0["batch_queries"]
     qps = a.nq * a.steps / (ms / 1e3)
     mean_scan_ms = float(np.mean(scan_ms)) if len(scan_ms) else float("nan")
-    oi, od, on, of = run.out(a.nq, a.k)
+    oi, od, on, of = run.out(a.nq, a.k, (a.steps - 1) % IN_FLIGHT)
     last_ids, last_dist, last_n = oi.cpu().numpy().astype(np.uint64), od.cpu().numpy(), on.cpu().numpy()
     assert (last_n == min(a.k, a.rows)).all() and (np.diff(last_dist, axis=1) >= 0).all(), "bench result check failed"
     uncertified_dev = int((of.cpu().numpy() & 1).sum())
@@ -461,19 +481,36 @@ def run_b200(a):
                                                       np.array_equal(ref[1].cpu().numpy(), nccl.pop("last_dist")))
     ix.set_option(_capi.OPT_TIMING, 0)
 
-    # ---- e2e: host buffers through the public call, copies inside the timed region (captured launch sequences on)
+    # ---- e2e: host buffers through the public call, copies inside the timed region (captured launch sequences on).
+    # CALLERS host threads issue the calls, like the goroutines of concurrent Search requests under the RLock
+    # (collection.go:570) -- and like the CPU arm, which runs one query per host thread; the single-caller figure is beside it.
     e2e = None
     if not a.no_e2e:
+        CALLERS = 2
         for s in range(max(a.warmup, 3)):
             ix.search_topk(hq[s % total_steps], a.k)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         for s in range(a.warmup, total_steps):
             e2e_last = ix.search_topk(hq[s], a.k)
-        el = time.perf_counter() - t0
+        el1 = time.perf_counter() - t0
         assert np.array_equal(e2e_last[0], last_ids) and np.array_equal(e2e_last[1], last_dist), "host and device paths disagree"
+        results = [None] * a.steps
+
+        def caller(c):
+            for s in range(c, a.steps, CALLERS):
+                results[s] = ix.search_topk(hq[a.warmup + s], a.k)
+        for c in range(CALLERS):  # every caller's workspace sees the shape once before the timed region
+            ix.search_topk(hq[c], a.k)
+        th = [threading.Thread(target=caller, args=(c,)) for c in range(CALLERS)]
+        t0 = time.perf_counter()
+        [t.start() for t in th]
+        [t.join() for t in th]
+        el = time.perf_counter() - t0
+        assert np.array_equal(results[-1][0], last_ids) and np.array_equal(results[-1][1], last_dist), "concurrent callers disagree"
         e2e = {"value": a.nq * a.steps / el, "unit": UNIT, "h2d_bytes_per_step": a.nq * a.dims * 8,
-               "d2h_bytes_per_step": a.nq * a.k * 16 + a.nq * 8, "ms_per_step": 1e3 * el / a.steps,
+               "d2h_bytes_per_step": a.nq * a.k * 16 + a.nq * 8, "ms_per_step": 1e3 * el / a.steps, "callers": CALLERS,
+               "single_caller": {"value": a.nq * a.steps / el1, "ms_per_step": 1e3 * el1 / a.steps},
                "graph_launches": ix.stats()["graph_launches"]}
 
     # ---- roofline of the step's dominant kernel
@@ -518,12 +555,14 @@ def run_b200(a):
     single_query = None
     if a.nq > 1:
         ix.set_option(_capi.OPT_TIMING, 2)
-        for s in range(3):
-            run.topk(dq[s][:1], a.k)
+        for s in range(4):
+            run.topk(dq[s % total_steps][:1], a.k, slot=s % IN_FLIGHT)
         torch.cuda.synchronize(dev)
         kernel_times()
-        ms1, _, _ = timed(torch, dev, lambda i: run.topk(dq[a.warmup + i][:1], a.k), a.steps)
-        sq_scan = kernel_times()
+        ms1_serial, _, _ = timed(torch, dev, lambda i, slot: run.topk(dq[a.warmup + i][:1], a.k, slot=slot), a.steps, run, 1)
+        sq_scan = kernel_times()  # scan launches of the one-at-a-time run: nothing else on the GPU while they run
+        ms1, _, _ = timed(torch, dev, lambda i, slot: run.topk(dq[a.warmup + i][:1], a.k, slot=slot), a.steps, run)
+        kernel_times()
         ix.set_option(_capi.OPT_TIMING, 0)
         sq_ms = float(np.mean(sq_scan)) if len(sq_scan) else float("nan")
         sq_ach = rows_gpu * rb / (sq_ms / 1e3) / 1e9 if sq_ms == sq_ms else None
@@ -534,7 +573,9 @@ def run_b200(a):
             lat.append(time.perf_counter() - t0)
         lat = lat[a.warmup:]
         single_query = {"value": a.steps / (ms1 / 1e3), "unit": UNIT, "queries_per_call": 1, "ms_per_query": ms1 / a.steps,
-                        "scan_launch_ms": sq_ms, "fixed_cost_us_over_scan": (ms1 / a.steps - sq_ms) * 1e3,
+                        "scan_launch_ms": sq_ms, "steps_in_flight": IN_FLIGHT,
+                        "one_step_at_a_time": {"value": a.steps / (ms1_serial / 1e3), "ms_per_query": ms1_serial / a.steps,
+                                               "fixed_cost_us_over_scan": (ms1_serial / a.steps - sq_ms) * 1e3},
                         "host_call_latency_us_median": 1e6 * statistics.median(lat), "host_call_qps": len(lat) / sum(lat),
                         "aggregate_hbm_frac": (a.rows * rb * a.steps / (ms1 / 1e3) / 1e9) / (peak * N),
                         "roofline": {"bound": "hbm", "achieved": sq_ach, "peak": peak, "unit": "GB/s",
@@ -551,7 +592,7 @@ def run_b200(a):
     if not a.no_extras and a.sustain_seconds > 0:
         per = ms / a.steps / 1e3
         n = max(a.steps, int(a.sustain_seconds / max(per, 1e-6)) + 1)
-        mss, w0, w1 = timed(torch, dev, lambda i: run.topk(dq[i % total_steps], a.k), n)
+        mss, w0, w1 = timed(torch, dev, lambda i, slot: run.topk(dq[i % total_steps], a.k, slot=slot), n, run)
         sustained = {"value": a.nq * n / (mss / 1e3), "unit": UNIT, "steps": n, "seconds": mss / 1e3, "ms_per_step": mss / n,
                      "clocks": sampler.window(w0, w1)}
 
@@ -582,6 +623,7 @@ def run_b200(a):
         "data": "synthetic" if a.dist == "uniform" else "synthetic (L2-normalised Gaussian rows through the reference's quantize)",
         "config": {"workload": workload_name(a.rows, a.dims, a.quant, a.metric, a.k), "rows": a.rows, "dims": a.dims,
                    "quantization": a.quant, "distance": a.metric, "k": a.k, "queries_per_step": a.nq, "rows_per_gpu": rows_gpu,
+                   "steps_in_flight": IN_FLIGHT,
                    "parallelism": (f"one handle over {N} GPUs (szg_create_sharded, one process): rows dealt to the devices, peer-store "
                                    "merge on GPU 0") if N > 1 else "one GPU",
                    "l2": f"shard payload {rows_gpu * rb / 1e6:.0f} MB per pass vs 126 MB L2: inputs larger than L2, no flush"
@@ -611,16 +653,16 @@ def batch_leg(a, np, torch, dev, ix, run, nq, k, rows_gpu, dims, quant, peaks, m
         bq_h /= np.linalg.norm(bq_h, axis=1, keepdims=True)
     bq = torch.from_numpy(bq_h).to(dev)
     ix.set_option(_capi.OPT_TIMING, 2)
-    for _ in range(3):
-        run.topk(bq, k, batched=True)
+    for w in range(4):
+        run.topk(bq, k, batched=True, slot=w % IN_FLIGHT)
     torch.cuda.synchronize(dev)
     ix.last_scan_times_ms(65536)
     b0 = ix.stats()["batch_queries"]
-    bms, w0, w1 = timed(torch, dev, lambda i: run.topk(bq, k, batched=True), steps)
+    bms, w0, w1 = timed(torch, dev, lambda i, slot: run.topk(bq, k, batched=True, slot=slot), steps, run)
     kern_ms = ix.last_scan_times_ms(65536)
     ix.set_option(_capi.OPT_TIMING, 0)
     served = ix.stats()["batch_queries"] - b0
-    oi, od, on, _ = run.out(nq, k)
+    oi, od, on, _ = run.out(nq, k, (steps - 1) % IN_FLIGHT)
     bi, bd = oi.cpu().numpy().astype(np.uint64), od.cpu().numpy()
     # the batch returns what single-query scans return: compare a few (tensor path off for them)
     nchk = min(3, nq)
@@ -696,18 +738,20 @@ def cfg2_leg(a, np, torch, dev, szg, _capi, peak):
         torch.cuda.synchronize(dev)
         ix.last_scan_times_ms(65536)
         pairs = []
-        for s in range(iters):
-            flush.fill_(s & 0xFF)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            run.topk(dq[3 + s:4 + s], k)
-            e1.record()
-            pairs.append((e0, e1))
+        st = run.streams[0]
+        with torch.cuda.stream(st):
+            for s in range(iters):
+                flush.fill_(s & 0xFF)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                run.topk(dq[3 + s:4 + s], k)
+                e1.record(st)
+                pairs.append((e0, e1))
         torch.cuda.synchronize(dev)
         per = [x.elapsed_time(y) for x, y in pairs]
         scan = ix.last_scan_times_ms(65536)
         # without the flush: L2-resident
-        ms_hot, _, _ = timed(torch, dev, lambda i: run.topk(dq[3 + i:4 + i], k), iters)
+        ms_hot, _, _ = timed(torch, dev, lambda i, slot: run.topk(dq[3 + i:4 + i], k, slot=slot), iters, run, 1)
         scan_hot = ix.last_scan_times_ms(65536)
         ix.set_option(_capi.OPT_TIMING, 0)
         lat = []

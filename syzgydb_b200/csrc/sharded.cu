@@ -29,8 +29,10 @@ struct ShardWs { // one in-flight sharded search
     PinBuf<unsigned char> h_out;
     DevBuf<double> d_q2;             // root: queries of an escalation pass
     cudaEvent_t ev_start = nullptr;
-    std::vector<cudaEvent_t> ev_done; // per shard: its lists are written (used when the merge must not spin, see sharded_pass)
+    std::vector<cudaEvent_t> ev_done; // per shard: its lists are written (used when the merge does not spin, see sharded_pass)
     bool bound = false;              // ws[0] belongs to a caller's stream
+    bool capturing = false;          // the pass being enqueued is recorded into a CUDA graph (all streams of the workspace)
+    std::map<uint64_t, GraphEntry> graphs; // captured host-buffer calls, as in search_host (search.cu)
 };
 
 struct SynthRange {
@@ -115,6 +117,8 @@ void free_shard_ws(Sharded *S, ShardWs *W) {
     }
     for (uint32_t g = 0; g < W->ev_done.size(); ++g)
         if (W->ev_done[g]) { DeviceGuard gd(S->devices[g]); cudaEventDestroy(W->ev_done[g]); }
+    for (auto &ge : W->graphs)
+        if (ge.second.exec) cudaGraphExecDestroy(ge.second.exec);
     {
         DeviceGuard gd(S->devices[0]);
         W->d_gather.release(); W->d_done.release(); W->d_out.release(); W->h_out.release(); W->d_q2.release();
@@ -134,7 +138,7 @@ int new_shard_ws(Sharded *S, void *bound_stream, ShardWs **out) {
             rc = ws_for_stream(S->shards[0], bound_stream, &W->ws[0]);
             W->bound = true;
         } else rc = acquire_ws(S->shards[g], &W->ws[g]);
-        if (!rc && !S->spin_merge) {
+        if (!rc) {
             W->ev_done.resize(S->G(), nullptr);
             cudaError_t e = cudaEventCreateWithFlags(&W->ev_done[g], cudaEventDisableTiming);
             if (e != cudaSuccess) rc = fail(SZG_ECUDA, "event creation failed: %s", cudaGetErrorString(e));
@@ -180,8 +184,11 @@ int sharded_pass(szg_index *h, ShardWs *W, const double *d_q_root, uint32_t nq, 
         CK(cudaMemsetAsync(W->d_done.p, 0, ((size_t)nq + 1) * 4, st0));
         CK(cudaEventRecord(W->ev_start, st0));
     }
+    // in-kernel wait of the merge for the other devices' counters -- or, when shards share a GPU or the pass is being
+    // captured into a graph (whose completion joins every stream anyway), plain event dependencies
+    const bool spin = S->spin_merge && !W->capturing;
     PeerSink sink;
-    sink.done_cnt = S->spin_merge ? W->d_done.p : nullptr;
+    sink.done_cnt = spin ? W->d_done.p : nullptr;
     for (uint32_t g = 0; g < G; ++g) {
         szg_index *sh = S->shards[g];
         DeviceGuard gd(sh->device);
@@ -198,10 +205,10 @@ int sharded_pass(szg_index *h, ShardWs *W, const double *d_q_root, uint32_t nq, 
                                reinterpret_cast<uint32_t *>(r + (size_t)nq * k * 16 + (size_t)nq * 4), &sink, &mode, &nd)))
             return rc;
         if (g == 0) { if (mode_out) *mode_out = mode; if (nd_out) *nd_out = nd; }
-        if (!S->spin_merge && g) CK(cudaEventRecord(W->ev_done[g], ws->main));
+        if (!spin && g) CK(cudaEventRecord(W->ev_done[g], ws->main));
     }
     DeviceGuard gd(S->devices[0]);
-    if (!S->spin_merge)
+    if (!spin)
         for (uint32_t g = 1; g < G; ++g) CK(cudaStreamWaitEvent(st0, W->ev_done[g], 0));
     MergeArgs a;
     memset(&a, 0, sizeof a);
@@ -213,7 +220,7 @@ int sharded_pass(szg_index *h, ShardWs *W, const double *d_q_root, uint32_t nq, 
     a.rank_stride = rec;
     a.G = G; a.nq = nq; a.k = k;
     a.out_ids = d_out_ids; a.out_dist = d_out_dist; a.out_n = d_out_n; a.out_flags = d_out_flags;
-    if (S->spin_merge) { a.wait_cnt = W->d_done.p; a.wait_target = G; a.wait_timeout_ns = S->wait_timeout_ns; a.err = W->d_done.p + nq; }
+    if (spin) { a.wait_cnt = W->d_done.p; a.wait_target = G; a.wait_timeout_ns = S->wait_timeout_ns; a.err = W->d_done.p + nq; }
     CK(launch_merge(a, st0));
     h->launches++;
     return SZG_OK;
@@ -495,6 +502,7 @@ int sharded_get_stats(szg_index *h, szg_stats *out) {
         }
     }
     acc.kernel_launches += h->launches.load();
+    acc.graph_launches += h->graph_launches.load();
     acc.escalations += h->escalations.load();
     acc.uncertain_results += h->uncertain.load();
     acc.batch_queries /= S->G(); // every shard serves every query of a batch
@@ -532,8 +540,8 @@ int sharded_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32
     const size_t pack = on * 16 + (size_t)nq * 8 + 8; // [ids | dist | n | flags | err word]
     if ((rc = w0->h_q.ensure(qn)) || (rc = w0->d_q.ensure(qn)) || (rc = W->d_out.ensure(pack)) || (rc = W->h_out.ensure(pack))) return rc;
     memcpy(w0->h_q.p, queries, qn * sizeof(double));
-    CK(cudaMemcpyAsync(w0->d_q.p, w0->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st0));
-    auto run = [&](const double *dq, uint32_t m, int min_mode, int force_nd, bool batch, int *mode, int *nd) -> int {
+    // enqueue: one pass over all shards + the copy of the merged results (and the error word) to the host
+    auto enqueue = [&](const double *dq, uint32_t m, int min_mode, int force_nd, bool batch, int *mode, int *nd) -> int {
         unsigned char *o = W->d_out.p;
         int r = sharded_pass(h, W, dq, m, k, mids, flags, batch, min_mode, force_nd, reinterpret_cast<unsigned long long *>(o),
                              reinterpret_cast<double *>(o + (size_t)m * k * 8), reinterpret_cast<uint32_t *>(o + (size_t)m * k * 16),
@@ -542,14 +550,95 @@ int sharded_search_topk(szg_index *h, const double *queries, uint32_t nq, uint32
         const size_t bytes = (size_t)m * k * 16 + (size_t)m * 8;
         CK(cudaMemcpyAsync(W->h_out.p, W->d_out.p, bytes, cudaMemcpyDeviceToHost, st0));
         CK(cudaMemcpyAsync(W->h_out.p + bytes, W->d_done.p + m, 4, cudaMemcpyDeviceToHost, st0));
+        return SZG_OK;
+    };
+    auto finish = [&](uint32_t m) -> int {
         CK(cudaStreamSynchronize(st0));
+        const size_t bytes = (size_t)m * k * 16 + (size_t)m * 8;
         uint32_t err;
         memcpy(&err, W->h_out.p + bytes, 4);
         if (err) return fail(SZG_EINTERNAL, "a shard did not deliver its results within %.0f s", (double)S->wait_timeout_ns / 1e9);
         return SZG_OK;
     };
+    auto run = [&](const double *dq, uint32_t m, int min_mode, int force_nd, bool batch, int *mode, int *nd) -> int {
+        int r = enqueue(dq, m, min_mode, force_nd, batch, mode, nd);
+        return r ? r : finish(m);
+    };
     int mode0 = 0, nd0 = 0;
-    if ((rc = run(w0->d_q.p, nq, 0, 0, prefer_batch, &mode0, &nd0))) return rc;
+    // Repeated call shapes are replayed as ONE captured launch sequence over all devices (the copy of the queries, every
+    // shard's prep + scan | batch + finalize, the merge, the copy back): a call then costs one graph launch instead of a
+    // few dozen stream operations issued device by device.  Same scheme as search_host: first call of a shape launch by
+    // launch (sizes the buffers), second one captures.
+    bool done = false;
+    const bool graphs_ok = root->use_graphs && root->timing == 0;
+    if (graphs_ok) {
+        const uint64_t key = ((uint64_t)nq << 40) ^ ((uint64_t)k << 28) ^ ((uint64_t)(uint32_t)(mask_id + 1) << 4) ^ ((uint64_t)(flags & 3u) << 1) ^
+                             (prefer_batch ? 1u : 0u);
+        GraphEntry &ge = W->graphs[key];
+        uint64_t gen = 0;
+        for (auto sh : S->shards) gen += sh->generation;
+        auto fingerprint = [&]() -> const void * {
+            uint64_t f = 1469598103934665603ULL;
+            auto mix = [&](const void *p) { f = (f ^ (uint64_t)(uintptr_t)p) * 1099511628211ULL; };
+            mix(w0->d_q.p); mix(w0->h_q.p); mix(W->d_gather.p); mix(W->d_done.p); mix(W->d_out.p); mix(W->h_out.p);
+            for (auto ws : W->ws) { mix(ws->d_pq.p); mix(ws->d_cand.p); mix(ws->d_gmth.p); }
+            return reinterpret_cast<const void *>((uintptr_t)f);
+        };
+        if (ge.exec && (ge.generation != gen || ge.buffers[0] != fingerprint())) {
+            cudaGraphExecDestroy(ge.exec);
+            ge.exec = nullptr;
+            if (ge.generation == gen) ge.generation = 0;
+        }
+        if (ge.exec && ge.generation == gen) {
+            mode0 = ge.mode0; nd0 = ge.nd0;
+            CK(cudaGraphLaunch(ge.exec, st0));
+            h->graph_launches++;
+            h->launches += ge.kernels;
+            done = true;
+        } else if (!ge.exec && ge.generation == gen && !ge.failed) {
+            uint64_t l0 = h->launches.load();
+            for (auto sh : S->shards) l0 += sh->launches.load();
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(st0, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                W->capturing = true;
+                for (auto ws : W->ws) ws->capturing = true;
+                int r = SZG_OK;
+                cudaError_t ce = cudaMemcpyAsync(w0->d_q.p, w0->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st0);
+                if (ce != cudaSuccess) r = SZG_ECUDA;
+                if (!r) r = enqueue(w0->d_q.p, nq, 0, 0, prefer_batch, &mode0, &nd0);
+                W->capturing = false;
+                for (auto ws : W->ws) ws->capturing = false;
+                e = cudaStreamEndCapture(st0, &g);
+                if (r == SZG_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&ge.exec, g, 0);
+                else if (e == cudaSuccess) e = cudaErrorUnknown;
+                if (g) cudaGraphDestroy(g);
+            }
+            if (e != cudaSuccess || !ge.exec) {
+                cudaGetLastError();
+                ge.exec = nullptr;
+                ge.failed = true;
+            } else {
+                uint64_t l1 = h->launches.load();
+                for (auto sh : S->shards) l1 += sh->launches.load();
+                ge.mode0 = mode0; ge.nd0 = nd0;
+                ge.kernels = (uint32_t)(l1 - l0);
+                ge.buffers[0] = fingerprint();
+                CK(cudaGraphLaunch(ge.exec, st0));
+                h->graph_launches++;
+                done = true;
+            }
+        } else if (ge.generation != gen) {
+            ge.generation = gen;
+            ge.failed = false;
+        }
+    }
+    if (done) {
+        if ((rc = finish(nq))) return rc;
+    } else {
+        CK(cudaMemcpyAsync(w0->d_q.p, w0->h_q.p, qn * sizeof(double), cudaMemcpyHostToDevice, st0));
+        if ((rc = run(w0->d_q.p, nq, 0, 0, prefer_batch, &mode0, &nd0))) return rc;
+    }
     for (uint32_t g = 0; g < S->G(); ++g) drain_timing(S->shards[g], W->ws[g]);
     memcpy(out_ids, W->h_out.p, on * 8);
     memcpy(out_dist, W->h_out.p + on * 8, on * 8);
