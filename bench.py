@@ -658,11 +658,12 @@ def batch_leg(a, np, torch, dev, ix, run, nq, k, rows_gpu, dims, quant, peaks, m
     torch.cuda.synchronize(dev)
     ix.last_scan_times_ms(65536)
     b0 = ix.stats()["batch_queries"]
-    bms, w0, w1 = timed(torch, dev, lambda i, slot: run.topk(bq, k, batched=True, slot=slot), steps, run)
+    # one batch at a time: a batch of this size fills the tensor pipe by itself (two in flight only time-slice)
+    bms, w0, w1 = timed(torch, dev, lambda i, slot: run.topk(bq, k, batched=True, slot=slot), steps, run, 1)
     kern_ms = ix.last_scan_times_ms(65536)
     ix.set_option(_capi.OPT_TIMING, 0)
     served = ix.stats()["batch_queries"] - b0
-    oi, od, on, _ = run.out(nq, k, (steps - 1) % IN_FLIGHT)
+    oi, od, on, _ = run.out(nq, k, 0)
     bi, bd = oi.cpu().numpy().astype(np.uint64), od.cpu().numpy()
     # the batch returns what single-query scans return: compare a few (tensor path off for them)
     nchk = min(3, nq)
@@ -817,7 +818,18 @@ def cfg3_leg(a, np, torch, dev, szg, _capi, peak, o):
             t0 = time.perf_counter()
             ix.rescore(hq[0], small)
             lat.append(time.perf_counter() - t0)
+        lsh = None
+        try:  # Precision "medium" through the C++ host mirror (LSH walk on the host + GPU re-scoring) next to "exact": SURVEY 8f-2
+            binp = os.path.join(ROOT, "tests", "cpp", "test_collection")
+            out = subprocess.run([binp, "--cfg3-bench", str(rows)], capture_output=True, text=True, timeout=600)
+            lsh = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+            lsh["what"] = ("Collection.Search through the C++ host mirror on 1 M x 384 float64 cosine documents: Precision medium = "
+                           "lshTree.search restated on the host (5 trees, leaf 100), leaf candidates re-scored by szg_rescore in "
+                           "speculative batches, consider / k_counter replayed; Precision exact = one GPU scan")
+        except Exception as e:  # noqa: BLE001
+            lsh = {"unavailable": repr(e)[:200]}
         return {"config": {"workload": workload_name(rows, dims, quant, "cosine", 10), "radius": 0.46, "filter": "bucket < 3 (30 %)"},
+                "lsh_medium_vs_exact": lsh,
                 "radius_search": {"value": 1.0 / rad, "unit": UNIT, "ms_per_query_host_call": 1e3 * rad, "hits_per_query": hits / 20,
                                   "ms_per_query_in_a_batch_of_8": 1e3 * rad8,
                                   "roofline": {"bound": "hbm", "achieved": payload / (sm / 1e3) / 1e9, "peak": peak, "unit": "GB/s",

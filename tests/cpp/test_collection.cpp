@@ -1,6 +1,7 @@
 // test_collection.cpp -- the reference's own Collection tests (collection_test.go, rest_test.go list mode)
 // restated against the C++ host mirror (syzgydb_b200/host), plus parity of the GPU-backed results with
 // the CPU oracle.  `--cpu` runs only the codec checks (no GPU needed).
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "collection.hpp"
@@ -335,7 +337,62 @@ static int open_mode(int argc, char **argv) {
     return 0;
 }
 
+// --cfg3-bench [rows]: BASELINE.json configs[2] timed through the host mirror -- what Precision "medium" (LSH-tree walk on the
+// host, candidates re-scored on the GPU in speculative batches, `consider` replayed) costs next to Precision "exact" (one GPU
+// scan) on the same collection and queries.  One JSON line; bench.py embeds it (is a device-side tree worth it?).
+static int cfg3_bench(int n) {
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const int dims = 384, nq = 20;
+    Corpus cp = make_corpus(n, dims, 64, 1234 + n + dims, true);
+    CollectionOptions o; o.Name = "cfg3"; o.DistanceMethod = Cosine; o.DimensionCount = dims; o.Quantization = 64; o.Seed = 99;
+    Collection c(o);
+    std::vector<std::string> meta;
+    for (uint64_t id : cp.ids) meta.push_back("{\"bucket\": " + std::to_string(id % 10) + "}");
+    auto t0 = clk::now();
+    c.AddDocuments(cp.ids, cp.vecs, meta);
+    const double build_ms = ms(t0, clk::now());
+    std::vector<std::vector<double>>().swap(cp.vecs);
+    std::mt19937_64 rng(5);
+    std::normal_distribution<double> g(0, 1);
+    std::vector<SearchArgs> qs((size_t)nq);
+    for (auto &a : qs) { a.Vector.resize((size_t)dims); for (auto &x : a.Vector) x = g(rng); a.K = 10; }
+    for (int w = 0; w < 2; ++w) { SearchArgs a = qs[(size_t)w]; c.Search(a); a.Precision = "exact"; c.Search(a); }
+    double med_ms = 0, pct = 0, batches = 0, ex_ms = 0, agree = 0;
+    for (auto &a : qs) {
+        SearchArgs m = a;
+        auto t1 = clk::now();
+        SearchResults r = c.Search(m);
+        med_ms += ms(t1, clk::now());
+        pct += r.PercentSearched;
+        batches += c.LastRescoreBatches();
+        SearchArgs e = a;
+        e.Precision = "exact";
+        t1 = clk::now();
+        SearchResults x = c.Search(e);
+        ex_ms += ms(t1, clk::now());
+        std::unordered_set<uint64_t> truth;
+        for (auto &h : x.Results) truth.insert(h.ID);
+        int hit = 0;
+        for (auto &h : r.Results) hit += (int)truth.count(h.ID);
+        agree += x.Results.empty() ? 1.0 : (double)hit / (double)x.Results.size();
+    }
+    std::printf("{\"rows\": %d, \"dims\": %d, \"queries\": %d, \"k\": 10, \"tree_build_ms_5_threads\": %.1f, "
+                "\"medium_ms_per_query\": %.3f, \"medium_percent_searched\": %.3f, \"medium_rescore_batches_per_query\": %.2f, "
+                "\"medium_recall_at_10_vs_exact\": %.3f, \"exact_ms_per_query\": %.3f}\n",
+                n, dims, nq, build_ms, med_ms / nq, pct / nq, batches / nq, agree / nq, ex_ms / nq);
+    return 0;
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "--cfg3-bench") {
+        try {
+            return cfg3_bench(argc > 2 ? std::atoi(argv[2]) : 1000000);
+        } catch (const std::exception &e) {
+            std::printf("{\"error\": \"%s\"}\n", e.what());
+            return 2;
+        }
+    }
     if (argc > 1 && std::string(argv[1]) == "--cfg3") {
         // BASELINE.json configs[2] at its stated size (default 1 M x 384 float64, cosine): LSH-tree candidate walk on the
         // host, candidates re-scored on the GPU, radius 0.46 with the `bucket < 3` filter, then top-k -- both against the

@@ -373,6 +373,35 @@ def test_sharded_device_resident_call_and_concurrency():
         assert not errs, errs[0]
 
 
+@pytest.mark.parametrize("devices", _device_lists(), ids=lambda v: "dev" + "".join(map(str, v)))
+def test_sharded_repeated_calls_are_replayed_as_one_graph_over_all_devices(devices):
+    d, bits, n, k = 768, 8, 40000, 10
+    with szg.Index(d, bits, szg.COSINE, devices=devices) as sh, szg.Index(d, bits, szg.COSINE) as one:
+        sh.fill_synthetic(77, 0, n)
+        one.fill_synthetic(77, 0, n)
+        for nq in (1, 32):
+            qsets = [o.synth_queries(200 + r, 0, nq, d) for r in range(4)]
+            want = [one.search_topk(q, k) for q in qsets]
+            g0 = sh.stats()["graph_launches"]
+            for rnd in range(3):
+                for q, w in zip(qsets, want):
+                    got = sh.search_topk(q, k)
+                    assert np.array_equal(got[0], w[0]) and np.array_equal(got[1], w[1]) and np.array_equal(got[2], w[2])
+            assert sh.stats()["graph_launches"] - g0 >= 8, sh.stats()
+        # a mutation through the router makes the captured sequences stale
+        q = o.synth_queries(200, 0, 1, d)[0]
+        code = o.encode(np.clip(q / np.abs(q).max(), -1, 1), bits)[None, :]
+        sh.upsert(np.array([10 ** 9 + 1], dtype=np.uint64), code)
+        for _ in range(3):
+            gi, gd, gn, _ = sh.search_topk(q, k)
+            assert gi[0, 0] == 10 ** 9 + 1
+        sh.remove(np.array([10 ** 9 + 1], dtype=np.uint64))
+        for _ in range(3):
+            got = sh.search_topk(q, k)
+            w = one.search_topk(q, k)
+            assert np.array_equal(got[0], w[0]) and np.array_equal(got[1], w[1])
+
+
 def test_sharded_near_duplicates_escalate_on_every_shard():
     # rows closer together than the 2-digit surrogate resolves: the sharded path must walk the same escalation ladder
     d, n, k = 64, 6000, 10
