@@ -762,6 +762,7 @@ def cfg2_leg(a, np, torch, dev, szg, _capi, peak):
             t0 = time.perf_counter()
             ix.search_topk(hq[3 + s], k)
             lat.append(time.perf_counter() - t0)
+        lat = lat[5:]  # the first calls of the shape run launch by launch and capture the launch sequence
         payload = rows * rowbytes(quant, dims)
         sm = float(np.mean(scan))
         return {"config": {"workload": workload_name(rows, dims, quant, "euclidean", k),

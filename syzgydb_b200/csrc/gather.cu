@@ -24,14 +24,14 @@ constexpr int kGatherThreads = 288; // all of them fetch; 2 x 128 + 1 of them ru
 template <int QT, int KP>
 __device__ __forceinline__ void score_batch(const uint4 *codes, const double *lut, uint32_t C, uint32_t dims, uint32_t metric,
                                             const double *q, const uint32_t *s_slot, unsigned char *stage, double *s_out, int tid) {
-    if (metric == COSINE) exact_staged<QT, COSINE, kGatherThreads>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
-    else exact_staged<QT, EUCLID, kGatherThreads>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+    if (metric == COSINE) exact_staged<QT, COSINE, kGatherThreads, 16>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+    else exact_staged<QT, EUCLID, kGatherThreads, 16>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
 }
 
 // CTA b scores candidates [b KP, b KP + KP) of the flat candidate array; where that range crosses a list boundary the
 // pieces are scored one after the other, each against its own query.
 template <int QT, int KP>
-__global__ void __launch_bounds__(kGatherThreads) rescore_kernel(const RescoreArgs a) {
+__global__ void __launch_bounds__(kGatherThreads, 2) rescore_kernel(const RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char stage[];
     __shared__ uint32_t s_slot[KP];
     __shared__ double s_out[KP];
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kGatherThreads) rescore_kernel(const RescoreAr
 }
 
 template <int QT, int KP>
-__global__ void __launch_bounds__(kGatherThreads) radius_exact_kernel(const RadiusFinishArgs a) {
+__global__ void __launch_bounds__(kGatherThreads, 2) radius_exact_kernel(const RadiusFinishArgs a) {
     extern __shared__ __align__(16) unsigned char stage[];
     __shared__ uint32_t s_slot[KP];
     __shared__ double s_out[KP];

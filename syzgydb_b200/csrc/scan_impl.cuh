@@ -498,7 +498,7 @@ __device__ __forceinline__ double staged_element(const uint4 *row, uint32_t e, c
 }
 
 
-template <int QT, int METRIC, int NT>
+template <int QT, int METRIC, int NT, int ESMAX = 32>
 __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__restrict__ lut, uint32_t C, uint32_t dims,
                              const double *__restrict__ q, const uint32_t *s_slot, int Kp, unsigned char *stage,
                              size_t stage_bytes, double *s_out, int tid, long long *trace = nullptr) {
@@ -525,7 +525,7 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     uint32_t ES = (uint32_t)(prod_bytes / (overlap ? 2 : 1) / 8 / ((size_t)Kp * NA + 1));
     ES = ES > 1 ? ES - 1 : 1;
     uint32_t ES_log = 0;
-    while (ES_log < 5 && (2u << ES_log) <= ES) ++ES_log;
+    while ((2u << ES_log) <= (uint32_t)ESMAX && (2u << ES_log) <= ES) ++ES_log;
     ES = 1u << ES_log;
     const uint32_t ESP = ES | 1u;
     const size_t buf_doubles = (size_t)Kp * NA * ESP + ((ES + 1) & ~1u); // one buffer: the products, then q_i^2
@@ -545,31 +545,43 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     const bool has_m1 = METRIC == COSINE && tid == (m1_own ? Kp * NA : 0);
     const bool live = chain && s_slot[chain ? cr : 0] != 0xFFFFFFFFu;
     double acc = 0.0, m1 = 0.0;
+    // Gathered rows: every load is a DRAM round trip of its own, so a thread keeps 8 of them in flight -- and the loads of
+    // slab s + 1 are issued BEFORE the arithmetic of slab s (they wait in registers), so that with many slabs per row
+    // (gathers of long float rows) the fetch latency hides behind the fp64 work.
+    constexpr int PF = 8;
+    uint4 pv[PF];
+    uint32_t pat[PF];
+    const bool one_round = (uint32_t)Kp * SC <= (uint32_t)NT * PF; // a slab's chunks fit one round of loads
+    auto issue = [&](uint32_t c0, uint32_t nc, uint32_t idx0) {
+        const uint32_t total = (uint32_t)Kp * nc;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const uint32_t idx = idx0 + (uint32_t)u * NT;
+            pat[u] = 0xFFFFFFFFu;
+            if (idx < total) {
+                const uint32_t r = idx / nc, c = idx - r * nc;
+                const uint32_t slot = s_slot[r];
+                if (slot != 0xFFFFFFFFu) {
+                    pv[u] = __ldg(codes + chunk_at<QT>(slot, C, c0 + c));
+                    pat[u] = r * (SC + 1) + c;
+                }
+            }
+        }
+    };
+    auto land = [&]() {
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if (pat[u] != 0xFFFFFFFFu) s_codes[pat[u]] = pv[u];
+    };
+    if (one_round) issue(0, min(SC, C), (uint32_t)tid);
     for (uint32_t c0 = 0; c0 < C; c0 += SC) {
         const uint32_t nc = min(SC, C - c0);
         __syncthreads(); // previous slab fully consumed (and the table written)
-        // gathered rows: every load is a DRAM round trip of its own, so a thread keeps 8 of them in flight
-        constexpr int PF = 8;
-        const uint32_t total = (uint32_t)Kp * nc;
-        for (uint32_t idx0 = tid; idx0 < total; idx0 += NT * PF) {
-            uint4 v[PF];
-            uint32_t at[PF];
-#pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const uint32_t idx = idx0 + (uint32_t)u * NT;
-                at[u] = 0xFFFFFFFFu;
-                if (idx < total) {
-                    const uint32_t r = idx / nc, c = idx - r * nc;
-                    const uint32_t slot = s_slot[r];
-                    if (slot != 0xFFFFFFFFu) {
-                        v[u] = __ldg(codes + chunk_at<QT>(slot, C, c0 + c));
-                        at[u] = r * (SC + 1) + c;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PF; ++u)
-                if (at[u] != 0xFFFFFFFFu) s_codes[at[u]] = v[u];
+        if (one_round) {
+            land();
+        } else {
+            const uint32_t total = (uint32_t)Kp * nc;
+            for (uint32_t idx0 = tid; idx0 < total; idx0 += NT * PF) { issue(c0, nc, idx0); land(); }
         }
         for (uint32_t e = tid; e < nc * EPC; e += NT) {
             const uint32_t i = c0 * EPC + e;
@@ -579,6 +591,7 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
         const uint32_t i_slab = c0 * EPC;
         if (trace && tid == 0 && c0 == 0) trace[6] = clock64();
         if (i_slab >= dims) break; // padding chunks only (uniform)
+        if (one_round && c0 + SC < C && (c0 + SC) * EPC < dims) issue(c0 + SC, min(SC, C - c0 - SC), (uint32_t)tid); // next slab: in flight during the arithmetic
         const uint32_t ne_slab = min(nc * (uint32_t)EPC, dims - i_slab); // real dimensions in this slab
         // ---- rounds of ES dimensions: products (parallel), then the chains (one thread per running sum, dimension order)
         auto produce = [&](uint32_t e0, uint32_t ne, double *buf, uint32_t pt, uint32_t pn) {
@@ -607,22 +620,22 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
             // path is one shared-memory latency plus ne fp64 add latencies
             if (live) {
                 const double *p = buf + (size_t)tid * ESP;
-                double v[32];
+                double v[ESMAX];
 #pragma unroll
-                for (uint32_t e = 0; e < 32; ++e)
+                for (uint32_t e = 0; e < (uint32_t)ESMAX; ++e)
                     if (e < ES) v[e] = e < ne ? p[e] : 0.0;
 #pragma unroll
-                for (uint32_t e = 0; e < 32; ++e)
+                for (uint32_t e = 0; e < (uint32_t)ESMAX; ++e)
                     if (e < ne) acc = __dadd_rn(acc, v[e]);
             }
             if (has_m1) {
                 const double *p = buf + (size_t)Kp * NA * ESP;
-                double v[32];
+                double v[ESMAX];
 #pragma unroll
-                for (uint32_t e = 0; e < 32; ++e)
+                for (uint32_t e = 0; e < (uint32_t)ESMAX; ++e)
                     if (e < ES) v[e] = e < ne ? p[e] : 0.0;
 #pragma unroll
-                for (uint32_t e = 0; e < 32; ++e)
+                for (uint32_t e = 0; e < (uint32_t)ESMAX; ++e)
                     if (e < ne) m1 = __dadd_rn(m1, v[e]);
             }
         };
