@@ -19,13 +19,21 @@ namespace {
 
 constexpr size_t kGatherStageBytes = 64 * 1024;
 
-constexpr int kGatherThreads = 288; // all of them fetch; 2 x 128 + 1 of them run the sums of a 128-candidate batch (dot, m2; sum q^2)
+constexpr int kGatherThreads = 256; // all of them fetch
 
+// KP = 32: few candidates (one speculative batch of the LSH walk) -- the latency form (exact_staged: products in parallel,
+// one thread per running sum); KP = 128: many -- the throughput form (exact_stream: a thread per candidate, fp64-pipe bound)
 template <int QT, int KP>
 __device__ __forceinline__ void score_batch(const uint4 *codes, const double *lut, uint32_t C, uint32_t dims, uint32_t metric,
-                                            const double *q, const uint32_t *s_slot, unsigned char *stage, double *s_out, int tid) {
-    if (metric == COSINE) exact_staged<QT, COSINE, kGatherThreads, 16>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
-    else exact_staged<QT, EUCLID, kGatherThreads, 16>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+                                            const double *q, double m1, const uint32_t *s_slot, unsigned char *stage, double *s_out,
+                                            int tid) {
+    if (KP <= 32) {
+        if (metric == COSINE) exact_staged<QT, COSINE, kGatherThreads, 16>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+        else exact_staged<QT, EUCLID, kGatherThreads, 16>(codes, lut, C, dims, q, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+    } else {
+        if (metric == COSINE) exact_stream<QT, COSINE, kGatherThreads>(codes, lut, C, dims, q, m1, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+        else exact_stream<QT, EUCLID, kGatherThreads>(codes, lut, C, dims, q, m1, s_slot, KP, stage, kGatherStageBytes, s_out, tid);
+    }
 }
 
 // CTA b scores candidates [b KP, b KP + KP) of the flat candidate array; where that range crosses a list boundary the
@@ -56,7 +64,7 @@ __global__ void __launch_bounds__(kGatherThreads, 2) rescore_kernel(const Rescor
             __syncthreads(); // the previous piece's s_out / s_slot readers are done
             if (tid < KP) s_slot[tid] = slot;
             __syncthreads();
-            score_batch<QT, KP>(a.codes, a.lut, a.C, a.dims, a.metric, a.q + (size_t)l * a.dims, s_slot, stage, s_out, tid);
+            score_batch<QT, KP>(a.codes, a.lut, a.C, a.dims, a.metric, a.q + (size_t)l * a.dims, a.m1 ? a.m1[l] : 0.0, s_slot, stage, s_out, tid);
             if ((uint32_t)tid < n) {
                 a.out_dist[base + tid] = slot == 0xFFFFFFFFu ? -1.0 /* SZG_MISSING_DISTANCE */ : s_out[tid];
                 if (a.out_ids) a.out_ids[base + tid] = slot == 0xFFFFFFFFu ? 0ull : a.ids[slot];
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(kGatherThreads, 2) radius_exact_kernel(const R
     const uint32_t n = min((uint32_t)KP, m - base);
     if (tid < KP) s_slot[tid] = (uint32_t)tid < n ? a.slots[base + tid] : 0xFFFFFFFFu;
     __syncthreads();
-    score_batch<QT, KP>(a.codes, a.lut, a.C, a.dims, a.metric, a.q, s_slot, stage, s_out, tid);
+    score_batch<QT, KP>(a.codes, a.lut, a.C, a.dims, a.metric, a.q, a.m1, s_slot, stage, s_out, tid);
     if ((uint32_t)tid < n) {
         const double d = s_out[tid];
         if (d <= a.radius) { // inclusive (collection.go:598); NaN fails

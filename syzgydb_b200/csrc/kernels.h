@@ -60,6 +60,7 @@ struct RescoreArgs {
     const unsigned long long *ids;
     const double *lut;
     const double *q;            // nlists x dims
+    const double *m1;           // nlists: sum of q_i^2 in dimension order (the reference's m1, collection.go:825), computed by the host
     const uint32_t *list_off;   // nlists + 1 offsets into slots: list l is scored against query l (NULL: one list, one query)
     uint32_t nlists;
     const uint32_t *slots;      // 0xFFFFFFFF = missing
@@ -82,6 +83,7 @@ struct RadiusFinishArgs {
     const uint32_t *count_ptr;   // how many (device); at most cap are present
     uint32_t cap;
     double radius;
+    double m1;                   // sum of q_i^2 in dimension order (cosine)
     unsigned long long *keys;    // scratch: pairs (distance bits, id); capacity = the power of two >= cap
     uint32_t *out_count;         // exact hits
     double *out_dist;            // [<= cap] ascending

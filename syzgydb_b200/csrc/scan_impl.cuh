@@ -465,6 +465,35 @@ struct Scorer<F64, ND> {
 constexpr int kFinalizeThreads = 512;
 constexpr size_t kFinalizeStageBytes = 64 * 1024; // staging area of the fp64 re-score
 
+// Fetches chunks [c0, c0 + nc) of the Kp candidates' rows into s_codes (row r at r * (SC + 1) uint4).  Gathered rows: every
+// load is a DRAM round trip of its own, so a thread keeps 8 of them in flight.
+template <int QT, int NT>
+__device__ __forceinline__ void gather_slab(const uint4 *__restrict__ codes, uint32_t C, uint32_t c0, uint32_t nc, uint32_t SC,
+                                            const uint32_t *s_slot, int Kp, uint4 *s_codes, int tid) {
+    constexpr int PF = 8;
+    const uint32_t total = (uint32_t)Kp * nc;
+    for (uint32_t idx0 = tid; idx0 < total; idx0 += NT * PF) {
+        uint4 v[PF];
+        uint32_t at[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const uint32_t idx = idx0 + (uint32_t)u * NT;
+            at[u] = 0xFFFFFFFFu;
+            if (idx < total) {
+                const uint32_t r = idx / nc, c = idx - r * nc;
+                const uint32_t slot = s_slot[r];
+                if (slot != 0xFFFFFFFFu) {
+                    v[u] = __ldg(codes + chunk_at<QT>(slot, C, c0 + c));
+                    at[u] = r * (SC + 1) + c;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if (at[u] != 0xFFFFFFFFu) s_codes[at[u]] = v[u];
+    }
+}
+
 // fp64 distances of up to NT / 2 candidates (s_slot[0 .. Kp), 0xFFFFFFFF = none) to the query q, bit for bit what the
 // reference computes: decodeVector + dequantize (collection.go:768-794, quantization.go:25-36), then euclideanDistance
 // (812-819) or angularDistance (821-832) -- sequential over the dimensions, un-fused multiply and add.  Organised so that
@@ -545,44 +574,10 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
     const bool has_m1 = METRIC == COSINE && tid == (m1_own ? Kp * NA : 0);
     const bool live = chain && s_slot[chain ? cr : 0] != 0xFFFFFFFFu;
     double acc = 0.0, m1 = 0.0;
-    // Gathered rows: every load is a DRAM round trip of its own, so a thread keeps 8 of them in flight -- and the loads of
-    // slab s + 1 are issued BEFORE the arithmetic of slab s (they wait in registers), so that with many slabs per row
-    // (gathers of long float rows) the fetch latency hides behind the fp64 work.
-    constexpr int PF = 8;
-    uint4 pv[PF];
-    uint32_t pat[PF];
-    const bool one_round = (uint32_t)Kp * SC <= (uint32_t)NT * PF; // a slab's chunks fit one round of loads
-    auto issue = [&](uint32_t c0, uint32_t nc, uint32_t idx0) {
-        const uint32_t total = (uint32_t)Kp * nc;
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const uint32_t idx = idx0 + (uint32_t)u * NT;
-            pat[u] = 0xFFFFFFFFu;
-            if (idx < total) {
-                const uint32_t r = idx / nc, c = idx - r * nc;
-                const uint32_t slot = s_slot[r];
-                if (slot != 0xFFFFFFFFu) {
-                    pv[u] = __ldg(codes + chunk_at<QT>(slot, C, c0 + c));
-                    pat[u] = r * (SC + 1) + c;
-                }
-            }
-        }
-    };
-    auto land = [&]() {
-#pragma unroll
-        for (int u = 0; u < PF; ++u)
-            if (pat[u] != 0xFFFFFFFFu) s_codes[pat[u]] = pv[u];
-    };
-    if (one_round) issue(0, min(SC, C), (uint32_t)tid);
     for (uint32_t c0 = 0; c0 < C; c0 += SC) {
         const uint32_t nc = min(SC, C - c0);
         __syncthreads(); // previous slab fully consumed (and the table written)
-        if (one_round) {
-            land();
-        } else {
-            const uint32_t total = (uint32_t)Kp * nc;
-            for (uint32_t idx0 = tid; idx0 < total; idx0 += NT * PF) { issue(c0, nc, idx0); land(); }
-        }
+        gather_slab<QT, NT>(codes, C, c0, nc, SC, s_slot, Kp, s_codes, tid);
         for (uint32_t e = tid; e < nc * EPC; e += NT) {
             const uint32_t i = c0 * EPC + e;
             s_q[e] = i < dims ? q[i] : 0.0;
@@ -591,7 +586,6 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
         const uint32_t i_slab = c0 * EPC;
         if (trace && tid == 0 && c0 == 0) trace[6] = clock64();
         if (i_slab >= dims) break; // padding chunks only (uniform)
-        if (one_round && c0 + SC < C && (c0 + SC) * EPC < dims) issue(c0 + SC, min(SC, C - c0 - SC), (uint32_t)tid); // next slab: in flight during the arithmetic
         const uint32_t ne_slab = min(nc * (uint32_t)EPC, dims - i_slab); // real dimensions in this slab
         // ---- rounds of ES dimensions: products (parallel), then the chains (one thread per running sum, dimension order)
         auto produce = [&](uint32_t e0, uint32_t ne, double *buf, uint32_t pt, uint32_t pn) {
@@ -682,6 +676,75 @@ __device__ void exact_staged(const uint4 *__restrict__ codes, const double *__re
             }
         } else {
             d = __dsqrt_rn(s_prod[tid]);
+        }
+        s_out[tid] = d;
+    }
+    __syncthreads();
+}
+
+// Throughput form of the same arithmetic, for gathers of many candidates (szg_rescore of long lists, radius hits): thread r
+// runs candidate r's whole loop body -- decode, the rounded products, the sequential adds -- out of the staged slab.  With
+// a warp-wide fp64 instruction occupying its pipe for ~16 cycles, four instructions per dimension keep the pipe busy from a
+// single warp's dependent chain, so nothing is gained by splitting products and sums (exact_staged does that for the
+// latency of FEW candidates); two CTAs per SM alternate between fetching and computing.  m1 = sum q_i^2 (cosine) is the
+// same for every candidate of a query: the caller supplies it (computed once on the host with the same IEEE operations).
+template <int QT, int METRIC, int NT>
+__device__ void exact_stream(const uint4 *__restrict__ codes, const double *__restrict__ lut, uint32_t C, uint32_t dims,
+                             const double *__restrict__ q, double m1, const uint32_t *s_slot, int Kp, unsigned char *stage,
+                             size_t stage_bytes, double *s_out, int tid) {
+    constexpr int EPC = QT == Q4 ? 32 : QT == Q8 ? 16 : QT == Q16 ? 8 : QT == F32 ? 4 : 2;
+    constexpr int LUTN = QT == Q4 ? 16 : QT == Q8 ? 256 : 0;
+    constexpr uint32_t GR = QT >= F32 ? (uint32_t)kGroupChunks : 1u;
+    double *s_lut = reinterpret_cast<double *>(stage);
+    unsigned char *body = stage + LUTN * sizeof(double);
+    const size_t budget = stage_bytes - LUTN * sizeof(double);
+    uint32_t SC = (uint32_t)((budget - (size_t)Kp * 16) / ((size_t)Kp * 16 + EPC * 8));
+    if (SC > C) SC = C;
+    SC = SC / GR * GR;
+    if (SC < GR) SC = GR;
+    uint4 *s_codes = reinterpret_cast<uint4 *>(body);
+    double *s_q = reinterpret_cast<double *>(body + (size_t)Kp * (SC + 1) * 16);
+    for (int i = tid; i < LUTN; i += NT) s_lut[i] = lut[i];
+    const bool mine = tid < Kp && s_slot[tid < Kp ? tid : 0] != 0xFFFFFFFFu;
+    double a0 = 0.0, a1 = 0.0; // cosine: dot, m2; euclid: sum
+    for (uint32_t c0 = 0; c0 < C; c0 += SC) {
+        const uint32_t nc = min(SC, C - c0);
+        __syncthreads();
+        gather_slab<QT, NT>(codes, C, c0, nc, SC, s_slot, Kp, s_codes, tid);
+        for (uint32_t e = tid; e < nc * EPC; e += NT) {
+            const uint32_t i = c0 * EPC + e;
+            s_q[e] = i < dims ? q[i] : 0.0;
+        }
+        __syncthreads();
+        const uint32_t i_slab = c0 * EPC;
+        if (i_slab >= dims) break;
+        const uint32_t ne = min(nc * (uint32_t)EPC, dims - i_slab);
+        if (mine) {
+            const uint4 *row = s_codes + (size_t)tid * (SC + 1);
+#pragma unroll 4
+            for (uint32_t e = 0; e < ne; ++e) {
+                const double x = staged_element<QT>(row, e, s_lut);
+                const double qi = s_q[e];
+                if (METRIC == COSINE) {
+                    a0 = __dadd_rn(a0, __dmul_rn(qi, x)); // dot += query[i] * vec[i]   (collection.go:824)
+                    a1 = __dadd_rn(a1, __dmul_rn(x, x));  // m2 += vec[i] * vec[i]     (826)
+                } else {
+                    const double diff = __dsub_rn(qi, x);  // (815)
+                    a0 = __dadd_rn(a0, __dmul_rn(diff, diff));
+                }
+            }
+        }
+    }
+    if (mine) {
+        double d;
+        if (METRIC == COSINE) {
+            if (m1 == 0.0 || a1 == 0.0) d = 1.0; // collection.go:828-830
+            else {
+                const double r = __ddiv_rn(a0, __dmul_rn(__dsqrt_rn(m1), __dsqrt_rn(a1)));
+                d = __ddiv_rn(go_acos(r), 3.141592653589793);
+            }
+        } else {
+            d = __dsqrt_rn(a0);
         }
         s_out[tid] = d;
     }

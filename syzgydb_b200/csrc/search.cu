@@ -733,6 +733,18 @@ int szg_merge_topk_dev(szg_index *h, const uint64_t *d_gathered_ids, const doubl
 
 namespace szg {
 
+// m1 of angularDistance (collection.go:821-827: m1 += query[i] * query[i], sequential) -- the same IEEE operations as on the
+// device (this file is compiled with -ffp-contract=off): the gather kernels take it from the host instead of re-adding it for
+// every candidate
+static double query_m1(const double *q, uint32_t dims) {
+    volatile double m1 = 0.0; // volatile: every product and every sum is rounded to double, in order
+    for (uint32_t i = 0; i < dims; ++i) {
+        const volatile double p = q[i] * q[i];
+        m1 = m1 + p;
+    }
+    return m1;
+}
+
 // ---- radius search of one device (collection.go:598-605): surrogate scan with warp-ballot compaction, exact fp64
 // distances of the compacted rows, the inclusive test and the (distance, lexicographic id) order ON THE DEVICE; the hits
 // come back with one copy.  nq queries share the launches (every query still streams the mirror on its own).
@@ -809,6 +821,7 @@ int radius_device(szg_index *h, const double *queries, uint32_t nq, const double
             fa.codes = h->codes.p; fa.ids = h->ids.p; fa.lut = h->lut.p; fa.q = ws->d_q.p + (size_t)q * h->dim;
             fa.slots = ws->d_slots.p + cap * q; fa.count_ptr = d_count + q; fa.cap = (uint32_t)cap;
             fa.radius = radii[q];
+            fa.m1 = query_m1(queries + (size_t)q * h->dim, (uint32_t)h->dim);
             fa.out_dist = ws->d_out_dist.p + cap * q; fa.out_ids = ws->d_out_ids.p + cap * q;
             fa.keys = ws->d_keys.p + 2 * kcap * q; fa.out_count = d_count + nq + q;
             fa.C = h->C; fa.dims = (uint32_t)h->dim; fa.metric = (uint32_t)h->metric; fa.qt = h->qt;
@@ -869,14 +882,17 @@ int rescore_device(szg_index *h, const double *queries, uint32_t nl, const uint6
     Workspace *ws;
     if ((rc = acquire_ws(h, &ws))) return rc;
     struct Rel { szg_index *h; Workspace *w; ~Rel() { release_ws(h, w); } } rel{h, ws};
-    // one pinned staging block: [queries nl*dim f64 | list offsets (nl+1) u32, padded | slots m u32]
-    const size_t qbytes = (size_t)nl * h->dim * 8, obytes = ((size_t)(nl + 1) * 4 + 7) / 8 * 8, sbytes = (size_t)m * 4;
+    // one pinned staging block: [queries nl*dim f64, m1 nl f64 | list offsets (nl+1) u32, padded | slots m u32]
+    const size_t qonly = (size_t)nl * h->dim * 8;
+    const size_t qbytes = qonly + (size_t)nl * 8, obytes = ((size_t)(nl + 1) * 4 + 7) / 8 * 8, sbytes = (size_t)m * 4;
     const size_t total = qbytes + obytes + sbytes;
     if ((rc = ws->h_out_pack.ensure(total)) || (rc = ws->d_out_pack.ensure(total)) || (rc = ws->d_out_dist.ensure(m)) ||
         (rc = ws->h_out_dist.ensure(m)))
         return rc;
     unsigned char *hp = ws->h_out_pack.p;
-    memcpy(hp, queries, qbytes);
+    memcpy(hp, queries, qonly);
+    double *hm1 = reinterpret_cast<double *>(hp + qonly);
+    for (uint32_t l = 0; l < nl; ++l) hm1[l] = query_m1(queries + (size_t)l * h->dim, (uint32_t)h->dim);
     uint32_t *ho = reinterpret_cast<uint32_t *>(hp + qbytes);
     for (uint32_t l = 0; l <= nl; ++l) ho[l] = (uint32_t)off[l];
     uint32_t *hs = reinterpret_cast<uint32_t *>(hp + qbytes + obytes);
@@ -890,6 +906,7 @@ int rescore_device(szg_index *h, const double *queries, uint32_t nl, const uint6
     memset(&ra, 0, sizeof ra);
     ra.codes = h->codes.p; ra.ids = h->ids.p; ra.lut = h->lut.p;
     ra.q = reinterpret_cast<const double *>(ws->d_out_pack.p);
+    ra.m1 = reinterpret_cast<const double *>(ws->d_out_pack.p + qonly);
     ra.list_off = reinterpret_cast<const uint32_t *>(ws->d_out_pack.p + qbytes); ra.nlists = nl;
     ra.slots = reinterpret_cast<const uint32_t *>(ws->d_out_pack.p + qbytes + obytes);
     ra.out_dist = ws->d_out_dist.p; ra.out_ids = nullptr;
