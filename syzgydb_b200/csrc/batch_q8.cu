@@ -572,7 +572,10 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         // (admission by the mth-best key, cheap), then -- after every range of the group has published -- for real.
         const uint32_t R = a.nranges, mthm1 = a.mth - 1;
         uint32_t *gmw = a.gmth + ((size_t)min(q0 + qw, a.nq - 1) * R + r);
-        const uint32_t poll_mask = R <= 16 ? 3u : R <= 64 ? 15u : 63u; // poll every 4 / 16 / 64 tiles (+ at powers of two)
+        // poll every 4 / 16 / 64 tiles (+ at powers of two); a poll is a round trip to L2 under full streaming load (measured
+        // ~14 us per poll with 148 ranges), during which this warp does not drain its accumulators
+        const uint32_t poll_mask = a.poll_mask ? a.poll_mask : (R <= 16 ? 3u : R <= 64 ? 15u : 63u);
+        const uint32_t poll_min = a.poll_min ? a.poll_min : 2u;
         // The bound of a query from the published keys: any value B such that `need` = ceil(Kp / mth) different ranges have
         // published a key <= B is valid (each of them has mth rows at or below its key, so need * mth >= Kp rows lie at or
         // below B).  The ranges are dealt into `need` groups (range r -> group r % need); B = max over the groups of the
@@ -611,7 +614,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             mbar_wait(&x_full[x], (tile / kAuxSlots) & 1u);
             const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&s_xsup[x]);
             if (cur == kNoBlock) break;
-            if (R > 1 && tile >= 2 && ((tile & (tile - 1)) == 0 || (tile & poll_mask) == 0)) {
+            if (R > 1 && tile >= poll_min && ((tile & (tile - 1)) == 0 || (tile & poll_mask) == 0)) {
                 poll_bounds();
                 ++npolls;
                 T = qs->T;

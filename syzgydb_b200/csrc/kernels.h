@@ -120,6 +120,7 @@ struct BatchArgs {
     uint32_t mth;              // ceil(keep / nranges)
     uint32_t keep;             // candidates per (query, row range) list handed to finalize (32, 64, 128)
     uint32_t debug;            // profiling aid: bit0 skip the epilogue math, bit1 skip aux loads, bit2 skip the MMAs
+    uint32_t poll_mask, poll_min; // 0 = defaults: when the epilogue warps re-read the shared bound (tuning: SZG_BATCH_POLL_MASK / _MIN)
     long long *trace;          // profiling aid (SZG_OPT_TRACE_BUFFER): clock64 stamps / counters of CTA 0's first epilogue warp
 };
 uint32_t batch_slice_chunks(uint32_t C, uint32_t want, size_t smem_limit); // chunks per K slice (ring stage); want = 0: automatic

@@ -320,6 +320,9 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, (size_t)nq * p.nranges * sizeof(unsigned int), st));
     static const uint32_t dbg = getenv("SZG_BATCH_DEBUG") ? (uint32_t)atoi(getenv("SZG_BATCH_DEBUG")) : 0u;
     b.debug = dbg;
+    static const uint32_t pmask = getenv("SZG_BATCH_POLL_MASK") ? (uint32_t)atoi(getenv("SZG_BATCH_POLL_MASK")) : 0u;
+    static const uint32_t pmin = getenv("SZG_BATCH_POLL_MIN") ? (uint32_t)atoi(getenv("SZG_BATCH_POLL_MIN")) : 0u;
+    b.poll_mask = pmask; b.poll_min = pmin;
     b.trace = h->trace ? h->trace + 8 : nullptr; // words 8..15 of the trace buffer
     const uint32_t nlaunch = (p.ngroups + p.gpl - 1) / p.gpl;
     uint32_t tbase = 0;
