@@ -412,22 +412,41 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         const uint32_t lq = (uint32_t)(warp & 3), L = lq * 32 + lane;
         const uint32_t q = q0 + lq * 16 + ((L >> 4) & 1u) * 8 + (L & 7u), plane = (L >> 3) & 1u;
         const unsigned char *src = a.pq + (size_t)(q < a.nq ? q : 0) * a.pq_stride + sizeof(PQHeader);
-        for (uint32_t ks = 0; ks < C / 2; ++ks) { // 2 chunks = 32 K-bytes = 8 columns = one MMA K step
-            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-            if (q < a.nq) {
-                v0 = __ldg(reinterpret_cast<const uint4 *>(src + ((size_t)(2 * ks) * 2 + plane) * 16));
-                v1 = __ldg(reinterpret_cast<const uint4 *>(src + ((size_t)(2 * ks + 1) * 2 + plane) * 16));
+        // 2 chunks = 32 K-bytes = 8 columns = one MMA K step.  The digit loads of 4 K steps are issued together before their
+        // stores (the stores are asm volatile with a memory clobber: one step at a time, every step paid a full L2 round
+        // trip -- ~15 us of every launch for 768-dimension rows)
+        constexpr uint32_t KB = 4;
+        for (uint32_t ks0 = 0; ks0 < C / 2; ks0 += KB) {
+            uint4 v0[KB], v1[KB];
+#pragma unroll
+            for (uint32_t u = 0; u < KB; ++u) {
+                const uint32_t ks = ks0 + u;
+                v0[u] = make_uint4(0, 0, 0, 0);
+                v1[u] = v0[u];
+                if (q < a.nq && ks < C / 2) {
+                    v0[u] = __ldg(reinterpret_cast<const uint4 *>(src + ((size_t)(2 * ks) * 2 + plane) * 16));
+                    v1[u] = __ldg(reinterpret_cast<const uint4 *>(src + ((size_t)(2 * ks + 1) * 2 + plane) * 16));
+                }
             }
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
-                             tmemA + ((lq * 32u) << 16) + ks * 8),
-                         "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w)
-                         : "memory");
+#pragma unroll
+            for (uint32_t u = 0; u < KB; ++u) {
+                const uint32_t ks = ks0 + u;
+                if (ks < C / 2) // warp-uniform
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
+                                     tmemA + ((lq * 32u) << 16) + ks * 8),
+                                 "r"(v0[u].x), "r"(v0[u].y), "r"(v0[u].z), "r"(v0[u].w), "r"(v1[u].x), "r"(v1[u].y), "r"(v1[u].z), "r"(v1[u].w)
+                                 : "memory");
+            }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // the query operand must be in TMEM before the first MMA -- a matter between the staging warps and the MMA warp.  The
+    // TMA producer (warp 0) does not wait: the first row tiles are in flight while the digits are still being staged.
+    if (warp != 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kBatchThreads - 32) : "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
 
     if (warp == 0) {
         // ================================================================ TMA producer
