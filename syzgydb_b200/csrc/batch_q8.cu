@@ -319,11 +319,26 @@ __device__ __noinline__ bool poll_bounds_grouped(const uint32_t *gmth, uint32_t 
     return all;
 }
 
-// first super tile >= sup with a live, unfiltered row; lanes 0..3 return the live words of its blocks.
-// Producer and epilogue warps run the same walk over the same immutable bitmaps, so they agree on the
-// sequence of tiles without exchanging it.
-__device__ __forceinline__ uint32_t next_live_tile(const BatchArgs &a, uint32_t sup, uint32_t sup1, int lane, uint32_t *words) {
-    for (; sup < sup1; ++sup) {
+// next super tile with a live, unfiltered row; lanes 0..3 return the live words of its blocks.  Tiles are dealt to the CTAs
+// of a query group on demand (one atomic counter per group, pre-set to 0xFFFFFFFF so that old + 1 is the tile): a CTA that
+// reaches its SM late -- the previous call's finalize kernel may still hold it -- simply takes fewer tiles, and the tail
+// of the launch is balanced to one tile.  Without a counter (ctr == nullptr) the CTA walks its fixed range [*, sup1).
+// Only the producer warp walks; the epilogue warps learn each tile's index through the side-data ring.
+// The counter is read one tile ahead (*pend = the grab issued during the previous call, lane 0): its L2 round trip runs
+// under the previous tile's ring waits instead of delaying this tile's copy (measured: +4 % on a 10M-row launch otherwise).
+__device__ __forceinline__ uint32_t grab_tile(uint32_t *ctr, int lane) {
+    uint32_t t = 0;
+    if (ctr && lane == 0) t = atomicAdd(ctr, 1u) + 1u;
+    return t;
+}
+__device__ __forceinline__ uint32_t next_live_tile(const BatchArgs &a, uint32_t *ctr, uint32_t *pend, uint32_t sup, uint32_t sup1,
+                                                   int lane, uint32_t *words) {
+    for (;; ++sup) {
+        if (ctr) {
+            sup = __shfl_sync(0xffffffffu, *pend, 0);
+            *pend = grab_tile(ctr, lane);
+        }
+        if (sup >= sup1) break;
         uint32_t lv = 0;
         if (lane < (int)kNB) {
             const uint32_t blk = sup * kNB + lane;
@@ -364,7 +379,8 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     const uint32_t g = blockIdx.x % a.ngroups, r = blockIdx.x / a.ngroups; // (query group, row range)
     const uint32_t nsup = (a.nblk + kNB - 1) / kNB;
     const uint32_t per = (nsup + a.nranges - 1) / a.nranges;
-    const uint32_t sup0 = min(nsup, r * per), sup1 = min(nsup, sup0 + per);
+    uint32_t *const ctr = a.tile_ctr ? a.tile_ctr + a.group0 + g : nullptr;
+    const uint32_t sup0 = ctr ? 0u : min(nsup, r * per), sup1 = ctr ? nsup : min(nsup, sup0 + per);
     const uint32_t q0 = (a.group0 + g) * kBatchQueries;
 
     if (tid == 0) {
@@ -456,8 +472,9 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         }
         uint32_t t = 0, xt = 0, words; // stage counter, tile counter
         bool again = a.nranges > 1; // the first tile of a range is sent twice (seeding pass, see the epilogue)
-        for (uint32_t sup = next_live_tile(a, sup0, sup1, lane, &words);;
-             sup = again ? sup : next_live_tile(a, sup + 1, sup1, lane, &words), again = false, ++xt) {
+        uint32_t pend = grab_tile(ctr, lane);
+        for (uint32_t sup = next_live_tile(a, ctr, &pend, sup0, sup1, lane, &words);;
+             sup = again ? sup : next_live_tile(a, ctr, &pend, sup + 1, sup1, lane, &words), again = false, ++xt) {
             // side data of the tile (or the end marker) for the epilogue warps
             const uint32_t x = xt % kAuxSlots;
             if (xt >= kAuxSlots) mbar_wait(&x_empty[x], ((xt / kAuxSlots) - 1) & 1u);

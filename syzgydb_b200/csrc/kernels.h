@@ -116,6 +116,7 @@ struct BatchArgs {
     uint32_t nranges, nlists;  // row ranges (CTAs per group); nlists = what finalize sees per query
     uint32_t stages;           // shared-memory ring stages (one K slice of a super tile each)
     uint32_t slice;            // chunks per K slice (even, <= C)
+    uint32_t *tile_ctr;        // [groups of the call] next-tile counters (pre-set to 0xFFFFFFFF), or nullptr: fixed row ranges
     uint32_t *gmth;            // [nq][nranges] ordered key of each range's mth-best row so far (0xFFFFFFFF = none yet)
     uint32_t mth;              // ceil(keep / nranges)
     uint32_t keep;             // candidates per (query, row range) list handed to finalize (32, 64, 128)

@@ -280,7 +280,7 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     // the query digits are laid out like an 8-bit row of Cb chunks in both cases
     const size_t stride = sizeof(PQHeader) + (size_t)p.Cb * nd * 16;
     if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * p.nranges * p.keep)) ||
-        (rc = ws->d_gmth.ensure((size_t)nq * p.nranges)))
+        (rc = ws->d_gmth.ensure((size_t)nq * p.nranges + p.ngroups)))
         return rc;
     const uint32_t nblk_now = (h->nslots + 31) / 32;
     if (p.p16 || p.p4) {
@@ -317,7 +317,10 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     b.C = p.Cb; b.nblk = nblk_now; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
     b.nranges = p.nranges; b.nlists = p.nranges; b.stages = p.stages; b.slice = p.slice;
     b.gmth = ws->d_gmth.p; b.mth = (p.keep + p.nranges - 1) / p.nranges;
-    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, (size_t)nq * p.nranges * sizeof(unsigned int), st));
+    // the groups' next-tile counters sit behind the bound keys: one memset presets both (a counter's first grab is old + 1 = 0)
+    static const bool fixed_ranges = getenv("SZG_BATCH_FIXED_RANGES") && atoi(getenv("SZG_BATCH_FIXED_RANGES")) != 0;
+    b.tile_ctr = (fixed_ranges || p.nranges < 2) ? nullptr : ws->d_gmth.p + (size_t)nq * p.nranges;
+    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, ((size_t)nq * p.nranges + p.ngroups) * sizeof(unsigned int), st));
     static const uint32_t dbg = getenv("SZG_BATCH_DEBUG") ? (uint32_t)atoi(getenv("SZG_BATCH_DEBUG")) : 0u;
     b.debug = dbg;
     static const uint32_t pmask = getenv("SZG_BATCH_POLL_MASK") ? (uint32_t)atoi(getenv("SZG_BATCH_POLL_MASK")) : 0u;
