@@ -40,7 +40,8 @@ namespace szg {
 namespace {
 
 constexpr int kBatchQueries = 64;          // queries per CTA (x 2 digit planes = M 128)
-constexpr int kBatchThreads = 320;         // producer, MMA, 8 epilogue warps
+constexpr int kBatchThreads = 384;         // producer, MMA, 8 epilogue warps, 2 bound pollers
+constexpr int kBatchPollWarp = 10;         // first poller warp (queries 0..31 of the group; the next one takes 32..63)
 constexpr uint32_t kNoBlock = 0xFFFFFFFFu;
 constexpr uint32_t kNB = 4;                // blocks per super tile (N = 4 x 32 = 128 rows)
 constexpr uint32_t kTileRows = kNB * 32;
@@ -180,7 +181,7 @@ template <bool COS, int E>
 __device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, const float2 *xaux /*shared: aux pairs of the tile*/,
                                         const uint32_t *xwords /*shared: live & filter words of the tile's 4 blocks*/,
                                         QState *wq /*the warp's 8 queries*/, unsigned long long *wl /*their lists*/, uint32_t slot0,
-                                        uint32_t *gmw /*gmth of the warp's first query, this range*/, uint32_t R, uint32_t mthm1,
+                                        uint32_t *gmw /*gmth of the warp's first query, this range*/, uint32_t gstride /*words per query*/, uint32_t mthm1,
                                         uint32_t capm1) {
     const int lane = threadIdx.x & 31;
     while (m) {
@@ -198,9 +199,13 @@ __device__ __noinline__ void batch_hits(unsigned m, float numf, uint32_t colb, c
         const unsigned long long k64 = make_key64(key, slot0 + col);
         if (k64 < s.thr) {
             if (lane == 0) ++s.inserts;
-            const unsigned long long last = list_insert<E>(wl + j * (32 * E), k64, lane, capm1, mthm1, gmw + (size_t)j * R, &s.pub);
+            const unsigned long long last = list_insert<E>(wl + j * (32 * E), k64, lane, capm1, mthm1, gmw + (size_t)j * gstride, &s.pub);
             __syncwarp();
-            if (lane == 0) { s.thr = last < s.gbound ? last : s.gbound; s.T = fast_threshold<COS>(s); }
+            if (lane == 0) {
+                const unsigned long long gb = *reinterpret_cast<volatile unsigned long long *>(&s.gbound);
+                s.thr = last < gb ? last : gb;
+                s.T = fast_threshold<COS>(s);
+            }
             __syncwarp();
         }
     }
@@ -213,7 +218,7 @@ template <bool COS, bool FITS, int E, bool P16 = false>
 __device__ __forceinline__ float score16(const uint32_t (&r)[32], const uint32_t (&rl)[32], const float4 (&ax)[8], int numc32, long long numc64,
                                          float T, float c2,
                                          uint32_t colp, const float2 *xaux, const uint32_t *xwords, QState *wq, unsigned long long *wl,
-                                         uint32_t slot0, const float *Tsrc, uint32_t *gmw, uint32_t R, uint32_t mthm1, uint32_t capm1,
+                                         uint32_t slot0, const float *Tsrc, uint32_t *gmw, uint32_t gstride, uint32_t mthm1, uint32_t capm1,
                                          bool seeding = false) {
     float numf[16], v[16];
 #pragma unroll
@@ -264,7 +269,7 @@ __device__ __forceinline__ float score16(const uint32_t (&r)[32], const uint32_t
 #pragma unroll
                 for (int i = 4 * g4; i < 4 * g4 + 4; ++i) {
                     const unsigned m = __ballot_sync(0xffffffffu, v[i] > T);
-                    if (m) batch_hits<COS, E>(m, numf[i], colp + (i >> 1) * 8 + (i & 1), xaux, xwords, wq, wl, slot0, gmw, R, mthm1, capm1);
+                    if (m) batch_hits<COS, E>(m, numf[i], colp + (i >> 1) * 8 + (i & 1), xaux, xwords, wq, wl, slot0, gmw, gstride, mthm1, capm1);
                 }
             }
         }
@@ -274,48 +279,51 @@ __device__ __forceinline__ float score16(const uint32_t (&r)[32], const uint32_t
 }
 
 
-// Shared bound of the warp's 8 queries from the keys the R row ranges of each query have published (see the epilogue).
-// Kept out of line: inlined, its 16 live registers of loads disturb the allocation of the scoring loop (measured
-// 2.04 vs 1.85 ms on the 1024-query case).  Returns true when every valid query has a bound.
-template <bool COS>
-__device__ __noinline__ bool poll_bounds_grouped(const uint32_t *gmth, uint32_t R, uint32_t need, uint32_t qfirst, uint32_t nq,
-                                                 QState *wq) {
-    const int lane = threadIdx.x & 31;
-    // branch-free, clamped loads (L2-coherent, non-volatile) so that the 8 queries' loads of one step are in flight
-    // together: with a conditional per query they were serialised into ~16 L2 round trips per poll
-    uint32_t v[8];
-    const bool voter = (uint32_t)lane < need;
-    const uint32_t *g0 = gmth + (size_t)min(qfirst, nq - 1) * R;
-#pragma unroll
-    for (uint32_t j = 0; j < 8; ++j) v[j] = voter ? 0xFFFFFFFFu : 0u; // lanes beyond `need` do not vote in the maximum
-    const uint32_t steps = (R + need - 1) / need; // uniform trip count
-    const uint32_t jmax = nq - 1 - min(qfirst, nq - 1); // clamp for the (invalid) queries past the batch
-    for (uint32_t t = 0; t < steps; ++t) {
-        const uint32_t rr = (uint32_t)lane + t * need;
-        const bool ok = voter && rr < R;
-        const uint32_t rc = min(rr, R - 1);
-        uint32_t x[8];
-#pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) x[j] = __ldcg(g0 + (size_t)min(j, jmax) * R + rc);
-#pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) v[j] = ok ? min(v[j], x[j]) : v[j];
-    }
+// Shared bound of a query from the keys its R row ranges (CTAs) have published.  Any value B such that `need` = ceil(Kp / mth)
+// different ranges have published a key <= B is valid: each of them holds mth rows at or below its key, so need * mth >= Kp
+// rows lie at or below B.  The ranges are dealt into `need` groups (range r -> group r % need); B = the largest of the
+// per-group minima.  With R = 148 ranges and Kp = 32 that is ~6x tighter than the plain maximum over all ranges.
+// Layout of the published keys: gmth[query][group][SP] (SP = members per group rounded up to 4 or 8 words, padding and
+// unpublished entries 0xFFFFFFFF), so a lane reads one group with one or two 16-byte loads and the loads of 8 (query, group)
+// units are in flight together: one L2 round trip per 8 / ceil(need / 32) queries.
+// Called by a poller warp for `nqv` consecutive valid queries; writes QState::gbound only (the owning epilogue warp folds
+// it into its thresholds).  Returns true when every one of them has a bound.
+__device__ __noinline__ bool poll_bounds(const uint32_t *gmth, uint32_t QS, uint32_t SP, uint32_t need, uint32_t qfirst, uint32_t nqv,
+                                         QState *sq, const uint32_t *epi_done /*shared: finished epilogue warps*/) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lg = need <= 32 ? 0u : need <= 64 ? 1u : 2u; // 32-group slabs per query = 1 << lg
+    const uint32_t QB = 8u >> lg;                                // queries per batch of 8 units
     bool all = true;
+    for (uint32_t j0 = 0; j0 < nqv; j0 += QB) {
+        if (*reinterpret_cast<const volatile uint32_t *>(epi_done) >= 8u) return true; // the CTA is done: do not hold up its exit
+        uint4 x0[8], x1[8];
 #pragma unroll
-    for (uint32_t j = 0; j < 8; ++j) {
-        if (!wq[j].valid) continue;
-        const uint32_t b = __reduce_max_sync(0xffffffffu, v[j]);
-        if (b == 0xFFFFFFFFu) { all = false; continue; }
-        if (lane == 0) {
-            const unsigned long long gb = ((unsigned long long)b << 32) | 0xFFFFFFFFull;
-            QState &s = wq[j];
-            if (gb < s.gbound) {
-                s.gbound = gb;
-                if (gb < s.thr) { s.thr = gb; s.T = fast_threshold<COS>(s); }
+        for (uint32_t u = 0; u < 8; ++u) {
+            const uint32_t j = min(j0 + (u >> lg), nqv - 1);
+            const uint32_t g = min(lane + 32u * (u & ((1u << lg) - 1u)), need - 1);
+            const uint32_t *p = gmth + (size_t)(qfirst + j) * QS + (size_t)g * SP;
+            x0[u] = __ldcg(reinterpret_cast<const uint4 *>(p));
+            x1[u] = SP > 4 ? __ldcg(reinterpret_cast<const uint4 *>(p + 4)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (uint32_t u = 0; u < 8; ++u) {
+            const uint32_t gi = u & ((1u << lg) - 1u);
+            const bool ok = lane + 32u * gi < need; // lanes past the last group do not vote in the maximum
+            const uint32_t m = min(min(min(x0[u].x, x0[u].y), min(x0[u].z, x0[u].w)), min(min(x1[u].x, x1[u].y), min(x1[u].z, x1[u].w)));
+            const uint32_t b = __reduce_max_sync(0xffffffffu, ok ? m : 0u);
+            acc = gi == 0 ? b : max(acc, b);
+            const uint32_t j = j0 + (u >> lg);
+            if (gi == (1u << lg) - 1u && j < nqv) { // last slab of query j: acc = its bound (0xFFFFFFFF: some group has not published)
+                if (acc == 0xFFFFFFFFu) all = false;
+                else if (lane == 0) {
+                    const unsigned long long gb = ((unsigned long long)acc << 32) | 0xFFFFFFFFull;
+                    volatile unsigned long long *dst = &sq[j].gbound;
+                    if (gb < *dst) *dst = gb;
+                }
             }
         }
     }
-    __syncwarp();
     return all;
 }
 
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     __shared__ __align__(8) uint64_t x_full[kAuxSlots], x_empty[kAuxSlots];
     __shared__ uint32_t s_tmem;
     __shared__ int s_fits;
+    __shared__ uint32_t s_epi_done; // epilogue warps that have finished (the poller warp's exit condition)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t C = a.C, S = a.stages;
     const uint32_t slc = a.slice;                        // chunks per K slice (= TMA box)
@@ -382,6 +391,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     uint32_t *const ctr = a.tile_ctr ? a.tile_ctr + a.group0 + g : nullptr;
     const uint32_t sup0 = ctr ? 0u : min(nsup, r * per), sup1 = ctr ? nsup : min(nsup, sup0 + per);
     const uint32_t q0 = (a.group0 + g) * kBatchQueries;
+    if (a.trace && blockIdx.x == 0 && tid == 128) a.trace[7] = clock64(); // kernel entry, same SM and thread as stamps 0..3
 
     if (tid == 0) {
         for (uint32_t s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -389,6 +399,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         for (uint32_t x = 0; x < kAuxSlots; ++x) { mbar_init(&x_full[x], 1); mbar_init(&x_empty[x], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_fits = 1;
+        s_epi_done = 0;
     }
     __syncthreads();
     if (tid < kBatchQueries) {
@@ -581,6 +592,27 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             }
             if (end) break;
         }
+    } else if (warp >= kBatchPollWarp) {
+        // ================================================================ bound pollers (2 warps, 32 queries each)
+        // Read the keys the R row ranges of each query have published and keep QState::gbound current.  Done by the epilogue
+        // warps themselves (round 1), a poll -- L2 round trips under full streaming load, ~14 us for 148 ranges -- kept the
+        // accumulators undrained and stalled the ring: 2.8 us per tile on a 66-tile range against 2.0 us on a 528-tile one
+        // with six polls each.  Here it costs the pipeline nothing and the bound is fresher.
+        const uint32_t R = a.nranges;
+        const uint32_t qp = (uint32_t)(warp - kBatchPollWarp) * 32u; // first query of this poller within the group
+        const uint32_t nqv = q0 + qp < a.nq ? min(32u, a.nq - (q0 + qp)) : 0u;
+        if (R > 1 && nqv) {
+            constexpr uint32_t Kp = 32 * E;
+            const uint32_t need = (Kp + a.mth - 1) / a.mth;
+            // with several query groups per launch the row tiles come from L2 and the polls compete with them: poll less often
+            const uint32_t pause = a.poll_ns ? a.poll_ns : 1000u * a.ngroups * a.ngroups;
+            while (*reinterpret_cast<volatile uint32_t *>(&s_epi_done) < 8u) {
+                const bool all = poll_bounds(a.gmth, a.gm_stride, a.gm_sp, need, q0 + qp, nqv, &s_q[qp], &s_epi_done);
+                // sleep in short slices: the CTA must not outlive its epilogue warps by a pause
+                for (uint32_t t = 0; t < (all ? pause : 100u) && *reinterpret_cast<volatile uint32_t *>(&s_epi_done) < 8u; t += 250u)
+                    __nanosleep(all ? 250u : 100u);
+            }
+        }
     } else {
         // ================================================================ epilogue (8 warps, 8 queries each)
         // warp = (TMEM lane quarter lq, half hh): TMEM lanes 32 lq + 16 hh + {0..15} = both planes of 8 queries
@@ -607,42 +639,26 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         // To have the bound from the start, the first tile of a range is processed twice: once "seeding"
         // (admission by the mth-best key, cheap), then -- after every range of the group has published -- for real.
         const uint32_t R = a.nranges, mthm1 = a.mth - 1;
-        uint32_t *gmw = a.gmth + ((size_t)min(q0 + qw, a.nq - 1) * R + r);
-        // poll every 4 / 16 / 64 tiles (+ at powers of two); a poll is a round trip to L2 under full streaming load (measured
-        // ~14 us per poll with 148 ranges), during which this warp does not drain its accumulators
-        const uint32_t poll_mask = a.poll_mask ? a.poll_mask : (R <= 16 ? 3u : R <= 64 ? 15u : 63u);
-        const uint32_t poll_min = a.poll_min ? a.poll_min : 2u;
-        // The bound of a query from the published keys: any value B such that `need` = ceil(Kp / mth) different ranges have
-        // published a key <= B is valid (each of them has mth rows at or below its key, so need * mth >= Kp rows lie at or
-        // below B).  The ranges are dealt into `need` groups (range r -> group r % need); B = max over the groups of the
-        // smallest key in the group.  With R = 148 ranges and Kp = 32 this is ~6x tighter than the plain maximum over all
-        // ranges, for ceil(R / need) loads per lane.  Returns true when every query of the warp has a bound.
-        const uint32_t need = (Kp + a.mth - 1) / a.mth;
-        auto poll_grouped = [&]() -> bool { return poll_bounds_grouped<COS>(a.gmth, R, need, q0 + qw, a.nq, wq); };
-        // few ranges: the plain maximum over all of them (one lane per query, one round trip) is as good and cheaper
-        auto poll_plain = [&]() -> bool {
+        const uint32_t need = (Kp + a.mth - 1) / a.mth, QS = a.gm_stride;
+        // this range's slot in the published keys of the warp's first query: [query][group r % need][member r / need]
+        uint32_t *gmw = a.gmth + ((size_t)min(q0 + qw, a.nq - 1) * QS + (size_t)(r % need) * a.gm_sp + r / need);
+        // The bound itself is kept current by the poller warp (QState::gbound); this warp folds it into its queries'
+        // thresholds at the start of every tile: shared-memory reads only.
+        auto fold_bounds = [&]() -> bool {
             bool have = true;
             if (lane < 8 && wq[lane].valid) {
-                const volatile uint32_t *g = a.gmth + (size_t)(q0 + qw + lane) * R;
-                uint32_t b = 0;
-                for (uint32_t rr = 0; rr < R; ++rr) b = max(b, g[rr]);
-                have = b != 0xFFFFFFFFu;
-                if (have) {
-                    const unsigned long long gb = ((unsigned long long)b << 32) | 0xFFFFFFFFull;
-                    QState &s = wq[lane];
-                    if (gb < s.gbound) {
-                        s.gbound = gb;
-                        if (gb < s.thr) { s.thr = gb; s.T = fast_threshold<COS>(s); }
-                    }
-                }
+                QState &s = wq[lane];
+                const unsigned long long gb = *reinterpret_cast<volatile unsigned long long *>(&s.gbound);
+                have = gb != kNoKey;
+                if (gb < s.thr) { s.thr = gb; s.T = fast_threshold<COS>(s); }
             }
-            return __all_sync(0xffffffffu, have);
+            have = __all_sync(0xffffffffu, have);
+            T = qs->T;
+            return have;
         };
-        auto poll_bounds = [&]() -> bool { return R <= 16 ? poll_plain() : poll_grouped(); };
         bool seeding = R > 1;
-        const bool tr = a.trace && blockIdx.x == 0 && warp == 2 && lane == 0;
+        const bool tr = a.trace && blockIdx.x == 0 && warp == 4 && lane == 0; // warp 4 owns queries 0..7 of the group
         if (tr) a.trace[0] = clock64();
-        uint32_t npolls = 0;
         for (uint32_t tile = 0;; ++tile) {
             const uint32_t d = P16 ? 0u : (tile & 1u), x = tile % kAuxSlots;
             // side data of the tile (aux pairs, live words): read in place; removed / filtered rows are rejected only
@@ -650,11 +666,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             mbar_wait(&x_full[x], (tile / kAuxSlots) & 1u);
             const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&s_xsup[x]);
             if (cur == kNoBlock) break;
-            if (R > 1 && tile >= poll_min && ((tile & (tile - 1)) == 0 || (tile & poll_mask) == 0)) {
-                poll_bounds();
-                ++npolls;
-                T = qs->T;
-            }
+            if (R > 1 && !seeding) fold_bounds();
             const uint32_t capm1 = seeding ? mthm1 : Kp - 1;
             mbar_wait(&d_full[d], (P16 ? tile : (tile >> 1)) & 1u); // 16-bit: d = 0, the high-byte buffer
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -684,8 +696,8 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             };
             const uint32_t slot0 = cur * kTileRows;
             auto score = [&](const uint32_t (&rr)[32], uint32_t part) {
-                if (fits) T = score16<COS, true, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
-                else T = score16<COS, false, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
+                if (fits) T = score16<COS, true, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, QS, mthm1, capm1, seeding);
+                else T = score16<COS, false, E>(rr, rr, ax, numc32, numc64, T, c2, part * 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, QS, mthm1, capm1, seeding);
             };
             if (P16) {
                 // high-byte accumulators in buffer 0, low-byte ones in buffer 1: each is drained to registers and released
@@ -708,9 +720,9 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[1]); // low-byte accumulators too
-                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
+                T = score16<COS, false, E, true>(ra, rb, ax, numc32, numc64, T, c2, 0, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, QS, mthm1, capm1, seeding);
                 load_ax(1);
-                T = score16<COS, false, E, true>(rc, rd, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, R, mthm1, capm1, seeding);
+                T = score16<COS, false, E, true>(rc, rd, ax, numc32, numc64, T, c2, 64, s_xaux[x], s_xwords[x], wq, wl, slot0, &qs->T, gmw, QS, mthm1, capm1, seeding);
             } else {
             // both halves of this warp's part of the accumulator go to registers first, so the buffer returns to the
             // MMA warp before any scoring (a warp that has rows to insert would otherwise hold it)
@@ -733,7 +745,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 seeding = false;
                 if (lane < 8 && wq[lane].valid && wq[lane].pub == 0xFFFFFFFFu) {
                     wq[lane].pub = 0xFFFFFFFEu;
-                    *reinterpret_cast<volatile uint32_t *>(gmw + (size_t)lane * R) = 0xFFFFFFFEu;
+                    *reinterpret_cast<volatile uint32_t *>(gmw + (size_t)lane * QS) = 0xFFFFFFFEu;
                 }
                 __syncwarp();
                 for (uint32_t i = lane; i < 8 * Kp; i += 32) wl[i] = kNoKey; // the tile comes again
@@ -743,9 +755,8 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
                 // bound is an optimisation only, so the wait is bounded (~4 ms) and the range simply goes on without it
                 if (tr) a.trace[1] = clock64();
                 int spin = 0;
-                for (; !poll_bounds() && spin < 20000; ++spin) __nanosleep(200);
+                for (; !fold_bounds() && spin < 40000; ++spin) __nanosleep(100);
                 if (tr) { a.trace[2] = clock64(); a.trace[5] = spin; }
-                T = qs->T;
             }
         }
         __syncwarp();
@@ -754,12 +765,13 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             uint32_t ins = 0;
             for (int j = 0; j < 8; ++j) ins += wq[j].inserts;
             a.trace[4] = ins;
-            a.trace[6] = npolls;
+            a.trace[6] = 0;
         }
         if (seeding && lane < 8 && wq[lane].valid) // a range without live rows: tell the others not to wait for it
-            *reinterpret_cast<volatile uint32_t *>(gmw + (size_t)lane * R) = 0xFFFFFFFEu;
+            *reinterpret_cast<volatile uint32_t *>(gmw + (size_t)lane * QS) = 0xFFFFFFFEu;
         // hand the lists to finalize_kernel: cand[query][row range][Kp]
         __syncwarp();
+        if (lane == 0) atomicAdd(&s_epi_done, 1u);
         for (uint32_t j = 0; j < 8; ++j) {
             if (!wq[j].valid) continue;
             unsigned long long *gb = a.cand + ((size_t)(q0 + qw + j) * a.nranges + r) * Kp;

@@ -117,11 +117,13 @@ struct BatchArgs {
     uint32_t stages;           // shared-memory ring stages (one K slice of a super tile each)
     uint32_t slice;            // chunks per K slice (even, <= C)
     uint32_t *tile_ctr;        // [groups of the call] next-tile counters (pre-set to 0xFFFFFFFF), or nullptr: fixed row ranges
-    uint32_t *gmth;            // [nq][nranges] ordered key of each range's mth-best row so far (0xFFFFFFFF = none yet)
+    uint32_t *gmth;            // [nq][need groups][gm_sp] ordered key of each range's mth-best row so far (range r -> group r % need,
+                               // member r / need; 0xFFFFFFFF = none yet / padding), need = ceil(keep / mth)
+    uint32_t gm_stride, gm_sp; // words per query (need * gm_sp) and per group (4 or 8)
     uint32_t mth;              // ceil(keep / nranges)
     uint32_t keep;             // candidates per (query, row range) list handed to finalize (32, 64, 128)
     uint32_t debug;            // profiling aid: bit0 skip the epilogue math, bit1 skip aux loads, bit2 skip the MMAs
-    uint32_t poll_mask, poll_min; // 0 = defaults: when the epilogue warps re-read the shared bound (tuning: SZG_BATCH_POLL_MASK / _MIN)
+    uint32_t poll_ns;          // pause of the bound poller warp between rounds once every query has a bound (0 = 2000 ns; SZG_BATCH_POLL_NS)
     long long *trace;          // profiling aid (SZG_OPT_TRACE_BUFFER): clock64 stamps / counters of CTA 0's first epilogue warp
 };
 uint32_t batch_slice_chunks(uint32_t C, uint32_t want, size_t smem_limit); // chunks per K slice (ring stage); want = 0: automatic

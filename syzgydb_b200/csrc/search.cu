@@ -241,7 +241,12 @@ int run_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32
 }
 
 // ---- batched queries on the tensor cores (batch_q8.cu)
-struct BatchPlan { uint32_t slice, stages, keep, nranges, gpl, ngroups, Cb; int mode; bool p16, p4; };
+struct BatchPlan {
+    uint32_t slice, stages, keep, nranges, gpl, ngroups, Cb;
+    uint32_t mth, gm_sp, gm_stride; // published bound keys: mth-best row per range; words per group / per query (batch_q8.cu)
+    int mode;
+    bool p16, p4;
+};
 
 // true when the tensor-core path can serve (collection, k, candidate mode): 4/8/16-bit rows, an even number of 16-byte
 // chunks that fits the TMEM columns reserved for the query digits, candidate lists of at most 128 keys, 2-digit queries
@@ -267,6 +272,14 @@ static bool plan_batch(const szg_index *h, uint32_t nq, uint32_t k, int mode, Ba
     p->gpl = std::min<uint32_t>(p->ngroups, 16); // query groups per launch (they share the L2 copy of a row range)
     const uint32_t nblk = (h->nslots + 31) / 32;
     p->nranges = std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)h->sm_count / p->gpl, (nblk + 3) / 4));
+    // ranges are dealt into need = ceil(keep / mth) groups; a group's published keys are read with at most two 16-byte loads
+    for (;; --p->nranges) {
+        p->mth = (p->keep + p->nranges - 1) / p->nranges;
+        const uint32_t need = (p->keep + p->mth - 1) / p->mth;
+        p->gm_sp = ((p->nranges + need - 1) / need + 3) & ~3u;
+        p->gm_stride = need * p->gm_sp;
+        if (p->gm_sp <= 8) break;
+    }
     return true;
 }
 
@@ -280,7 +293,7 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     // the query digits are laid out like an 8-bit row of Cb chunks in both cases
     const size_t stride = sizeof(PQHeader) + (size_t)p.Cb * nd * 16;
     if ((rc = ws->d_pq.ensure(stride * nq)) || (rc = ws->d_cand.ensure((size_t)nq * p.nranges * p.keep)) ||
-        (rc = ws->d_gmth.ensure((size_t)nq * p.nranges + p.ngroups)))
+        (rc = ws->d_gmth.ensure((size_t)nq * p.gm_stride + p.ngroups)))
         return rc;
     const uint32_t nblk_now = (h->nslots + 31) / 32;
     if (p.p16 || p.p4) {
@@ -316,16 +329,15 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     b.pq = ws->d_pq.p; b.pq_stride = stride; b.cand = ws->d_cand.p; b.keep = p.keep;
     b.C = p.Cb; b.nblk = nblk_now; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
     b.nranges = p.nranges; b.nlists = p.nranges; b.stages = p.stages; b.slice = p.slice;
-    b.gmth = ws->d_gmth.p; b.mth = (p.keep + p.nranges - 1) / p.nranges;
+    b.gmth = ws->d_gmth.p; b.mth = p.mth; b.gm_sp = p.gm_sp; b.gm_stride = p.gm_stride;
     // the groups' next-tile counters sit behind the bound keys: one memset presets both (a counter's first grab is old + 1 = 0)
     static const bool fixed_ranges = getenv("SZG_BATCH_FIXED_RANGES") && atoi(getenv("SZG_BATCH_FIXED_RANGES")) != 0;
-    b.tile_ctr = (fixed_ranges || p.nranges < 2) ? nullptr : ws->d_gmth.p + (size_t)nq * p.nranges;
-    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, ((size_t)nq * p.nranges + p.ngroups) * sizeof(unsigned int), st));
+    b.tile_ctr = (fixed_ranges || p.nranges < 2) ? nullptr : ws->d_gmth.p + (size_t)nq * p.gm_stride;
+    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, ((size_t)nq * p.gm_stride + p.ngroups) * sizeof(unsigned int), st));
     static const uint32_t dbg = getenv("SZG_BATCH_DEBUG") ? (uint32_t)atoi(getenv("SZG_BATCH_DEBUG")) : 0u;
     b.debug = dbg;
-    static const uint32_t pmask = getenv("SZG_BATCH_POLL_MASK") ? (uint32_t)atoi(getenv("SZG_BATCH_POLL_MASK")) : 0u;
-    static const uint32_t pmin = getenv("SZG_BATCH_POLL_MIN") ? (uint32_t)atoi(getenv("SZG_BATCH_POLL_MIN")) : 0u;
-    b.poll_mask = pmask; b.poll_min = pmin;
+    static const uint32_t pns = getenv("SZG_BATCH_POLL_NS") ? (uint32_t)atoi(getenv("SZG_BATCH_POLL_NS")) : 0u;
+    b.poll_ns = pns;
     b.trace = h->trace ? h->trace + 8 : nullptr; // words 8..15 of the trace buffer
     const uint32_t nlaunch = (p.ngroups + p.gpl - 1) / p.gpl;
     uint32_t tbase = 0;

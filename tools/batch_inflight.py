@@ -18,13 +18,17 @@ for rows in sizes:
     with szg.Index(768, 8, szg.COSINE) as ix:
         ix.fill_synthetic(0x5A590004, 0, rows)
         ix.set_option(_capi.OPT_COMBINE, 0)
-        qs = [rng.uniform(-1, 1, size=(32, 768)) for _ in range(2)]
-        for callers in (1, 2):
+        qs = [rng.uniform(-1, 1, size=(32, 768)) for _ in range(3)]
+        for callers in (1, 2, 3):
             n = 300
+
+            lat = [[] for _ in range(callers)]
 
             def work(i):
                 for _ in range(n):
+                    t = time.perf_counter()
                     ix.search_topk(qs[i], 10)
+                    lat[i].append(time.perf_counter() - t)
 
             for i in range(callers):
                 for _ in range(5):
@@ -36,4 +40,7 @@ for rows in sizes:
             for t in ts:
                 t.join()
             dt = time.perf_counter() - t0
-            print(f"rows {rows} callers {callers}: {dt / (n * callers) * 1e3:.4f} ms/step, fixed_ranges={os.environ.get('SZG_BATCH_FIXED_RANGES', '0')}", flush=True)
+            a = np.sort(np.concatenate(lat)) * 1e3
+            print(f"rows {rows} callers {callers}: {dt / (n * callers) * 1e3:.4f} ms/step; call latency ms p50 {a[len(a) // 2]:.3f} p90 {a[int(len(a) * 0.9)]:.3f} "
+                  f"p99 {a[int(len(a) * 0.99)]:.3f} max {a[-1]:.3f}, calls > 1.5 x p50: {int((a > 1.5 * a[len(a) // 2]).sum())}; "
+                  f"fixed_ranges={os.environ.get('SZG_BATCH_FIXED_RANGES', '0')} priority={os.environ.get('SZG_PRIORITY', 'default')}", flush=True)

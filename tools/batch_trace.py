@@ -24,5 +24,5 @@ for rows in (1_250_000, 10_000_000):
                 torch.cuda.synchronize()
                 t = buf.cpu().numpy()[8:]
             ms = ix.last_scan_times_ms()
-            print(f"rows {rows} nq {nq}: kernel {ms[-1]:.4f} ms; epilogue warp cycles: first tile (seeding) {t[1]-t[0]}, wait for all ranges {t[2]-t[1]} "
+            print(f"rows {rows} nq {nq}: kernel {ms[-1]:.4f} ms; epilogue warp cycles: setup {t[0]-t[7]}, first tile (seeding) {t[1]-t[0]}, wait for all ranges {t[2]-t[1]} "
                   f"({t[5]} sleeps), rest {t[3]-t[2]}; inserts of the warp's 8 queries {t[4]}, polls {t[6]}", flush=True)
