@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     uint32_t *const ctr = a.tile_ctr ? a.tile_ctr + a.group0 + g : nullptr;
     const uint32_t sup0 = ctr ? 0u : min(nsup, r * per), sup1 = ctr ? nsup : min(nsup, sup0 + per);
     const uint32_t q0 = (a.group0 + g) * kBatchQueries;
+    grid_launch_dependents(); // finalize_kernel may take its place on an SM as soon as one has room (it waits for this grid)
     if (a.trace && blockIdx.x == 0 && tid == 128) a.trace[7] = clock64(); // kernel entry, same SM and thread as stamps 0..3
 
     if (tid == 0) {

@@ -12,8 +12,34 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace szg {
+
+// Launch of the kernel that ends a search pass (finalize) as a programmatic dependent of the scan before it in the stream: its
+// CTAs may become resident as soon as every CTA of the scan has executed griddepcontrol.launch_dependents (the scans do so at
+// their start) and an SM has room, and they block in griddepcontrol.wait -- the first thing the kernel does -- until the scan
+// has completed and its writes are visible.  What it buys: the launch latency of the dependent disappears behind the scan,
+// and, with several calls in flight, this call's last kernel is already queued on the SMs when the scan's CTAs retire
+// instead of lining up behind the next call's full-device scan.  SZG_PDL=0 turns the attribute off (plain stream order).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    static const bool pdl = !(getenv("SZG_PDL") && atoi(getenv("SZG_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// device side of the above
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 constexpr int kRowsPerBlock = 32;
 constexpr int kChunkBytes = 16;

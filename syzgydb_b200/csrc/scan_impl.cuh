@@ -846,6 +846,7 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
     const uint32_t qi = blockIdx.x;
     const unsigned long long *cand = a.cand + (size_t)qi * a.nlists * Kp;
     const bool tr = a.trace && qi == 0 && tid == 0;
+    grid_dependency_wait(); // launched as a programmatic dependent of the scan (launch_dependent): its lists are complete from here on
     if (tr) a.trace[0] = clock64();
     WarpList<E> list;
     list.init();
@@ -901,6 +902,7 @@ template <int QT, int MODE, int ND, bool SHARE = false>
 __global__ void __launch_bounds__(kMaxScanWarps * 32, 1) scan_kernel(const ScanArgs a) {
     constexpr int E = (MODE == MODE_RADIUS) ? 1 : (1 << MODE);
     constexpr int Kp = 32 * E;
+    grid_launch_dependents(); // a finalize_kernel launched as programmatic dependent may queue behind this grid's CTAs now
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar[kMaxScanWarps][kMaxStages];
     __shared__ RingMeta s_meta[kMaxScanWarps];
@@ -1132,13 +1134,12 @@ template <int QT>
 cudaError_t launch_finalize_t(int mode, uint32_t nq, cudaStream_t st, const FinalizeArgs &a) {
     const size_t smem = finalize_smem_bytes(mode);
     switch (mode) {
-    case 0: finalize_kernel<QT, 0><<<nq, kFinalizeThreads, smem, st>>>(a); break;
-    case 1: finalize_kernel<QT, 1><<<nq, kFinalizeThreads, smem, st>>>(a); break;
-    case 2: finalize_kernel<QT, 2><<<nq, kFinalizeThreads, smem, st>>>(a); break;
-    case 3: finalize_kernel<QT, 3><<<nq, kFinalizeThreads, smem, st>>>(a); break;
+    case 0: return launch_dependent(finalize_kernel<QT, 0>, nq, kFinalizeThreads, smem, st, a);
+    case 1: return launch_dependent(finalize_kernel<QT, 1>, nq, kFinalizeThreads, smem, st, a);
+    case 2: return launch_dependent(finalize_kernel<QT, 2>, nq, kFinalizeThreads, smem, st, a);
+    case 3: return launch_dependent(finalize_kernel<QT, 3>, nq, kFinalizeThreads, smem, st, a);
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 template <int QT>

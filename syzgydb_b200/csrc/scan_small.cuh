@@ -92,6 +92,7 @@ struct SmallOps<Q16, ND> {
 
 template <int QT, int ND, int C, int Q, bool CQ>
 __global__ void __launch_bounds__(kSmallWarps * 32, 1) scan_small_kernel(const ScanArgs a) {
+    grid_launch_dependents(); // see launch_dependent (common.cuh): finalize_kernel queues behind this grid's CTAs
     // a lane holds 16 uint4 of row data at a time: U = 16 / C whole rows (of U different blocks) when C <= 8, else
     // pieces of 8 chunks of two rows (C = 12: 4 chunks of four rows).  The digits of a chunk are read once for the U
     // rows: the L1 data pipe, which carries the row loads and (through shared memory) the digit broadcasts, limited the
