@@ -403,9 +403,19 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         s_epi_done = 0;
     }
     __syncthreads();
-    if (tid < kBatchQueries) {
-        const uint32_t q = q0 + tid;
-        QState &s = s_q[tid];
+    // The launch is a programmatic dependent of prep_kernel (launch_batch): everything up to here, the TMEM allocation and the
+    // producer warp's first row tiles (rows, live words and tile counters are older than prep) overlap prep's execution.  The
+    // warps that read prep's output -- query headers and digits -- wait for it here; warp 0 (TMA producer) never does.
+    uint32_t tmem = 0, tmemA = 0;
+    if (warp != 0) {
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    grid_dependency_wait();
+    if (tid >= 64 && tid < 64 + kBatchQueries) {
+        const uint32_t q = q0 + (uint32_t)(tid - 64);
+        QState &s = s_q[tid - 64];
         s.valid = q < a.nq;
         const PQHeader *hdr = reinterpret_cast<const PQHeader *>(a.pq + (size_t)(s.valid ? q : 0) * a.pq_stride);
         s.thr = s.valid ? kNoKey : 0ull;
@@ -425,15 +435,11 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         const bool fits = 255.0 * ldexp(1.0, hdr->F) * sqrt((double)a.dims * hdr->qn2) < 2.0e9;
         if (s.valid && (!fits || P16)) atomicAnd(&s_fits, 0);
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(kBatchThreads - 32) : "memory"); // query state and the TMEM address are in shared memory
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
-    const uint32_t tmemA = tmem + 2 * kAccCols;
+    tmem = s_tmem;
+    tmemA = tmem + 2 * kAccCols;
 
     // ---- A operand: TMEM lane L = 32 lq + 16 h + 8 plane + j holds digit plane `plane` of query 16 lq + 8 h + j
     if (warp >= 2 && warp < 6) {
@@ -470,7 +476,6 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
     }
     // the query operand must be in TMEM before the first MMA -- a matter between the staging warps and the MMA warp.  The
     // TMA producer (warp 0) does not wait: the first row tiles are in flight while the digits are still being staged.
-    if (warp != 0) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(kBatchThreads - 32) : "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -850,18 +855,15 @@ static cudaError_t make_tmap(const BatchArgs &a, const uint4 *codes, CUtensorMap
 }
 
 template <bool P16>
-static void launch_variant(const BatchArgs &a, const CUtensorMap &tm, const CUtensorMap &tl, dim3 grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_variant(const BatchArgs &a, const CUtensorMap &tm, const CUtensorMap &tl, dim3 grid, size_t smem, cudaStream_t st) {
     const bool cos = a.metric == COSINE;
-    if (a.keep == 32) {
-        if (cos) batch_kernel<true, 1, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
-        else batch_kernel<false, 1, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
-    } else if (a.keep == 64) {
-        if (cos) batch_kernel<true, 2, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
-        else batch_kernel<false, 2, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
-    } else {
-        if (cos) batch_kernel<true, 4, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
-        else batch_kernel<false, 4, P16><<<grid, kBatchThreads, smem, st>>>(a, tm, tl);
-    }
+    // programmatic dependent of the prep_kernel before it in the stream (see the kernel's set-up)
+    if (a.keep == 32) return cos ? launch_dependent(batch_kernel<true, 1, P16>, grid, kBatchThreads, smem, st, a, tm, tl)
+                                 : launch_dependent(batch_kernel<false, 1, P16>, grid, kBatchThreads, smem, st, a, tm, tl);
+    if (a.keep == 64) return cos ? launch_dependent(batch_kernel<true, 2, P16>, grid, kBatchThreads, smem, st, a, tm, tl)
+                                 : launch_dependent(batch_kernel<false, 2, P16>, grid, kBatchThreads, smem, st, a, tm, tl);
+    return cos ? launch_dependent(batch_kernel<true, 4, P16>, grid, kBatchThreads, smem, st, a, tm, tl)
+               : launch_dependent(batch_kernel<false, 4, P16>, grid, kBatchThreads, smem, st, a, tm, tl);
 }
 
 cudaError_t launch_batch(const BatchArgs &a, cudaStream_t st) {
@@ -873,9 +875,7 @@ cudaError_t launch_batch(const BatchArgs &a, cudaStream_t st) {
     if (a.slice < 2 || a.slice > a.C || (a.slice & 1u)) return cudaErrorInvalidValue;
     const size_t smem = batch_smem_bytes(a.slice, a.stages, a.keep);
     const dim3 grid(a.ngroups * a.nranges);
-    if (a.codes_lo) launch_variant<true>(a, tm, tl, grid, smem, st);
-    else launch_variant<false>(a, tm, tl, grid, smem, st);
-    return cudaGetLastError();
+    return a.codes_lo ? launch_variant<true>(a, tm, tl, grid, smem, st) : launch_variant<false>(a, tm, tl, grid, smem, st);
 }
 
 } // namespace szg

@@ -13,6 +13,7 @@ namespace szg {
 //   32/64-bit rows: the query converted to fp32 / kept fp64, padded per chunk.
 // The header carries the scale factors and the rigorous surrogate error bound.
 __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
+    grid_launch_dependents(); // batch_kernel (a programmatic dependent) sets itself up and prefetches rows while this runs
     __shared__ double s_red[2][8];
     __shared__ double s_out[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

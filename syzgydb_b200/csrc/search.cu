@@ -314,6 +314,10 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
             h->planar_nblk = nblk_now;
         }
     }
+    // The groups' next-tile counters sit behind the bound keys: one memset presets both (a counter's first grab is old + 1 = 0).
+    // Before prep, not between prep and the scan: batch_kernel is a programmatic dependent of prep_kernel and starts while it
+    // runs, so everything else the scan reads must be complete before prep starts.
+    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, ((size_t)nq * p.gm_stride + p.ngroups) * sizeof(unsigned int), st));
     PrepArgs pa;
     pa.queries = d_q; pa.pq = ws->d_pq.p; pa.pq_stride = stride;
     pa.dims = (uint32_t)h->dim; pa.C = p.Cb; pa.metric = (uint32_t)h->metric; pa.maxint = h->maxint;
@@ -330,10 +334,8 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
     b.C = p.Cb; b.nblk = nblk_now; b.metric = (uint32_t)h->metric; b.nq = nq; b.dims = (uint32_t)h->dim;
     b.nranges = p.nranges; b.nlists = p.nranges; b.stages = p.stages; b.slice = p.slice;
     b.gmth = ws->d_gmth.p; b.mth = p.mth; b.gm_sp = p.gm_sp; b.gm_stride = p.gm_stride;
-    // the groups' next-tile counters sit behind the bound keys: one memset presets both (a counter's first grab is old + 1 = 0)
     static const bool fixed_ranges = getenv("SZG_BATCH_FIXED_RANGES") && atoi(getenv("SZG_BATCH_FIXED_RANGES")) != 0;
     b.tile_ctr = (fixed_ranges || p.nranges < 2) ? nullptr : ws->d_gmth.p + (size_t)nq * p.gm_stride;
-    CK(cudaMemsetAsync(ws->d_gmth.p, 0xFF, ((size_t)nq * p.gm_stride + p.ngroups) * sizeof(unsigned int), st));
     static const uint32_t dbg = getenv("SZG_BATCH_DEBUG") ? (uint32_t)atoi(getenv("SZG_BATCH_DEBUG")) : 0u;
     b.debug = dbg;
     static const uint32_t pns = getenv("SZG_BATCH_POLL_NS") ? (uint32_t)atoi(getenv("SZG_BATCH_POLL_NS")) : 0u;
