@@ -610,12 +610,17 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         if (R > 1 && nqv) {
             constexpr uint32_t Kp = 32 * E;
             const uint32_t need = (Kp + a.mth - 1) / a.mth;
-            // with several query groups per launch the row tiles come from L2 and the polls compete with them: poll less often
-            const uint32_t pause = a.poll_ns ? a.poll_ns : 1000u * a.ngroups * a.ngroups;
+            // pause between rounds once every query has a bound: doubling from 0.5 us (the bound tightens fastest over the first
+            // tiles) up to 2 us x (query groups per launch) -- with several groups the row tiles come from L2 and the polls
+            // compete with them (measured, 1024 queries = 16 groups on 1.25 M rows: cap 16 / 64 / 256 / 1000 us -> 1.77 / 1.80 / 1.87 / 1.88 ms)
+            const uint32_t pause_max = a.poll_ns ? a.poll_ns : (a.ngroups == 1 ? 1000u : 2000u * a.ngroups);
+            uint32_t pause = min(500u, pause_max);
             while (*reinterpret_cast<volatile uint32_t *>(&s_epi_done) < 8u) {
                 const bool all = poll_bounds(a.gmth, a.gm_stride, a.gm_sp, need, q0 + qp, nqv, &s_q[qp], &s_epi_done);
                 // sleep in short slices: the CTA must not outlive its epilogue warps by a pause
-                for (uint32_t t = 0; t < (all ? pause : 100u) && *reinterpret_cast<volatile uint32_t *>(&s_epi_done) < 8u; t += 250u)
+                const uint32_t nap = all ? pause : 100u;
+                if (all) pause = min(pause * 2u, pause_max);
+                for (uint32_t t = 0; t < nap && *reinterpret_cast<volatile uint32_t *>(&s_epi_done) < 8u; t += 250u)
                     __nanosleep(all ? 250u : 100u);
             }
         }
