@@ -668,6 +668,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             return have;
         };
         bool seeding = R > 1;
+        const bool idle = q0 + qw >= a.nq; // none of this warp's queries exists
         const bool tr = a.trace && blockIdx.x == 0 && warp == 4 && lane == 0; // warp 4 owns queries 0..7 of the group
         if (tr) a.trace[0] = clock64();
         for (uint32_t tile = 0;; ++tile) {
@@ -677,6 +678,20 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
             mbar_wait(&x_full[x], (tile / kAuxSlots) & 1u);
             const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(&s_xsup[x]);
             if (cur == kNoBlock) break;
+            if (idle) {
+                // a warp whose 8 queries lie past the end of the batch (32 queries per call: half of the epilogue warps) only
+                // keeps the pipeline's books: no accumulator reads, no scoring -- that work bought nothing and, at the power
+                // cap this kernel runs into under sustained load, cost clock
+                mbar_wait(&d_full[d], (P16 ? tile : (tile >> 1)) & 1u);
+                if (lane == 0) mbar_arrive(&d_empty[d]);
+                if (P16) {
+                    mbar_wait(&d_full[1], tile & 1u);
+                    if (lane == 0) mbar_arrive(&d_empty[1]);
+                }
+                if (lane == 0) mbar_arrive(&x_empty[x]);
+                seeding = false;
+                continue;
+            }
             if (R > 1 && !seeding) fold_bounds();
             const uint32_t capm1 = seeding ? mthm1 : Kp - 1;
             mbar_wait(&d_full[d], (P16 ? tile : (tile >> 1)) & 1u); // 16-bit: d = 0, the high-byte buffer
