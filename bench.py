@@ -458,14 +458,25 @@ def run_b200(a):
         return ix.last_scan_times_ms(65536)
     sampler.wait_first()
 
-    # ---- value: queries resident in HBM.  The library's per-launch event pairs (SZG_OPT_TIMING = 2) are off here: an event record
-    # between a scan and its finalize kernel would undo their programmatic dependent launch; kernel durations come from a
-    # serial pass of the same steps right after the timed region.
+    # ---- value: queries resident in HBM.  The library's per-launch event pairs (SZG_OPT_TIMING = 2) are off in the timed region: an
+    # event record between a scan and its finalize kernel would undo their programmatic dependent launch.
+    # Kernel durations for the roofline: the timed steps ONE at a time, with the library's CUDA event pair around every scan
+    # launch, BEFORE the timed region and followed by a second of idle, so that both run in the same power state (a long run of
+    # these steps hits the board's power cap and drops the SM clock -- the sustained leg below reports that regime).  With several
+    # steps in flight the scans of consecutive steps share the SMs (row tiles are dealt to CTAs on demand), so an event pair
+    # around one launch inside the timed region would also span part of its neighbour's work.
+    ix.set_option(_capi.OPT_TIMING, 2)
+    for s in range(max(a.warmup, 3)):
+        run.topk(dq[s % total_steps], a.k, slot=0)
+    torch.cuda.synchronize(dev)
+    kernel_times()
+    ms_serial, _, _ = timed(torch, dev, lambda i, slot: run.topk(dq[a.warmup + i], a.k, slot=slot), a.steps, run, 1)
+    scan_ms = kernel_times()
+    time.sleep(1.0)
     ix.set_option(_capi.OPT_TIMING, 0)
     for s in range(max(a.warmup, IN_FLIGHT)):
         run.topk(dq[s % total_steps], a.k, slot=s % IN_FLIGHT)
     torch.cuda.synchronize(dev)
-    kernel_times()
     st0 = ix.stats()
     ms, w0, w1 = timed(torch, dev, lambda i, slot: run.topk(dq[a.warmup + i], a.k, slot=slot), a.steps, run)
     clocks = sampler.window(w0, w1)
@@ -473,15 +484,6 @@ def run_b200(a):
         clocks = sampler.window(w0 - 0.3, w1 + 0.3)
         clocks["note"] = "timed region shorter than the 100 ms sampling interval: samples within +-0.3 s of it; sustained.clocks covers >= 2 s of the same steps"
     st1 = ix.stats()
-    # kernel durations for the roofline: the same steps once more, ONE at a time, with the library's CUDA event pair around every
-    # scan launch.  (With several steps in flight the scans of consecutive steps share the SMs -- row tiles are dealt to CTAs on
-    # demand -- so an event pair around one launch would also span part of its neighbour's work.)
-    ix.set_option(_capi.OPT_TIMING, 2)
-    run.topk(dq[a.warmup], a.k, slot=0)
-    torch.cuda.synchronize(dev)
-    kernel_times()
-    ms_serial, _, _ = timed(torch, dev, lambda i, slot: run.topk(dq[a.warmup + i], a.k, slot=slot), a.steps, run, 1)
-    scan_ms = kernel_times()
     launches = st1["kernel_launches"] - st0["kernel_launches"]
     tensor_served = st1["batch_queries"] - st0["batch_queries"]
     qps = a.nq * a.steps / (ms / 1e3)
@@ -578,8 +580,8 @@ def run_b200(a):
                 "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel, "alg_bytes_per_launch": alg_bytes,
                 "alg_bytes_note": alg_note, "mean_launch_ms": mean_scan_ms, "launches_timed": int(len(scan_ms)),
                 "serial_ms_per_step": ms_serial / a.steps,
-                "launch_ms_note": ("mean_launch_ms: CUDA events around every scan launch of the timed steps, re-run one step at a time right "
-                                   "after the timed region (same queries; serial_ms_per_step is that pass's step time).  In the timed region "
+                "launch_ms_note": ("mean_launch_ms: CUDA events around every scan launch of the timed steps, run one step at a time right "
+                                   "before the timed region (same queries, then 1 s idle; serial_ms_per_step is that pass's step time).  In the timed region "
                                    "itself steps are in flight together and neighbouring launches share the SMs, so a per-launch event pair "
                                    "there would span part of the neighbour's work; step_floor_gbs = algorithmic bytes / ms_per_step is the "
                                    "throughput the timed region itself proves"),

@@ -916,3 +916,38 @@ def test_short_row_kernel_matches_general_kernel_and_oracle(bits, dims):
                                            passmask=passmask[keep] if masked else None)
                 assert_results_match(a[0][qi, :a[2][qi]], a[1][qi, :a[2][qi]], ri, rd, what=f"short rows b{bits} d{dims} nq{nq}")
                 assert a[2][qi] == min(k, int(live.sum()))
+
+
+@pytest.mark.parametrize("metric", [szg.COSINE, szg.EUCLIDEAN])
+@pytest.mark.parametrize("nq,k", [(20, 10), (20, 40), (5, 100), (64, 100), (130, 60)])
+def test_batch_every_sm_has_a_range_and_lists_are_wider_than_a_warp(metric, nq, k):
+    """Enough rows that a query group is spread over all 148 CTAs (row tiles dealt on demand), with candidate lists of 32 / 64 /
+    128 keys: the shared bound is then built from 32 / 64 / 128 groups of published keys (more groups than lanes of the polling
+    warp for the wider lists).  Results are what nq single Search calls return, bit for bit."""
+    dims, n = 64, 40_000
+    seed = 7100 + nq + k
+    codes = o.synth_rows(seed, 0, n, dims, 8)
+    ids = np.arange(n, dtype=np.uint64) * 3 + 1
+    queries = o.synth_queries(seed + 1, 0, nq, dims)
+    with _build(codes, ids, dims, 8, metric) as ix:
+        gi, gd, gn, scanned = _batch_vs_oracle(ix, codes, ids, dims, metric, queries, k, what=f"148 ranges m{metric} nq{nq} k{k}")
+        assert scanned == n
+        ix.set_option(_capi.OPT_BATCH_TENSOR, 0)
+        si, sd, sn, _ = ix.search_topk(queries, k)
+        assert np.array_equal(gn, sn) and np.array_equal(gi, si) and np.array_equal(gd, sd)
+
+
+def test_batch_sparse_filter_over_all_ranges():
+    """A 1 % filter over a collection that fills all 148 ranges: most ranges cannot seed the shared bound from their first tile
+    (its best row is filtered out) and publish "no bound"; the others' keys must still never cut a passing row."""
+    dims, n, nq, k = 64, 40_000, 24, 10
+    codes = o.synth_rows(7301, 0, n, dims, 8)
+    ids = np.arange(n, dtype=np.uint64)
+    queries = o.synth_queries(7302, 0, nq, dims)
+    rng = np.random.default_rng(7303)
+    with _build(codes, ids, dims, 8, szg.COSINE) as ix:
+        for density in (0.01, 0.0005):
+            passmask = (rng.random(n) < density).astype(np.uint8)
+            mask = ix.mask_create(ids, passmask)
+            _batch_vs_oracle(ix, codes, ids, dims, szg.COSINE, queries, k, mask_id=mask, passmask=passmask,
+                             what=f"sparse filter {density}")
