@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kBatchThreads, 1) batch_kernel(const BatchArgs
         // 2 chunks = 32 K-bytes = 8 columns = one MMA K step.  The digit loads of 4 K steps are issued together before their
         // stores (the stores are asm volatile with a memory clobber: one step at a time, every step paid a full L2 round
         // trip -- ~15 us of every launch for 768-dimension rows)
-        constexpr uint32_t KB = 4;
+        constexpr uint32_t KB = 12;
         for (uint32_t ks0 = 0; ks0 < C / 2; ks0 += KB) {
             uint4 v0[KB], v1[KB];
 #pragma unroll
