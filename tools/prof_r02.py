@@ -2,7 +2,8 @@
    python tools/prof_r02.py single   -- 1 query per call on 10M x 768 8-bit (scan_small + finalize)
    python tools/prof_r02.py batch32  -- 32 queries per call (batch_kernel, the headline launch)
    python tools/prof_r02.py rescore  -- 200 k gathered fp64 rows (rescore_kernel) and 200-candidate calls
-   python tools/prof_r02.py radius   -- cfg3 radius search"""
+   python tools/prof_r02.py radius   -- cfg3 radius search
+   python tools/prof_r02.py batch1024 [rows] [bits] -- 1024 queries per call (batch_kernel, 16 query groups per launch)"""
 import os
 import sys
 
@@ -24,6 +25,16 @@ if mode in ("single", "batch32"):
         nq = 1 if mode == "single" else 32
         for _ in range(4):
             ix.search_topk(rng.uniform(-1, 1, size=(nq, 768)), 10)
+elif mode == "batch1024":
+    n = rows or 1_250_000
+    bits = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    with szg.Index(768, bits, szg.COSINE if bits == 8 else szg.EUCLIDEAN) as ix:
+        ix.fill_synthetic(0x5A590004, 0, n)
+        ix.set_option(_capi.OPT_GRAPHS, 0)
+        ix.set_option(_capi.OPT_COMBINE, 0)
+        q = rng.uniform(-1, 1, size=(1024, 768))
+        for _ in range(3):
+            ix.search_topk(q, 10 if bits == 8 else 100)
 elif mode == "rescore":
     n = rows or 1_000_000
     with szg.Index(384, 64, szg.COSINE) as ix:
