@@ -13,7 +13,8 @@
 //                 so TMA lands K slices of a super tile in shared memory ([chunk][block][512 B]) and
 //                 tcgen05.mma consumes them without any reshuffle;
 //   D           : 128 x 128 s32 accumulators in TMEM, double buffered.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-9 = epilogue (8 queries each).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-9 = epilogue (8 queries each), warps 10-11 = bound
+// pollers (they keep the bound shared by a query's CTAs current, see poll_bounds).
 // Pipelines: a ring of K slices (full/empty mbarriers; the ring never drains between super tiles) and the
 // two accumulator buffers (tcgen05.commit -> epilogue -> release).
 //
@@ -27,8 +28,10 @@
 // occasional compaction (bitonic sort in registers) and threshold updates need warp-level
 // synchronisation only.  Liveness / filter bits are checked only for rows that pass the fast test (a removed or
 // filtered row passes it as rarely as a live one does).
-// CTAs are (query group g, row range r): the groups of a batch walk the same row range at the same time,
-// so HBM is read once per range and the other reads hit L2.
+// CTAs are (query group g, range r).  The 128-row tiles of the collection are dealt to the CTAs of a group on demand (one atomic
+// counter per group, next_live_tile), every group in ascending tile order at about the same pace, so HBM is read once and the
+// other groups' reads hit L2.  A CTA keeps one sorted candidate list per query for the rows it saw ("range" below = the rows of
+// one CTA).  The launch is a programmatic dependent of prep_kernel and finalize_kernel one of this launch (common.cuh).
 // The candidate buffers feed the same finalize_kernel as the scan path (fp64 re-score, ordering,
 // certification against the surrogate error bound), so results are identical to single queries.
 #include <cuda.h>
