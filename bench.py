@@ -553,7 +553,7 @@ def run_b200(a):
     if on_tensor:
         kernel = (f"batch_kernel<{a.metric}> (tcgen05.mma kind::i8: {a.nq} queries x 2 digit planes on M = 128, 128 rows per MMA; TMA "
                   f"3-D tile loads; fused threshold top-k epilogue); one launch per device and step, {rows_gpu} rows each")
-        alg_bytes = rows_gpu * rb * (2 if a.quant == 16 else 1) / max(launches_per_step, 1e-9) * 1.0
+        alg_bytes = rows_gpu * rb / max(launches_per_step, 1e-9)  # 16-bit: the two byte planes together are the row's 2 bytes per code
         alg_note = ("algorithmic bytes of this launch = rows_per_gpu x getVectorSize: the queries of a step share ONE pass over the "
                     "shard (SURVEY 8d's per-query figure would count the same bytes once per query)")
         tkey = f"batch_q{a.quant}_d{a.dims}_nq{a.nq}"
