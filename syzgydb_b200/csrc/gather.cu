@@ -11,6 +11,8 @@
 // (exact_staged, scan_impl.cuh) and lets thread r run candidate r's sequential fp64 chain out of shared memory.  Float rows
 // keep their 16-byte chunks in groups of 8 (common.cuh), so the fetch reads whole 128-byte lines: algorithmic bytes =
 // m x rowbytes, and that is what comes from DRAM.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace szg {
@@ -205,6 +207,10 @@ cudaError_t launch_rescore(const RescoreArgs &a, cudaStream_t st) {
     if (!a.m) return cudaSuccess;
     // few candidates (one speculative batch of the LSH walk: ~200): small CTAs spread them over the SMs and the slabs get
     // long; many (radius hits, bulk re-scoring): 128 candidates per CTA keep the fetches wide
+    // (8 per CTA for one LSH batch: a CTA's rows then fit one slab -- one round of fetch latency instead of four -- and the
+    // products of 8 candidates leave the fp64 pipe to the chains; SZG_RESCORE_KP=32 for the A/B)
+    static const unsigned small_kp = getenv("SZG_RESCORE_KP") ? (unsigned)atoi(getenv("SZG_RESCORE_KP")) : 8u;
+    if (small_kp == 8u && a.m <= 8u * 296u) return rescore_nt<8>(a, st);
     return a.m <= 32u * 296u ? rescore_nt<32>(a, st) : rescore_nt<128>(a, st);
 }
 

@@ -929,11 +929,14 @@ int rescore_device(szg_index *h, const double *queries, uint32_t nl, const uint6
     ra.m1 = reinterpret_cast<const double *>(ws->d_out_pack.p + qonly);
     ra.list_off = reinterpret_cast<const uint32_t *>(ws->d_out_pack.p + qbytes); ra.nlists = nl;
     ra.slots = reinterpret_cast<const uint32_t *>(ws->d_out_pack.p + qbytes + obytes);
-    ra.out_dist = ws->d_out_dist.p; ra.out_ids = nullptr;
+    // one LSH batch (a few hundred distances): the kernel stores them straight into the pinned host buffer (unified addressing:
+    // the same pointer is valid on the device) -- one asynchronous operation less on a call that is all latency
+    const bool direct = m <= 4096;
+    ra.out_dist = direct ? ws->h_out_dist.p : ws->d_out_dist.p; ra.out_ids = nullptr;
     ra.C = h->C; ra.dims = (uint32_t)h->dim; ra.metric = (uint32_t)h->metric; ra.m = (uint32_t)m; ra.qt = h->qt;
     CK(launch_rescore(ra, st));
     h->launches++;
-    CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, m * 8, cudaMemcpyDeviceToHost, st));
+    if (!direct) CK(cudaMemcpyAsync(ws->h_out_dist.p, ws->d_out_dist.p, m * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     memcpy(out_dist, ws->h_out_dist.p, m * 8);
     return SZG_OK;
