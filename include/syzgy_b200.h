@@ -212,8 +212,8 @@ int szg_meta_dictionary_get(szg_index *h, uint32_t code, const char **str, uint3
 
 
 /*
- * Exact top-k for nq queries.  One to three queries are memory-bound scans (each streams the whole
- * mirror: single-query GEMV semantics); from SZG_OPT_BATCH_MIN_QUERIES queries on the call is a
+ * Exact top-k for nq queries.  A single query is a memory-bound scan (it streams the whole
+ * mirror: single-query GEMV semantics); from SZG_OPT_BATCH_MIN_QUERIES queries on (2 to 12 by default, see there) the call is a
  * batch and takes the tensor-core contraction of szg_search_batch when the geometry fits -- same
  * results, bit for bit.  Replaces: Search with Precision=="exact",
  * Radius==0, K>0 (collection.go:672-684 driving consider 583-629 and the drain 693-697).
@@ -389,8 +389,10 @@ int szg_get_stats(szg_index *h, szg_stats *out);
                                         RLock, collection.go:570) with the same k / mask / flags share one launch: whoever
                                         arrives while a launch is running is answered together by the next one; 0: off */
 #define SZG_OPT_BATCH_MIN_QUERIES 10 /* szg_search_topk(_dev) calls with at least this many queries are batches: they take
-                                        the tensor-core contraction when its geometry fits (default 4, the measured
-                                        crossover: one or two queries are HBM-bound scans, four cost one batched pass) */
+                                        the tensor-core contraction when its geometry fits.  0 (default): chosen by the size
+                                        of the mirror from the measured crossovers -- 2 from 2 GB on, 3 from 512 MB on (the
+                                        rows stream from HBM once per call instead of once per query), else 12 (cache-resident
+                                        scans cost 3-13 us per extra query, the contraction ~100 us per call) */
 #define SZG_OPT_GRAPHS 11            /* 1 (default): repeated host-buffer top-k call shapes are replayed as one captured
                                         launch sequence (CUDA graph) instead of launch by launch; 0: off */
 #define SZG_OPT_TRACE_BUFFER 12      /* profiling: a device pointer to 8 int64 words that finalize_kernel's first CTA fills with

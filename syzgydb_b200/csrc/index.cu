@@ -234,7 +234,7 @@ int szg_set_option(szg_index *h, int option, int64_t value) {
         return SZG_OK;
     case SZG_OPT_BATCH_TENSOR: h->batch_disabled = value == 0; return SZG_OK;
     case SZG_OPT_BATCH_MIN_QUERIES:
-        if (value < 1 || value > 4096) return fail(SZG_EINVAL, "batch threshold must be in [1, 4096]");
+        if (value < 0 || value > 4096) return fail(SZG_EINVAL, "batch threshold must be in [0, 4096]");
         h->batch_min = (int)value;
         return SZG_OK;
     case SZG_OPT_GRAPHS: h->use_graphs = value != 0; return SZG_OK;

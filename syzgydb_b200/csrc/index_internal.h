@@ -211,7 +211,7 @@ struct szg_index {
     int scan_warps = 16, scan_stages = 2, scan_tile_chunks = 8;
     bool scan_geometry_set = false; // SZG_OPT_SCAN_* given: no automatic choice
     int batch_disabled = 0; // SZG_OPT_BATCH_TENSOR = 0 routes batches to the streaming scan
-    int batch_min = 4;      // SZG_OPT_BATCH_MIN_QUERIES: calls with at least this many queries take the tensor-core path
+    int batch_min = 0;      // SZG_OPT_BATCH_MIN_QUERIES: calls with at least this many queries take the tensor-core path (0: by size)
     int use_graphs = 1;     // SZG_OPT_GRAPHS
     long long *trace = nullptr; // SZG_OPT_TRACE_BUFFER: device buffer of 8 clock64 stamps written by finalize_kernel (profiling)
     // 16-bit / 4-bit collections: byte copy of the codes, the operand of the batched path (rebuilt lazily after mutations)

@@ -367,7 +367,7 @@ static int run_batch(szg_index *h, Workspace *ws, const BatchPlan &p, const doub
 }
 
 // One top-k pass for nq queries: the tensor-core contraction when the call is a batch (prefer_batch, or at least
-// batch_min queries -- measured crossover: a combined batch of 4 single-query callers already wins)
+// batch_min queries, by default a threshold that depends on the size of the mirror, see below)
 // and its geometry fits, else the streaming scan.
 int enqueue_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, uint32_t k, const uint32_t *mask, uint32_t flags,
                  bool prefer_batch, int min_mode, int force_nd, unsigned long long *d_out_ids, double *d_out_dist, uint32_t *d_out_n,
@@ -384,7 +384,17 @@ int enqueue_topk(szg_index *h, Workspace *ws, const double *d_q, uint32_t nq, ui
         return SZG_OK;
     }
     BatchPlan p;
-    if (nd == 2 && (prefer_batch || nq >= (uint32_t)std::max(1, h->batch_min)) && plan_batch(h, nq, k, mode, &p))
+    // From how many queries on a call is a batch.  Default (batch_min == 0): by the size of the mirror -- a collection that
+    // streams from HBM is read once per call by the contraction against once per query by the scans, so two queries are
+    // enough (10 M x 768 8-bit: 1.14 vs 1.40 ms, three: 1.30 vs 1.91 ms); a cache-resident one pays the contraction's fixed
+    // ~90-150 us against 3-13 us per extra scan (100 k x 384 8-bit, eight queries: 101 vs 78 us; 1 M x 128 4-bit: 157 vs 129 us).
+    // profiles/r02_dispatch_crossover.log
+    uint32_t bmin = (uint32_t)h->batch_min;
+    if (bmin == 0) {
+        const size_t bytes = (size_t)h->nslots * h->rowbytes;
+        bmin = bytes >= ((size_t)2 << 30) ? 2u : bytes >= ((size_t)512 << 20) ? 3u : 12u;
+    }
+    if (nd == 2 && (prefer_batch || nq >= bmin) && plan_batch(h, nq, k, mode, &p))
         return run_batch(h, ws, p, d_q, nq, k, mask, flags, d_out_ids, d_out_dist, d_out_n, d_out_flags, sink);
     return run_topk(h, ws, d_q, nq, k, mask, flags, mode, nd, d_out_ids, d_out_dist, d_out_n, d_out_flags, sink);
 }
